@@ -1,0 +1,191 @@
+/* lnrf.h — C ABI of the B200-native learn-nerf hot path (liblnrf.so).
+ *
+ * One entry point per implicit op group of the reference's hot path
+ * (SURVEY.md §2.1 K1..K10).  The reference (unixpickle/learn-nerf) has no
+ * plugin/FFI interface of its own: the path is ordinary JAX code behind three
+ * Python call seams (render.py:320 model.apply, render.py:39 render_rays,
+ * train.py:78 step_fn).  Each function below names the reference lines whose
+ * arithmetic it replaces; learn-nerf_b200/learn_nerf/ binds them with ctypes and
+ * re-exposes the reference's Python signatures, and INTEGRATION.md shows the
+ * XLA-FFI handler a JAX maintainer would register instead.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the parameter is marked "host";
+ *  - all arrays are dense, row-major, fp32 unless stated; `mask` is uint8 0/1;
+ *  - the library never allocates, frees or synchronises: the caller owns every
+ *    buffer (incl. workspaces sized by the *_workspace_bytes queries) and every
+ *    call only enqueues work on `stream` (a cudaStream_t passed as void*);
+ *  - return value: 0 ok; <0 invalid argument (see LNRF_E_*); >0 a cudaError_t.
+ *    lnrf_last_error() returns a thread-local message for the last failure;
+ *  - no CPU fallback exists anywhere: without a CUDA device every compute
+ *    entry fails with a cudaError_t.
+ */
+#ifndef LNRF_H_
+#define LNRF_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LNRF_OK 0
+#define LNRF_E_INVALID (-1)     /* null pointer, negative size, bad enum */
+#define LNRF_E_UNSUPPORTED (-2) /* shape outside what the kernels implement */
+#define LNRF_E_WORKSPACE (-3)   /* workspace too small / misaligned */
+
+#define LNRF_PREC_FP32 0 /* fp32 SIMT FFMA path: 1e-5 abs vs the oracle */
+#define LNRF_PREC_BF16 1 /* bf16 tcgen05/TMEM path: 2e-2 abs vs the oracle */
+
+typedef void* lnrf_stream_t; /* cudaStream_t */
+
+const char* lnrf_last_error(void);
+int lnrf_version(void);
+/* One-time per-process setup for `device` (function attributes, SM count). */
+int lnrf_init(int device);
+
+/* ---------------------------------------------------------------- K1 sampling
+ * ray_t_range (render.py:346-389, vmapped at :93-111) + stratified_sampling
+ * (render.py:121-143).  Bit-exact with oracle.render_np given the same `u`.
+ * rays [n,2,3]; bbox_min/bbox_max host[3]; u [n,T] in [0,1);
+ * out: t_min[n], t_max[n], mask[n] (uint8), ts[n,T].                         */
+int lnrf_sample_coarse(const float* rays, int64_t n, const float* bbox_min_host,
+                       const float* bbox_max_host, float min_t_range, float epsilon,
+                       const float* u, int32_t T, float* t_min, float* t_max,
+                       uint8_t* mask, float* ts, lnrf_stream_t stream);
+
+/* stratified_sampling alone (render.py:121-143) on given bounds t_min/t_max[n]:
+ * ts[n,T] = (k*bin + t_min) + u*bin, bin = (t_max - t_min)/T.  Bit-exact.        */
+int lnrf_stratified(const float* t_min, const float* t_max, const float* u, int64_t n, int32_t T,
+                    float* ts, lnrf_stream_t stream);
+
+/* ---------------------------------------------------------------- K4 fine sampling
+ * RaySamples.fine_sampling (render.py:211-257) incl. termination_probs
+ * (:270-287), the inverse CDF via jnp.interp and the final sort.  Bit-exact with
+ * the oracle given the same (ts, densities, u).  ts_c/dens_c [n,Tc]; u [n,Tf];
+ * out ts_out [n,Tc+Tf] ascending.  Optional (nullable) debug outputs:
+ * idx_out [n,Tf] int32 = interp bin index i in [1,Tc]; new_ts_out [n,Tf] =
+ * the unsorted inverse-CDF samples.  Tc <= 256, Tc+Tf <= 1024.               */
+int lnrf_sample_fine(const float* ts_c, const float* dens_c, const float* t_min,
+                     const float* t_max, const float* u, int64_t n, int32_t Tc, int32_t Tf,
+                     float eps, float* ts_out, int32_t* idx_out, float* new_ts_out,
+                     lnrf_stream_t stream);
+
+/* ---------------------------------------------------------------- K3 compositing
+ * termination_probs + RaySamples.render_rays / render_alpha and the coords
+ * render (render.py:155-190, 270-287, 329-331).  dens [n,T]; rgb [n,T,3];
+ * background device[3]; out outputs[n,3], alphas[n] ([n,1]), coords[n,3]
+ * (alphas/coords nullable).                                                  */
+int lnrf_composite_fwd(const float* rays, const float* ts, const float* t_min,
+                       const float* t_max, const uint8_t* mask, const float* dens,
+                       const float* rgb, const float* background, int64_t n, int32_t T,
+                       float* outputs, float* alphas, float* coords, lnrf_stream_t stream);
+
+/* K5: reverse-scan gradient of K3 w.r.t. dens, rgb and background given
+ * d_outputs[n,3] (what jax.grad derives at train.py:90).
+ * d_dens[n,T], d_rgb[n,T,3] are overwritten; d_background[3] is ACCUMULATED
+ * (caller zeroes it).                                                         */
+int lnrf_composite_bwd(const float* ts, const float* t_min, const float* t_max,
+                       const uint8_t* mask, const float* dens, const float* rgb,
+                       const float* background, const float* d_outputs, int64_t n, int32_t T,
+                       float* d_dens, float* d_rgb, float* d_background, lnrf_stream_t stream);
+
+/* MSE loss and its gradient (train.py:140-142): loss_sum[0] += sum((out-tgt)^2)
+ * over this call's n*3 values (caller divides by the global count);
+ * d_outputs = 2*(out-tgt)*inv_count.  targets is a strided view: element
+ * (i,c) at targets[i*target_stride + c] (batch[:,2] of an [n,3,3] batch has
+ * stride 9).                                                                  */
+int lnrf_mse_loss(const float* outputs, const float* targets, int64_t target_stride, int64_t n,
+                  float inv_count, float* loss_sum, float* d_outputs, lnrf_stream_t stream);
+
+/* ---------------------------------------------------------------- K2/K6 NeRF MLP
+ * NeRFModel.__call__ with the default architecture (model.py:35-62):
+ * sinusoidal_emb(x,10)/(d,4), 5+4 Dense(256) with the skip concat, softplus
+ * density head, 128-wide colour layer, tanh rgb.  Other sizes: LNRF_E_UNSUPPORTED.
+ *
+ * params: flat fp32, Dense_0.kernel[60,256], Dense_0.bias[256], Dense_1.kernel,
+ * ... Dense_11.bias[3] (kernel row-major [in,out] as in Flax), every tensor
+ * starting on a 4-float boundary (zero padding): see lnrf_nerf_param_offsets.
+ *
+ * Inputs are either explicit points (x[m,3], d[m,3]; rays==NULL) as in
+ * model.apply (render.py:320-324), or ray mode (x==NULL): rays[n,2,3] and
+ * ts[n,T] with m = n*T, point = o + d*t (render.py:145-153, :319).
+ * Outputs dens[m], rgb[m,3].  With save_for_backward != 0 the activations
+ * needed by lnrf_nerf_mlp_bwd are kept in `workspace`.                        */
+int64_t lnrf_nerf_param_count(void);  /* logical parameters: 593,924 */
+int64_t lnrf_nerf_param_floats(void); /* floats in the flat buffer incl. 16-byte padding */
+/* host out[24]: float offsets of kernel_i (out[2i]) and bias_i (out[2i+1]). */
+int lnrf_nerf_param_offsets(int64_t* out_host);
+/* bf16 path: bf16 UMMA operand images of `params` (lnrf_nerf_packed_bytes() bytes,
+ * 1024-byte aligned).  Rebuild with lnrf_nerf_pack_weights after every update.  */
+int64_t lnrf_nerf_packed_bytes(void);
+int lnrf_nerf_pack_weights(const float* params, void* packed, lnrf_stream_t stream);
+int lnrf_nerf_mlp_workspace_bytes(int64_t m, int32_t precision, int32_t save_for_backward,
+                                  int64_t* bytes_out_host);
+/* `packed` is required for LNRF_PREC_BF16 and ignored (may be NULL) for fp32. */
+int lnrf_nerf_mlp_fwd(const float* params, const void* packed, const float* x, const float* d,
+                      const float* rays, const float* ts, int64_t n, int32_t T, int32_t precision,
+                      int32_t save_for_backward, void* workspace, int64_t workspace_bytes,
+                      float* dens, float* rgb, lnrf_stream_t stream);
+/* Gradient of the above w.r.t. params given d_dens[m], d_rgb[m,3]; uses the
+ * workspace written by the matching forward call.  d_params
+ * (lnrf_nerf_param_floats() floats) is ACCUMULATED.  Inputs x/d/rays/ts carry
+ * no gradient.                                                 */
+int lnrf_nerf_mlp_bwd(const float* params, const void* packed, int64_t m, int32_t precision,
+                      void* workspace, int64_t workspace_bytes, const float* dens, const float* rgb,
+                      const float* d_dens, const float* d_rgb, float* d_params,
+                      lnrf_stream_t stream);
+
+/* ---------------------------------------------------------------- K10 optimiser
+ * tree_norm x2 + optax.adam + apply_updates (train.py:59,92-106) over one flat
+ * buffer.  g' = grads*grad_scale (1/world after an all-reduce);
+ * norms_out[0] += sum(g'^2), norms_out[1] += sum(params_before^2) (caller
+ * zeroes, takes sqrt); m,v,params updated in place; step is 1-based.          */
+int lnrf_adam_step(float* params, const float* grads, float* m, float* v, int64_t count,
+                   float lr, float b1, float b2, float eps, int32_t step, float grad_scale,
+                   float* norms_out, lnrf_stream_t stream);
+
+/* ---------------------------------------------------------------- K7/K8 hash grid
+ * MultiresHashTableEncoding / HashTableEncoding / hash_table_lookup
+ * (instant_ngp.py:92-224), feature_dim F=2.  tables: all levels concatenated,
+ * level l starts at float offset level_offsets_host[l]; level l has
+ * grid_sizes_host[l]; it is hashed iff grid^3 > table_sizes_host[l].
+ * x[m,3] -> enc[m,2L].  L <= 16.                                              */
+int lnrf_hashgrid_fwd(const float* tables, const int64_t* level_offsets_host,
+                      const int32_t* grid_sizes_host, const int32_t* table_sizes_host, int32_t L,
+                      const float* bbox_min_host, const float* bbox_max_host, int32_t smooth,
+                      const float* x, const float* rays, const float* ts, int64_t n, int32_t T,
+                      float* enc, lnrf_stream_t stream);
+/* scatter-add of d_enc[m,2L] into d_tables (ACCUMULATED; same layout as tables). */
+int lnrf_hashgrid_bwd(const int64_t* level_offsets_host, const int32_t* grid_sizes_host,
+                      const int32_t* table_sizes_host, int32_t L, const float* bbox_min_host,
+                      const float* bbox_max_host, int32_t smooth, const float* x,
+                      const float* rays, const float* ts, int64_t n, int32_t T,
+                      const float* d_enc, float* d_tables, lnrf_stream_t stream);
+
+/* InstantNGPModel heads (instant_ngp.py:37,46-53) on a precomputed encoding:
+ * enc[m,2L] (+ d[m,3] or ray mode) -> dens[m], rgb[m,3].  params: Dense_0..4
+ * flat (kernel then bias each).  Workspace keeps activations for bwd.         */
+int64_t lnrf_ngp_mlp_param_count(int32_t L);
+int lnrf_ngp_mlp_workspace_bytes(int64_t m, int32_t L, int64_t* bytes_out_host);
+int lnrf_ngp_mlp_fwd(const float* params, int32_t L, const float* enc, const float* d,
+                     const float* rays, int64_t n, int32_t T, void* workspace,
+                     int64_t workspace_bytes, float* dens, float* rgb, lnrf_stream_t stream);
+int lnrf_ngp_mlp_bwd(const float* params, int32_t L, const float* enc, int64_t m, void* workspace,
+                     int64_t workspace_bytes, const float* dens, const float* rgb,
+                     const float* d_dens, const float* d_rgb, float* d_params, float* d_enc,
+                     lnrf_stream_t stream);
+
+/* ---------------------------------------------------------------- diagnostics
+ * Single 128xNxK bf16 GEMM tile on tcgen05 (A[128,K], B[N,K] both K-major,
+ * D fp32 [128,N]) used by tests to pin the UMMA descriptor encodings.         */
+int lnrf_debug_umma_gemm(const float* a, const float* b, int32_t N, int32_t K, float* d_out,
+                         lnrf_stream_t stream);
+/* Tuning knob of the fused bf16 kernel: 1 = one weight-ring stage and two CTAs
+ * per SM (default); >= 2 = four stages, one CTA per SM.                       */
+int lnrf_set_tc_stages(int32_t stages);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LNRF_H_ */

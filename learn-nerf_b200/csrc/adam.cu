@@ -1,0 +1,78 @@
+// K10: tree_norm x2 + optax.adam + apply_updates over one flat fp32 buffer
+// (learn_nerf/train.py:59,92-106).  HBM-bound: 16 B read + 12 B written per parameter.
+#include "lnrf_common.cuh"
+#include "lnrf_math.cuh"
+
+namespace lnrf {
+
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ params, const float* __restrict__ grads, float* __restrict__ m,
+            float* __restrict__ v, int64_t count, float lr, float b1, float b2, float eps,
+            float inv_bc1, float inv_bc2, float grad_scale, float* __restrict__ norms_out) {
+  float gsq = 0.0f, psq = 0.0f;
+  const int64_t nvec = count >> 2;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  auto upd = [&](float& p, float g, float& mm, float& vv) {
+    g *= grad_scale;
+    gsq = fmaf(g, g, gsq);
+    psq = fmaf(p, p, psq);
+    mm = b1 * mm + (1.0f - b1) * g;
+    vv = b2 * vv + (1.0f - b2) * g * g;
+    p -= lr * ((mm * inv_bc1) / (sqrtf(vv * inv_bc2) + eps));
+  };
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    float4 p = reinterpret_cast<float4*>(params)[i];
+    float4 g = __ldg(reinterpret_cast<const float4*>(grads) + i);
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    upd(p.x, g.x, mm.x, vv.x);
+    upd(p.y, g.y, mm.y, vv.y);
+    upd(p.z, g.z, mm.z, vv.z);
+    upd(p.w, g.w, mm.w, vv.w);
+    reinterpret_cast<float4*>(params)[i] = p;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  for (int64_t i = (nvec << 2) + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) {
+    float p = params[i], mm = m[i], vv = v[i];
+    upd(p, grads[i], mm, vv);
+    params[i] = p; m[i] = mm; v[i] = vv;
+  }
+  if (norms_out) {
+    gsq = warp_sum(gsq);
+    psq = warp_sum(psq);
+    __shared__ float s[2][8];
+    if ((threadIdx.x & 31) == 0) { s[0][threadIdx.x >> 5] = gsq; s[1][threadIdx.x >> 5] = psq; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float a = 0.f, b = 0.f;
+      for (int w = 0; w < 8; ++w) { a += s[0][w]; b += s[1][w]; }
+      atomicAdd(norms_out + 0, a);
+      atomicAdd(norms_out + 1, b);
+    }
+  }
+}
+
+}  // namespace lnrf
+
+extern "C" int lnrf_adam_step(float* params, const float* grads, float* m, float* v, int64_t count,
+                              float lr, float b1, float b2, float eps, int32_t step, float grad_scale,
+                              float* norms_out, lnrf_stream_t stream) {
+  LNRF_REQUIRE(count >= 0 && step >= 1, LNRF_E_INVALID, "lnrf_adam_step: count=%lld step=%d",
+               (long long)count, step);
+  if (count == 0) return LNRF_OK;
+  LNRF_REQUIRE(params && grads && m && v, LNRF_E_INVALID, "lnrf_adam_step: null pointer");
+  LNRF_REQUIRE(((uintptr_t)params | (uintptr_t)grads | (uintptr_t)m | (uintptr_t)v) % 16 == 0,
+               LNRF_E_INVALID, "lnrf_adam_step: buffers must be 16-byte aligned");
+  // bias corrections in double on the host, as optax does with python scalars
+  double bc1 = 1.0 - pow((double)b1, (double)step), bc2 = 1.0 - pow((double)b2, (double)step);
+  int64_t blocks = lnrf::ceil_div(lnrf::ceil_div(count, 4), 256);
+  int64_t cap = int64_t(lnrf::sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  lnrf::adam_kernel<<<(unsigned)blocks, 256, 0, lnrf::as_stream(stream)>>>(
+      params, grads, m, v, count, lr, b1, b2, eps, (float)(1.0 / bc1), (float)(1.0 / bc2), grad_scale,
+      norms_out);
+  LNRF_LAUNCH_CHECK("adam_kernel");
+  return LNRF_OK;
+}

@@ -1,0 +1,282 @@
+// K1 (bbox clip + stratified coarse sampling) and K4 (inverse-CDF fine sampling).
+//
+// Both are bit-exact twins of oracle/render_np.py: every reference op is one
+// individually rounded fp32 op (__fadd_rn/__fmul_rn/__fdiv_rn forbid FMA
+// contraction), cumulative sums run strictly left to right, exp is lnrf_expf.
+// A warp owns one ray; loads/stores of the [n,T] arrays are lane-contiguous.
+#include <math_constants.h>
+
+#include "lnrf_common.cuh"
+#include "lnrf_math.cuh"
+
+namespace lnrf {
+
+// np.minimum / np.maximum propagate NaN; fminf/fmaxf do not.
+__device__ __forceinline__ float np_min(float a, float b) {
+  return (a != a || b != b) ? CUDART_NAN_F : fminf(a, b);
+}
+__device__ __forceinline__ float np_max(float a, float b) {
+  return (a != a || b != b) ? CUDART_NAN_F : fmaxf(a, b);
+}
+
+struct BBox {
+  float lo[3];
+  float hi[3];
+};
+
+// ray_t_range, render.py:346-389
+__device__ __forceinline__ void ray_t_range(const float* __restrict__ ray, const BBox& bb,
+                                            float min_t_range, float epsilon, float& t_min,
+                                            float& t_max, bool& mask) {
+  float lo_max = 0.0f, hi_min = 0.0f;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float o = __ldg(ray + a), d = __ldg(ray + 3 + a);
+    float denom = __fadd_rn(d, epsilon);                    // :369
+    float t0 = __fdiv_rn(__fsub_rn(bb.lo[a], o), denom);    // :368-369
+    float t1 = __fdiv_rn(__fsub_rn(bb.hi[a], o), denom);
+    float lo = np_min(t0, t1), hi = np_max(t0, t1);         // :372-378
+    lo_max = (a == 0) ? lo : np_max(lo_max, lo);
+    hi_min = (a == 0) ? hi : np_min(hi_min, hi);
+  }
+  float min_t = np_max(0.0f, lo_max);                        // :381
+  float max_t = hi_min;                                      // :382
+  float max_t_clipped = np_max(max_t, __fadd_rn(min_t, min_t_range));  // :383
+  mask = min_t < max_t;                                      // :386
+  t_min = mask ? min_t : 0.0f;                               // :387
+  t_max = mask ? max_t_clipped : min_t_range;
+}
+
+__global__ void __launch_bounds__(256)
+sample_coarse_kernel(const float* __restrict__ rays, int64_t n, BBox bb, float min_t_range,
+                     float epsilon, const float* __restrict__ u, int T, float* __restrict__ t_min_out,
+                     float* __restrict__ t_max_out, uint8_t* __restrict__ mask_out,
+                     float* __restrict__ ts_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t r = warp; r < n; r += nwarps) {
+    float t_min, t_max;
+    bool mask;
+    ray_t_range(rays + r * 6, bb, min_t_range, epsilon, t_min, t_max, mask);
+    if (lane == 0) {
+      t_min_out[r] = t_min;
+      t_max_out[r] = t_max;
+      mask_out[r] = mask ? 1 : 0;
+    }
+    // stratified_sampling, render.py:138-143
+    const float bin = __fdiv_rn(__fsub_rn(t_max, t_min), float(T));
+    for (int i = lane; i < T; i += 32) {
+      float start = __fadd_rn(__fmul_rn(float(i), bin), t_min);
+      float rnd = __fmul_rn(__ldg(u + r * T + i), bin);
+      ts_out[r * T + i] = __fadd_rn(start, rnd);
+    }
+  }
+}
+
+// stratified_sampling (render.py:138-143) on precomputed bounds, for the standalone
+// RaySamples.stratified_sampling API; one thread per sample.
+__global__ void __launch_bounds__(256)
+stratified_kernel(const float* __restrict__ t_min, const float* __restrict__ t_max,
+                  const float* __restrict__ u, int64_t n, int T, float* __restrict__ ts_out) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n * T;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = i / T;
+    const int k = int(i - r * T);
+    const float lo = __ldg(t_min + r);
+    const float bin = __fdiv_rn(__fsub_rn(__ldg(t_max + r), lo), float(T));
+    ts_out[i] = __fadd_rn(__fadd_rn(__fmul_rn(float(k), bin), lo), __fmul_rn(__ldg(u + i), bin));
+  }
+}
+
+// ------------------------------------------------------------------ K4
+// dynamic smem per warp (floats): ts[Tc] ddt[Tc] accprev[Tc] w[Tc] xs[Tc+1] ys[Tc+1] sort[P]
+__host__ __device__ inline int fine_smem_floats(int Tc, int P) { return 4 * Tc + 2 * (Tc + 1) + P; }
+
+__global__ void __launch_bounds__(256)
+sample_fine_kernel(const float* __restrict__ ts_c, const float* __restrict__ dens_c,
+                   const float* __restrict__ t_min_in, const float* __restrict__ t_max_in,
+                   const float* __restrict__ u, int64_t n, int Tc, int Tf, int P, float eps,
+                   float* __restrict__ ts_out, int32_t* __restrict__ idx_out,
+                   float* __restrict__ new_ts_out) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  float* s_ts = smem + size_t(wib) * fine_smem_floats(Tc, P);
+  float* s_ddt = s_ts + Tc;
+  float* s_acc = s_ddt + Tc;
+  float* s_w = s_acc + Tc;
+  float* s_xs = s_w + Tc;
+  float* s_ys = s_xs + Tc + 1;
+  float* s_sort = s_ys + Tc + 1;
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  const int T2 = Tc + Tf;
+  const float ubin = __fdiv_rn(__fsub_rn(1.0f, 0.0f), float(Tf));  // render.py:244-250 -> :138
+
+  for (int64_t r = warp; r < n; r += nwarps) {
+    const float t_min = __ldg(t_min_in + r), t_max = __ldg(t_max_in + r);
+    for (int i = lane; i < Tc; i += 32) s_ts[i] = __ldg(ts_c + r * Tc + i);
+    __syncwarp();
+    // starts/ends/deltas (render.py:259-268) and density_dt (:271)
+    for (int i = lane; i < Tc; i += 32) {
+      float t = s_ts[i];
+      float start = (i == 0) ? t_min : __fdiv_rn(__fadd_rn(t, s_ts[i - 1]), 2.0f);
+      float end = (i == Tc - 1) ? t_max : __fdiv_rn(__fadd_rn(s_ts[i + 1], t), 2.0f);
+      float delta = __fsub_rn(end, start);
+      s_ddt[i] = __fmul_rn(__ldg(dens_c + r * Tc + i), delta);
+      s_ys[i + 1] = end;  // ys = [t_min, ends()]  (:238-241)
+      s_sort[i] = t;
+    }
+    if (lane == 0) s_ys[0] = t_min;
+    __syncwarp();
+    // cumsum(density_dt) strictly sequential (:275); acc_prev = [0, acc][:Tc]
+    if (lane == 0) {
+      float acc = 0.0f;
+      for (int i = 0; i < Tc; ++i) {
+        s_acc[i] = acc;
+        acc = __fadd_rn(acc, s_ddt[i]);
+      }
+    }
+    __syncwarp();
+    // w = surv * term + eps  (:279-287, :232)
+    for (int i = lane; i < Tc; i += 32) {
+      float surv = lnrf_expf(-s_acc[i]);
+      float term = __fsub_rn(1.0f, lnrf_expf(-s_ddt[i]));
+      s_w[i] = __fadd_rn(__fmul_rn(surv, term), eps);
+    }
+    __syncwarp();
+    // xs = [0, cumsum(w)] (:235-236), sequential
+    if (lane == 0) {
+      float acc = 0.0f;
+      s_xs[0] = 0.0f;
+      for (int i = 0; i < Tc; ++i) {
+        acc = __fadd_rn(acc, s_w[i]);
+        s_xs[i + 1] = acc;
+      }
+    }
+    __syncwarp();
+    const float total = s_xs[Tc];
+    __syncwarp();
+    for (int i = lane; i <= Tc; i += 32) s_xs[i] = __fdiv_rn(s_xs[i], total);  // :237
+    __syncwarp();
+    // inverse CDF at stratified points: vmap(jnp.interp) (:251)
+    const float xp_first = s_xs[0], xp_last = s_xs[Tc];
+    const float fp_first = s_ys[0], fp_last = s_ys[Tc];
+    for (int j = lane; j < Tf; j += 32) {
+      float x = __fadd_rn(__fmul_rn(float(j), ubin), __fmul_rn(__ldg(u + r * Tf + j), ubin));
+      // searchsorted(xs, x, side='right') over Tc+1 entries
+      int lo = 0, hi = Tc + 1;
+      while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (s_xs[mid] <= x) lo = mid + 1; else hi = mid;
+      }
+      int i = min(max(lo, 1), Tc);
+      float df = __fsub_rn(s_ys[i], s_ys[i - 1]);
+      float dx = __fsub_rn(s_xs[i], s_xs[i - 1]);
+      float delta = __fsub_rn(x, s_xs[i - 1]);
+      bool dx0 = fabsf(dx) <= 1.4210854715202004e-14f;  // np.spacing(finfo(f32).eps)
+      float ratio = __fdiv_rn(delta, dx0 ? 1.0f : dx);
+      float f = dx0 ? s_ys[i - 1] : __fadd_rn(s_ys[i - 1], __fmul_rn(ratio, df));
+      if (x < xp_first) f = fp_first;
+      if (x > xp_last) f = fp_last;
+      s_sort[Tc + j] = f;
+      if (idx_out) idx_out[r * Tf + j] = i;
+      if (new_ts_out) new_ts_out[r * Tf + j] = f;
+    }
+    for (int i = T2 + lane; i < P; i += 32) s_sort[i] = CUDART_INF_F;
+    __syncwarp();
+    // jnp.sort(concat[ts, new_ts]) (:253-255): bitonic network over P >= T2 slots
+    for (int k = 2; k <= P; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = lane; i < P; i += 32) {
+          int l = i ^ j;
+          if (l > i) {
+            float a = s_sort[i], b = s_sort[l];
+            bool up = (i & k) == 0;
+            if (up ? (a > b) : (a < b)) {
+              s_sort[i] = b;
+              s_sort[l] = a;
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    for (int i = lane; i < T2; i += 32) ts_out[r * T2 + i] = s_sort[i];
+    __syncwarp();
+  }
+}
+
+}  // namespace lnrf
+
+extern "C" {
+
+int lnrf_sample_coarse(const float* rays, int64_t n, const float* bbox_min_host,
+                       const float* bbox_max_host, float min_t_range, float epsilon,
+                       const float* u, int32_t T, float* t_min, float* t_max, uint8_t* mask,
+                       float* ts, lnrf_stream_t stream) {
+  LNRF_REQUIRE(n >= 0 && T > 0, LNRF_E_INVALID, "lnrf_sample_coarse: n=%lld T=%d", (long long)n, T);
+  if (n == 0) return LNRF_OK;
+  LNRF_REQUIRE(rays && bbox_min_host && bbox_max_host && u && t_min && t_max && mask && ts,
+               LNRF_E_INVALID, "lnrf_sample_coarse: null pointer");
+  lnrf::BBox bb;
+  for (int a = 0; a < 3; ++a) {
+    bb.lo[a] = bbox_min_host[a];
+    bb.hi[a] = bbox_max_host[a];
+  }
+  const int threads = 256;
+  int64_t blocks = lnrf::ceil_div(n, threads / 32);
+  int64_t cap = int64_t(lnrf::sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  lnrf::sample_coarse_kernel<<<(unsigned)blocks, threads, 0, lnrf::as_stream(stream)>>>(
+      rays, n, bb, min_t_range, epsilon, u, T, t_min, t_max, mask, ts);
+  LNRF_LAUNCH_CHECK("sample_coarse_kernel");
+  return LNRF_OK;
+}
+
+int lnrf_stratified(const float* t_min, const float* t_max, const float* u, int64_t n, int32_t T,
+                    float* ts, lnrf_stream_t stream) {
+  LNRF_REQUIRE(n >= 0 && T > 0, LNRF_E_INVALID, "lnrf_stratified: n=%lld T=%d", (long long)n, T);
+  if (n == 0) return LNRF_OK;
+  LNRF_REQUIRE(t_min && t_max && u && ts, LNRF_E_INVALID, "lnrf_stratified: null pointer");
+  int64_t blocks = lnrf::ceil_div(n * T, 256);
+  int64_t cap = int64_t(lnrf::sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  lnrf::stratified_kernel<<<(unsigned)blocks, 256, 0, lnrf::as_stream(stream)>>>(t_min, t_max, u, n,
+                                                                                T, ts);
+  LNRF_LAUNCH_CHECK("stratified_kernel");
+  return LNRF_OK;
+}
+
+int lnrf_sample_fine(const float* ts_c, const float* dens_c, const float* t_min,
+                     const float* t_max, const float* u, int64_t n, int32_t Tc, int32_t Tf,
+                     float eps, float* ts_out, int32_t* idx_out, float* new_ts_out,
+                     lnrf_stream_t stream) {
+  LNRF_REQUIRE(n >= 0 && Tc > 0 && Tf > 0, LNRF_E_INVALID, "lnrf_sample_fine: n=%lld Tc=%d Tf=%d",
+               (long long)n, Tc, Tf);
+  LNRF_REQUIRE(Tc <= 256 && Tc + Tf <= 1024, LNRF_E_UNSUPPORTED,
+               "lnrf_sample_fine: Tc=%d Tf=%d exceeds Tc<=256, Tc+Tf<=1024", Tc, Tf);
+  if (n == 0) return LNRF_OK;
+  LNRF_REQUIRE(ts_c && dens_c && t_min && t_max && u && ts_out, LNRF_E_INVALID,
+               "lnrf_sample_fine: null pointer");
+  int P = 2;
+  while (P < Tc + Tf) P <<= 1;
+  const int warps = 8, threads = warps * 32;
+  size_t smem = size_t(warps) * lnrf::fine_smem_floats(Tc, P) * sizeof(float);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    LNRF_CUDA(cudaFuncSetAttribute(lnrf::sample_fine_kernel,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  int64_t blocks = lnrf::ceil_div(n, warps);
+  int64_t cap = int64_t(lnrf::sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  lnrf::sample_fine_kernel<<<(unsigned)blocks, threads, smem, lnrf::as_stream(stream)>>>(
+      ts_c, dens_c, t_min, t_max, u, n, Tc, Tf, P, eps, ts_out, idx_out, new_ts_out);
+  LNRF_LAUNCH_CHECK("sample_fine_kernel");
+  return LNRF_OK;
+}
+
+}  // extern "C"

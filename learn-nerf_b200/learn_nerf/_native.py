@@ -1,0 +1,277 @@
+"""ctypes binding of liblnrf.so (include/lnrf.h).
+
+PyTorch is used only for device memory and streams; every compute call below lands
+in a hand-written sm_100a kernel.  There is NO fallback: if the shared library is
+missing or a call fails, an exception is raised.
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int32, c_int64, c_void_p
+from typing import Optional
+
+import torch
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "liblnrf.so")
+
+PREC_FP32 = 0
+PREC_BF16 = 1
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16}
+
+
+class LnrfError(RuntimeError):
+    pass
+
+
+_lib = None
+_inited_devices = set()
+
+_SIGS = {
+    "lnrf_last_error": (c_char_p, []),
+    "lnrf_version": (c_int32, []),
+    "lnrf_init": (c_int32, [c_int32]),
+    "lnrf_sample_coarse": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_float, c_float,
+                                     c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p]),
+    "lnrf_stratified": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
+    "lnrf_sample_fine": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                   c_int32, c_int32, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lnrf_composite_fwd": (c_int32, [c_void_p] * 8 + [c_int64, c_int32] + [c_void_p] * 4),
+    "lnrf_composite_bwd": (c_int32, [c_void_p] * 8 + [c_int64, c_int32] + [c_void_p] * 4),
+    "lnrf_mse_loss": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p, c_void_p,
+                                c_void_p]),
+    "lnrf_nerf_param_count": (c_int64, []),
+    "lnrf_nerf_param_floats": (c_int64, []),
+    "lnrf_nerf_param_offsets": (c_int32, [c_void_p]),
+    "lnrf_nerf_packed_bytes": (c_int64, []),
+    "lnrf_nerf_pack_weights": (c_int32, [c_void_p, c_void_p, c_void_p]),
+    "lnrf_nerf_mlp_workspace_bytes": (c_int32, [c_int64, c_int32, c_int32, c_void_p]),
+    "lnrf_nerf_mlp_fwd": (c_int32, [c_void_p] * 6 + [c_int64, c_int32, c_int32, c_int32, c_void_p,
+                                                     c_int64, c_void_p, c_void_p, c_void_p]),
+    "lnrf_nerf_mlp_bwd": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int64] +
+                          [c_void_p] * 6),
+    "lnrf_adam_step": (c_int32, [c_void_p] * 4 + [c_int64, c_float, c_float, c_float, c_float,
+                                                  c_int32, c_float, c_void_p, c_void_p]),
+    "lnrf_debug_umma_gemm": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    "lnrf_set_tc_stages": (c_int32, [c_int32]),
+}
+
+# entry points that exist only once the corresponding kernels are built
+_OPTIONAL_SIGS = {
+    "lnrf_hashgrid_fwd": (c_int32, [c_void_p] * 4 + [c_int32, c_void_p, c_void_p, c_int32,
+                                                     c_void_p, c_void_p, c_void_p, c_int64, c_int32,
+                                                     c_void_p, c_void_p]),
+    "lnrf_hashgrid_bwd": (c_int32, [c_void_p] * 3 + [c_int32, c_void_p, c_void_p, c_int32,
+                                                     c_void_p, c_void_p, c_void_p, c_int64, c_int32,
+                                                     c_void_p, c_void_p, c_void_p]),
+    "lnrf_ngp_mlp_param_count": (c_int64, [c_int32]),
+    "lnrf_ngp_mlp_workspace_bytes": (c_int32, [c_int64, c_int32, c_void_p]),
+    "lnrf_ngp_mlp_fwd": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
+                                   c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "lnrf_ngp_mlp_bwd": (c_int32, [c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_int64] +
+                         [c_void_p] * 7),
+}
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def load() -> ctypes.CDLL:
+    """dlopen liblnrf.so and declare the prototypes.  Needs no GPU."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise LnrfError(
+                f"{_LIB_PATH} not found: build it with `python learn-nerf_b200/build.py` "
+                "(there is no CPU or PyTorch fallback for the render/train hot path)")
+        lib = ctypes.CDLL(_LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        for name, (res, args) in _OPTIONAL_SIGS.items():
+            if hasattr(lib, name):
+                fn = getattr(lib, name)
+                fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def exported_symbols():
+    return sorted(list(_SIGS) + [n for n in _OPTIONAL_SIGS if hasattr(load(), n)])
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        msg = load().lnrf_last_error()
+        raise LnrfError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")
+
+
+def ensure_init(device: torch.device):
+    if device.type != "cuda":
+        raise LnrfError(f"liblnrf kernels need CUDA tensors, got device {device} (no CPU fallback)")
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _inited_devices:
+        with torch.cuda.device(idx):
+            _check(load().lnrf_init(idx), "lnrf_init")
+        _inited_devices.add(idx)
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def _stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda:
+        raise LnrfError(f"{name}: expected a contiguous CUDA float32 tensor, got {t.dtype} "
+                        f"{t.device} contiguous={t.is_contiguous()}")
+    return t
+
+
+def _host3(v):
+    arr = (c_float * 3)(*[float(x) for x in v])
+    return arr
+
+
+# --------------------------------------------------------------------------- wrappers
+def sample_coarse(rays, bbox_min, bbox_max, u, min_t_range=1e-3, epsilon=1e-8):
+    rays, u = _f32c(rays, "rays"), _f32c(u, "u")
+    ensure_init(rays.device)
+    n, T = u.shape
+    t_min = torch.empty(n, device=rays.device)
+    t_max = torch.empty(n, device=rays.device)
+    mask = torch.empty(n, dtype=torch.uint8, device=rays.device)
+    ts = torch.empty(n, T, device=rays.device)
+    lo, hi = _host3(bbox_min), _host3(bbox_max)
+    _check(load().lnrf_sample_coarse(_p(rays), n, lo, hi, min_t_range, epsilon, _p(u), T, _p(t_min),
+                                     _p(t_max), _p(mask), _p(ts), _stream()), "lnrf_sample_coarse")
+    return t_min, t_max, mask, ts
+
+
+def stratified(t_min, t_max, u):
+    u = _f32c(u, "u")
+    ensure_init(u.device)
+    n, T = u.shape
+    ts = torch.empty(n, T, device=u.device)
+    _check(load().lnrf_stratified(_p(_f32c(t_min, "t_min")), _p(_f32c(t_max, "t_max")), _p(u), n, T,
+                                  _p(ts), _stream()), "lnrf_stratified")
+    return ts
+
+
+def sample_fine(ts_c, dens_c, t_min, t_max, u, eps=1e-8, debug=False):
+    ts_c, dens_c, u = _f32c(ts_c, "ts"), _f32c(dens_c, "densities"), _f32c(u, "u")
+    ensure_init(ts_c.device)
+    n, Tc = ts_c.shape
+    Tf = u.shape[1]
+    out = torch.empty(n, Tc + Tf, device=ts_c.device)
+    idx = torch.empty(n, Tf, dtype=torch.int32, device=ts_c.device) if debug else None
+    new_ts = torch.empty(n, Tf, device=ts_c.device) if debug else None
+    _check(load().lnrf_sample_fine(_p(ts_c), _p(dens_c), _p(_f32c(t_min, "t_min")),
+                                   _p(_f32c(t_max, "t_max")), _p(u), n, Tc, Tf, eps, _p(out), _p(idx),
+                                   _p(new_ts), _stream()), "lnrf_sample_fine")
+    return (out, idx, new_ts) if debug else out
+
+
+def composite_fwd(rays, ts, t_min, t_max, mask, dens, rgb, background, want_aux=True):
+    ensure_init(ts.device)
+    n, T = ts.shape
+    dev = ts.device
+    outputs = torch.empty(n, 3, device=dev)
+    alphas = torch.empty(n, 1, device=dev) if want_aux else None
+    coords = torch.empty(n, 3, device=dev) if want_aux else None
+    _check(load().lnrf_composite_fwd(_p(_f32c(rays, "rays")), _p(_f32c(ts, "ts")), _p(t_min), _p(t_max),
+                                     _p(mask), _p(_f32c(dens, "densities")), _p(_f32c(rgb, "rgbs")),
+                                     _p(_f32c(background, "background")), n, T, _p(outputs),
+                                     _p(alphas), _p(coords), _stream()), "lnrf_composite_fwd")
+    return outputs, alphas, coords
+
+
+def composite_bwd(ts, t_min, t_max, mask, dens, rgb, background, d_outputs, d_background):
+    ensure_init(ts.device)
+    n, T = ts.shape
+    d_dens = torch.empty(n, T, device=ts.device)
+    d_rgb = torch.empty(n, T, 3, device=ts.device)
+    _check(load().lnrf_composite_bwd(_p(ts), _p(t_min), _p(t_max), _p(mask), _p(_f32c(dens, "dens")),
+                                     _p(_f32c(rgb, "rgb")), _p(background),
+                                     _p(_f32c(d_outputs, "d_outputs")), n, T, _p(d_dens), _p(d_rgb),
+                                     _p(d_background), _stream()), "lnrf_composite_bwd")
+    return d_dens, d_rgb
+
+
+def mse_loss(outputs, targets_base, target_stride, n, inv_count, loss_sum, d_outputs):
+    """targets_base: tensor whose data_ptr is element (0,0) of the strided targets view."""
+    ensure_init(outputs.device)
+    _check(load().lnrf_mse_loss(_p(_f32c(outputs, "outputs")), _p(targets_base), target_stride, n,
+                                inv_count, _p(loss_sum), _p(d_outputs), _stream()), "lnrf_mse_loss")
+
+
+def nerf_param_count() -> int:
+    return int(load().lnrf_nerf_param_count())
+
+
+def nerf_param_floats() -> int:
+    return int(load().lnrf_nerf_param_floats())
+
+
+def nerf_param_offsets():
+    buf = (c_int64 * 24)()
+    _check(load().lnrf_nerf_param_offsets(buf), "lnrf_nerf_param_offsets")
+    return [int(v) for v in buf]
+
+
+def nerf_packed_bytes() -> int:
+    return int(load().lnrf_nerf_packed_bytes())
+
+
+def nerf_pack_weights(flat: torch.Tensor, packed: torch.Tensor):
+    ensure_init(flat.device)
+    _check(load().lnrf_nerf_pack_weights(_p(_f32c(flat, "params")), _p(packed), _stream()),
+           "lnrf_nerf_pack_weights")
+
+
+def nerf_mlp_workspace_bytes(m: int, precision: int, save: bool) -> int:
+    out = c_int64(0)
+    _check(load().lnrf_nerf_mlp_workspace_bytes(m, precision, int(save), ctypes.byref(out)),
+           "lnrf_nerf_mlp_workspace_bytes")
+    return int(out.value)
+
+
+def nerf_mlp_fwd(flat, packed, x, d, rays, ts, n, T, precision, save, workspace, dens, rgb):
+    ensure_init(flat.device)
+    ws_bytes = 0 if workspace is None else workspace.numel() * workspace.element_size()
+    _check(load().lnrf_nerf_mlp_fwd(_p(flat), _p(packed), _p(x), _p(d), _p(rays), _p(ts), n, T,
+                                    precision, int(save), _p(workspace), ws_bytes, _p(dens), _p(rgb),
+                                    _stream()), "lnrf_nerf_mlp_fwd")
+
+
+def nerf_mlp_bwd(flat, packed, m, precision, workspace, dens, rgb, d_dens, d_rgb, d_flat):
+    ensure_init(flat.device)
+    ws_bytes = workspace.numel() * workspace.element_size()
+    _check(load().lnrf_nerf_mlp_bwd(_p(flat), _p(packed), m, precision, _p(workspace), ws_bytes,
+                                    _p(dens), _p(rgb), _p(_f32c(d_dens, "d_dens")),
+                                    _p(_f32c(d_rgb, "d_rgb")), _p(d_flat), _stream()),
+           "lnrf_nerf_mlp_bwd")
+
+
+def adam_step(params, grads, m, v, lr, b1, b2, eps, step, grad_scale, norms_out):
+    ensure_init(params.device)
+    _check(load().lnrf_adam_step(_p(_f32c(params, "params")), _p(_f32c(grads, "grads")), _p(m), _p(v),
+                                 params.numel(), lr, b1, b2, eps, step, grad_scale, _p(norms_out),
+                                 _stream()), "lnrf_adam_step")
+
+
+def debug_umma_gemm(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """D[128,N] = bf16(A[128,K]) @ bf16(B[N,K])^T on tcgen05 (descriptor self-test)."""
+    ensure_init(a.device)
+    N, K = b.shape
+    out = torch.empty(128, N, device=a.device)
+    _check(load().lnrf_debug_umma_gemm(_p(_f32c(a, "a")), _p(_f32c(b, "b")), N, K, _p(out), _stream()),
+           "lnrf_debug_umma_gemm")
+    return out
+
+
+def set_tc_stages(stages: int):
+    _check(load().lnrf_set_tc_stages(stages), "lnrf_set_tc_stages")

@@ -1,0 +1,212 @@
+"""Host-side mirror of learn_nerf/model.py: ModelBase, NeRFModel, sinusoidal_emb.
+
+``NeRFModel.apply(dict(params=params), x, d)`` keeps the reference signature and
+return contract (model.py:12-27); the arithmetic runs in liblnrf.so
+(lnrf_nerf_mlp_fwd / _bwd).  Parameters are a Flax-shaped tree
+(``Dense_i/{kernel[in,out], bias[out]}``) whose leaves are views into one flat fp32
+CUDA buffer laid out as the C ABI expects (include/lnrf.h).
+"""
+import math
+from dataclasses import dataclass
+from typing import Any, Dict, Optional, Tuple
+
+import torch
+
+from . import _native
+from .prng import KeyLike, _as_key
+
+
+class ParamTree(dict):
+    """Nested dict of tensors that are views of ``flat`` (one contiguous buffer)."""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.flat: Optional[torch.Tensor] = None
+        self._packed: Optional[torch.Tensor] = None
+        self._packed_key = None
+        self._manual_version = 0
+
+    def mark_updated(self):
+        """Call after the flat buffer was modified by a native kernel (Adam)."""
+        self._manual_version += 1
+
+    def version_key(self):
+        return (self.flat._version, self._manual_version, self.flat.data_ptr())
+
+
+class ModelBase:
+    """model.py:7-27: ``(x[N,3], d[N,3]) -> (density[N,1], rgb[N,3], aux{name: [N]})``."""
+
+    def init(self, rngs, x=None, d=None, device=None) -> Dict[str, Any]:
+        raise NotImplementedError
+
+    def apply(self, variables: Dict[str, Any], x: torch.Tensor, d: torch.Tensor
+              ) -> Tuple[torch.Tensor, torch.Tensor, Dict[str, torch.Tensor]]:
+        raise NotImplementedError
+
+    def __call__(self, x, d):
+        raise NotImplementedError("call model.apply(dict(params=params), x, d)")
+
+
+def sinusoidal_emb(coords: torch.Tensor, freqs: int) -> torch.Tensor:
+    """model.py:65-77 (host-side torch helper; the kernels compute this in-line)."""
+    coeffs = 2.0 ** torch.arange(freqs, dtype=torch.float32, device=coords.device)
+    inputs = coords[..., None] * coeffs
+    combined = torch.cat([torch.sin(inputs), torch.cos(inputs)], dim=-1)
+    return combined.reshape(combined.shape[:-2] + (-1,))
+
+
+def _trunc_normal_(t: torch.Tensor, std: float, gen: torch.Generator):
+    # lecun_normal-like (flax nn.Dense default is un-pinned in the reference): N(0, std) cut at 2 std
+    t.normal_(0.0, 1.0, generator=gen)
+    bad = t.abs() > 2.0
+    while bool(bad.any()):
+        t[bad] = torch.empty(int(bad.sum()), device=t.device).normal_(0.0, 1.0, generator=gen)
+        bad = t.abs() > 2.0
+    t.mul_(std)
+
+
+def _rng_seed(rngs) -> int:
+    if isinstance(rngs, dict):
+        rngs = rngs["params"]
+    return _as_key(rngs).seed
+
+
+@dataclass
+class NeRFModel(ModelBase):
+    """model.py:30-62.  ``precision``: "fp32" (FFMA, 1e-5) or "bf16" (tcgen05, 2e-2)."""
+
+    input_layers: int = 5
+    mid_layers: int = 4
+    hidden_dim: int = 256
+    color_layer_dim: int = 128
+    x_freqs: int = 10
+    d_freqs: int = 4
+    precision: str = "fp32"
+
+    # ------------------------------------------------------------------ layout
+    def _check_arch(self):
+        if (self.input_layers, self.mid_layers, self.hidden_dim, self.color_layer_dim, self.x_freqs,
+                self.d_freqs) != (5, 4, 256, 128, 10, 4):
+            raise _native.LnrfError("liblnrf implements the default NeRFModel architecture only "
+                                    "(5+4 x 256, colour 128, x_freqs 10, d_freqs 4)")
+        if self.precision not in _native.PRECISIONS:
+            raise ValueError(f"precision must be one of {list(_native.PRECISIONS)}")
+
+    def layer_dims(self):
+        xe, de, h = 6 * self.x_freqs, 6 * self.d_freqs, self.hidden_dim
+        dims = [(xe, h)] + [(h, h)] * (self.input_layers - 1)
+        dims += [(h + xe, h)] + [(h, h)] * (self.mid_layers - 1)
+        dims += [(h, 1), (h + de, self.color_layer_dim), (self.color_layer_dim, 3)]
+        return dims
+
+    def param_floats(self) -> int:
+        self._check_arch()
+        return _native.nerf_param_floats()
+
+    def param_count(self) -> int:
+        return sum(a * b + b for a, b in self.layer_dims())
+
+    def bind(self, flat: torch.Tensor) -> ParamTree:
+        """Flax-shaped tree of views into ``flat`` (len == param_floats())."""
+        self._check_arch()
+        offs = _native.nerf_param_offsets()
+        tree = ParamTree()
+        for i, (a, b) in enumerate(self.layer_dims()):
+            tree[f"Dense_{i}"] = dict(kernel=flat[offs[2 * i]: offs[2 * i] + a * b].view(a, b),
+                                      bias=flat[offs[2 * i + 1]: offs[2 * i + 1] + b])
+        tree.flat = flat
+        return tree
+
+    def flatten_params(self, params: Dict[str, Any], device=None) -> ParamTree:
+        """Accept a plain nested dict (e.g. an un-pickled checkpoint) and re-home it."""
+        if isinstance(params, ParamTree) and params.flat is not None:
+            return params
+        first = params["Dense_0"]["kernel"]
+        device = device or (first.device if isinstance(first, torch.Tensor) else "cuda")
+        flat = torch.zeros(self.param_floats(), device=device)
+        tree = self.bind(flat)
+        for name, leaf in tree.items():
+            for k in ("kernel", "bias"):
+                leaf[k].copy_(torch.as_tensor(params[name][k], dtype=torch.float32))
+        return tree
+
+    def init(self, rngs, x=None, d=None, device=None, flat: Optional[torch.Tensor] = None):
+        """Mirror of ``model.init(dict(params=rng), x, d)`` -> ``{"params": tree}``."""
+        device = torch.device(device or (x.device if isinstance(x, torch.Tensor) else "cuda"))
+        if flat is None:
+            flat = torch.zeros(self.param_floats(), device=device)
+        else:
+            flat.zero_()
+        tree = self.bind(flat)
+        gen = torch.Generator(device=device)
+        gen.manual_seed(_rng_seed(rngs))
+        for i, (a, _) in enumerate(self.layer_dims()):
+            _trunc_normal_(tree[f"Dense_{i}"]["kernel"], math.sqrt(1.0 / a), gen)
+        return {"params": tree}
+
+    # ------------------------------------------------------------------ native calls
+    def _packed(self, tree: ParamTree) -> Optional[torch.Tensor]:
+        if self.precision != "bf16":
+            return None
+        key = tree.version_key()
+        if tree._packed is None or tree._packed_key != key:
+            if tree._packed is None:
+                nbytes = _native.nerf_packed_bytes()
+                raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=tree.flat.device)
+                shift = (-raw.data_ptr()) % 1024
+                tree._packed = raw[shift: shift + nbytes]
+            _native.nerf_pack_weights(tree.flat, tree._packed)
+            tree._packed_key = key
+        return tree._packed
+
+    def _workspace(self, m: int, save: bool, device, slot=None) -> Optional[torch.Tensor]:
+        nbytes = _native.nerf_mlp_workspace_bytes(m, _native.PRECISIONS[self.precision], save)
+        if nbytes == 0:
+            return None
+        cache = self.__dict__.setdefault("_ws_cache", {})
+        key = (str(device), bool(save), slot)
+        ws = cache.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            cache[key] = ws
+        return ws
+
+    def _forward(self, tree: ParamTree, x, d, rays, ts, n: int, T: int, save: bool, slot=None):
+        self._check_arch()
+        dev = tree.flat.device
+        m = n * T
+        dens = torch.empty(m, device=dev)
+        rgb = torch.empty(m, 3, device=dev)
+        ws = self._workspace(m, save, dev, slot)
+        _native.nerf_mlp_fwd(tree.flat, self._packed(tree), x, d, rays, ts, n, T,
+                             _native.PRECISIONS[self.precision], save, ws, dens, rgb)
+        return dens, rgb, ws
+
+    def apply(self, variables, x: torch.Tensor, d: torch.Tensor):
+        """model.apply(dict(params=params), x[N,3], d[N,3]) -> (density[N,1], rgb[N,3], {})."""
+        tree = self.flatten_params(variables["params"])
+        x = _native._f32c(x.contiguous(), "x")
+        d = _native._f32c(d.contiguous(), "d")
+        dens, rgb, _ = self._forward(tree, x, d, None, None, x.shape[0], 1, save=False)
+        return dens[:, None], rgb, {}
+
+    def apply_rays(self, params, rays: torch.Tensor, ts: torch.Tensor, save: bool = False, slot=None):
+        """Fused seam used by render_rays: points/directions are formed in-kernel from
+        rays[N,2,3] and ts[N,T] (render.py:318-324).  Returns dens[N,T], rgb[N,T,3], aux, ctx.
+        ``slot`` names the saved-activation workspace so that one model instance can hold
+        several forward passes (coarse and fine) until their backward runs."""
+        tree = self.flatten_params(params)
+        n, T = ts.shape
+        dens, rgb, ws = self._forward(tree, None, None, _native._f32c(rays, "rays"),
+                                      _native._f32c(ts, "ts"), n, T, save, slot)
+        ctx = dict(tree=tree, ws=ws, m=n * T, dens=dens, rgb=rgb) if save else None
+        return dens.view(n, T), rgb.view(n, T, 3), {}, ctx
+
+    def backward_rays(self, ctx, d_dens: torch.Tensor, d_rgb: torch.Tensor, d_flat: torch.Tensor,
+                      d_aux=None):
+        """Accumulate dL/dparams into ``d_flat`` (same layout as the flat params)."""
+        tree = ctx["tree"]
+        _native.nerf_mlp_bwd(tree.flat, self._packed(tree), ctx["m"],
+                             _native.PRECISIONS[self.precision], ctx["ws"], ctx["dens"], ctx["rgb"],
+                             d_dens.reshape(-1), d_rgb.reshape(-1, 3), d_flat)

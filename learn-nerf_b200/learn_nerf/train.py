@@ -1,0 +1,186 @@
+"""Host-side mirror of learn_nerf/train.py: TrainLoop (losses, step_fn, save/load).
+
+Same constructor arguments and logging-dict keys as the reference (train.py:22-165).
+One step = K1 sampling -> K2 MLP fwd (coarse) -> K3 composite -> K4 fine sampling ->
+K2 (fine) -> K3 -> MSE -> K5 composite bwd -> K6 MLP bwd (both levels) ->
+[NCCL all-reduce of the flat gradient when world > 1] -> K10 fused Adam + norms.
+All parameters, gradients and Adam moments live in single flat fp32 buffers
+``[coarse | fine | background]`` so the optimiser and the all-reduce are one launch.
+"""
+import math
+import os
+import pickle
+from typing import Any, Callable, Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _native, prng
+from .model import ModelBase
+from .render import NeRFRenderer, RaySamples, _vec3
+
+
+class TrainState:
+    """Stand-in for flax TrainState (train.py:51-60): params tree + Adam moments + step."""
+
+    def __init__(self, params: Dict[str, Any], flat: torch.Tensor):
+        self.params = params
+        self.flat = flat
+        self.m = torch.zeros_like(flat)
+        self.v = torch.zeros_like(flat)
+        self.step = 0
+
+
+def default_loss_weights() -> Dict[str, float]:  # train.py:187-191
+    return dict(normal_mse=3e-4, neg_normal=0.1)
+
+
+class TrainLoop:
+    """A stateful training loop (train.py:17-60)."""
+
+    def __init__(self, coarse: ModelBase, fine: ModelBase, init_rng, lr: float, coarse_ts: int,
+                 fine_ts: int, adam_b1: float = 0.9, adam_b2: float = 0.999, adam_eps: float = 1e-7,
+                 loss_weights: Dict[str, float] = None, density_penalty: Optional[float] = None,
+                 density_penalty_batch_size: int = 128, device=None, ray_chunk: Optional[int] = None):
+        if density_penalty is not None:
+            raise NotImplementedError("density_penalty (train.py:153-184) is default-off in the "
+                                      "reference and not part of the native hot path yet")
+        self.coarse, self.fine = coarse, fine
+        self.coarse_ts, self.fine_ts = coarse_ts, fine_ts
+        self.lr, self.b1, self.b2, self.eps = lr, adam_b1, adam_b2, adam_eps
+        self.loss_weights = loss_weights if loss_weights is not None else default_loss_weights()
+        self.density_penalty = density_penalty
+        self.density_penalty_batch_size = density_penalty_batch_size
+        self.ray_chunk = ray_chunk
+        device = torch.device(device or "cuda")
+        if device.type == "cuda" and device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = device
+
+        coarse_rng, fine_rng = prng.split(init_rng)  # :46
+        nc, nf = coarse.param_floats(), fine.param_floats()
+        flat = torch.zeros(nc + nf + 4, device=device)
+        coarse_vars = coarse.init(dict(params=coarse_rng), device=device, flat=flat[:nc])
+        fine_vars = fine.init(dict(params=fine_rng), device=device, flat=flat[nc:nc + nf])
+        flat[nc + nf: nc + nf + 3] = -1.0  # background starts black (:56-57) and is trained
+        self._slices = dict(coarse=(0, nc), fine=(nc, nc + nf), background=(nc + nf, nc + nf + 3))
+        self.state = TrainState(
+            params=dict(coarse=coarse_vars["params"], fine=fine_vars["params"],
+                        background=flat[nc + nf: nc + nf + 3]),
+            flat=flat)
+        self._grads = torch.zeros_like(flat)
+        self._scalars = torch.zeros(4, device=device)  # loss_c, loss_f, |g|^2, |p|^2
+
+    # ------------------------------------------------------------------ checkpoints
+    def save(self, path: str):
+        """train.py:62-69: pickle of the params tree (numpy leaves), atomic tmp + rename."""
+        def to_np(t):
+            if isinstance(t, dict):
+                return {k: to_np(v) for k, v in t.items()}
+            return t.detach().cpu().numpy().copy()
+        tmp_path = path + ".tmp"
+        with open(tmp_path, "wb") as f:
+            pickle.dump(to_np(self.state.params), f)
+        os.rename(tmp_path, path)
+
+    def load(self, path: str):
+        """train.py:71-76: replaces params only (Adam moments restart, as in the reference)."""
+        with open(path, "rb") as f:
+            tree = pickle.load(f)
+        def put(dst, src):
+            if isinstance(dst, dict):
+                for k in dst:
+                    put(dst[k], src[k])
+            else:
+                dst.copy_(torch.as_tensor(np.asarray(src), dtype=torch.float32))
+        put(self.state.params, tree)
+        for name in ("coarse", "fine"):
+            self.state.params[name].mark_updated()
+
+    # ------------------------------------------------------------------ step
+    def step_fn(self, bbox_min, bbox_max) -> Callable[[Any, torch.Tensor], Dict[str, torch.Tensor]]:
+        """train.py:78-112: returns ``step(key, batch[N,3,3]) -> logging dict`` (in place)."""
+        bmin, bmax = _vec3(bbox_min), _vec3(bbox_max)
+
+        def in_place_step(key, batch: torch.Tensor) -> Dict[str, torch.Tensor]:
+            return self._step(key, bmin, bmax, batch)
+
+        return in_place_step
+
+    def _renderer(self, bmin, bmax, params) -> NeRFRenderer:
+        return NeRFRenderer(coarse=self.coarse, fine=self.fine, coarse_params=params["coarse"],
+                            fine_params=params["fine"], background=params["background"],
+                            bbox_min=bmin, bbox_max=bmax, coarse_ts=self.coarse_ts,
+                            fine_ts=self.fine_ts)
+
+    @staticmethod
+    def _split_key(key, n, tc, tf, a, b):
+        """Per-chunk key: explicit uniforms are sliced, PRNG keys are re-split."""
+        if isinstance(key, (tuple, list)) and isinstance(key[0], torch.Tensor):
+            return (key[0][a:b].contiguous(), key[1][a:b].contiguous())
+        return key if (a == 0 and b == n) else prng.split(key, 2 + a)[-1]
+
+    def _step(self, key, bmin, bmax, batch: torch.Tensor) -> Dict[str, torch.Tensor]:
+        st = self.state
+        batch = _native._f32c(batch.contiguous(), "batch")
+        n = batch.shape[0]
+        world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
+        if not isinstance(key, (tuple, list)):
+            key, _density_key = prng.split(key)  # train.py:137
+        g = self._grads
+        g.zero_()
+        self._scalars.zero_()
+        renderer = self._renderer(bmin, bmax, st.params)
+        inv_count = 1.0 / (3.0 * n)  # jnp.mean over N*3 (:141-142)
+        chunk = self.ray_chunk or n
+        sc, sf, sb = self._slices["coarse"], self._slices["fine"], self._slices["background"]
+        for a in range(0, n, chunk):
+            b = min(a + chunk, n)
+            sub = batch[a:b]
+            rays = sub[:, :2].contiguous()
+            out = renderer.render_rays(self._split_key(key, n, self.coarse_ts, self.fine_ts, a, b),
+                                       rays, _save=True)
+            targets = sub[:, 2]  # strided view: element (i,c) at base + 9 i + c
+            for li, (level, model, sl) in enumerate((("coarse", self.coarse, sc),
+                                                     ("fine", self.fine, sf))):
+                lv = out[level]
+                d_out = torch.empty_like(lv["outputs"])
+                _native.mse_loss(lv["outputs"], targets, 9, b - a, inv_count,
+                                 self._scalars[li:li + 1], d_out)
+                ts: RaySamples = lv["_ts"]
+                d_dens, d_rgb = _native.composite_bwd(ts.ts, ts.t_min, ts.t_max, ts._mask_u8(),
+                                                      lv["densities"], lv["rgbs"],
+                                                      st.params["background"], d_out,
+                                                      g[sb[0]:sb[0] + 3])
+                model.backward_rays(lv["_ctx"], d_dens, d_rgb, g[sl[0]:sl[1]])
+        if world > 1:
+            torch.distributed.all_reduce(g)  # NCCL sum over NVLink; 1/world folded into Adam
+            torch.distributed.all_reduce(self._scalars[:2])
+        st.step += 1
+        _native.adam_step(st.flat, g, st.m, st.v, self.lr, self.b1, self.b2, self.eps, st.step,
+                          1.0 / world, self._scalars[2:4])
+        for name in ("coarse", "fine"):
+            st.params[name].mark_updated()
+        s = self._scalars
+        scale = inv_count / world
+        return dict(coarse=s[0] * scale, fine=s[1] * scale, grad_norm=torch.sqrt(s[2]),
+                    param_norm=torch.sqrt(s[3]))
+
+    def losses(self, key, bbox_min, bbox_max, batch: torch.Tensor, params):
+        """train.py:114-165 (forward only) -> (total_loss, loss_dict)."""
+        batch = _native._f32c(batch.contiguous(), "batch")
+        n = batch.shape[0]
+        if not isinstance(key, (tuple, list)):
+            key, _density_key = prng.split(key)
+        renderer = self._renderer(_vec3(bbox_min), _vec3(bbox_max), params)
+        out = renderer.render_rays(key, batch[:, :2].contiguous())
+        sums = torch.zeros(2, device=batch.device)
+        for li, level in enumerate(("coarse", "fine")):
+            _native.mse_loss(out[level]["outputs"], batch[:, 2], 9, n, 0.0, sums[li:li + 1], None)
+        loss_dict = dict(coarse=sums[0] / (3.0 * n), fine=sums[1] / (3.0 * n))
+        total = loss_dict["coarse"] + loss_dict["fine"]
+        for prefix in ("coarse", "fine"):
+            for name, loss in out[f"{prefix}_aux"].items():
+                loss_dict[f"{prefix}_{name}"] = loss
+                total = total + self.loss_weights[name] * loss
+        return total, loss_dict

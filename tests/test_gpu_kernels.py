@@ -1,0 +1,184 @@
+"""GPU parity tests, stage by stage, CUDA path (through the C ABI) vs the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import BBOX_MAX, BBOX_MIN, F, make_rays, make_uniforms
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.fixture(scope="module")
+def nat():
+    from learn_nerf import _native
+    _native.ensure_init(torch.device("cuda", 0))
+    return _native
+
+
+# ------------------------------------------------------------------ tcgen05 building block
+@pytest.mark.parametrize("N,K", [(256, 64), (256, 256), (144, 128), (16, 64), (128, 192)])
+def test_umma_debug_gemm(nat, N, K):
+    """Pins the UMMA smem/instruction descriptor encodings and the TMEM read-back layout."""
+    g = torch.Generator(device="cuda").manual_seed(N * 1000 + K)
+    a = torch.randn(128, K, device="cuda", generator=g)
+    b = torch.randn(N, K, device="cuda", generator=g)
+    out = nat.debug_umma_gemm(a, b)
+    torch.cuda.synchronize()
+    ref = a.bfloat16().float() @ b.bfloat16().float().T
+    err = (out - ref).abs().max().item()
+    assert err <= 2e-3 * max(1.0, ref.abs().max().item()), err
+
+
+# ------------------------------------------------------------------ K1
+def _edge_rays():
+    r = make_rays(512, seed=3, miss_frac=0.3, with_targets=False)
+    r[0] = [[0, 0, -3], [0, 0, 1]]           # axis aligned: d == 0 on two axes
+    r[1] = [[0, 5, -3], [0, 0, 1]]           # misses the box
+    r[2] = [[0.5, 0.5, 0.5], [1, 0, 0]]      # starts inside
+    r[3] = [[-1, -1, -3], [0, 0, 1]]         # grazes an edge
+    r[4] = [[0, 0, -3], [0, 0, -1]]          # points away
+    r[5] = [[0, 0, -3], [-1e-8, 0, 1]]       # d + eps == 0 on x
+    return r
+
+
+def test_sample_coarse_bit_exact(nat):
+    from oracle import render_np
+    rays = _edge_rays()
+    n = len(rays)
+    u = make_uniforms(n, 64, 7)
+    t_min, t_max, mask, ts = nat.sample_coarse(dev(rays), BBOX_MIN, BBOX_MAX, dev(u))
+    o_min, o_max, o_mask = render_np.ray_t_range(BBOX_MIN, BBOX_MAX, rays)
+    o = render_np.RaySamples.stratified_sampling(o_min, o_max, o_mask, 64, u)
+    np.testing.assert_array_equal(mask.cpu().numpy().astype(bool), o_mask)
+    np.testing.assert_array_equal(t_min.cpu().numpy().view(np.uint32), o_min.view(np.uint32))
+    np.testing.assert_array_equal(t_max.cpu().numpy().view(np.uint32), o_max.view(np.uint32))
+    np.testing.assert_array_equal(ts.cpu().numpy().view(np.uint32), o.ts.view(np.uint32))
+    # standalone stratified kernel, odd T
+    u2 = make_uniforms(n, 37, 8)
+    ts2 = nat.stratified(t_min, t_max, dev(u2))
+    o2 = render_np.RaySamples.stratified_sampling(o_min, o_max, o_mask, 37, u2)
+    np.testing.assert_array_equal(ts2.cpu().numpy().view(np.uint32), o2.ts.view(np.uint32))
+
+
+def test_sample_coarse_empty_and_errors(nat):
+    e = torch.empty(0, 2, 3, device="cuda")
+    t_min, t_max, mask, ts = nat.sample_coarse(e, BBOX_MIN, BBOX_MAX, torch.empty(0, 64, device="cuda"))
+    assert ts.shape == (0, 64)
+    with pytest.raises(nat.LnrfError):
+        nat.sample_coarse(torch.zeros(2, 2, 3), BBOX_MIN, BBOX_MAX, torch.zeros(2, 4))  # CPU tensors
+
+
+# ------------------------------------------------------------------ K4
+def test_sample_fine_golden_bit_exact(nat):
+    g = np.load(os.path.join(GOLDEN, "fine_sampling_small.npz"))
+    out, idx, new_ts = nat.sample_fine(dev(g["ts"]), dev(g["densities"]), dev(g["t_min"]),
+                                       dev(g["t_max"]), dev(g["u"]), debug=True)
+    np.testing.assert_array_equal(idx.cpu().numpy(), g["idx"])
+    np.testing.assert_array_equal(new_ts.cpu().numpy().view(np.uint32), g["new_ts"].view(np.uint32))
+    np.testing.assert_array_equal(out.cpu().numpy().view(np.uint32), g["fine_ts"].view(np.uint32))
+
+
+@pytest.mark.parametrize("Tc,Tf", [(64, 128), (16, 48), (33, 17)])
+def test_sample_fine_random_bit_exact(nat, Tc, Tf):
+    from oracle import render_np
+    n = 300
+    rays = make_rays(n, seed=5, miss_frac=0.2, with_targets=False)
+    t_min, t_max, mask = render_np.ray_t_range(BBOX_MIN, BBOX_MAX, rays)
+    cs = render_np.RaySamples.stratified_sampling(t_min, t_max, mask, Tc, make_uniforms(n, Tc, 9))
+    rs = np.random.RandomState(4)
+    dens = (rs.gamma(0.3, 10.0, (n, Tc)) * (rs.uniform(size=(n, Tc)) < 0.5)).astype(F)
+    u = make_uniforms(n, Tf, 10)
+    o, o_idx = cs.fine_sampling(Tf, u, dens, return_indices=True)
+    out, idx, _ = nat.sample_fine(dev(cs.ts), dev(dens), dev(t_min), dev(t_max), dev(u), debug=True)
+    np.testing.assert_array_equal(idx.cpu().numpy(), o_idx)
+    np.testing.assert_array_equal(out.cpu().numpy().view(np.uint32), o.ts.view(np.uint32))
+    assert bool((out[:, 1:] >= out[:, :-1]).all())
+
+
+# ------------------------------------------------------------------ K3 / K5
+def _composite_case(n, T, seed, miss=0.25):
+    from oracle import render_np
+    rays = make_rays(n, seed=seed, miss_frac=miss, with_targets=False)
+    t_min, t_max, mask = render_np.ray_t_range(BBOX_MIN, BBOX_MAX, rays)
+    s = render_np.RaySamples.stratified_sampling(t_min, t_max, mask, T, make_uniforms(n, T, seed + 1))
+    rs = np.random.RandomState(seed + 2)
+    dens = rs.gamma(0.7, 3.0, (n, T)).astype(F)
+    rgb = rs.uniform(-1, 1, (n, T, 3)).astype(F)
+    bg = np.array([-1.0, 0.3, 0.8], F)
+    return rays, s, dens, rgb, bg
+
+
+@pytest.mark.parametrize("T", [64, 192, 7, 100])
+def test_composite_fwd(nat, T):
+    rays, s, dens, rgb, bg = _composite_case(257, T, 20 + T)
+    out, alphas, coords = nat.composite_fwd(dev(rays), dev(s.ts), dev(s.t_min), dev(s.t_max),
+                                            dev(s.mask.astype(np.uint8)), dev(dens), dev(rgb), dev(bg))
+    np.testing.assert_allclose(out.cpu().numpy(), s.render_rays(dens, rgb, bg), atol=1e-5)
+    np.testing.assert_allclose(alphas.cpu().numpy(), s.render_alpha(dens), atol=1e-5)
+    np.testing.assert_allclose(coords.cpu().numpy(),
+                               s.render_rays(dens, s.points(rays), np.zeros(3, F)), atol=2e-5)
+
+
+@pytest.mark.parametrize("T", [64, 192, 5])
+def test_composite_bwd_vs_autograd(nat, T):
+    from oracle.render_torch import composite
+    rays, s, dens, rgb, bg = _composite_case(130, T, 40 + T)
+    rs = np.random.RandomState(1)
+    d_out = rs.randn(130, 3).astype(F)
+    td = torch.from_numpy(dens).double().requires_grad_(True)
+    tc = torch.from_numpy(rgb).double().requires_grad_(True)
+    tb = torch.from_numpy(bg).double().requires_grad_(True)
+    out = composite(torch.from_numpy(s.ts).double(), torch.from_numpy(s.t_min).double(),
+                    torch.from_numpy(s.t_max).double(), torch.from_numpy(s.mask), td, tc, tb)
+    (out * torch.from_numpy(d_out).double()).sum().backward()
+    d_bg = torch.zeros(3, device="cuda")
+    d_dens, d_rgb = nat.composite_bwd(dev(s.ts), dev(s.t_min), dev(s.t_max),
+                                      dev(s.mask.astype(np.uint8)), dev(dens), dev(rgb), dev(bg),
+                                      dev(d_out), d_bg)
+    def rel(a, b):
+        return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+    assert rel(d_dens.cpu().numpy(), td.grad.numpy()) < 1e-4   # stated tolerance: rel-L2 1e-4 (fp32)
+    assert rel(d_rgb.cpu().numpy(), tc.grad.numpy()) < 1e-5
+    assert rel(d_bg.cpu().numpy(), tb.grad.numpy()) < 1e-5
+
+
+def test_mse_loss(nat):
+    rs = np.random.RandomState(0)
+    batch = rs.randn(100, 3, 3).astype(F)
+    out = rs.randn(100, 3).astype(F)
+    tb = dev(batch)
+    loss = torch.zeros(1, device="cuda")
+    d_out = torch.empty(100, 3, device="cuda")
+    nat.mse_loss(dev(out), tb[:, 2], 9, 100, 1.0 / 300, loss, d_out)
+    ref = ((out - batch[:, 2]) ** 2).sum()
+    np.testing.assert_allclose(loss.item(), ref, rtol=1e-5)
+    np.testing.assert_allclose(d_out.cpu().numpy(), 2 * (out - batch[:, 2]) / 300, rtol=1e-6, atol=1e-9)
+
+
+# ------------------------------------------------------------------ K10
+def test_adam_step(nat):
+    from oracle import train_torch as T
+    rs = np.random.RandomState(0)
+    n = 10007
+    p0 = rs.randn(n).astype(F)
+    params = dict(w=torch.from_numpy(p0.copy()))
+    st = T.AdamState(params)
+    p, m, v = dev(p0.copy()), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    for step in range(1, 4):
+        g = rs.randn(n).astype(F)
+        norms = torch.zeros(2, device="cuda")
+        p_before = p.cpu().numpy().copy()
+        nat.adam_step(p, dev(g * 2.0), m, v, 1e-3, 0.9, 0.999, 1e-7, step, 0.5, norms)
+        params = T.adam_update(params, dict(w=torch.from_numpy(g)), st, 1e-3, eps=1e-7)
+        np.testing.assert_allclose(p.cpu().numpy(), params["w"].numpy(), rtol=2e-6, atol=1e-7)
+        np.testing.assert_allclose(norms.cpu().numpy(),
+                                   [(g.astype(np.float64) ** 2).sum(), (p_before.astype(np.float64) ** 2).sum()],
+                                   rtol=1e-5)

@@ -1,0 +1,232 @@
+"""GPU parity tests of the NeRF MLP (K2/K6), the full renderer and the train step,
+through the reference-shaped Python API (learn_nerf.*) against the CPU oracle.
+
+Stated tolerances (north star): rendered RGB / alpha / coords 1e-5 abs on the fp32
+path, 2e-2 abs on the bf16 path; gradients rel-L2 <= 1e-4 per tensor (fp32).
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import BBOX_MAX, BBOX_MIN, F, make_rays, make_uniforms
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def oracle_setup(seed=2):
+    from oracle import models_torch as M
+    from oracle import train_torch as T
+    nerf = M.NeRFModel()
+    return M, T, nerf, T.init_params(nerf, nerf, seed)
+
+
+def to_native(model, oracle_tree):
+    return model.flatten_params({k: {kk: vv.cuda() for kk, vv in v.items()} for k, v in oracle_tree.items()})
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+
+
+def test_param_layout_roundtrip():
+    from learn_nerf.model import NeRFModel
+    m = NeRFModel()
+    assert m.param_count() == 593_924
+    _, _, nerf, params = oracle_setup()
+    tree = to_native(m, params["coarse"])
+    for name, leaf in params["coarse"].items():
+        for k in ("kernel", "bias"):
+            np.testing.assert_array_equal(tree[name][k].cpu().numpy(), leaf[k].numpy())
+    assert tree.flat.numel() == m.param_floats()
+
+
+@pytest.mark.parametrize("m_samples", [1, 127, 128, 1000, 4096 + 5])
+def test_mlp_fp32_forward_points(m_samples):
+    """model.apply(dict(params=params), x, d) seam, fp32 path: 1e-5 abs."""
+    from learn_nerf.model import NeRFModel
+    _, _, nerf, params = oracle_setup()
+    rs = np.random.RandomState(m_samples)
+    x = rs.uniform(-1.5, 1.5, (m_samples, 3)).astype(F)
+    d = rs.randn(m_samples, 3).astype(F)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    with torch.no_grad():
+        o_d, o_rgb, _ = nerf.apply(params["fine"], torch.from_numpy(x), torch.from_numpy(d))
+    model = NeRFModel(precision="fp32")
+    dens, rgb, aux = model.apply(dict(params=to_native(model, params["fine"])), dev(x), dev(d))
+    assert dens.shape == (m_samples, 1) and rgb.shape == (m_samples, 3) and aux == {}
+    np.testing.assert_allclose(dens.cpu().numpy(), o_d.numpy(), atol=1e-5, rtol=1e-5)
+    np.testing.assert_allclose(rgb.cpu().numpy(), o_rgb.numpy(), atol=1e-5)
+
+
+@pytest.mark.parametrize("stages", [1, 2])
+@pytest.mark.parametrize("m_samples", [128, 1000, 128 * 300 + 17])
+def test_mlp_bf16_forward_points(m_samples, stages):
+    """bf16 tcgen05 path: 2e-2 abs on rgb / density (random-init weights)."""
+    from learn_nerf import _native
+    from learn_nerf.model import NeRFModel
+    _, _, nerf, params = oracle_setup()
+    rs = np.random.RandomState(m_samples + 1)
+    x = rs.uniform(-1.2, 1.2, (m_samples, 3)).astype(F)
+    d = rs.randn(m_samples, 3).astype(F)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    with torch.no_grad():
+        o_d, o_rgb, _ = nerf.apply(params["coarse"], torch.from_numpy(x), torch.from_numpy(d))
+    model = NeRFModel(precision="bf16")
+    _native.set_tc_stages(stages)
+    try:
+        dens, rgb, _ = model.apply(dict(params=to_native(model, params["coarse"])), dev(x), dev(d))
+        torch.cuda.synchronize()
+    finally:
+        _native.set_tc_stages(1)
+    np.testing.assert_allclose(dens.cpu().numpy(), o_d.numpy(), atol=2e-2)
+    np.testing.assert_allclose(rgb.cpu().numpy(), o_rgb.numpy(), atol=2e-2)
+
+
+def _render_case(n, seed):
+    batch = make_rays(n, seed=seed, miss_frac=0.2)
+    return batch, make_uniforms(n, 64, seed + 1), make_uniforms(n, 128, seed + 2)
+
+
+def _oracle_render(M, nerf, params, batch, uc, uf):
+    from oracle import render_np
+    r = render_np.NeRFRenderer(M.as_numpy_model_fn(nerf, params["coarse"]),
+                               M.as_numpy_model_fn(nerf, params["fine"]),
+                               params["background"].numpy(), BBOX_MIN, BBOX_MAX, 64, 128)
+    smp = {}
+    return r.render_rays(uc, uf, batch[:, :2], smp), smp
+
+
+def _native_renderer(precision, params):
+    from learn_nerf.model import NeRFModel
+    from learn_nerf.render import NeRFRenderer
+    coarse, fine = NeRFModel(precision=precision), NeRFModel(precision=precision)
+    return NeRFRenderer(coarse=coarse, fine=fine, coarse_params=to_native(coarse, params["coarse"]),
+                        fine_params=to_native(fine, params["fine"]),
+                        background=params["background"].cuda(), bbox_min=torch.tensor(BBOX_MIN),
+                        bbox_max=torch.tensor(BBOX_MAX), coarse_ts=64, fine_ts=128)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 2e-2)])
+def test_render_rays_end_to_end(precision, tol):
+    """NeRFRenderer.render_rays (render.py:39-91) with explicit uniforms vs the oracle."""
+    M, _, nerf, params = oracle_setup()
+    batch, uc, uf = _render_case(300, 30)
+    o_out, smp = _oracle_render(M, nerf, params, batch, uc, uf)
+    r = _native_renderer(precision, params)
+    out = r.render_rays((dev(uc), dev(uf)), dev(batch[:, :2]))
+    assert set(out) == {"coarse", "fine", "coarse_aux", "fine_aux"}
+    assert set(out["fine"]) == {"outputs", "rgbs", "densities", "alphas", "coords"}
+    assert out["fine"]["rgbs"].shape == (300, 192, 3) and out["fine"]["alphas"].shape == (300, 1)
+    # coarse sample positions do not depend on the MLP: bit-exact
+    for level in ("coarse", "fine"):
+        for k in ("outputs", "alphas", "coords"):
+            np.testing.assert_allclose(out[level][k].cpu().numpy(), o_out[level][k], atol=tol,
+                                       err_msg=f"{level}/{k}")
+    np.testing.assert_allclose(out["coarse"]["densities"].cpu().numpy(), o_out["coarse"]["densities"],
+                               atol=tol, rtol=tol)
+    if precision == "fp32":
+        # fine positions follow the coarse densities; 1-ulp density noise moves them by ~1e-6
+        fine_ts = None  # positions are checked bit-exactly in test_fine_positions_given_same_densities
+        np.testing.assert_allclose(out["fine"]["rgbs"].cpu().numpy(), o_out["fine"]["rgbs"], atol=1e-4)
+
+
+def test_fine_positions_given_same_densities():
+    """North star: positions and indices bit-exact given the same uniforms (and inputs)."""
+    from learn_nerf.render import RaySamples
+    M, _, nerf, params = oracle_setup()
+    batch, uc, uf = _render_case(200, 50)
+    o_out, smp = _oracle_render(M, nerf, params, batch, uc, uf)
+    cs = smp["coarse"]
+    s = RaySamples(t_min=dev(cs.t_min), t_max=dev(cs.t_max), mask=dev(cs.mask), ts=dev(cs.ts))
+    fine = s.fine_sampling(128, dev(uf), dev(o_out["coarse"]["densities"]))
+    np.testing.assert_array_equal(fine.ts.cpu().numpy().view(np.uint32), smp["fine"].ts.view(np.uint32))
+
+
+def test_render_key_api_and_masked_rays():
+    """PRNG-key entry point runs; rays that miss the bbox show the background exactly."""
+    _, _, nerf, params = oracle_setup()
+    r = _native_renderer("fp32", params)
+    batch = make_rays(64, seed=9, miss_frac=1.0, with_targets=False)
+    out = r.render_rays(1234, dev(batch))
+    bg = params["background"].numpy()
+    np.testing.assert_array_equal(out["fine"]["outputs"].cpu().numpy(), np.tile(bg, (64, 1)))
+    np.testing.assert_array_equal(out["fine"]["alphas"].cpu().numpy(), np.zeros((64, 1), F))
+    out2 = r.render_rays(1234, dev(batch))
+    np.testing.assert_array_equal(out2["coarse"]["densities"].cpu().numpy(),
+                                  out["coarse"]["densities"].cpu().numpy())
+
+
+def _train_loop(precision, params, ray_chunk=None, lr=1e-4):
+    from learn_nerf.model import NeRFModel
+    from learn_nerf.train import TrainLoop
+    coarse, fine = NeRFModel(precision=precision), NeRFModel(precision=precision)
+    loop = TrainLoop(coarse, fine, init_rng=0, lr=lr, coarse_ts=64, fine_ts=128, ray_chunk=ray_chunk)
+    for name in ("coarse", "fine"):
+        for lname, leaf in params[name].items():
+            for k in ("kernel", "bias"):
+                loop.state.params[name][lname][k].copy_(leaf[k])
+        loop.state.params[name].mark_updated()
+    loop.state.params["background"].copy_(params["background"])
+    return loop
+
+
+@pytest.mark.parametrize("ray_chunk", [None, 100])
+def test_train_step_fp32_vs_oracle(ray_chunk):
+    """TrainLoop.step_fn (train.py:78-112): losses, gradients (via one Adam step), norms."""
+    M, T, nerf, params = oracle_setup()
+    n = 256
+    batch, uc, uf = _render_case(n, 70)
+    loop = _train_loop("fp32", params, ray_chunk)
+    step = loop.step_fn(torch.tensor(BBOX_MIN), torch.tensor(BBOX_MAX))
+    # fine positions from the CUDA path so both sides differentiate the same sample set
+    fine_ts = loop._renderer(list(BBOX_MIN), list(BBOX_MAX), loop.state.params).render_rays(
+        (dev(uc), dev(uf)), dev(batch[:, :2]), _save=True)["fine"]["_ts"].ts.cpu().numpy()
+    g, ld, _ = T.grads(nerf, nerf, params, BBOX_MIN, BBOX_MAX, batch, uc, uf, 64, 128,
+                       fixed_fine_ts=fine_ts)
+    logs = step((dev(uc), dev(uf)), dev(batch))
+    assert set(logs) == {"coarse", "fine", "grad_norm", "param_norm"}
+    np.testing.assert_allclose(float(logs["coarse"]), ld["coarse"], rtol=1e-4)
+    np.testing.assert_allclose(float(logs["fine"]), ld["fine"], rtol=1e-4)
+    np.testing.assert_allclose(float(logs["grad_norm"]), T.tree_norm(g), rtol=1e-4)
+    np.testing.assert_allclose(float(logs["param_norm"]), T.tree_norm(params), rtol=1e-5)
+    # gradient parity per tensor (rel-L2 <= 1e-4)
+    grads = loop._grads
+    for name in ("coarse", "fine"):
+        gt = getattr(loop, name).bind(grads[loop._slices[name][0]:loop._slices[name][1]])
+        for lname, leaf in g[name].items():
+            for k in ("kernel", "bias"):
+                assert rel_l2(gt[lname][k].cpu().numpy(), leaf[k].numpy()) < 1e-4, (name, lname, k)
+    sb = loop._slices["background"]
+    assert rel_l2(grads[sb[0]:sb[1]].cpu().numpy(), g["background"].numpy()) < 1e-4
+    # one Adam step
+    new_params = T.adam_update(params, g, T.AdamState(params), 1e-4, eps=1e-7)
+    for name in ("coarse", "fine"):
+        for lname, leaf in new_params[name].items():
+            np.testing.assert_allclose(loop.state.params[name][lname]["kernel"].cpu().numpy(),
+                                       leaf["kernel"].numpy(), atol=2e-6)
+    np.testing.assert_allclose(loop.state.params["background"].cpu().numpy(),
+                               new_params["background"].numpy(), atol=2e-6)
+
+
+def test_train_loss_decreases_and_checkpoint_roundtrip(tmp_path):
+    _, _, nerf, params = oracle_setup()
+    loop = _train_loop("fp32", params, lr=5e-4)
+    step = loop.step_fn(BBOX_MIN, BBOX_MAX)
+    batch = dev(make_rays(512, seed=5))
+    first = None
+    for i in range(8):
+        logs = step(i, batch)
+        first = first if first is not None else float(logs["fine"])
+    assert float(logs["fine"]) < first
+    path = str(tmp_path / "nerf.pkl")
+    loop.save(path)
+    loop2 = _train_loop("fp32", params)
+    loop2.load(path)
+    np.testing.assert_array_equal(loop2.state.flat.cpu().numpy(), loop.state.flat.cpu().numpy())
+    total, ld = loop2.losses(3, BBOX_MIN, BBOX_MAX, batch, loop2.state.params)
+    assert np.isfinite(float(total)) and set(ld) == {"coarse", "fine"}

@@ -1,0 +1,190 @@
+"""CPU tests of the oracle itself: self-derived known-answer tests (the
+reference holds no golden vectors for this path -> parity unpinned) + regression
+against the committed fixtures in tests/golden/."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import models_torch as M
+from oracle import render_np
+from oracle import train_torch as T
+from oracle.expf import expf
+
+from helpers import BBOX_MAX, BBOX_MIN, F, make_rays, make_uniforms
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_expf_accuracy():
+    x = np.concatenate([np.linspace(-87, 0, 200001), -np.logspace(-30, 1.9, 20000)]).astype(F)
+    y = expf(x)
+    ref = np.exp(x.astype(np.float64))
+    ulp = np.spacing(ref.astype(F)).astype(np.float64)
+    assert np.max(np.abs(y.astype(np.float64) - ref) / ulp) <= 1.0
+    assert expf(F(0.0)) == F(1.0)
+    assert expf(F(-100.0)) == F(0.0)
+    assert np.isinf(expf(F(100.0)))
+
+
+def test_ray_t_range_kat():
+    rays = np.array([[[0, 0, -3], [0, 0, 1]], [[0, 5, -3], [0, 0, 1]]], F)
+    t_min, t_max, mask = render_np.ray_t_range(BBOX_MIN, BBOX_MAX, rays)
+    assert mask.tolist() == [True, False]
+    np.testing.assert_array_equal(t_min, np.array([2, 0], F))
+    np.testing.assert_array_equal(t_max, np.array([4, 1e-3], F))
+
+
+def test_termination_probs_sum_to_one():
+    rays = make_rays(32, with_targets=False)
+    t_min, t_max, mask = render_np.ray_t_range(BBOX_MIN, BBOX_MAX, rays)
+    s = render_np.RaySamples.stratified_sampling(t_min, t_max, mask, 64, make_uniforms(32, 64))
+    dens = np.random.RandomState(3).gamma(1.0, 2.0, (32, 64)).astype(F)
+    p = s.termination_probs(dens)
+    assert p.shape == (32, 65)
+    np.testing.assert_allclose(p.sum(1), 1.0, atol=2e-6)
+
+
+def test_zero_density_renders_background_and_uniform_cdf():
+    n = 16
+    rays = make_rays(n, with_targets=False)
+    t_min, t_max, mask = render_np.ray_t_range(BBOX_MIN, BBOX_MAX, rays)
+    s = render_np.RaySamples.stratified_sampling(t_min, t_max, mask, 64, make_uniforms(n, 64))
+    bg = np.array([0.25, -0.5, 1.0], F)
+    zeros = np.zeros((n, 64), F)
+    out = s.render_rays(zeros, np.ones((n, 64, 3), F), bg)
+    np.testing.assert_array_equal(out, np.tile(bg, (n, 1)))
+    np.testing.assert_array_equal(s.render_alpha(zeros), np.zeros((n, 1), F))
+    fs, idx = s.fine_sampling(128, make_uniforms(n, 128, 5), zeros, combine=False, return_indices=True)
+    # uniform CDF over [t_min, t_max]: new_ts ~ t_min + u' * (t_max - t_min)
+    u = render_np.RaySamples.stratified_sampling(np.zeros(n, F), np.ones(n, F), mask, 128,
+                                                 make_uniforms(n, 128, 5)).ts
+    expect = t_min[:, None] + u * (t_max - t_min)[:, None]
+    np.testing.assert_allclose(fs.ts, expect, atol=2e-2)  # bins are mid-point based, not exact
+    assert idx.min() >= 1 and idx.max() <= 64
+
+
+def test_opaque_first_sample_returns_its_colour():
+    rays = make_rays(4, with_targets=False)
+    t_min, t_max, mask = render_np.ray_t_range(BBOX_MIN, BBOX_MAX, rays)
+    s = render_np.RaySamples.stratified_sampling(t_min, t_max, mask, 8, make_uniforms(4, 8))
+    dens = np.zeros((4, 8), F)
+    dens[:, 0] = 1e9
+    rgb = np.random.RandomState(0).uniform(-1, 1, (4, 8, 3)).astype(F)
+    out = s.render_rays(dens, rgb, np.zeros(3, F))
+    np.testing.assert_allclose(out, rgb[:, 0], atol=1e-6)
+
+
+def test_sinusoidal_emb_layout():
+    e = M.sinusoidal_emb(torch.tensor([[0.1, 0.2, 0.3]]), 10)[0]
+    np.testing.assert_allclose(e[:3].numpy(), np.sin([0.1, 0.2, 0.4]), atol=1e-7)
+    np.testing.assert_allclose(float(e[10]), np.cos(0.1), atol=1e-7)
+    np.testing.assert_allclose(float(e[20]), np.sin(0.2), atol=1e-7)
+
+
+def test_param_counts():
+    nerf = M.NeRFModel()
+    p = T.init_params(nerf, nerf, 0)
+    assert sum(t.numel() for _, t in M.tree_leaves(p)) == 1_187_851
+    assert sum(a * b + b for a, b in nerf.layer_dims()) == 593_924
+    ref = M.RefNERFModel()
+    assert sum(a * b + b for a, b in ref.layer_dims()) == 592_771
+
+
+def test_hash_kats():
+    assert int(M.hash_table_lookup_indices(torch.tensor([[0, 0, 0]]), 2 ** 18)) == 0
+    c = torch.tensor([[1, 2, 3]])
+    expect = (1 ^ ((19_349_663 * 2) & 0xFFFFFFFF) ^ ((83_492_791 * 3) & 0xFFFFFFFF)) % (2 ** 18)
+    assert int(M.hash_table_lookup_indices(c, 2 ** 18)) == expect
+    assert M.hash_level_rows(2 ** 18, 64) == 64 ** 3  # 64^3 == 2^18 is NOT > table_size -> dense
+    assert M.hash_level_rows(2 ** 18, 128) == 2 ** 18
+    # at an exact grid vertex the encoding equals that row; weights sum to one
+    g = 16
+    table = torch.rand(g ** 3, 2)
+    x = torch.tensor([[-1 + 2 * 3 / 15, -1 + 2 * 5 / 15, -1 + 2 * 7 / 15]], dtype=torch.float64)
+    f, dbg = M.hash_table_encoding(table.double(), x, 2 ** 18, g, torch.tensor([-1.0] * 3).double(),
+                                   torch.tensor([1.0] * 3).double(), return_debug=True)
+    np.testing.assert_allclose(f[0].numpy(), table[3 + g * (5 + g * 7)].numpy(), atol=1e-6)
+    np.testing.assert_allclose(sum(float(w) for _, w in dbg), 1.0, atol=1e-12)
+
+
+def test_sh_and_ide_kats():
+    v = torch.tensor([[0.0, 0.0, 1.0], [0.6, 0.0, 0.8]])
+    sh = M.spherical_harmonic(4, v)
+    assert sh.shape == (2, 16)
+    np.testing.assert_allclose(sh[:, 0].numpy(), 0.28209479177387814, atol=1e-7)
+    ide = M.integrated_directional_encoding(4, v, torch.zeros(2, 1))
+    np.testing.assert_allclose(ide.numpy(), sh.numpy(), atol=0)
+    a, b = torch.tensor([0.0031308]), torch.tensor([0.0031308 + 1e-7])
+    assert abs(float(M.linear_rgb_to_srgb(a)) - float(M.linear_rgb_to_srgb(b))) < 1e-5
+
+
+def test_composite_gradient_matches_finite_differences():
+    """fp64 finite differences pin the autograd oracle used for K5/K6 checks."""
+    from oracle.render_torch import composite
+    torch.manual_seed(0)
+    n, t = 3, 9
+    ts = torch.sort(torch.rand(n, t, dtype=torch.float64) * 2 + 2, dim=1).values
+    t_min, t_max = torch.full((n,), 2.0, dtype=torch.float64), torch.full((n,), 4.0, dtype=torch.float64)
+    mask = torch.tensor([True, True, False])
+    dens = torch.rand(n, t, dtype=torch.float64, requires_grad=True)
+    rgb = torch.rand(n, t, 3, dtype=torch.float64, requires_grad=True)
+    bg = torch.rand(3, dtype=torch.float64, requires_grad=True)
+    assert torch.autograd.gradcheck(lambda d, c, b: composite(ts, t_min, t_max, mask, d, c, b),
+                                    (dens, rgb, bg), eps=1e-6, atol=1e-6)
+
+
+def test_adam_matches_torch_optim():
+    torch.manual_seed(0)
+    p = dict(a=torch.randn(5, 3), b=dict(c=torch.randn(7)))
+    ref = [p["a"].clone().requires_grad_(True), p["b"]["c"].clone().requires_grad_(True)]
+    opt = torch.optim.Adam(ref, lr=1e-2, betas=(0.9, 0.999), eps=1e-7)
+    st = T.AdamState(p)
+    for _ in range(3):
+        g = dict(a=torch.randn(5, 3), b=dict(c=torch.randn(7)))
+        ref[0].grad, ref[1].grad = g["a"].clone(), g["b"]["c"].clone()
+        opt.step()
+        p = T.adam_update(p, g, st, 1e-2, eps=1e-7)
+    # torch adds eps to sqrt(v_hat) exactly as optax (eps_root = 0)
+    np.testing.assert_allclose(p["a"].numpy(), ref[0].detach().numpy(), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(p["b"]["c"].numpy(), ref[1].detach().numpy(), rtol=1e-5, atol=1e-7)
+
+
+def _golden_case():
+    n = 24
+    batch = make_rays(n, seed=11, miss_frac=0.25)
+    return batch, make_uniforms(n, 64, 12), make_uniforms(n, 128, 13)
+
+
+def test_golden_render_fixture():
+    """Regression: the committed fixture was produced by tests/golden/make_golden.py from this
+    oracle (self-generated; it guards the oracle against drift, it does not pin the reference)."""
+    path = os.path.join(GOLDEN, "nerf_render_small.npz")
+    g = np.load(path)
+    batch, uc, uf = _golden_case()
+    np.testing.assert_array_equal(g["batch"], batch)
+    nerf = M.NeRFModel()
+    params = T.init_params(nerf, nerf, 2)
+    r = render_np.NeRFRenderer(M.as_numpy_model_fn(nerf, params["coarse"]),
+                               M.as_numpy_model_fn(nerf, params["fine"]),
+                               params["background"].numpy(), BBOX_MIN, BBOX_MAX, 64, 128)
+    smp = {}
+    out = r.render_rays(uc, uf, batch[:, :2], smp)
+    np.testing.assert_array_equal(smp["coarse"].ts, g["coarse_ts"])  # bit-exact stage
+    np.testing.assert_array_equal(smp["coarse"].mask, g["mask"])
+    # fine positions depend on MLP densities (BLAS summation order): tolerance, not bits
+    np.testing.assert_allclose(smp["fine"].ts, g["fine_ts"], atol=1e-4)
+    np.testing.assert_allclose(out["fine"]["outputs"], g["fine_outputs"], atol=1e-5)
+    np.testing.assert_allclose(out["coarse"]["outputs"], g["coarse_outputs"], atol=1e-5)
+    np.testing.assert_allclose(out["fine"]["alphas"], g["fine_alphas"], atol=1e-5)
+    np.testing.assert_allclose(out["fine"]["coords"], g["fine_coords"], atol=1e-5)
+
+
+def test_golden_fine_sampling_fixture_bit_exact():
+    """Given stored (ts, densities, u) the fine sampler is pure fp32 elementwise work: bit-exact."""
+    g = np.load(os.path.join(GOLDEN, "fine_sampling_small.npz"))
+    s = render_np.RaySamples(t_min=g["t_min"], t_max=g["t_max"], mask=g["mask"], ts=g["ts"])
+    out, idx = s.fine_sampling(128, g["u"], g["densities"], return_indices=True)
+    np.testing.assert_array_equal(out.ts, g["fine_ts"])
+    np.testing.assert_array_equal(idx, g["idx"])
