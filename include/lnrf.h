@@ -43,6 +43,8 @@ const char* lnrf_last_error(void);
 int lnrf_version(void);
 /* One-time per-process setup for `device` (function attributes, SM count). */
 int lnrf_init(int device);
+/* Number of kernels this process has launched through the library so far. */
+int64_t lnrf_launch_count(void);
 
 /* ---------------------------------------------------------------- K1 sampling
  * ray_t_range (render.py:346-389, vmapped at :93-111) + stratified_sampling

@@ -8,6 +8,9 @@ namespace lnrf {
 
 static thread_local char g_err[512] = "";
 static int g_sm_count = 0;
+static unsigned long long g_launches = 0;
+
+void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -42,6 +45,8 @@ extern "C" {
 const char* lnrf_last_error(void) { return lnrf::g_err; }
 
 int lnrf_version(void) { return 1; }
+
+int64_t lnrf_launch_count(void) { return (int64_t)lnrf::g_launches; }
 
 int lnrf_init(int device) {
   LNRF_CUDA(cudaSetDevice(device));

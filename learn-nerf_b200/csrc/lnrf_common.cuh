@@ -12,6 +12,7 @@ namespace lnrf {
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 int sm_count();
+void count_launch();  // bumps the counter behind lnrf_launch_count()
 
 #define LNRF_REQUIRE(cond, code, ...)     \
   do {                                    \
@@ -30,6 +31,7 @@ int sm_count();
 // after a kernel launch: report launch-configuration errors without syncing
 #define LNRF_LAUNCH_CHECK(name)                                        \
   do {                                                                 \
+    ::lnrf::count_launch();                                            \
     cudaError_t e__ = cudaGetLastError();                              \
     if (e__ != cudaSuccess) return ::lnrf::cuda_fail(e__, name);       \
   } while (0)

@@ -29,6 +29,7 @@ _SIGS = {
     "lnrf_last_error": (c_char_p, []),
     "lnrf_version": (c_int32, []),
     "lnrf_init": (c_int32, [c_int32]),
+    "lnrf_launch_count": (c_int64, []),
     "lnrf_sample_coarse": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_float, c_float,
                                      c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p]),
@@ -206,6 +207,10 @@ def mse_loss(outputs, targets_base, target_stride, n, inv_count, loss_sum, d_out
     ensure_init(outputs.device)
     _check(load().lnrf_mse_loss(_p(_f32c(outputs, "outputs")), _p(targets_base), target_stride, n,
                                 inv_count, _p(loss_sum), _p(d_outputs), _stream()), "lnrf_mse_loss")
+
+
+def launch_count() -> int:
+    return int(load().lnrf_launch_count())
 
 
 def nerf_param_count() -> int:

@@ -92,7 +92,7 @@ def grads(coarse, fine, params, *args, **kwargs):
                 g = next(it)
                 tree[k] = torch.zeros_like(ref[k]) if g is None else g
     fill(grad_tree, leaf_params)
-    return grad_tree, {k: float(v) for k, v in loss_dict.items()}, render_out
+    return grad_tree, {k: float(v.detach()) for k, v in loss_dict.items()}, render_out
 
 
 def tree_norm(tree) -> float:  # train.py:92-97

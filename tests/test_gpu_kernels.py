@@ -146,8 +146,8 @@ def test_composite_bwd_vs_autograd(nat, T):
     def rel(a, b):
         return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
     assert rel(d_dens.cpu().numpy(), td.grad.numpy()) < 1e-4   # stated tolerance: rel-L2 1e-4 (fp32)
-    assert rel(d_rgb.cpu().numpy(), tc.grad.numpy()) < 1e-5
-    assert rel(d_bg.cpu().numpy(), tb.grad.numpy()) < 1e-5
+    assert rel(d_rgb.cpu().numpy(), tc.grad.numpy()) < 1e-4
+    assert rel(d_bg.cpu().numpy(), tb.grad.numpy()) < 1e-4
 
 
 def test_mse_loss(nat):
