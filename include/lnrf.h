@@ -183,6 +183,10 @@ int lnrf_ngp_mlp_bwd(const float* params, int32_t L, const float* enc, int64_t m
  * D fp32 [128,N]) used by tests to pin the UMMA descriptor encodings.         */
 int lnrf_debug_umma_gemm(const float* a, const float* b, int32_t N, int32_t K, float* d_out,
                          lnrf_stream_t stream);
+/* Same for the transposed (dW) shape: D[M,N] = At[128,M]^T * Bt[128,N], both operands
+ * MN-major views of [128 x 64] SW128 block images; M in {128,256}, N in {64,128,192,256}. */
+int lnrf_debug_umma_gemm_tn(const float* at, const float* bt, int32_t M, int32_t N, float* d_out,
+                            lnrf_stream_t stream);
 /* Tuning knob of the fused bf16 kernel: 1 = one weight-ring stage and two CTAs
  * per SM (default); >= 2 = four stages, one CTA per SM.                       */
 int lnrf_set_tc_stages(int32_t stages);

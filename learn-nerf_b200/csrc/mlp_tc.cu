@@ -8,89 +8,41 @@
 // write the next layer's A operand.  Positional encoding is computed in-kernel
 // straight into the A operand; the density head rides as column 128 of the colour
 // layer GEMM, the 128->3 rgb head is done in fp32 FMAs in the last epilogue.
+// With SAVE the per-layer activation tiles (the shared-memory images themselves) and
+// the ReLU bit masks are streamed to the stash with bulk stores for the backward.
 //
 // Warp roles (192 threads): warps 0-3 = epilogue (thread r <-> tile row r <-> TMEM
 // lane r), warp 4 = weight producer (bulk copies), warp 5 = MMA issuer (one thread).
-#include <cuda_bf16.h>
-
-#include "lnrf_common.cuh"
-#include "lnrf_math.cuh"
-#include "nerf_layout.cuh"
-#include "sm100_ptx.cuh"
+#include "tc_common.cuh"
 
 namespace lnrf {
 
 using namespace ptx;
 
-// ---------------------------------------------------------------- packed weights
-// Tensor layers of the fused kernel and their K chunks (64 rows of K each):
-//   T0: Dense_0            K = x_emb block            N = 256
-//   T1..T4: Dense_1..4     K = 4 act blocks           N = 256
-//   T5: Dense_5            K = 4 act blocks + x_emb   N = 256
-//   T6..T8: Dense_6..8     K = 4 act blocks           N = 256
-//   T9: Dense_10 (+Dense_9 as column 128)  K = 4 act blocks + d_emb   N = 144
-constexpr int kTcLayers = 10;
-constexpr int kTcChunks = 39;
-constexpr int kNColor = 144;                  // 128 colour units + density column + pad to 16
-constexpr uint32_t kChunkBytes256 = 256 * 128;      // 32768
-constexpr uint32_t kChunkBytes144 = kNColor * 128;  // 18432
-constexpr int64_t kPackedBytes = 34 * int64_t(kChunkBytes256) + 5 * int64_t(kChunkBytes144);
-
-struct ChunkInfo {
-  int layer;    // Dense index providing the rows
-  int k0;       // first kernel row of this chunk
-  int kvalid;   // rows that exist (rest are zero padding)
-  int n;        // B-operand rows (= output columns of the tensor layer)
-  int ablock;   // which A block the MMA reads: 0..3 activations, 4 = embedding block
-  int tlayer;   // tensor layer index 0..9
-  uint32_t offset;  // byte offset inside the packed image
-};
-
-struct ChunkTable { ChunkInfo c[kTcChunks]; };
-
-static ChunkTable build_chunk_table() {
-  ChunkTable t{};
-  int n = 0;
-  uint32_t off = 0;
-  auto add = [&](int layer, int k0, int kvalid, int ncols, int ablock, int tlayer) {
-    t.c[n] = ChunkInfo{layer, k0, kvalid, ncols, ablock, tlayer, off};
-    off += uint32_t(ncols) * 128u;
-    ++n;
-  };
-  add(0, 0, kXE, 256, 4, 0);
-  for (int l = 1; l <= 4; ++l)
-    for (int b = 0; b < 4; ++b) add(l, b * 64, 64, 256, b, l);
-  for (int b = 0; b < 4; ++b) add(5, b * 64, 64, 256, b, 5);
-  add(5, 256, kXE, 256, 4, 5);
-  for (int l = 6; l <= 8; ++l)
-    for (int b = 0; b < 4; ++b) add(l, b * 64, 64, 256, b, l);
-  for (int b = 0; b < 4; ++b) add(10, b * 64, 64, kNColor, b, 9);
-  add(10, 256, kDE, kNColor, 4, 9);
-  return t;
-}
-
-__constant__ ChunkTable c_chunks;
-__constant__ NerfLayout c_nerf;  // device copy of kNerf (runtime-indexed in kernels)
-
-// One thread per (chunk, n, 16-byte group of 8 k): writes the bf16 B-operand image
-// B[n][k] = W[k0 + k][n] in the SW128 K-major layout the MMA expects.
+// One thread per (chunk, n, 16-byte group of 8 k): writes the bf16 B-operand image in the
+// SW128 K-major layout the MMA expects (see tc_common.cuh for the two chunk forms).
 __global__ void __launch_bounds__(256)
 pack_weights_kernel(const float* __restrict__ P, uint8_t* __restrict__ packed) {
   const int ci = blockIdx.y;
-  const ChunkInfo c = c_chunks.c[ci];
+  const ChunkInfo c = ci < kTcChunks ? c_chunks.f[ci] : c_chunks.b[ci - kTcChunks];
   const int items = c.n * 8;
+  const int out_dim = c_nerf.out[c.layer];
+  const float* W = P + c_nerf.w[c.layer];
   for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += gridDim.x * blockDim.x) {
     const int n = it >> 3, kg = it & 7;
-    const int out_dim = c_nerf.out[c.layer];
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int k = kg * 8 + j;
       float w = 0.0f;
       if (k < c.kvalid) {
-        if (n < out_dim) w = __ldg(P + c_nerf.w[c.layer] + int64_t(c.k0 + k) * out_dim + n);
-        else if (c.layer == 10 && n == kHC && c.ablock < 4)  // density head column (Dense_9)
+        if (c.transposed) {
+          w = __ldg(W + int64_t(n) * out_dim + (c.k0 + k));
+        } else if (n < out_dim) {
+          w = __ldg(W + int64_t(c.k0 + k) * out_dim + n);
+        } else if (c.layer == 10 && n == kHC && c.ablock < 4) {  // density column (Dense_9)
           w = __ldg(P + c_nerf.w[9] + (c.k0 + k));
+        }
       }
       v[j] = w;
     }
@@ -103,7 +55,7 @@ pack_weights_kernel(const float* __restrict__ P, uint8_t* __restrict__ packed) {
   }
 }
 
-// ---------------------------------------------------------------- debug GEMM
+// ---------------------------------------------------------------- debug GEMMs
 // D[128,N] = A[128,K] * B[N,K]^T, one CTA, same operand layouts / descriptors /
 // TMEM read-back as the fused kernel.  K multiple of 64 (<= 256), N multiple of 16.
 __global__ void __launch_bounds__(128)
@@ -112,20 +64,18 @@ debug_umma_gemm_kernel(const float* __restrict__ A, const float* __restrict__ B,
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int kb = K / 64;
-  uint8_t* sA = smem;                       // kb blocks of 128 x 128 B
-  uint8_t* sB = smem + kb * 16384;          // kb blocks of N x 128 B
+  uint8_t* sA = smem;               // kb blocks of 128 x 128 B
+  uint8_t* sB = smem + kb * 16384;  // kb blocks of N x 128 B
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5;
   for (int i = tid; i < 128 * K; i += 128) {
     int r = i / K, k = i % K;
-    __nv_bfloat16 h = __float2bfloat16(A[i]);
-    *reinterpret_cast<__nv_bfloat16*>(sA + (k / 64) * 16384 + sw128_offset(r, k % 64)) = h;
+    *reinterpret_cast<__nv_bfloat16*>(sA + (k / 64) * 16384 + sw128_offset(r, k % 64)) = __float2bfloat16(A[i]);
   }
   for (int i = tid; i < N * K; i += 128) {
     int r = i / K, k = i % K;
-    __nv_bfloat16 h = __float2bfloat16(B[i]);
-    *reinterpret_cast<__nv_bfloat16*>(sB + (k / 64) * (N * 128) + sw128_offset(r, k % 64)) = h;
+    *reinterpret_cast<__nv_bfloat16*>(sB + (k / 64) * (N * 128) + sw128_offset(r, k % 64)) = __float2bfloat16(B[i]);
   }
   if (tid == 0) {
     mbar_init(smem_u32(&bar), 1);
@@ -165,6 +115,66 @@ debug_umma_gemm_kernel(const float* __restrict__ A, const float* __restrict__ B,
   if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
+// D[M,N] = At[K,M]^T * Bt[K,N] with BOTH operands MN-major (the dW = act^T @ grad shape:
+// K = 128 samples are the rows of the same [128 x 64] SW128 block images the forward
+// writes).  M in {128, 256} (two M halves -> two TMEM column ranges), N multiple of 64.
+__global__ void __launch_bounds__(128)
+debug_umma_gemm_tn_kernel(const float* __restrict__ At, const float* __restrict__ Bt, int M, int N,
+                          float* __restrict__ D) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                     // M/64 blocks of [128 samples x 64 features]
+  uint8_t* sB = smem + (M / 64) * 16384;  // N/64 blocks
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 128 * M; i += 128) {
+    int r = i / M, c = i % M;
+    *reinterpret_cast<__nv_bfloat16*>(sA + (c / 64) * 16384 + sw128_offset(r, c % 64)) = __float2bfloat16(At[i]);
+  }
+  for (int i = tid; i < 128 * N; i += 128) {
+    int r = i / N, c = i % N;
+    *reinterpret_cast<__nv_bfloat16*>(sB + (c / 64) * 16384 + sw128_offset(r, c % 64)) = __float2bfloat16(Bt[i]);
+  }
+  if (tid == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(smem_u32(&tmem_base_s), 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  if (tid == 0) {
+    const uint32_t idesc = umma_idesc_bf16_mn(128, N);
+    for (int h = 0; h < M / 128; ++h) {
+      for (int k = 0; k < 8; ++k) {  // 8 x 16 samples
+        uint64_t ad = umma_desc_sw128_mnmajor(smem_u32(sA + h * 2 * 16384) + k * 2048, 16384);
+        uint64_t bd = umma_desc_sw128_mnmajor(smem_u32(sB) + k * 2048, 16384);
+        umma_bf16(tmem + h * N, ad, bd, idesc, k ? 1u : 0u);
+      }
+    }
+    umma_commit(smem_u32(&bar));
+  }
+  mbar_wait(smem_u32(&bar), 0);
+  tc_fence_after();
+  for (int h = 0; h < M / 128; ++h) {
+    for (int c0 = 0; c0 < N; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem + (uint32_t(warp * 32) << 16) + h * N + c0, v);
+      tmem_wait_ld();
+      for (int j = 0; j < 32; ++j) D[(h * 128 + tid) * N + c0 + j] = __uint_as_float(v[j]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 // ---------------------------------------------------------------- fused forward
 struct TcFwdArgs {
   const uint8_t* packed;  // packed bf16 weight image (kPackedBytes)
@@ -177,10 +187,9 @@ struct TcFwdArgs {
   int64_t m;
   float* dens;
   float* rgb;
+  TcStash stash;          // used when SAVE
 };
 
-constexpr int kTcThreads = 192;
-constexpr uint32_t kABlockBytes = 128 * 128;  // one [128 x 64] bf16 block
 constexpr uint32_t kABytes = 5 * kABlockBytes;
 
 template <int STAGES>
@@ -192,13 +201,7 @@ struct TcSmem {
   static constexpr uint32_t alloc = total;          // dynamic smem base is declared 1024-aligned
 };
 
-// writes 8 packed bf16 pairs groups (64 values, one full row of a block) is done by callers
-__device__ __forceinline__ void store_row_chunk(uint32_t block_base, int row, int chunk, uint32_t a,
-                                                uint32_t b, uint32_t c, uint32_t d) {
-  st_shared_v4(block_base + row * 128 + (((chunk ^ (row & 7)) & 7) << 4), a, b, c, d);
-}
-
-template <int STAGES>
+template <int STAGES, bool SAVE>
 __global__ void __launch_bounds__(kTcThreads, STAGES <= 1 ? 2 : 1)
 nerf_fwd_tc_kernel(TcFwdArgs args) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -215,7 +218,7 @@ nerf_fwd_tc_kernel(TcFwdArgs args) {
   const uint32_t bar_full = bars, bar_empty = bars + 8 * STAGES;
   const uint32_t bar_a_ready = bars + 16 * STAGES, bar_acc_ready = bar_a_ready + 8;
   const uint32_t tmem_slot = bar_acc_ready + 8;
-  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_base));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t tiles = (args.m + 127) / 128;
@@ -245,10 +248,10 @@ nerf_fwd_tc_kernel(TcFwdArgs args) {
       uint32_t stage = 0, phase = 0;
       for (int64_t t = 0; t < my_tiles; ++t) {
         for (int ci = 0; ci < kTcChunks; ++ci) {
-          const uint32_t bytes = uint32_t(c_chunks.c[ci].n) * 128u;
+          const uint32_t bytes = uint32_t(c_chunks.f[ci].n) * 128u;
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           mbar_arrive_expect_tx(bar_full + 8 * stage, bytes);
-          bulk_g2s(sW + stage * kChunkBytes256, args.packed + c_chunks.c[ci].offset, bytes,
+          bulk_g2s(sW + stage * kChunkBytes256, args.packed + c_chunks.f[ci].offset, bytes,
                    bar_full + 8 * stage);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -264,8 +267,8 @@ nerf_fwd_tc_kernel(TcFwdArgs args) {
           mbar_wait(bar_a_ready, ev & 1);  // A operand of this layer is in smem, accumulator is free
           tc_fence_after();
           bool first = true;
-          while (ci < kTcChunks && c_chunks.c[ci].tlayer == tl) {
-            const ChunkInfo c = c_chunks.c[ci];
+          while (ci < kTcChunks && c_chunks.f[ci].tlayer == tl) {
+            const ChunkInfo c = c_chunks.f[ci];
             const uint32_t idesc = umma_idesc_bf16(128, c.n);
             mbar_wait(bar_full + 8 * stage, phase);
             tc_fence_after();
@@ -296,6 +299,7 @@ nerf_fwd_tc_kernel(TcFwdArgs args) {
       const int64_t tile = blockIdx.x + t * gridDim.x;
       const int64_t s = tile * 128 + r;
       const bool valid = s < args.m;
+      uint32_t* mask_tile = SAVE ? args.stash.MASK + (tile * 9) * 1024 + warp * 256 : nullptr;
       // ---- inputs: point and direction of this sample
       float px[3] = {0.f, 0.f, 0.f}, dv[3] = {0.f, 0.f, 0.f};
       if (valid) {
@@ -311,6 +315,10 @@ nerf_fwd_tc_kernel(TcFwdArgs args) {
             px[k] = __fadd_rn(__ldg(args.rays + ray * 6 + k), __fmul_rn(dv[k], tt));  // render.py:153
           }
         }
+      }
+      if (SAVE) {  // block 4 may still be read by the previous tile's d_emb bulk store
+        if (tid == 0) bulk_wait_read0();
+        epi_bar();
       }
       // ---- sinusoidal_emb(x, 10) -> A block 4 (cols dim*20 + [sin f | cos f]), cols 60..63 = 0
       {
@@ -344,6 +352,13 @@ nerf_fwd_tc_kernel(TcFwdArgs args) {
         de[dim * 4 + 3] = pack_bf16x2(cs[2], cs[3]);
       }
       fence_proxy_async_smem();
+      if (SAVE) {
+        epi_bar();
+        if (tid == 0) {
+          bulk_s2g(args.stash.XE + tile * kABlockBytes, sA + 4 * kABlockBytes, kABlockBytes);
+          bulk_commit();
+        }
+      }
       tc_fence_before();
       mbar_arrive(bar_a_ready);  // event: layer T0 may start
       // ---- hidden layers T0..T8
@@ -351,6 +366,10 @@ nerf_fwd_tc_kernel(TcFwdArgs args) {
         mbar_wait(bar_acc_ready, ev & 1);
         ++ev;
         tc_fence_after();
+        if (SAVE) {  // the previous layer's tile image must have left smem before we overwrite it
+          if (tid == 0) bulk_wait_read0();
+          epi_bar();
+        }
         const float* bias = P + c_nerf.b[tl];
         const bool relu = tl < 8;  // Dense_8's output feeds the heads raw (model.py:53-58)
 #pragma unroll 1
@@ -366,12 +385,23 @@ nerf_fwd_tc_kernel(TcFwdArgs args) {
             const float f2 = __uint_as_float(v[j + 2]) + b.z, f3 = __uint_as_float(v[j + 3]) + b.w;
             pk[j / 2] = relu ? pack_bf16x2_relu(f0, f1) : pack_bf16x2(f0, f1);
             pk[j / 2 + 1] = relu ? pack_bf16x2_relu(f2, f3) : pack_bf16x2(f2, f3);
+            if (SAVE) {  // reuse v[] for the mask words: bit `lane` of word j = (h[row, c0+j] > 0)
+              v[j] = __ballot_sync(0xffffffffu, f0 > 0.0f);
+              v[j + 1] = __ballot_sync(0xffffffffu, f1 > 0.0f);
+              v[j + 2] = __ballot_sync(0xffffffffu, f2 > 0.0f);
+              v[j + 3] = __ballot_sync(0xffffffffu, f3 > 0.0f);
+            }
           }
           const uint32_t blk = sA + (c0 >> 6) * kABlockBytes;
           const int cbase = (c0 & 63) >> 3;
 #pragma unroll
           for (int q = 0; q < 4; ++q)
             store_row_chunk(blk, r, cbase + q, pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+          if (SAVE && relu && lane == 0) {
+            uint4* dst = reinterpret_cast<uint4*>(mask_tile + tl * 1024 + c0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) dst[q] = make_uint4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+          }
         }
         if (tl == 8) {  // x_emb is dead after T5: block 4 now carries d_emb (24 cols) + zeros
           const uint32_t blk = sA + 4 * kABlockBytes;
@@ -382,6 +412,14 @@ nerf_fwd_tc_kernel(TcFwdArgs args) {
           for (int c = 3; c < 8; ++c) store_row_chunk(blk, r, c, 0u, 0u, 0u, 0u);
         }
         fence_proxy_async_smem();
+        if (SAVE) {
+          epi_bar();
+          if (tid == 0) {
+            bulk_s2g(args.stash.H[tl] + tile * kTileBytes, sA, kTileBytes);
+            if (tl == 8) bulk_s2g(args.stash.DE + tile * kABlockBytes, sA + 4 * kABlockBytes, kABlockBytes);
+            bulk_commit();
+          }
+        }
         tc_fence_before();
         mbar_arrive(bar_a_ready);
       }
@@ -389,6 +427,10 @@ nerf_fwd_tc_kernel(TcFwdArgs args) {
       mbar_wait(bar_acc_ready, ev & 1);
       ++ev;
       tc_fence_after();
+      if (SAVE) {  // blocks 0,1 get the colour-hidden image once the z8 image has left smem
+        if (tid == 0) bulk_wait_read0();
+        epi_bar();
+      }
       float o0 = 0.f, o1 = 0.f, o2 = 0.f;
       const float* b10 = P + c_nerf.b[10];
       const float* w11 = P + c_nerf.w[11];
@@ -397,12 +439,34 @@ nerf_fwd_tc_kernel(TcFwdArgs args) {
         uint32_t v[32];
         tmem_ld32(tm_lane + c0, v);
         tmem_wait_ld();
+        uint32_t pk[16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float h = fmaxf(__uint_as_float(v[j]) + __ldg(b10 + c0 + j), 0.0f);  // model.py:59
-          o0 = fmaf(h, __ldg(w11 + (c0 + j) * 3 + 0), o0);
-          o1 = fmaf(h, __ldg(w11 + (c0 + j) * 3 + 1), o1);
-          o2 = fmaf(h, __ldg(w11 + (c0 + j) * 3 + 2), o2);
+        for (int j = 0; j < 32; j += 2) {
+          const float h0 = fmaxf(__uint_as_float(v[j]) + __ldg(b10 + c0 + j), 0.0f);  // model.py:59
+          const float h1 = fmaxf(__uint_as_float(v[j + 1]) + __ldg(b10 + c0 + j + 1), 0.0f);
+          o0 = fmaf(h0, __ldg(w11 + (c0 + j) * 3 + 0), o0);
+          o1 = fmaf(h0, __ldg(w11 + (c0 + j) * 3 + 1), o1);
+          o2 = fmaf(h0, __ldg(w11 + (c0 + j) * 3 + 2), o2);
+          o0 = fmaf(h1, __ldg(w11 + (c0 + j) * 3 + 3), o0);
+          o1 = fmaf(h1, __ldg(w11 + (c0 + j) * 3 + 4), o1);
+          o2 = fmaf(h1, __ldg(w11 + (c0 + j) * 3 + 5), o2);
+          if (SAVE) {
+            pk[j / 2] = pack_bf16x2(h0, h1);
+            v[j] = __ballot_sync(0xffffffffu, h0 > 0.0f);
+            v[j + 1] = __ballot_sync(0xffffffffu, h1 > 0.0f);
+          }
+        }
+        if (SAVE) {
+          const uint32_t blk = sA + (c0 >> 6) * kABlockBytes;
+          const int cbase = (c0 & 63) >> 3;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            store_row_chunk(blk, r, cbase + q, pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+          if (lane == 0) {
+            uint4* dst = reinterpret_cast<uint4*>(mask_tile + 8 * 1024 + c0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) dst[q] = make_uint4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+          }
         }
       }
       {
@@ -417,8 +481,17 @@ nerf_fwd_tc_kernel(TcFwdArgs args) {
           args.rgb[s * 3 + 2] = tanhf(o2 + __ldg(b11 + 2));
         }
       }
+      if (SAVE) {
+        fence_proxy_async_smem();
+        epi_bar();
+        if (tid == 0) {
+          bulk_s2g(args.stash.C + tile * 2 * kABlockBytes, sA, 2 * kABlockBytes);
+          bulk_commit();
+        }
+      }
       tc_fence_before();  // orders these TMEM reads before the next a_ready arrive
     }
+    if (SAVE && tid == 0) bulk_wait0();  // all stash stores complete before the CTA exits
   }
   tc_fence_before();
   __syncthreads();
@@ -428,66 +501,64 @@ nerf_fwd_tc_kernel(TcFwdArgs args) {
 static bool g_tc_ready = false;
 static int g_tc_stages = 1;
 
+int init_mlp_tc_bwd();  // mlp_tc_bwd.cu
+
+template <typename K>
+static int set_smem(K kernel, int bytes) {
+  LNRF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  LNRF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared));
+  return LNRF_OK;
+}
+
 int init_mlp_tc() {
-  ChunkTable t = build_chunk_table();
-  LNRF_CUDA(cudaMemcpyToSymbol(c_chunks, &t, sizeof(t)));
-  NerfLayout lay = kNerf;
-  LNRF_CUDA(cudaMemcpyToSymbol(c_nerf, &lay, sizeof(lay)));
-  LNRF_CUDA(cudaFuncSetAttribute(nerf_fwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)TcSmem<1>::alloc));
-  LNRF_CUDA(cudaFuncSetAttribute(nerf_fwd_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)TcSmem<4>::alloc));
-  LNRF_CUDA(cudaFuncSetAttribute(nerf_fwd_tc_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                 cudaSharedmemCarveoutMaxShared));
-  LNRF_CUDA(cudaFuncSetAttribute(nerf_fwd_tc_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                 cudaSharedmemCarveoutMaxShared));
-  LNRF_CUDA(cudaFuncSetAttribute(debug_umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 200 * 1024));
+  int rc = upload_tc_tables();
+  if (rc) return rc;
+  if ((rc = set_smem(nerf_fwd_tc_kernel<1, false>, (int)TcSmem<1>::alloc))) return rc;
+  if ((rc = set_smem(nerf_fwd_tc_kernel<1, true>, (int)TcSmem<1>::alloc))) return rc;
+  if ((rc = set_smem(nerf_fwd_tc_kernel<4, false>, (int)TcSmem<4>::alloc))) return rc;
+  if ((rc = set_smem(nerf_fwd_tc_kernel<4, true>, (int)TcSmem<4>::alloc))) return rc;
+  if ((rc = set_smem(debug_umma_gemm_kernel, 200 * 1024))) return rc;
+  if ((rc = set_smem(debug_umma_gemm_tn_kernel, 200 * 1024))) return rc;
+  if ((rc = init_mlp_tc_bwd())) return rc;
   g_tc_ready = true;
   return LNRF_OK;
 }
 
+bool tc_ready() { return g_tc_ready; }
+
 int64_t tc_workspace_bytes(int64_t m, bool save) {
-  (void)m;
-  (void)save;
-  return 0;  // the fused forward keeps every activation on chip
+  return save ? carve_stash(nullptr, m).bytes : 0;  // render keeps every activation on chip
 }
 
 int nerf_fwd_tc(const float* P, const void* packed, const float* x, const float* d, const float* rays,
                 const float* ts, int64_t m, int T, bool save, void* ws, int64_t ws_bytes, float* dens,
                 float* rgb, cudaStream_t st) {
-  (void)ws;
-  (void)ws_bytes;
   LNRF_REQUIRE(g_tc_ready, LNRF_E_INVALID, "lnrf_nerf_mlp_fwd(bf16): call lnrf_init first");
-  LNRF_REQUIRE(!save, LNRF_E_UNSUPPORTED,
-               "lnrf_nerf_mlp_fwd(bf16): save_for_backward is not implemented on the bf16 path yet");
-  TcFwdArgs a{reinterpret_cast<const uint8_t*>(packed), P, x, d, rays, ts, T, m, dens, rgb};
+  TcFwdArgs a{reinterpret_cast<const uint8_t*>(packed), P, x, d, rays, ts, T, m, dens, rgb, TcStash{}};
+  if (save) {
+    LNRF_REQUIRE(ws && (uintptr_t)ws % 1024 == 0 && ws_bytes >= tc_workspace_bytes(m, true),
+                 LNRF_E_WORKSPACE, "lnrf_nerf_mlp_fwd(bf16): workspace %lld < %lld bytes or not "
+                 "1024-byte aligned", (long long)ws_bytes, (long long)tc_workspace_bytes(m, true));
+    a.stash = carve_stash(ws, m);
+  }
   const int64_t tiles = ceil_div(m, 128);
+  int64_t grid = int64_t(sm_count()) * (g_tc_stages == 1 ? 2 : 1);
+  if (grid > tiles) grid = tiles;
   if (g_tc_stages == 1) {
-    int64_t grid = int64_t(sm_count()) * 2;
-    if (grid > tiles) grid = tiles;
-    nerf_fwd_tc_kernel<1><<<(unsigned)grid, kTcThreads, TcSmem<1>::alloc, st>>>(a);
+    if (save) nerf_fwd_tc_kernel<1, true><<<(unsigned)grid, kTcThreads, TcSmem<1>::alloc, st>>>(a);
+    else nerf_fwd_tc_kernel<1, false><<<(unsigned)grid, kTcThreads, TcSmem<1>::alloc, st>>>(a);
   } else {
-    int64_t grid = sm_count();
-    if (grid > tiles) grid = tiles;
-    nerf_fwd_tc_kernel<4><<<(unsigned)grid, kTcThreads, TcSmem<4>::alloc, st>>>(a);
+    if (save) nerf_fwd_tc_kernel<4, true><<<(unsigned)grid, kTcThreads, TcSmem<4>::alloc, st>>>(a);
+    else nerf_fwd_tc_kernel<4, false><<<(unsigned)grid, kTcThreads, TcSmem<4>::alloc, st>>>(a);
   }
   LNRF_LAUNCH_CHECK("nerf_fwd_tc_kernel");
   return LNRF_OK;
 }
 
-int nerf_bwd_tc(const float* P, const void* packed, int64_t m, void* ws, int64_t ws_bytes,
-                const float* dens, const float* rgb, const float* d_dens, const float* d_rgb, float* G,
-                cudaStream_t st) {
-  (void)P; (void)packed; (void)m; (void)ws; (void)ws_bytes; (void)dens; (void)rgb; (void)d_dens;
-  (void)d_rgb; (void)G; (void)st;
-  LNRF_REQUIRE(false, LNRF_E_UNSUPPORTED, "lnrf_nerf_mlp_bwd(bf16): not implemented yet");
-  return LNRF_OK;
-}
-
 int nerf_pack_weights(const float* P, void* packed, cudaStream_t st) {
   LNRF_REQUIRE(g_tc_ready, LNRF_E_INVALID, "lnrf_nerf_pack_weights: call lnrf_init first");
-  dim3 grid(8, kTcChunks);
+  dim3 grid(8, kTcChunks + kBwChunks);
   pack_weights_kernel<<<grid, 256, 0, st>>>(P, reinterpret_cast<uint8_t*>(packed));
   LNRF_LAUNCH_CHECK("pack_weights_kernel");
   return LNRF_OK;
@@ -510,6 +581,18 @@ int lnrf_debug_umma_gemm(const float* a, const float* b, int32_t N, int32_t K, f
   size_t smem = size_t(K / 64) * (16384 + N * 128) + 1024;
   lnrf::debug_umma_gemm_kernel<<<1, 128, smem, lnrf::as_stream(stream)>>>(a, b, N, K, d_out);
   LNRF_LAUNCH_CHECK("debug_umma_gemm_kernel");
+  return LNRF_OK;
+}
+
+int lnrf_debug_umma_gemm_tn(const float* at, const float* bt, int32_t M, int32_t N, float* d_out,
+                            lnrf_stream_t stream) {
+  LNRF_REQUIRE(lnrf::g_tc_ready, LNRF_E_INVALID, "lnrf_debug_umma_gemm_tn: call lnrf_init first");
+  LNRF_REQUIRE(at && bt && d_out, LNRF_E_INVALID, "lnrf_debug_umma_gemm_tn: null pointer");
+  LNRF_REQUIRE((M == 128 || M == 256) && N >= 64 && N <= 256 && N % 64 == 0 && (M / 128) * N <= 512,
+               LNRF_E_UNSUPPORTED, "lnrf_debug_umma_gemm_tn: M=%d N=%d", M, N);
+  size_t smem = size_t(M / 64 + N / 64) * 16384 + 1024;
+  lnrf::debug_umma_gemm_tn_kernel<<<1, 128, smem, lnrf::as_stream(stream)>>>(at, bt, M, N, d_out);
+  LNRF_LAUNCH_CHECK("debug_umma_gemm_tn_kernel");
   return LNRF_OK;
 }
 

@@ -126,11 +126,29 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_kmajor(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major SW128 canonical layout (cute: ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units):
+// 64 contiguous MN elements (128 B) per K row, K rows 128 B apart in groups of 8 (SBO =
+// 1024 B between groups), further 64-element MN blocks LBO bytes apart.  This is the SAME
+// byte image as a K-major SW128 block of [rows x 64] read "transposed": rows become K.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= uint64_t((smem_addr & 0x3FFFFu) >> 4);
+  d |= uint64_t((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= uint64_t(1024 >> 4) << 32;
+  d |= uint64_t(1) << 46;
+  d |= uint64_t(2) << 61;
+  return d;
+}
+
 // Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16 with bf16 A/B,
 // fp32 accumulate, both operands K-major: c_format=1 @4, a_format=1 @7, b_format=1 @10,
 // N>>3 @17, M>>4 @24.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+// same with both operands MN-major (a_major @15, b_major @16)
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_mn(int M, int N) {
+  return umma_idesc_bf16(M, N) | (1u << 15) | (1u << 16);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread on behalf of the CTA.

@@ -53,6 +53,7 @@ _SIGS = {
     "lnrf_adam_step": (c_int32, [c_void_p] * 4 + [c_int64, c_float, c_float, c_float, c_float,
                                                   c_int32, c_float, c_void_p, c_void_p]),
     "lnrf_debug_umma_gemm": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    "lnrf_debug_umma_gemm_tn": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "lnrf_set_tc_stages": (c_int32, [c_int32]),
 }
 
@@ -275,6 +276,16 @@ def debug_umma_gemm(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     out = torch.empty(128, N, device=a.device)
     _check(load().lnrf_debug_umma_gemm(_p(_f32c(a, "a")), _p(_f32c(b, "b")), N, K, _p(out), _stream()),
            "lnrf_debug_umma_gemm")
+    return out
+
+
+def debug_umma_gemm_tn(at: torch.Tensor, bt: torch.Tensor) -> torch.Tensor:
+    """D[M,N] = bf16(At[128,M])^T @ bf16(Bt[128,N]) with MN-major descriptors (dW shape)."""
+    ensure_init(at.device)
+    M, N = at.shape[1], bt.shape[1]
+    out = torch.empty(M, N, device=at.device)
+    _check(load().lnrf_debug_umma_gemm_tn(_p(_f32c(at, "at")), _p(_f32c(bt, "bt")), M, N, _p(out),
+                                          _stream()), "lnrf_debug_umma_gemm_tn")
     return out
 
 

@@ -168,7 +168,9 @@ class NeRFModel(ModelBase):
         key = (str(device), bool(save), slot)
         ws = cache.get(key)
         if ws is None or ws.numel() < nbytes:
-            ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+            shift = (-raw.data_ptr()) % 1024  # the bf16 stash holds 1024-byte aligned tile images
+            ws = raw[shift: shift + nbytes]
             cache[key] = ws
         return ws
 

@@ -37,6 +37,19 @@ def test_umma_debug_gemm(nat, N, K):
     assert err <= 2e-3 * max(1.0, ref.abs().max().item()), err
 
 
+@pytest.mark.parametrize("M,N", [(128, 64), (128, 256), (256, 256), (256, 192), (256, 128)])
+def test_umma_debug_gemm_tn(nat, M, N):
+    """MN-major (transposed) operand descriptors used by the dW = act^T @ grad GEMMs."""
+    g = torch.Generator(device="cuda").manual_seed(M * 1000 + N)
+    at = torch.randn(128, M, device="cuda", generator=g)
+    bt = torch.randn(128, N, device="cuda", generator=g)
+    out = nat.debug_umma_gemm_tn(at, bt)
+    torch.cuda.synchronize()
+    ref = at.bfloat16().float().T @ bt.bfloat16().float()
+    err = (out - ref).abs().max().item()
+    assert err <= 2e-3 * max(1.0, ref.abs().max().item()), err
+
+
 # ------------------------------------------------------------------ K1
 def _edge_rays():
     r = make_rays(512, seed=3, miss_frac=0.3, with_targets=False)

