@@ -190,6 +190,9 @@ int lnrf_debug_umma_gemm_tn(const float* at, const float* bt, int32_t M, int32_t
 /* Tuning knob of the fused bf16 kernel: 1 = one weight-ring stage and two CTAs
  * per SM (default); >= 2 = four stages, one CTA per SM.                       */
 int lnrf_set_tc_stages(int32_t stages);
+/* Profiling ablations of the bf16 dW kernel (1 skip loads, 2 skip MMAs, 4 skip worker math);
+ * results are WRONG while non-zero.  Default 0.                                  */
+int lnrf_set_debug_flags(int32_t flags);
 
 #ifdef __cplusplus
 }

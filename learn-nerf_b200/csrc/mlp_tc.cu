@@ -502,6 +502,7 @@ static bool g_tc_ready = false;
 static int g_tc_stages = 1;
 
 int init_mlp_tc_bwd();  // mlp_tc_bwd.cu
+void set_dw_debug(int flags);
 
 template <typename K>
 static int set_smem(K kernel, int bytes) {
@@ -599,6 +600,12 @@ int lnrf_debug_umma_gemm_tn(const float* at, const float* bt, int32_t M, int32_t
 // tuning knob used by bench/tests: 1 = one ring stage, 2 CTAs/SM; >=2 = 4 stages, 1 CTA/SM
 int lnrf_set_tc_stages(int32_t stages) {
   lnrf::set_tc_stages(stages);
+  return LNRF_OK;
+}
+
+// ablation switches for profiling the dW kernel (results are wrong when non-zero)
+int lnrf_set_debug_flags(int32_t flags) {
+  lnrf::set_dw_debug(flags);
   return LNRF_OK;
 }
 

@@ -248,6 +248,7 @@ constexpr int kDwStages = 3;
 constexpr uint32_t kHalfBlock = 8192;              // 64 samples x 128 B
 constexpr uint32_t kDwStageBytes = 8 * kHalfBlock;  // A: 4 half-blocks, B: 4 half-blocks
 constexpr int kDwThreads = 192;                    // warp 0 producer, warp 1 MMA, warps 2-5 workers
+constexpr uint32_t kDwSmemBytes = kDwStages * kDwStageBytes + 128 + 2 * 64 * 16;  // ring + barriers + row strip
 
 struct DwJob {
   const uint8_t* A;   // stash image, a_blocks x 16 KB per tile
@@ -269,6 +270,7 @@ struct DwArgs {
   int64_t tiles;
   const float* SPRE;
   const float* DPRE;
+  int debug;  // ablation flags (tests/bench only): 1 = skip loads, 2 = skip MMAs, 4 = skip worker math
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -327,6 +329,11 @@ nerf_bwd_dw_kernel(DwArgs args) {
         const int64_t tile = t_begin + (it >> 1);
         const uint32_t half = uint32_t(it & 1) * kHalfBlock;
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        if (args.debug & 1) {
+          mbar_arrive(bar_full + 8 * stage);
+          if (++stage == kDwStages) { stage = 0; phase ^= 1; }
+          continue;
+        }
         mbar_arrive_expect_tx(bar_full + 8 * stage, uint32_t(job.a_blocks + job.b_blocks) * kHalfBlock);
         const uint32_t sa = smem_base + stage * kDwStageBytes, sb = sa + 4 * kHalfBlock;
         for (int b = 0; b < job.a_blocks; ++b)
@@ -345,7 +352,7 @@ nerf_bwd_dw_kernel(DwArgs args) {
       for (int64_t it = 0; it < n_iters; ++it) {
         mbar_wait(bar_full + 8 * stage, phase);
         tc_fence_after();
-        if (job.b_blocks > 0) {
+        if (job.b_blocks > 0 && !(args.debug & 2)) {
           const uint32_t sa = smem_base + stage * kDwStageBytes, sb = sa + 4 * kHalfBlock;
           for (int mh = 0; mh < job.m_halves; ++mh) {
 #pragma unroll
@@ -365,12 +372,29 @@ nerf_bwd_dw_kernel(DwArgs args) {
     uint32_t stage = 0, phase = 0;
     float s0 = 0.f, s1 = 0.f;                  // db of columns 2wt, 2wt+1
     float e0 = 0.f, e1 = 0.f, e2 = 0.f;        // extra accumulators
+    // Per-row head gradients (spre / dpre) of the next slot are fetched one iteration ahead
+    // with one coalesced load and parked in a double-buffered smem strip, so the inner
+    // loops below never wait on DRAM.
+    float4* s_rows = reinterpret_cast<float4*>(smem_raw + kDwStages * kDwStageBytes + 128);  // [2][64]
+    float4 pre = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto fetch_rows = [&](int64_t it) {
+      const int64_t base = (t_begin + (it >> 1)) * 128 + int(it & 1) * 64 + (wt & 63);
+      if (job.extra == 1) pre.x = __ldg(args.SPRE + base);
+      else pre = __ldg(reinterpret_cast<const float4*>(args.DPRE) + base);
+    };
+    if (job.extra != 0 && wt < 64 && n_iters > 0) fetch_rows(0);
     for (int64_t it = 0; it < n_iters; ++it) {
-      const int64_t tile = t_begin + (it >> 1);
-      const int row0 = int(it & 1) * 64;
+      if (job.extra != 0) {
+        if (wt < 64) {
+          s_rows[(it & 1) * 64 + wt] = pre;
+          if (it + 1 < n_iters) fetch_rows(it + 1);
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+      }
+      const float4* rows = s_rows + (it & 1) * 64;
       mbar_wait(bar_full + 8 * stage, phase);
       const uint32_t sa = smem_base + stage * kDwStageBytes, sb = sa + 4 * kHalfBlock;
-      if (job.db != nullptr && 2 * wt < N) {
+      if (job.db != nullptr && 2 * wt < N && !(args.debug & 4)) {
         const int c = 2 * wt;
         const uint32_t blk = sb + (c >> 6) * kHalfBlock;
 #pragma unroll 4
@@ -381,27 +405,26 @@ nerf_bwd_dw_kernel(DwArgs args) {
           s1 += __uint_as_float(u & 0xffff0000u);
         }
       }
-      if (job.extra == 1) {  // dW9[f] += z8[row, f] * spre[row], f = 2wt, 2wt+1
+      if (args.debug & 4) {
+      } else if (job.extra == 1) {  // dW9[f] += z8[row, f] * spre[row], f = 2wt, 2wt+1
         const int c = 2 * wt;
         const uint32_t blk = sa + (c >> 6) * kHalfBlock;
-        const float* sp = args.SPRE + tile * 128 + row0;
 #pragma unroll 4
         for (int rr = 0; rr < 64; ++rr) {
           uint32_t u;
           asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(blk + sw128_offset(rr, c & 63)));
-          const float w = __ldg(sp + rr);
+          const float w = rows[rr].x;
           e0 = fmaf(__uint_as_float(u << 16), w, e0);
           e1 = fmaf(__uint_as_float(u & 0xffff0000u), w, e1);
         }
       } else if (job.extra == 2) {  // dW11[k, :] += c[row, k] * dpre[row, :], k = wt
         const uint32_t blk = sa + (wt >> 6) * kHalfBlock;
-        const float4* dpp = reinterpret_cast<const float4*>(args.DPRE) + tile * 128 + row0;
 #pragma unroll 4
         for (int rr = 0; rr < 64; ++rr) {
           uint32_t u;
           asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(blk + sw128_offset(rr, (wt & 63) & ~1)));
           const float cv = (wt & 1) ? __uint_as_float(u & 0xffff0000u) : __uint_as_float(u << 16);
-          const float4 d4 = __ldg(dpp + rr);
+          const float4 d4 = rows[rr];
           e0 = fmaf(cv, d4.x, e0);
           e1 = fmaf(cv, d4.y, e1);
           e2 = fmaf(cv, d4.z, e2);
@@ -451,6 +474,9 @@ nerf_bwd_dw_kernel(DwArgs args) {
 }
 
 // ================================================================ host side
+static int g_dw_debug = 0;
+void set_dw_debug(int flags) { g_dw_debug = flags; }
+
 int init_mlp_tc_bwd() {
   int rc = upload_tc_tables();
   if (rc) return rc;
@@ -459,7 +485,7 @@ int init_mlp_tc_bwd() {
   LNRF_CUDA(cudaFuncSetAttribute(nerf_bwd_dx_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared));
   LNRF_CUDA(cudaFuncSetAttribute(nerf_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(kDwStages * kDwStageBytes + 128)));
+                                 (int)(kDwSmemBytes)));
   LNRF_CUDA(cudaFuncSetAttribute(nerf_bwd_dw_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared));
   return LNRF_OK;
@@ -487,6 +513,7 @@ int nerf_bwd_tc(const float* P, const void* packed, int64_t m, void* ws, int64_t
   d.tiles = tiles;
   d.SPRE = s.SPRE;
   d.DPRE = s.DPRE;
+  d.debug = g_dw_debug;
   int nj = 0;
   auto add = [&](const uint8_t* A, int ab, const uint8_t* B, int bb, int mh, int rows, int ld, float* dW,
                  float* db, int extra, float* extra_out) {
@@ -503,7 +530,8 @@ int nerf_bwd_tc(const float* P, const void* packed, int64_t m, void* ws, int64_t
   const int total_ctas = sm_count();
   double wsum = 0.0;
   double wj[kDwMaxJobs];
-  for (int j = 0; j < nj; ++j) {
+    wj[j] = d.jobs[j].a_blocks + d.jobs[j].b_blocks;
+    if (d.jobs[j].extra == 2) wj[j] = 4;  // CUDA-core only job: bounded by its row loop, not by bytes
     wj[j] = d.jobs[j].a_blocks + d.jobs[j].b_blocks;
     wsum += wj[j];
   }
@@ -516,7 +544,7 @@ int nerf_bwd_tc(const float* P, const void* packed, int64_t m, void* ws, int64_t
     d.jobs[j].cta_count = c;
     begin += c;
   }
-  nerf_bwd_dw_kernel<<<(unsigned)begin, kDwThreads, kDwStages * kDwStageBytes + 128, st>>>(d);
+  nerf_bwd_dw_kernel<<<(unsigned)begin, kDwThreads, kDwSmemBytes, st>>>(d);
   LNRF_LAUNCH_CHECK("nerf_bwd_dw_kernel");
   return LNRF_OK;
 }

@@ -55,6 +55,7 @@ _SIGS = {
     "lnrf_debug_umma_gemm": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "lnrf_debug_umma_gemm_tn": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "lnrf_set_tc_stages": (c_int32, [c_int32]),
+    "lnrf_set_debug_flags": (c_int32, [c_int32]),
 }
 
 # entry points that exist only once the corresponding kernels are built
