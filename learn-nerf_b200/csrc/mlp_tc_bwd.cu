@@ -530,9 +530,9 @@ int nerf_bwd_tc(const float* P, const void* packed, int64_t m, void* ws, int64_t
   const int total_ctas = sm_count();
   double wsum = 0.0;
   double wj[kDwMaxJobs];
+  for (int j = 0; j < nj; ++j) {
     wj[j] = d.jobs[j].a_blocks + d.jobs[j].b_blocks;
     if (d.jobs[j].extra == 2) wj[j] = 4;  // CUDA-core only job: bounded by its row loop, not by bytes
-    wj[j] = d.jobs[j].a_blocks + d.jobs[j].b_blocks;
     wsum += wj[j];
   }
   int begin = 0;
