@@ -2,43 +2,13 @@
 // This is the 1e-5-accurate path (SURVEY §7 hard part 1); the tensor-core path is
 // mlp_tc.cu.  Reference: learn_nerf/model.py:42-77 (forward); the backward is what
 // jax.grad derives at train.py:90.
+#include "embed.cuh"
 #include "lnrf_common.cuh"
 #include "lnrf_math.cuh"
 #include "nerf_layout.cuh"
 #include "sgemm.cuh"
 
 namespace lnrf {
-
-// ---------------------------------------------------------------- embedding
-// sinusoidal_emb (model.py:65-77): per coordinate [sin 2^0..2^{F-1}, cos 2^0..2^{F-1}].
-// One thread per (sample, dim, freq).  Ray mode computes the point as o + d*t with
-// two roundings (render.py:153).
-template <int FREQS>
-__global__ void __launch_bounds__(256)
-embed_kernel(const float* __restrict__ v, const float* __restrict__ rays, const float* __restrict__ ts,
-             int T, int which /*0: position, 1: direction*/, int64_t m, float* __restrict__ out) {
-  const int64_t total = m * 3 * FREQS;
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += int64_t(gridDim.x) * blockDim.x) {
-    const int64_t s = i / (3 * FREQS);
-    const int rem = int(i - s * 3 * FREQS);
-    const int dim = rem / FREQS, f = rem - dim * FREQS;
-    float c;
-    if (v) {
-      c = __ldg(v + s * 3 + dim);
-    } else {
-      const int64_t r = s / T;
-      const float dd = __ldg(rays + r * 6 + 3 + dim);
-      c = which ? dd : __fadd_rn(__ldg(rays + r * 6 + dim), __fmul_rn(dd, __ldg(ts + s)));
-    }
-    const float a = c * float(1 << f);
-    float sn, cs;
-    sincosf(a, &sn, &cs);
-    float* o = out + s * (6 * FREQS) + dim * 2 * FREQS;
-    o[f] = sn;
-    o[FREQS + f] = cs;
-  }
-}
 
 // ---------------------------------------------------------------- heads
 // density = softplus(z8 . w9 + b9)  (model.py:57).  Warp per sample.
@@ -180,26 +150,6 @@ density_head_bwd_kernel(const float* __restrict__ z8, const float* __restrict__ 
   if (lane == 0) atomicAdd(db9, gbias);
 }
 
-// db[n] += sum_m G[m,n]; N in {128, 256}.
-__global__ void __launch_bounds__(256)
-colsum_kernel(const float* __restrict__ G, int64_t m, int N, float* __restrict__ db) {
-  const int col = threadIdx.x % N;
-  const int rsub = threadIdx.x / N, rstep = blockDim.x / N;
-  const int64_t rows_per_block = ceil_div(m, gridDim.x);
-  const int64_t r0 = int64_t(blockIdx.x) * rows_per_block;
-  const int64_t r1 = min(r0 + rows_per_block, m);
-  float acc = 0.0f;
-  for (int64_t r = r0 + rsub; r < r1; r += rstep) acc += __ldg(G + r * N + col);
-  __shared__ float s[256];
-  s[threadIdx.x] = acc;
-  __syncthreads();
-  if (threadIdx.x < N) {
-    float t = 0.0f;
-    for (int k = 0; k < rstep; ++k) t += s[k * N + threadIdx.x];
-    atomicAdd(db + threadIdx.x, t);
-  }
-}
-
 // ---------------------------------------------------------------- workspace
 struct Fp32Ws {
   float* xe;     // [m,60]
@@ -243,12 +193,6 @@ static Fp32Ws carve_fp32(void* base, int64_t m, bool save) {
 }
 
 int64_t fp32_workspace_bytes(int64_t m, bool save) { return carve_fp32(nullptr, m, save).bytes; }
-
-static inline unsigned ew_blocks(int64_t work_items, int per_block) {
-  int64_t b = ceil_div(work_items, per_block);
-  int64_t cap = int64_t(sm_count()) * 16;
-  return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
-}
 
 int nerf_fwd_fp32(const float* P, const float* x, const float* d, const float* rays, const float* ts,
                   int64_t m, int T, bool save, void* ws_base, int64_t ws_bytes, float* dens,
@@ -316,7 +260,7 @@ int nerf_bwd_fp32(const float* P, int64_t m, void* ws_base, int64_t ws_bytes, co
   if (rc) return rc;
   rc = gemm_tn_acc(st, kDE, kHC, w.de, kDE, w.dc, kHC, m, G + kNerf.w[10] + int64_t(kH) * kHC, kHC);
   if (rc) return rc;
-  colsum_kernel<<<cb, 256, 0, st>>>(w.dc, m, kHC, G + kNerf.b[10]);
+  colsum_kernel<><<<cb, 256, 0, st>>>(w.dc, m, kHC, G + kNerf.b[10]);
   LNRF_LAUNCH_CHECK("colsum_kernel");
   // g8 = dc @ W10[:256]^T + spre (x) w9
   float* g = w.gA;
@@ -332,7 +276,7 @@ int nerf_bwd_fp32(const float* P, int64_t m, void* ws_base, int64_t ws_bytes, co
       rc = gemm_tn_acc(st, kXE, kH, w.xe, kXE, g, kH, m, G + kNerf.w[5] + int64_t(kH) * kH, kH);
       if (rc) return rc;
     }
-    colsum_kernel<<<cb, 256, 0, st>>>(g, m, kH, G + kNerf.b[l]);
+    colsum_kernel<><<<cb, 256, 0, st>>>(g, m, kH, G + kNerf.b[l]);
     LNRF_LAUNCH_CHECK("colsum_kernel");
     rc = gemm_nt<EPI_MASK>(st, m, kH, g, kH, kH, P + kNerf.w[l], kH, gn, kH, w.h[l - 1], kH);
     if (rc) return rc;
@@ -340,7 +284,7 @@ int nerf_bwd_fp32(const float* P, int64_t m, void* ws_base, int64_t ws_bytes, co
   }
   rc = gemm_tn_acc(st, kXE, kH, w.xe, kXE, g, kH, m, G + kNerf.w[0], kH);
   if (rc) return rc;
-  colsum_kernel<<<cb, 256, 0, st>>>(g, m, kH, G + kNerf.b[0]);
+  colsum_kernel<><<<cb, 256, 0, st>>>(g, m, kH, G + kNerf.b[0]);
   LNRF_LAUNCH_CHECK("colsum_kernel");
   return LNRF_OK;
 }

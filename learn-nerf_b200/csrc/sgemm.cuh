@@ -169,6 +169,28 @@ __global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g) {
   }
 }
 
+// db[n] += sum_m G[m,n]; N must divide 256 (bias gradients).  Template only so that the
+// definition can live in this header.
+template <int UNUSED = 0>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ G, int64_t m, int N, float* __restrict__ db) {
+  const int col = threadIdx.x % N;
+  const int rsub = threadIdx.x / N, rstep = blockDim.x / N;
+  const int64_t rows_per_block = ceil_div(m, gridDim.x);
+  const int64_t r0 = int64_t(blockIdx.x) * rows_per_block;
+  const int64_t r1 = min(r0 + rows_per_block, m);
+  float acc = 0.0f;
+  for (int64_t r = r0 + rsub; r < r1; r += rstep) acc += __ldg(G + r * N + col);
+  __shared__ float s[256];
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x < N) {
+    float t = 0.0f;
+    for (int k = 0; k < rstep; ++k) t += s[k * N + threadIdx.x];
+    atomicAdd(db + threadIdx.x, t);
+  }
+}
+
 template <bool ATRANS, bool BTRANS, int EPI>
 static int launch_sgemm(const GemmArgs& g, int splits, cudaStream_t stream) {
   dim3 grid((unsigned)ceil_div(g.M, GBM), (unsigned)ceil_div(g.N, GBN), (unsigned)splits);

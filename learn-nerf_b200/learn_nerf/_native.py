@@ -56,10 +56,7 @@ _SIGS = {
     "lnrf_debug_umma_gemm_tn": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "lnrf_set_tc_stages": (c_int32, [c_int32]),
     "lnrf_set_debug_flags": (c_int32, [c_int32]),
-}
-
-# entry points that exist only once the corresponding kernels are built
-_OPTIONAL_SIGS = {
+    "lnrf_ngp_mlp_param_offsets": (c_int32, [c_int32, c_void_p]),
     "lnrf_hashgrid_fwd": (c_int32, [c_void_p] * 4 + [c_int32, c_void_p, c_void_p, c_int32,
                                                      c_void_p, c_void_p, c_void_p, c_int64, c_int32,
                                                      c_void_p, c_void_p]),
@@ -91,16 +88,12 @@ def load() -> ctypes.CDLL:
         for name, (res, args) in _SIGS.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        for name, (res, args) in _OPTIONAL_SIGS.items():
-            if hasattr(lib, name):
-                fn = getattr(lib, name)
-                fn.restype, fn.argtypes = res, args
         _lib = lib
     return _lib
 
 
 def exported_symbols():
-    return sorted(list(_SIGS) + [n for n in _OPTIONAL_SIGS if hasattr(load(), n)])
+    return sorted(_SIGS)
 
 
 def _check(rc: int, what: str):
@@ -288,6 +281,70 @@ def debug_umma_gemm_tn(at: torch.Tensor, bt: torch.Tensor) -> torch.Tensor:
     _check(load().lnrf_debug_umma_gemm_tn(_p(_f32c(at, "at")), _p(_f32c(bt, "bt")), M, N, _p(out),
                                           _stream()), "lnrf_debug_umma_gemm_tn")
     return out
+
+
+# --------------------------------------------------------------------------- Instant-NGP
+class GridSpec:
+    """Host-side description of a multiresolution table set (instant_ngp.py:92-118)."""
+
+    def __init__(self, table_sizes, grid_sizes, bbox_min, bbox_max, smooth=False, base_offset=0):
+        self.L = len(grid_sizes)
+        self.table_sizes = [int(t) for t in table_sizes]
+        self.grid_sizes = [int(g) for g in grid_sizes]
+        self.rows = [t if g ** 3 > t else g ** 3 for t, g in zip(self.table_sizes, self.grid_sizes)]
+        offs, off = [], int(base_offset)
+        for r in self.rows:
+            offs.append(off)
+            off += (r * 2 + 3) // 4 * 4
+        self.offsets, self.end = offs, off
+        self.smooth = int(bool(smooth))
+        self._off = (c_int64 * self.L)(*offs)
+        self._grid = (c_int32 * self.L)(*self.grid_sizes)
+        self._tab = (c_int32 * self.L)(*self.table_sizes)
+        self._lo, self._hi = _host3(bbox_min), _host3(bbox_max)
+
+
+def hashgrid_fwd(tables_flat, spec: GridSpec, x, rays, ts, n, T, enc):
+    ensure_init(tables_flat.device)
+    _check(load().lnrf_hashgrid_fwd(_p(tables_flat), spec._off, spec._grid, spec._tab, spec.L, spec._lo,
+                                    spec._hi, spec.smooth, _p(x), _p(rays), _p(ts), n, T, _p(enc),
+                                    _stream()), "lnrf_hashgrid_fwd")
+
+
+def hashgrid_bwd(spec: GridSpec, x, rays, ts, n, T, d_enc, d_tables_flat):
+    ensure_init(d_enc.device)
+    _check(load().lnrf_hashgrid_bwd(spec._off, spec._grid, spec._tab, spec.L, spec._lo, spec._hi,
+                                    spec.smooth, _p(x), _p(rays), _p(ts), n, T, _p(_f32c(d_enc, "d_enc")),
+                                    _p(d_tables_flat), _stream()), "lnrf_hashgrid_bwd")
+
+
+def ngp_mlp_param_floats(L: int) -> int:
+    return int(load().lnrf_ngp_mlp_param_count(L))
+
+
+def ngp_mlp_param_offsets(L: int):
+    buf = (c_int64 * 10)()
+    _check(load().lnrf_ngp_mlp_param_offsets(L, buf), "lnrf_ngp_mlp_param_offsets")
+    return [int(v) for v in buf]
+
+
+def ngp_mlp_workspace_bytes(m: int, L: int) -> int:
+    out = c_int64(0)
+    _check(load().lnrf_ngp_mlp_workspace_bytes(m, L, ctypes.byref(out)), "lnrf_ngp_mlp_workspace_bytes")
+    return int(out.value)
+
+
+def ngp_mlp_fwd(flat, L, enc, d, rays, n, T, workspace, dens, rgb):
+    ensure_init(flat.device)
+    _check(load().lnrf_ngp_mlp_fwd(_p(flat), L, _p(enc), _p(d), _p(rays), n, T, _p(workspace),
+                                   workspace.numel(), _p(dens), _p(rgb), _stream()), "lnrf_ngp_mlp_fwd")
+
+
+def ngp_mlp_bwd(flat, L, enc, m, workspace, dens, rgb, d_dens, d_rgb, d_flat, d_enc):
+    ensure_init(flat.device)
+    _check(load().lnrf_ngp_mlp_bwd(_p(flat), L, _p(enc), m, _p(workspace), workspace.numel(), _p(dens),
+                                   _p(rgb), _p(_f32c(d_dens, "d_dens")), _p(_f32c(d_rgb, "d_rgb")),
+                                   _p(d_flat), _p(d_enc), _stream()), "lnrf_ngp_mlp_bwd")
 
 
 def set_tc_stages(stages: int):

@@ -1,0 +1,169 @@
+"""Host-side mirror of learn_nerf/instant_ngp.py: InstantNGPModel (+ the encodings).
+
+Same constructor fields as the reference (instant_ngp.py:16-31); parameters keep the Flax
+names (``Dense_0..4`` and ``MultiresHashTableEncoding_0/HashTableEncoding_l/table``) as
+views into one flat fp32 buffer ``[MLP | table_0 | table_1 | ...]``.  The arithmetic runs
+in liblnrf.so: lnrf_hashgrid_fwd/_bwd (K7/K8) and lnrf_ngp_mlp_fwd/_bwd.
+"""
+import math
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional
+
+import torch
+
+from . import _native
+from .model import ModelBase, ParamTree, _rng_seed, _trunc_normal_
+
+
+def hash_table_lookup(table: torch.Tensor, coords: torch.Tensor) -> torch.Tensor:
+    """instant_ngp.py:211-224 (host helper for tools/tests; the kernels hash in-line)."""
+    c = coords.to(torch.int64) & 0xFFFFFFFF
+    idx = (c[:, 0] ^ ((19_349_663 * c[:, 1]) & 0xFFFFFFFF) ^ ((83_492_791 * c[:, 2]) & 0xFFFFFFFF))
+    return table[idx % table.shape[0]]
+
+
+@dataclass
+class InstantNGPModel(ModelBase):
+    """instant_ngp.py:16-54."""
+
+    table_sizes: List[int]
+    grid_sizes: List[int]
+    bbox_min: Any
+    bbox_max: Any
+    table_feature_dim: int = 2
+    table_smooth: bool = False
+    d_freqs: int = 4
+    hidden_dim: int = 64
+    density_dim: int = 16
+    density_layers: int = 1
+    color_layers: int = 2
+    precision: str = "fp32"
+    _spec: Optional[_native.GridSpec] = field(default=None, repr=False, compare=False)
+
+    def _check_arch(self):
+        if (self.table_feature_dim, self.d_freqs, self.hidden_dim, self.density_dim,
+                self.density_layers, self.color_layers) != (2, 4, 64, 16, 1, 2):
+            raise _native.LnrfError("liblnrf implements the default InstantNGPModel head sizes only "
+                                    "(F=2, hidden 64, density_dim 16, 1 density + 2 colour layers)")
+        if len(self.grid_sizes) != len(self.table_sizes) or not 1 <= len(self.grid_sizes) <= 16:
+            raise _native.LnrfError("1..16 levels supported")
+
+    @property
+    def L(self) -> int:
+        return len(self.grid_sizes)
+
+    def spec(self) -> _native.GridSpec:
+        if self._spec is None:
+            self._check_arch()
+            def v3(v):
+                return [float(x) for x in (v.tolist() if hasattr(v, "tolist") else v)]
+            self._spec = _native.GridSpec(self.table_sizes, self.grid_sizes, v3(self.bbox_min),
+                                          v3(self.bbox_max), self.table_smooth,
+                                          base_offset=_native.ngp_mlp_param_floats(self.L))
+        return self._spec
+
+    def layer_dims(self):
+        return [(2 * self.L, 64), (64, 16), (24 + 16, 64), (64, 64), (64, 3)]
+
+    def param_floats(self) -> int:
+        return self.spec().end
+
+    def param_count(self) -> int:
+        return sum(a * b + b for a, b in self.layer_dims()) + sum(r * 2 for r in self.spec().rows)
+
+    def bind(self, flat: torch.Tensor) -> ParamTree:
+        spec = self.spec()
+        offs = _native.ngp_mlp_param_offsets(self.L)
+        tree = ParamTree()
+        for i, (a, b) in enumerate(self.layer_dims()):
+            tree[f"Dense_{i}"] = dict(kernel=flat[offs[2 * i]: offs[2 * i] + a * b].view(a, b),
+                                      bias=flat[offs[2 * i + 1]: offs[2 * i + 1] + b])
+        tree["MultiresHashTableEncoding_0"] = {
+            f"HashTableEncoding_{l}": dict(table=flat[o: o + r * 2].view(r, 2))
+            for l, (o, r) in enumerate(zip(spec.offsets, spec.rows))}
+        tree.flat = flat
+        return tree
+
+    def flatten_params(self, params: Dict[str, Any], device=None) -> ParamTree:
+        if isinstance(params, ParamTree) and params.flat is not None:
+            return params
+        first = params["Dense_0"]["kernel"]
+        device = device or (first.device if isinstance(first, torch.Tensor) else "cuda")
+        tree = self.bind(torch.zeros(self.param_floats(), device=device))
+        def put(dst, src):
+            for k, v in dst.items():
+                if isinstance(v, dict):
+                    put(v, src[k])
+                else:
+                    v.copy_(torch.as_tensor(src[k], dtype=torch.float32))
+        put(tree, params)
+        return tree
+
+    def init(self, rngs, x=None, d=None, device=None, flat: Optional[torch.Tensor] = None):
+        device = torch.device(device or (x.device if isinstance(x, torch.Tensor) else "cuda"))
+        if flat is None:
+            flat = torch.zeros(self.param_floats(), device=device)
+        else:
+            flat.zero_()
+        tree = self.bind(flat)
+        gen = torch.Generator(device=device)
+        gen.manual_seed(_rng_seed(rngs))
+        for i, (a, _) in enumerate(self.layer_dims()):
+            _trunc_normal_(tree[f"Dense_{i}"]["kernel"], math.sqrt(1.0 / a), gen)
+        for leaf in tree["MultiresHashTableEncoding_0"].values():  # 1e-4 * U(-1, 1), :181-186
+            leaf["table"].uniform_(-1e-4, 1e-4, generator=gen)
+        return {"params": tree}
+
+    # ------------------------------------------------------------------ native calls
+    def _workspace(self, m: int, device, slot):
+        cache = self.__dict__.setdefault("_ws_cache", {})
+        nbytes = _native.ngp_mlp_workspace_bytes(m, self.L)
+        ws = cache.get((str(device), slot))
+        if ws is None or ws[0].numel() < nbytes or ws[1].shape[0] < m:
+            ws = (torch.empty(nbytes, dtype=torch.uint8, device=device),
+                  torch.empty(m, 2 * self.L, device=device))
+            cache[(str(device), slot)] = ws
+        return ws
+
+    def _forward(self, tree, x, d, rays, ts, n, T, slot=None):
+        spec = self.spec()
+        dev = tree.flat.device
+        m = n * T
+        ws, enc = self._workspace(m, dev, slot)
+        enc = enc[:m]
+        _native.hashgrid_fwd(tree.flat, spec, x, rays, ts, n, T, enc)
+        dens = torch.empty(m, device=dev)
+        rgb = torch.empty(m, 3, device=dev)
+        _native.ngp_mlp_fwd(tree.flat, self.L, enc, d, rays, n, T, ws, dens, rgb)
+        return dens, rgb, ws, enc
+
+    def encode(self, params, x: torch.Tensor) -> torch.Tensor:
+        """MultiresHashTableEncoding(x) -> [N, 2L] (instant_ngp.py:92-118)."""
+        tree = self.flatten_params(params)
+        x = _native._f32c(x.contiguous(), "x")
+        enc = torch.empty(x.shape[0], 2 * self.L, device=x.device)
+        _native.hashgrid_fwd(tree.flat, self.spec(), x, None, None, x.shape[0], 1, enc)
+        return enc
+
+    def apply(self, variables, x: torch.Tensor, d: torch.Tensor):
+        tree = self.flatten_params(variables["params"])
+        x = _native._f32c(x.contiguous(), "x")
+        d = _native._f32c(d.contiguous(), "d")
+        dens, rgb, _, _ = self._forward(tree, x, d, None, None, x.shape[0], 1)
+        return dens[:, None], rgb, {}
+
+    def apply_rays(self, params, rays, ts, save: bool = False, slot=None):
+        tree = self.flatten_params(params)
+        n, T = ts.shape
+        rays, ts = _native._f32c(rays, "rays"), _native._f32c(ts, "ts")
+        dens, rgb, ws, enc = self._forward(tree, None, None, rays, ts, n, T, slot if save else None)
+        ctx = dict(tree=tree, ws=ws, enc=enc, rays=rays, ts=ts, n=n, T=T, dens=dens, rgb=rgb) if save else None
+        return dens.view(n, T), rgb.view(n, T, 3), {}, ctx
+
+    def backward_rays(self, ctx, d_dens, d_rgb, d_flat, d_aux=None):
+        tree = ctx["tree"]
+        m = ctx["n"] * ctx["T"]
+        d_enc = torch.empty_like(ctx["enc"])
+        _native.ngp_mlp_bwd(tree.flat, self.L, ctx["enc"], m, ctx["ws"], ctx["dens"], ctx["rgb"],
+                            d_dens.reshape(-1), d_rgb.reshape(-1, 3), d_flat, d_enc)
+        _native.hashgrid_bwd(self.spec(), None, ctx["rays"], ctx["ts"], ctx["n"], ctx["T"], d_enc, d_flat)

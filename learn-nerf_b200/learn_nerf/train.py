@@ -15,7 +15,7 @@ from typing import Any, Callable, Dict, Optional
 import numpy as np
 import torch
 
-from . import _native, prng
+from . import _native, parallel, prng
 from .model import ModelBase
 from .render import NeRFRenderer, RaySamples, _vec3
 
@@ -124,7 +124,7 @@ class TrainLoop:
         st = self.state
         batch = _native._f32c(batch.contiguous(), "batch")
         n = batch.shape[0]
-        world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
+        world = parallel.world()[1]
         if not isinstance(key, (tuple, list)):
             key, _density_key = prng.split(key)  # train.py:137
         g = self._grads
@@ -154,8 +154,8 @@ class TrainLoop:
                                                       g[sb[0]:sb[0] + 3])
                 model.backward_rays(lv["_ctx"], d_dens, d_rgb, g[sl[0]:sl[1]])
         if world > 1:
-            torch.distributed.all_reduce(g)  # NCCL sum over NVLink; 1/world folded into Adam
-            torch.distributed.all_reduce(self._scalars[:2])
+            parallel.allreduce_sum_(g)  # one NCCL sum over NVLink; 1/world is folded into Adam
+            parallel.allreduce_sum_(self._scalars[:2])
         st.step += 1
         _native.adam_step(st.flat, g, st.m, st.v, self.lr, self.b1, self.b2, self.eps, st.step,
                           1.0 / world, self._scalars[2:4])

@@ -1,0 +1,157 @@
+"""GPU parity tests of the Instant-NGP path (K7/K8 hash grid + InstantNGPModel heads)
+against the CPU oracle (oracle.models_torch restating learn_nerf/instant_ngp.py)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import BBOX_MAX, BBOX_MIN, F, make_rays, make_uniforms
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+
+
+def models(levels, smooth=False):
+    from learn_nerf.instant_ngp import InstantNGPModel
+    from oracle import models_torch as M
+    grids = [2 ** (4 + i // 2) for i in range(levels)]
+    tabs = [2 ** 18] * levels
+    o = M.InstantNGPModel(tabs, grids, BBOX_MIN, BBOX_MAX, table_smooth=smooth)
+    n = InstantNGPModel(table_sizes=tabs, grid_sizes=grids, bbox_min=BBOX_MIN, bbox_max=BBOX_MAX,
+                        table_smooth=smooth)
+    return o, n
+
+
+def oracle_params(o, seed, table_scale=1.0):
+    p = o.init(torch.Generator().manual_seed(seed))
+    for leaf in p["MultiresHashTableEncoding_0"].values():
+        leaf["table"] *= table_scale / 1e-4  # O(1) tables make the comparison meaningful
+    return p
+
+
+def to_native(n, p):
+    def cu(t):
+        return {k: cu(v) if isinstance(v, dict) else v.cuda() for k, v in t.items()}
+    return n.flatten_params(cu(p))
+
+
+def test_ngp_layout_matches_reference_shapes():
+    o, n = models(16)
+    # levels 0-5 dense (16^3, 16^3, 32^3, 32^3, 64^3, 64^3; 64^3 == 2^18 is not > table_size), 6-15 hashed
+    assert n.spec().rows == [4096, 4096, 32768, 32768, 262144, 262144] + [2 ** 18] * 10
+    assert n.param_count() == sum(t.numel() for _, t in __import__("oracle.models_torch", fromlist=["x"]).tree_leaves(
+        o.init(torch.Generator().manual_seed(0))))
+    _, nc = models(6)
+    assert nc.param_count() + n.param_count() + 3 == 7_653_929
+
+
+@pytest.mark.parametrize("levels,smooth", [(6, False), (16, False), (16, True)])
+def test_hashgrid_forward(levels, smooth):
+    o, n = models(levels, smooth)
+    p = oracle_params(o, 3)
+    rs = np.random.RandomState(levels)
+    x = rs.uniform(-1.3, 1.3, (5000, 3)).astype(F)  # includes points outside the bbox (clipped)
+    x[0] = [-1, -1, -1]
+    x[1] = [1, 1, 1]
+    x[2] = [-1 + 2 * 3 / 15, -1 + 2 * 5 / 15, -1 + 2 * 7 / 15]  # exact vertex of the 16^3 level
+    with torch.no_grad():
+        ref = o.encode(p, torch.from_numpy(x)).numpy()
+    enc = n.encode(to_native(n, p), dev(x)).cpu().numpy()
+    np.testing.assert_allclose(enc, ref, atol=2e-5)
+
+
+def test_hashgrid_backward_scatter():
+    """d_tables from lnrf_hashgrid_bwd vs fp64 autograd of the oracle encoding."""
+    from learn_nerf import _native
+    o, n = models(16)
+    p = oracle_params(o, 4)
+    rs = np.random.RandomState(1)
+    x = rs.uniform(-1, 1, (3000, 3)).astype(F)
+    d_enc = rs.randn(3000, 32).astype(F)
+    pd = {k: ({kk: {"table": vv["table"].double().requires_grad_(True)} for kk, vv in v.items()}
+              if k.startswith("Multires") else v) for k, v in p.items()}
+    enc = o.encode(pd, torch.from_numpy(x).double())
+    (enc * torch.from_numpy(d_enc).double()).sum().backward()
+    tree = to_native(n, p)
+    g = torch.zeros_like(tree.flat)
+    _native.hashgrid_bwd(n.spec(), dev(x), None, None, 3000, 1, dev(d_enc), g)
+    gt = n.bind(g)
+    for l in range(16):
+        name = f"HashTableEncoding_{l}"
+        ref = pd["MultiresHashTableEncoding_0"][name]["table"].grad.numpy()
+        got = gt["MultiresHashTableEncoding_0"][name]["table"].cpu().numpy()
+        assert rel_l2(got, ref) < 1e-5, l
+
+
+@pytest.mark.parametrize("levels", [6, 16])
+def test_ngp_model_apply(levels):
+    o, n = models(levels)
+    p = oracle_params(o, 5)
+    rs = np.random.RandomState(levels + 7)
+    x = rs.uniform(-1, 1, (4097, 3)).astype(F)
+    d = rs.randn(4097, 3).astype(F)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    with torch.no_grad():
+        o_d, o_rgb, _ = o.apply(p, torch.from_numpy(x), torch.from_numpy(d))
+    dens, rgb, aux = n.apply(dict(params=to_native(n, p)), dev(x), dev(d))
+    assert dens.shape == (4097, 1) and aux == {}
+    np.testing.assert_allclose(dens.cpu().numpy(), o_d.numpy(), rtol=2e-5, atol=1e-5)
+    np.testing.assert_allclose(rgb.cpu().numpy(), o_rgb.numpy(), atol=1e-5)
+
+
+def test_ngp_train_step_vs_oracle():
+    """TrainLoop with InstantNGPModel coarse (L=6) + fine (L=16), Adam(0.9, 0.99, 1e-15)
+    (train_nerf.py:149-161): losses and gradients against fp64 autograd."""
+    from learn_nerf.train import TrainLoop
+    from oracle import models_torch as M
+    from oracle import train_torch as T
+    oc, nc = models(6)
+    of, nf = models(16)
+    gen = torch.Generator().manual_seed(11)
+    params = dict(coarse=oc.init(gen), fine=of.init(gen), background=torch.tensor([-1.0, -1.0, -1.0]))
+    for k in ("coarse", "fine"):  # larger tables so that the hash grid matters to the loss
+        for leaf in params[k]["MultiresHashTableEncoding_0"].values():
+            leaf["table"] *= 3e3
+    n = 192
+    batch = make_rays(n, seed=21, miss_frac=0.2)
+    uc, uf = make_uniforms(n, 64, 22), make_uniforms(n, 128, 23)
+    loop = TrainLoop(nc, nf, init_rng=0, lr=1e-3, coarse_ts=64, fine_ts=128, adam_eps=1e-15,
+                     adam_b1=0.9, adam_b2=0.99)
+    def put(dst, src):
+        for k, v in dst.items():
+            if isinstance(v, dict):
+                put(v, src[k])
+            else:
+                v.copy_(src[k])
+    for k in ("coarse", "fine"):
+        put(loop.state.params[k], params[k])
+        loop.state.params[k].mark_updated()
+    step = loop.step_fn(BBOX_MIN, BBOX_MAX)
+    fine_ts = loop._renderer(list(BBOX_MIN), list(BBOX_MAX), loop.state.params).render_rays(
+        (dev(uc), dev(uf)), dev(batch[:, :2]), _save=True)["fine"]["_ts"].ts.cpu().numpy()
+    g, ld, _ = T.grads(oc, of, params, BBOX_MIN, BBOX_MAX, batch, uc, uf, 64, 128,
+                       fixed_fine_ts=fine_ts, dtype=torch.float64)
+    logs = step((dev(uc), dev(uf)), dev(batch))
+    np.testing.assert_allclose(float(logs["coarse"]), ld["coarse"], rtol=1e-4)
+    np.testing.assert_allclose(float(logs["fine"]), ld["fine"], rtol=1e-4)
+    np.testing.assert_allclose(float(logs["grad_norm"]), T.tree_norm(g), rtol=1e-3)
+    grads = loop._grads
+    worst = []
+    for name, model in (("coarse", nc), ("fine", nf)):
+        gt = model.bind(grads[loop._slices[name][0]:loop._slices[name][1]])
+        for path, leaf in M.tree_leaves(g[name]):
+            node = gt
+            for part in path.split("/"):
+                node = node[part]
+            if float(leaf.abs().max()) > 0:
+                worst.append((rel_l2(node.cpu().numpy(), leaf.numpy()), name, path))
+    worst.sort(reverse=True)
+    print("worst NGP grad rel-L2:", worst[:4])
+    assert worst[0][0] < 2e-3, worst[:4]
