@@ -37,7 +37,8 @@ __device__ __forceinline__ Corners level_corners(const GridLevels& g, int l, con
   for (int a = 0; a < 3; ++a) {
     float frac = (x[a] - g.lo[a]) / (g.hi[a] - g.lo[a]);                 // :138-139
     frac = fminf(fmaxf(frac, 0.0f), 1.0f);                                // clip :138-140
-    const float fi = g.smooth ? 0.5f + float(G - 2) * frac : float(G - 1) * frac;  // :141-146
+    // :141-146; the reference rounds the product before the add (no FMA contraction)
+    const float fi = g.smooth ? __fadd_rn(0.5f, __fmul_rn(float(G - 2), frac)) : float(G - 1) * frac;
     const float fl = fminf(floorf(fi), float(G - 2));                     // :147-150
     float c = fi - fl;                                                    // :152
     if (g.smooth) c = (c * c) * (3.0f - 2.0f * c);                        // :154
