@@ -54,53 +54,65 @@ def synth_batch(n, seed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region (NVML, every 10 ms)."""
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.samples, self.reasons, self.smax = index, [], set(), None
+        self._stop = threading.Event()
+        self.thread = None
+        self.err = None
+
+    def _uuid_index(self):
+        # CUDA_VISIBLE_DEVICES may remap ordinals; torch's index -> NVML handle by UUID
+        try:
+            return "GPU-" + str(torch.cuda.get_device_properties(self.index).uuid).replace("GPU-", "")
+        except Exception:
+            return None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            uuid = self._uuid_index()
+            try:
+                h = pynvml.nvmlDeviceGetHandleByUUID(uuid) if uuid else None
+            except Exception:
+                h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            names = {pynvml.nvmlClocksEventReasonHwSlowdown: "hw_slowdown",
+                     pynvml.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     pynvml.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     pynvml.nvmlClocksEventReasonSwPowerCap: "sw_power_cap"}
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        for bit, nm in names.items():
+                            if r & bit:
+                                self.reasons.add(nm)
+                    except Exception as e:  # noqa: BLE001
+                        self.err = repr(e)
+                        return
+                    time.sleep(0.01)
+
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
 
     def stop(self):
-        if self.proc is None:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0]))
-                smax = float(f[1])
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=smax,
-                    reasons=sorted(reasons), samples=len(sm))
+        self._stop.set()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        if not self.samples:
+            return dict(sm_mhz=None, sm_max_mhz=self.smax, reasons=[f"nvml unavailable: {self.err}"],
+                        samples=0)
+        return dict(sm_mhz=float(np.median(self.samples)), sm_max_mhz=self.smax,
+                    reasons=sorted(self.reasons), samples=len(self.samples))
 
 
 # ------------------------------------------------------------------------------ CPU arm
@@ -153,6 +165,26 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------ GPU arm
+def build_models(args, dev):
+    """(coarse, fine, train_kwargs) as scripts/train_nerf.py:141-170 create_model does."""
+    if args.model == "ngp":
+        from learn_nerf.instant_ngp import InstantNGPModel
+        mk = lambda L: InstantNGPModel(table_sizes=[2 ** 18] * L,
+                                       grid_sizes=[2 ** (4 + i // 2) for i in range(L)],
+                                       bbox_min=[-1.0] * 3, bbox_max=[1.0] * 3)
+        return mk(6), mk(16), dict(adam_eps=1e-15, adam_b1=0.9, adam_b2=0.99)
+    from learn_nerf.model import NeRFModel
+    return NeRFModel(precision=args.precision), NeRFModel(precision=args.precision), {}
+
+
+# algorithmic HBM/L2 bytes per point of the hash-grid kernels (SURVEY 8d): 8 corners x 8 B per
+# level gathered (+8 B/level written, +12 B coordinate); backward counts the RMW twice + d_enc.
+def ngp_grid_bytes_per_ray(train):
+    fwd = 64 * (6 * 72 + 12) + 192 * (16 * 72 + 12)
+    bwd = 64 * (6 * (128 + 8) + 12) + 192 * (16 * (128 + 8) + 12)
+    return fwd + (bwd if train else 0)
+
+
 def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -163,41 +195,43 @@ def run_ours(args):
         torch.distributed.init_process_group("nccl", device_id=dev)
 
     from learn_nerf import _native
-    from learn_nerf.model import NeRFModel
     from learn_nerf.render import NeRFRenderer
     from learn_nerf.train import TrainLoop
 
     peaks = load_peaks()
     if args.tc_stages is not None:
         _native.set_tc_stages(args.tc_stages)
-    n = args.rays
-    prec = args.precision
-    coarse, fine = NeRFModel(precision=prec), NeRFModel(precision=prec)
+    n = args.rays or (32768 if args.model == "ngp" else 4096)
+    prec = args.precision if args.model == "nerf" else "fp32"
+    coarse, fine, train_kwargs = build_models(args, dev)
     loop = TrainLoop(coarse, fine, init_rng=2, lr=1e-4, coarse_ts=64, fine_ts=128, device=dev,
-                     ray_chunk=args.ray_chunk)
+                     ray_chunk=args.ray_chunk, **train_kwargs)
     bbox = ([-1.0, -1.0, -1.0], [1.0, 1.0, 1.0])
     step = loop.step_fn(*bbox)
     host_batch = synth_batch(n, rank).pin_memory()
     batch = host_batch.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    mlp_events = []
+    # the dominant kernels, timed with CUDA events on the launching (current) stream
+    dom_names = (["hashgrid_fwd", "hashgrid_bwd"] if args.model == "ngp"
+                 else ["nerf_mlp_fwd", "nerf_mlp_bwd"])
+    dom_events = []
 
-    def timed_mlp(fn):
+    def timed(fn):
         def wrapper(*a, **k):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             r = fn(*a, **k)
             e1.record()
-            mlp_events.append((e0, e1))
+            dom_events.append((e0, e1))
             return r
         return wrapper
 
-    orig_fwd, orig_bwd = _native.nerf_mlp_fwd, _native.nerf_mlp_bwd
+    originals = {nm: getattr(_native, nm) for nm in dom_names}
 
     def one_step(i, host=False):
+        b = host_batch.to(dev, non_blocking=True) if host else batch
         if args.workload == "train":
-            b = host_batch.to(dev, non_blocking=True) if host else batch
             logs = step(1000 + i, b)
             if host:
                 return [float(v) for v in logs.values()]  # D2H read of the step's result
@@ -206,7 +240,6 @@ def run_ours(args):
                          fine_params=loop.state.params["fine"],
                          background=loop.state.params["background"], bbox_min=bbox[0],
                          bbox_max=bbox[1], coarse_ts=64, fine_ts=128)
-        b = host_batch.to(dev, non_blocking=True) if host else batch
         out = r.render_rays(1000 + i, b[:, :2].contiguous())["fine"]["outputs"]
         return out.cpu() if host else out
 
@@ -220,7 +253,8 @@ def run_ours(args):
     barrier()
 
     # ---- timed region 1: device-resident inputs, per-step CUDA events, L2 flushed between steps
-    _native.nerf_mlp_fwd, _native.nerf_mlp_bwd = timed_mlp(orig_fwd), timed_mlp(orig_bwd)
+    for nm in dom_names:
+        setattr(_native, nm, timed(originals[nm]))
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = _native.launch_count()
@@ -236,9 +270,10 @@ def run_ours(args):
     barrier()
     launches = (_native.launch_count() - launches0) // max(args.steps, 1)
     clocks = sampler.stop()
-    _native.nerf_mlp_fwd, _native.nerf_mlp_bwd = orig_fwd, orig_bwd
+    for nm in dom_names:
+        setattr(_native, nm, originals[nm])
     step_ms = [a.elapsed_time(b) for a, b in evs]
-    mlp_ms = sum(a.elapsed_time(b) for a, b in mlp_events) / max(args.steps, 1)
+    dom_ms = sum(a.elapsed_time(b) for a, b in dom_events) / max(args.steps, 1)
     ms = float(np.mean(step_ms))
 
     # ---- timed region 2 (e2e): host pinned batch -> H2D -> step -> D2H of the logged scalars
@@ -254,44 +289,63 @@ def run_ours(args):
     barrier()
     e2e_ms = float(np.mean(t_e2e)) * 1e3
 
-    t = torch.tensor([ms, e2e_ms, mlp_ms], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms, e2e_ms, dom_ms], device=dev, dtype=torch.float64)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    ms, e2e_ms, mlp_ms = [float(x) for x in t.tolist()]
+    ms, e2e_ms, dom_ms = [float(x) for x in t.tolist()]
 
     if rank == 0:
         total_rays = n * world
         value = total_rays / (ms * 1e-3)
         e2e_value = total_rays / (e2e_ms * 1e-3)
-        flop_per_sample = FLOP_TRAIN_PER_SAMPLE if args.workload == "train" else FLOP_FWD_PER_SAMPLE
-        mlp_flops = flop_per_sample * SAMPLES_PER_RAY * n  # per rank, per step
-        achieved_tf = mlp_flops / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0
+        train = args.workload == "train"
+        what = {"nerf": "NeRF coarse+fine", "ngp": "Instant-NGP coarse (L=6) + fine (L=16)"}[args.model]
+        cfg_name = {("nerf", True): "configs[1]: ", ("ngp", True): "configs[2]: ",
+                    ("nerf", False): "configs[4]-style: ", ("ngp", False): ""}[(args.model, train)]
+        if args.model == "nerf":
+            flop_per_sample = FLOP_TRAIN_PER_SAMPLE if train else FLOP_FWD_PER_SAMPLE
+            flops = flop_per_sample * SAMPLES_PER_RAY * n  # per rank, per step
+            achieved = flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+            roofline = {"bound": "tensor",
+                        "kernel": "nerf_fwd_tc_kernel" + (" + nerf_bwd_dx_kernel + nerf_bwd_dw_kernel"
+                                                          if train else "") if prec == "bf16"
+                                  else "sgemm_kernel chain (fp32 FFMA)",
+                        "achieved": achieved, "peak": peaks["tf"], "unit": "TFLOP/s",
+                        "frac": achieved / peaks["tf"], "traffic": None,
+                        "peak_source": peaks["source"] + " (sustained bf16 cuBLAS)",
+                        "kernel_ms_per_step": dom_ms, "kernel_share_of_step": dom_ms / ms,
+                        "algorithmic_flop_per_sample": flop_per_sample}
+        else:
+            nbytes = ngp_grid_bytes_per_ray(train) * n
+            achieved = nbytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+            roofline = {"bound": "hbm", "kernel": "hashgrid_fwd_kernel" + (" + hashgrid_bwd_kernel" if train else ""),
+                        "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s",
+                        "frac": achieved / peaks["hbm"], "traffic": None,
+                        "peak_source": peaks["source"] + " (HBM copy); the 30.6 MB of tables are "
+                                       "L2-resident, so gathers are served by L2",
+                        "kernel_ms_per_step": dom_ms, "kernel_share_of_step": dom_ms / ms,
+                        "algorithmic_bytes_per_ray": ngp_grid_bytes_per_ray(train)}
         line = {
-            "metric": "rays/sec (NeRF train step fwd+bwd+Adam)" if args.workload == "train"
-                      else "rays/sec (NeRF render)",
+            "metric": f"rays/sec ({'NeRF' if args.model == 'nerf' else 'Instant-NGP'} "
+                      f"{'train step fwd+bwd+Adam' if train else 'render'})",
             "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": prec, "data": "synthetic",
-            "config": {"workload": ("configs[1]: NeRF coarse+fine train step" if args.workload == "train"
-                                    else "NeRF coarse+fine render") +
-                                   ", 64+128 samples/ray, random-init 8x256 MLP, bbox [-1,1]^3",
+            "config": {"workload": cfg_name + what + (" train step" if train else " render") +
+                                   ", 64+128 samples/ray, random-init weights, bbox [-1,1]^3",
                        "rays_per_gpu": n, "mlp_precision": prec, "ray_chunk": args.ray_chunk,
                        "l2": "256 MiB flush between timed steps; per-step working set >> 126 MB L2",
-                       "parallelism": f"ray-sharded dp{world}, NCCL all-reduce of flat grads"},
+                       "parallelism": f"ray-sharded dp{world}" +
+                                      (", one NCCL all-reduce of the flat gradient per step" if train else
+                                       ", no collective")},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "rays/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(host_batch.numel() * 4),
-                    "d2h_bytes_per_step": 16 if args.workload == "train" else int(n * 3 * 4)},
+                    "d2h_bytes_per_step": 16 if train else int(n * 3 * 4)},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "NeRF MLP fwd+bwd (all launches of "
-                         "lnrf_nerf_mlp_fwd/_bwd)" if args.workload == "train" else "NeRF MLP fwd",
-                         "achieved": achieved_tf, "peak": peaks["tf"], "unit": "TFLOP/s",
-                         "frac": achieved_tf / peaks["tf"], "traffic": None,
-                         "peak_source": peaks["source"] + " (sustained bf16 cuBLAS)",
-                         "mlp_ms_per_step": mlp_ms, "mlp_share_of_step": mlp_ms / ms,
-                         "algorithmic_flop_per_sample": flop_per_sample},
+            "roofline": roofline,
         }
-        if args.cpu_baseline and world == 1:
+        if args.cpu_baseline and world == 1 and args.model == "nerf" and train:
             threads = os.cpu_count() or 1
             v, sec = cpu_train_sample(args.cpu_rays, 2, 1, threads)
             line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": threads, "kind": "port",
@@ -307,12 +361,14 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="train", choices=["train", "render"])
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
-    ap.add_argument("--rays", type=int, default=4096, help="rays per GPU per step")
+    ap.add_argument("--model", default="nerf", choices=["nerf", "ngp"])
+    ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
+                    help="NeRF MLP path: bf16 tcgen05 (2e-2) or fp32 FFMA (1e-5)")
+    ap.add_argument("--rays", type=int, default=None, help="rays per GPU per step (4096 NeRF, 32768 NGP)")
     ap.add_argument("--ray_chunk", type=int, default=None)
     ap.add_argument("--cpu_rays", type=int, default=512, help="rays per step of the CPU sample")
     ap.add_argument("--tc_stages", type=int, default=None, help="bf16 kernel tuning knob")
