@@ -24,12 +24,30 @@ using namespace ptx;
 __global__ void __launch_bounds__(256)
 pack_weights_kernel(const float* __restrict__ P, uint8_t* __restrict__ packed) {
   const int ci = blockIdx.y;
-  const ChunkInfo c = ci < kTcChunks ? c_chunks.f[ci] : c_chunks.b[ci - kTcChunks];
+  if (ci == kAllChunks) {  // gather the small fp32 parameters (SmallParams image)
+    float* out = reinterpret_cast<float*>(packed + kSmallOffset);
+    const int total = int(sizeof(SmallParams) / 4);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+      float v;
+      if (i < 9 * 256) v = __ldg(P + c_nerf.b[i >> 8] + (i & 255));
+      else if (i < 9 * 256 + 128) v = __ldg(P + c_nerf.b[10] + (i - 9 * 256));
+      else if (i < 9 * 256 + 128 + 384) v = __ldg(P + c_nerf.w[11] + (i - 9 * 256 - 128));
+      else if (i == 9 * 256 + 128 + 384) v = __ldg(P + c_nerf.b[9]);
+      else v = __ldg(P + c_nerf.b[11] + (i - 9 * 256 - 128 - 384 - 1));
+      out[i] = v;
+    }
+    return;
+  }
+  const ChunkInfo c = ci < kTcChunks ? c_chunks.f[ci]
+                      : ci < kTcChunks + kBwChunks ? c_chunks.b[ci - kTcChunks]
+                      : ci < kTcChunks + kBwChunks + kF2Chunks ? c_chunks.f2[ci - kTcChunks - kBwChunks]
+                                                                : c_chunks.b2[ci - kTcChunks - kBwChunks - kF2Chunks];
   const int items = c.n * 8;
   const int out_dim = c_nerf.out[c.layer];
   const float* W = P + c_nerf.w[c.layer];
   for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += gridDim.x * blockDim.x) {
     const int n = it >> 3, kg = it & 7;
+    const int ng = c.n0 + n;  // global row index of this B-operand row
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -37,10 +55,10 @@ pack_weights_kernel(const float* __restrict__ P, uint8_t* __restrict__ packed) {
       float w = 0.0f;
       if (k < c.kvalid) {
         if (c.transposed) {
-          w = __ldg(W + int64_t(n) * out_dim + (c.k0 + k));
-        } else if (n < out_dim) {
-          w = __ldg(W + int64_t(c.k0 + k) * out_dim + n);
-        } else if (c.layer == 10 && n == kHC && c.ablock < 4) {  // density column (Dense_9)
+          w = __ldg(W + int64_t(ng) * out_dim + (c.k0 + k));
+        } else if (ng < out_dim) {
+          w = __ldg(W + int64_t(c.k0 + k) * out_dim + ng);
+        } else if (c.layer == 10 && ng == kHC && c.ablock < 4) {  // density column (Dense_9)
           w = __ldg(P + c_nerf.w[9] + (c.k0 + k));
         }
       }
@@ -499,9 +517,12 @@ nerf_fwd_tc_kernel(TcFwdArgs args) {
 }
 
 static bool g_tc_ready = false;
-static int g_tc_stages = 1;
+static int g_tc_stages = 0;  // 0 = pair kernel (default); 1 / 4 = single-tile kernels (render only)
 
 int init_mlp_tc_bwd();  // mlp_tc_bwd.cu
+int init_mlp_tc_fwd2();  // mlp_tc_fwd2.cu
+int nerf_fwd_pair(const void* packed, const float* x, const float* d, const float* rays, const float* ts,
+                  int64_t m, int T, bool save, const TcStash& stash, float* dens, float* rgb, cudaStream_t st);
 void set_dw_debug(int flags);
 
 template <typename K>
@@ -522,6 +543,7 @@ int init_mlp_tc() {
   if ((rc = set_smem(debug_umma_gemm_kernel, 200 * 1024))) return rc;
   if ((rc = set_smem(debug_umma_gemm_tn_kernel, 200 * 1024))) return rc;
   if ((rc = init_mlp_tc_bwd())) return rc;
+  if ((rc = init_mlp_tc_fwd2())) return rc;
   g_tc_ready = true;
   return LNRF_OK;
 }
@@ -543,6 +565,8 @@ int nerf_fwd_tc(const float* P, const void* packed, const float* x, const float*
                  "1024-byte aligned", (long long)ws_bytes, (long long)tc_workspace_bytes(m, true));
     a.stash = carve_stash(ws, m);
   }
+  if (save || g_tc_stages == 0)  // the stash (row-major masks) is only written by the pair kernel
+    return nerf_fwd_pair(packed, x, d, rays, ts, m, T, save, a.stash, dens, rgb, st);
   const int64_t tiles = ceil_div(m, 128);
   int64_t grid = int64_t(sm_count()) * (g_tc_stages == 1 ? 2 : 1);
   if (grid > tiles) grid = tiles;
@@ -559,7 +583,7 @@ int nerf_fwd_tc(const float* P, const void* packed, const float* x, const float*
 
 int nerf_pack_weights(const float* P, void* packed, cudaStream_t st) {
   LNRF_REQUIRE(g_tc_ready, LNRF_E_INVALID, "lnrf_nerf_pack_weights: call lnrf_init first");
-  dim3 grid(8, kTcChunks + kBwChunks);
+  dim3 grid(8, kAllChunks + 1);
   pack_weights_kernel<<<grid, 256, 0, st>>>(P, reinterpret_cast<uint8_t*>(packed));
   LNRF_LAUNCH_CHECK("pack_weights_kernel");
   return LNRF_OK;
@@ -567,7 +591,7 @@ int nerf_pack_weights(const float* P, void* packed, cudaStream_t st) {
 
 int64_t nerf_packed_bytes() { return kPackedBytes; }
 
-void set_tc_stages(int stages) { g_tc_stages = (stages >= 2) ? 4 : 1; }
+void set_tc_stages(int stages) { g_tc_stages = stages <= 0 ? 0 : (stages >= 2 ? 4 : 1); }
 
 }  // namespace lnrf
 

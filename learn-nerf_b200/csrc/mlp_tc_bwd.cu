@@ -118,7 +118,6 @@ nerf_bwd_dx_kernel(TcBwdArgs args) {
     // ===== epilogue warps: thread r owns tile row r
     const int r = tid;
     const uint32_t tm_lane = tmem + (uint32_t(warp * 32) << 16);
-    const uint32_t lanebit = 1u << lane;
     const float* P = args.P;
     const float* w11 = P + c_nerf.w[11];
     const float* w9 = P + c_nerf.w[9];
@@ -128,7 +127,9 @@ nerf_bwd_dx_kernel(TcBwdArgs args) {
       const int64_t tile = blockIdx.x + t * gridDim.x;
       const int64_t s = tile * 128 + r;
       const bool valid = s < args.m;
-      const uint32_t* mask_tile = args.stash.MASK + (tile * 9) * 1024 + warp * 256;
+      // row-major ReLU masks written by the forward: [tile][layer 9][row 128][8 words], column
+      // 32 w + j of a row is bit (31 - j) of word w
+      const uint4* mask_row = reinterpret_cast<const uint4*>(args.stash.MASK + ((tile * 9) * 128 + r) * 8);
       // ---- head gradients (model.py:57,60): softplus' = sigmoid(pre) = 1 - exp(-density)
       float spre = 0.f, dp[3] = {0.f, 0.f, 0.f};
       if (valid) {
@@ -146,18 +147,19 @@ nerf_bwd_dx_kernel(TcBwdArgs args) {
       // ---- dc = (dpre @ W11^T) * (c > 0) -> A blocks 0,1 (and the DC stash image)
       if (tid == 0) bulk_wait_read0();  // previous tile's last image has left smem
       epi_bar();
-#pragma unroll 1
+      const uint4 mc4 = __ldg(mask_row + 8 * 256);
+      const uint32_t mc[4] = {mc4.x, mc4.y, mc4.z, mc4.w};
+#pragma unroll
       for (int c0 = 0; c0 < kHC; c0 += 32) {
         uint32_t pk[16];
+        const uint32_t mwd = mc[c0 >> 5];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
-          const uint32_t m0 = __ldg(mask_tile + 8 * 1024 + c0 + j);
-          const uint32_t m1 = __ldg(mask_tile + 8 * 1024 + c0 + j + 1);
           const float* wa = w11 + (c0 + j) * 3;
           float v0 = dp[0] * __ldg(wa + 0) + dp[1] * __ldg(wa + 1) + dp[2] * __ldg(wa + 2);
           float v1 = dp[0] * __ldg(wa + 3) + dp[1] * __ldg(wa + 4) + dp[2] * __ldg(wa + 5);
-          v0 = (m0 & lanebit) ? v0 : 0.0f;
-          v1 = (m1 & lanebit) ? v1 : 0.0f;
+          v0 = (mwd & (0x80000000u >> j)) ? v0 : 0.0f;
+          v1 = (mwd & (0x80000000u >> (j + 1))) ? v1 : 0.0f;
           pk[j / 2] = pack_bf16x2(v0, v1);
         }
         const uint32_t blk = sA + (c0 >> 6) * kABlockBytes;
@@ -182,8 +184,13 @@ nerf_bwd_dx_kernel(TcBwdArgs args) {
         if (tid == 0) bulk_wait_read0();
         epi_bar();
         const int out_layer = 8 - tl;  // index of the g tile produced here (g8 .. g0)
-        const uint32_t* mrow = mask_tile + out_layer * 1024;
-#pragma unroll 1
+        uint32_t mw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        if (tl > 0) {
+          const uint4 ma = __ldg(mask_row + out_layer * 256), mb = __ldg(mask_row + out_layer * 256 + 1);
+          mw[0] = ma.x; mw[1] = ma.y; mw[2] = ma.z; mw[3] = ma.w;
+          mw[4] = mb.x; mw[5] = mb.y; mw[6] = mb.z; mw[7] = mb.w;
+        }
+#pragma unroll
         for (int c0 = 0; c0 < 256; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(tm_lane + c0, v);
@@ -199,13 +206,13 @@ nerf_bwd_dx_kernel(TcBwdArgs args) {
                                           fmaf(spre, w.w, __uint_as_float(v[j + 3])));
             }
           } else {
+            const uint32_t mwd = mw[c0 >> 5];
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              const uint4 mk = __ldg(reinterpret_cast<const uint4*>(mrow + c0 + j));
-              const float f0 = (mk.x & lanebit) ? __uint_as_float(v[j]) : 0.0f;
-              const float f1 = (mk.y & lanebit) ? __uint_as_float(v[j + 1]) : 0.0f;
-              const float f2 = (mk.z & lanebit) ? __uint_as_float(v[j + 2]) : 0.0f;
-              const float f3 = (mk.w & lanebit) ? __uint_as_float(v[j + 3]) : 0.0f;
+              const float f0 = (mwd & (0x80000000u >> j)) ? __uint_as_float(v[j]) : 0.0f;
+              const float f1 = (mwd & (0x80000000u >> (j + 1))) ? __uint_as_float(v[j + 1]) : 0.0f;
+              const float f2 = (mwd & (0x80000000u >> (j + 2))) ? __uint_as_float(v[j + 2]) : 0.0f;
+              const float f3 = (mwd & (0x80000000u >> (j + 3))) ? __uint_as_float(v[j + 3]) : 0.0f;
               pk[j / 2] = pack_bf16x2(f0, f1);
               pk[j / 2 + 1] = pack_bf16x2(f2, f3);
             }
