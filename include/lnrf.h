@@ -180,6 +180,31 @@ int lnrf_ngp_mlp_bwd(const float* params, int32_t L, const float* enc, int64_t m
                      const float* d_dens, const float* d_rgb, float* d_params, float* d_enc,
                      lnrf_stream_t stream);
 
+/* ---------------------------------------------------------------- K9 Ref-NeRF
+ * RefNERFModel(sh_degree=4) (ref_nerf.py:34-107): spatial MLP (as NeRF's trunk), real_normal
+ * from the input gradient of -spatial_out[:,0] (:38-43), activations, reflection direction,
+ * integrated directional encoding, directional block, sRGB colour and the two aux losses
+ * normal_mse / neg_normal (:72-75).  fp32 only.  params: Dense_0..10 flat, kernel then bias,
+ * 16-byte aligned; Dense_9's kernel is stored with 276 rows (273 used, 3 zero rows).
+ * Inputs as for lnrf_nerf_mlp_fwd: (x[m,3], d[m,3]) or ray mode (rays[n,2,3], ts[n,T]).
+ * Outputs dens[m], rgb[m,3], aux_normal_mse[m], aux_neg_normal[m].                    */
+int64_t lnrf_refnerf_param_count(void);  /* logical parameters: 592,771 */
+int64_t lnrf_refnerf_param_floats(void);
+/* host out[22]: float offsets of kernel_i (out[2i]) and bias_i (out[2i+1]), i = 0..10. */
+int lnrf_refnerf_param_offsets(int64_t* out_host);
+int lnrf_refnerf_workspace_bytes(int64_t m, int32_t save_for_backward, int64_t* bytes_out_host);
+int lnrf_refnerf_fwd(const float* params, const float* x, const float* d, const float* rays, const float* ts,
+                     int64_t n, int32_t T, int32_t save_for_backward, void* workspace, int64_t workspace_bytes,
+                     float* dens, float* rgb, float* aux_normal_mse, float* aux_neg_normal,
+                     lnrf_stream_t stream);
+/* Gradient w.r.t. params (ACCUMULATED into d_params) given the gradients of all four outputs;
+ * includes the second-order term through real_normal.  Same inputs and workspace as the
+ * forward call it follows.                                                             */
+int lnrf_refnerf_bwd(const float* params, const float* x, const float* d, const float* rays, const float* ts,
+                     int64_t n, int32_t T, void* workspace, int64_t workspace_bytes, const float* d_dens,
+                     const float* d_rgb, const float* d_aux_normal_mse, const float* d_aux_neg_normal,
+                     float* d_params, lnrf_stream_t stream);
+
 /* ---------------------------------------------------------------- diagnostics
  * Single 128xNxK bf16 GEMM tile on tcgen05 (A[128,K], B[N,K] both K-major,
  * D fp32 [128,N]) used by tests to pin the UMMA descriptor encodings.         */

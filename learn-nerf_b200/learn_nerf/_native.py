@@ -55,6 +55,13 @@ _SIGS = {
     "lnrf_debug_umma_gemm": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "lnrf_debug_umma_gemm_tn": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "lnrf_set_tc_stages": (c_int32, [c_int32]),
+    "lnrf_refnerf_param_count": (c_int64, []),
+    "lnrf_refnerf_param_floats": (c_int64, []),
+    "lnrf_refnerf_param_offsets": (c_int32, [c_void_p]),
+    "lnrf_refnerf_workspace_bytes": (c_int32, [c_int64, c_int32, c_void_p]),
+    "lnrf_refnerf_fwd": (c_int32, [c_void_p] * 5 + [c_int64, c_int32, c_int32, c_void_p, c_int64] +
+                         [c_void_p] * 5),
+    "lnrf_refnerf_bwd": (c_int32, [c_void_p] * 5 + [c_int64, c_int32, c_void_p, c_int64] + [c_void_p] * 6),
     "lnrf_set_debug_flags": (c_int32, [c_int32]),
     "lnrf_ngp_mlp_param_offsets": (c_int32, [c_int32, c_void_p]),
     "lnrf_hashgrid_fwd": (c_int32, [c_void_p] * 4 + [c_int32, c_void_p, c_void_p, c_int32,
@@ -345,6 +352,43 @@ def ngp_mlp_bwd(flat, L, enc, m, workspace, dens, rgb, d_dens, d_rgb, d_flat, d_
     _check(load().lnrf_ngp_mlp_bwd(_p(flat), L, _p(enc), m, _p(workspace), workspace.numel(), _p(dens),
                                    _p(rgb), _p(_f32c(d_dens, "d_dens")), _p(_f32c(d_rgb, "d_rgb")),
                                    _p(d_flat), _p(d_enc), _stream()), "lnrf_ngp_mlp_bwd")
+
+
+# --------------------------------------------------------------------------- Ref-NeRF
+def refnerf_param_count() -> int:
+    return int(load().lnrf_refnerf_param_count())
+
+
+def refnerf_param_floats() -> int:
+    return int(load().lnrf_refnerf_param_floats())
+
+
+def refnerf_param_offsets():
+    buf = (c_int64 * 22)()
+    _check(load().lnrf_refnerf_param_offsets(buf), "lnrf_refnerf_param_offsets")
+    return [int(v) for v in buf]
+
+
+def refnerf_workspace_bytes(m: int, save: bool) -> int:
+    out = c_int64(0)
+    _check(load().lnrf_refnerf_workspace_bytes(m, int(save), ctypes.byref(out)), "lnrf_refnerf_workspace_bytes")
+    return int(out.value)
+
+
+def refnerf_fwd(flat, x, d, rays, ts, n, T, save, workspace, dens, rgb, aux_mse, aux_neg):
+    ensure_init(flat.device)
+    _check(load().lnrf_refnerf_fwd(_p(flat), _p(x), _p(d), _p(rays), _p(ts), n, T, int(save), _p(workspace),
+                                   workspace.numel(), _p(dens), _p(rgb), _p(aux_mse), _p(aux_neg), _stream()),
+           "lnrf_refnerf_fwd")
+
+
+def refnerf_bwd(flat, x, d, rays, ts, n, T, workspace, d_dens, d_rgb, d_aux_mse, d_aux_neg, d_flat):
+    ensure_init(flat.device)
+    _check(load().lnrf_refnerf_bwd(_p(flat), _p(x), _p(d), _p(rays), _p(ts), n, T, _p(workspace),
+                                   workspace.numel(), _p(_f32c(d_dens, "d_dens")), _p(_f32c(d_rgb, "d_rgb")),
+                                   _p(_f32c(d_aux_mse, "d_aux_normal_mse")),
+                                   _p(_f32c(d_aux_neg, "d_aux_neg_normal")), _p(d_flat), _stream()),
+           "lnrf_refnerf_bwd")
 
 
 def set_tc_stages(stages: int):

@@ -162,22 +162,30 @@ def render_rays(model: ModelBase, params: Any, background: torch.Tensor, batch: 
     if _save is not None:
         out["_ctx"] = ctx
         out["_ts"] = ts
+        out["_aux"] = aux
     return out, aux_mean
 
 
+def _pack_aux(aux: Dict[str, torch.Tensor]):
+    """Up to three per-sample aux values as the colour channels of one [N,T,3] tensor."""
+    names = sorted(aux)
+    if len(names) > 3:
+        raise _native.LnrfError("at most three aux losses per model are supported")
+    first = aux[names[0]]
+    cols = torch.zeros(first.shape + (3,), device=first.device)
+    for i, k in enumerate(names):
+        cols[..., i] = aux[k]
+    return names, cols
+
+
 def average_aux_losses(ts: RaySamples, densities, aux: Dict[str, torch.Tensor]):
-    """render.py:192-209 via the compositing kernel: sum_t v*p is the first channel of a
-    composite with colours (v,0,0) and a zero background."""
-    n, T = ts.ts.shape
-    out = {}
+    """render.py:192-209 via the compositing kernel: sum_t v*p is one colour channel of a
+    composite with the aux values as colours and a zero background; then the mean over rays."""
+    names, cols = _pack_aux(aux)
     zero_bg = torch.zeros(3, device=ts.ts.device)
-    for k, v in aux.items():
-        cols = torch.zeros(n, T, 3, device=ts.ts.device)
-        cols[..., 0] = v
-        comp, _, _ = _native.composite_fwd(_dummy_rays(ts.ts), ts.ts, ts.t_min, ts.t_max,
-                                           ts._mask_u8(), densities, cols, zero_bg, want_aux=False)
-        out[k] = comp[:, 0].mean()
-    return out
+    comp, _, _ = _native.composite_fwd(_dummy_rays(ts.ts), ts.ts, ts.t_min, ts.t_max, ts._mask_u8(),
+                                       densities, cols, zero_bg, want_aux=False)
+    return {k: comp[:, i].mean() for i, k in enumerate(names)}
 
 
 def ray_t_range(bbox: torch.Tensor, ray: torch.Tensor, min_t_range: float = 1e-3,

@@ -17,7 +17,7 @@ import torch
 
 from . import _native, parallel, prng
 from .model import ModelBase
-from .render import NeRFRenderer, RaySamples, _vec3
+from .render import NeRFRenderer, RaySamples, _pack_aux, _vec3
 
 
 class TrainState:
@@ -70,6 +70,8 @@ class TrainLoop:
             flat=flat)
         self._grads = torch.zeros_like(flat)
         self._scalars = torch.zeros(4, device=device)  # loss_c, loss_f, |g|^2, |p|^2
+        self._zero3 = torch.zeros(3, device=device)
+        self._scratch3 = torch.zeros(3, device=device)
 
     # ------------------------------------------------------------------ checkpoints
     def save(self, path: str):
@@ -130,6 +132,7 @@ class TrainLoop:
         g = self._grads
         g.zero_()
         self._scalars.zero_()
+        aux_sums: Dict[str, torch.Tensor] = {}
         renderer = self._renderer(bmin, bmax, st.params)
         inv_count = 1.0 / (3.0 * n)  # jnp.mean over N*3 (:141-142)
         chunk = self.ray_chunk or n
@@ -152,7 +155,23 @@ class TrainLoop:
                                                       lv["densities"], lv["rgbs"],
                                                       st.params["background"], d_out,
                                                       g[sb[0]:sb[0] + 3])
-                model.backward_rays(lv["_ctx"], d_dens, d_rgb, g[sl[0]:sl[1]])
+                d_aux = None
+                if lv["_aux"]:
+                    # aux losses (:146-151): total += w * mean_rays(where(mask, sum_t v_t p_t, 0)).
+                    # Their gradient w.r.t. the densities and the aux values is the compositing
+                    # gradient with the aux values as colours, a zero background and d_out = w / N.
+                    names, cols = _pack_aux(lv["_aux"])
+                    d_comp = torch.zeros(b - a, 3, device=batch.device)
+                    for i, name in enumerate(names):
+                        d_comp[:, i] = self.loss_weights[name] / n
+                        key_name = f"{level}_{name}"
+                        aux_sums[key_name] = aux_sums.get(key_name, 0.0) + out[f"{level}_aux"][name] * (b - a)
+                    d_dens_aux, d_cols = _native.composite_bwd(ts.ts, ts.t_min, ts.t_max, ts._mask_u8(),
+                                                               lv["densities"], cols, self._zero3, d_comp,
+                                                               self._scratch3)
+                    d_dens = d_dens + d_dens_aux
+                    d_aux = {name: d_cols[..., i].contiguous() for i, name in enumerate(names)}
+                model.backward_rays(lv["_ctx"], d_dens, d_rgb, g[sl[0]:sl[1]], d_aux=d_aux)
         if world > 1:
             parallel.allreduce_sum_(g)  # one NCCL sum over NVLink; 1/world is folded into Adam
             parallel.allreduce_sum_(self._scalars[:2])
@@ -163,8 +182,17 @@ class TrainLoop:
             st.params[name].mark_updated()
         s = self._scalars
         scale = inv_count / world
-        return dict(coarse=s[0] * scale, fine=s[1] * scale, grad_norm=torch.sqrt(s[2]),
-                    param_norm=torch.sqrt(s[3]))
+        logs = dict(coarse=s[0] * scale, fine=s[1] * scale)
+        if aux_sums:
+            names = sorted(aux_sums)
+            vals = torch.stack([aux_sums[k] for k in names]) / n
+            if world > 1:
+                parallel.mean_scalars_(vals)
+            for i, k in enumerate(names):
+                logs[k] = vals[i]
+        logs["grad_norm"] = torch.sqrt(s[2])
+        logs["param_norm"] = torch.sqrt(s[3])
+        return logs
 
     def losses(self, key, bbox_min, bbox_max, batch: torch.Tensor, params):
         """train.py:114-165 (forward only) -> (total_loss, loss_dict)."""
