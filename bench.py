@@ -27,6 +27,10 @@ import torch  # noqa: E402
 
 FLOP_FWD_PER_SAMPLE = 1_182_976          # 2 x 591,488 MAC
 FLOP_TRAIN_PER_SAMPLE = 3_481_344        # fwd + dW + dX, no padding / recompute
+# Ref-NeRF: fwd 590,336 MAC + normal chain 489,472 MAC; backward adds directional
+# dW/dX 71,040, trunk dW 555,008 + dX 524,288, tangent pass 489,472 + its dW 489,472 MAC
+REF_FLOP_FWD_PER_SAMPLE = 2 * (590_336 + 489_472)
+REF_FLOP_TRAIN_PER_SAMPLE = 2 * 3_709_088
 SAMPLES_PER_RAY = 64 + 192
 
 
@@ -173,6 +177,9 @@ def build_models(args, dev):
                                        grid_sizes=[2 ** (4 + i // 2) for i in range(L)],
                                        bbox_min=[-1.0] * 3, bbox_max=[1.0] * 3)
         return mk(6), mk(16), dict(adam_eps=1e-15, adam_b1=0.9, adam_b2=0.99)
+    if args.model == "refnerf":
+        from learn_nerf.ref_nerf import RefNERFModel
+        return RefNERFModel(sh_degree=4), RefNERFModel(sh_degree=4), {}
     from learn_nerf.model import NeRFModel
     return NeRFModel(precision=args.precision), NeRFModel(precision=args.precision), {}
 
@@ -203,6 +210,8 @@ def run_ours(args):
         _native.set_tc_stages(args.tc_stages)
     n = args.rays or (32768 if args.model == "ngp" else 4096)
     prec = args.precision if args.model == "nerf" else "fp32"
+    if args.model == "refnerf" and args.ray_chunk is None and n > 2048:
+        args.ray_chunk = 2048  # 24 KB of saved activations per sample: keep the workspace near 10 GB
     coarse, fine, train_kwargs = build_models(args, dev)
     loop = TrainLoop(coarse, fine, init_rng=2, lr=1e-4, coarse_ts=64, fine_ts=128, device=dev,
                      ray_chunk=args.ray_chunk, **train_kwargs)
@@ -213,8 +222,8 @@ def run_ours(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     # the dominant kernels, timed with CUDA events on the launching (current) stream
-    dom_names = (["hashgrid_fwd", "hashgrid_bwd"] if args.model == "ngp"
-                 else ["nerf_mlp_fwd", "nerf_mlp_bwd"])
+    dom_names = {"ngp": ["hashgrid_fwd", "hashgrid_bwd"], "refnerf": ["refnerf_fwd", "refnerf_bwd"],
+                 "nerf": ["nerf_mlp_fwd", "nerf_mlp_bwd"]}[args.model]
     dom_events = []
 
     def timed(fn):
@@ -299,16 +308,20 @@ def run_ours(args):
         value = total_rays / (ms * 1e-3)
         e2e_value = total_rays / (e2e_ms * 1e-3)
         train = args.workload == "train"
-        what = {"nerf": "NeRF coarse+fine", "ngp": "Instant-NGP coarse (L=6) + fine (L=16)"}[args.model]
-        cfg_name = {("nerf", True): "configs[1]: ", ("ngp", True): "configs[2]: ",
-                    ("nerf", False): "configs[4]-style: ", ("ngp", False): ""}[(args.model, train)]
-        if args.model == "nerf":
-            flop_per_sample = FLOP_TRAIN_PER_SAMPLE if train else FLOP_FWD_PER_SAMPLE
+        what = {"nerf": "NeRF coarse+fine", "ngp": "Instant-NGP coarse (L=6) + fine (L=16)",
+                "refnerf": "Ref-NeRF (sh_degree 4) coarse+fine"}[args.model]
+        cfg_name = {("nerf", True): "configs[1]: ", ("ngp", True): "configs[2]: ", ("refnerf", True): "configs[3]: ",
+                    ("nerf", False): "configs[4]-style: "}.get((args.model, train), "")
+        if args.model in ("nerf", "refnerf"):
+            if args.model == "nerf":
+                flop_per_sample = FLOP_TRAIN_PER_SAMPLE if train else FLOP_FWD_PER_SAMPLE
+            else:
+                flop_per_sample = REF_FLOP_TRAIN_PER_SAMPLE if train else REF_FLOP_FWD_PER_SAMPLE
             flops = flop_per_sample * SAMPLES_PER_RAY * n  # per rank, per step
             achieved = flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
             roofline = {"bound": "tensor",
-                        "kernel": "nerf_fwd_tc_kernel" + (" + nerf_bwd_dx_kernel + nerf_bwd_dw_kernel"
-                                                          if train else "") if prec == "bf16"
+                        "kernel": "nerf_fwd_pair_kernel" + (" + nerf_bwd_dx_kernel + nerf_bwd_dw_kernel"
+                                                            if train else "") if prec == "bf16"
                                   else "sgemm_kernel chain (fp32 FFMA)",
                         "achieved": achieved, "peak": peaks["tf"], "unit": "TFLOP/s",
                         "frac": achieved / peaks["tf"], "traffic": None,
@@ -326,7 +339,7 @@ def run_ours(args):
                         "kernel_ms_per_step": dom_ms, "kernel_share_of_step": dom_ms / ms,
                         "algorithmic_bytes_per_ray": ngp_grid_bytes_per_ray(train)}
         line = {
-            "metric": f"rays/sec ({'NeRF' if args.model == 'nerf' else 'Instant-NGP'} "
+            "metric": f"rays/sec ({dict(nerf='NeRF', ngp='Instant-NGP', refnerf='Ref-NeRF')[args.model]} "
                       f"{'train step fwd+bwd+Adam' if train else 'render'})",
             "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -365,7 +378,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="train", choices=["train", "render"])
-    ap.add_argument("--model", default="nerf", choices=["nerf", "ngp"])
+    ap.add_argument("--model", default="nerf", choices=["nerf", "ngp", "refnerf"])
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
                     help="NeRF MLP path: bf16 tcgen05 (2e-2) or fp32 FFMA (1e-5)")
     ap.add_argument("--rays", type=int, default=None, help="rays per GPU per step (4096 NeRF, 32768 NGP)")
