@@ -404,7 +404,7 @@ nerf_bwd_dw_kernel(DwArgs args) {
       if (job.db != nullptr && 2 * wt < N && !(args.debug & 4)) {
         const int c = 2 * wt;
         const uint32_t blk = sb + (c >> 6) * kHalfBlock;
-#pragma unroll 4
+#pragma unroll 16
         for (int rr = 0; rr < 64; ++rr) {
           uint32_t u;
           asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(blk + sw128_offset(rr, c & 63)));
@@ -416,7 +416,7 @@ nerf_bwd_dw_kernel(DwArgs args) {
       } else if (job.extra == 1) {  // dW9[f] += z8[row, f] * spre[row], f = 2wt, 2wt+1
         const int c = 2 * wt;
         const uint32_t blk = sa + (c >> 6) * kHalfBlock;
-#pragma unroll 4
+#pragma unroll 16
         for (int rr = 0; rr < 64; ++rr) {
           uint32_t u;
           asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(blk + sw128_offset(rr, c & 63)));
@@ -426,7 +426,7 @@ nerf_bwd_dw_kernel(DwArgs args) {
         }
       } else if (job.extra == 2) {  // dW11[k, :] += c[row, k] * dpre[row, :], k = wt
         const uint32_t blk = sa + (wt >> 6) * kHalfBlock;
-#pragma unroll 4
+#pragma unroll 16
         for (int rr = 0; rr < 64; ++rr) {
           uint32_t u;
           asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(blk + sw128_offset(rr, (wt & 63) & ~1)));
@@ -482,7 +482,15 @@ nerf_bwd_dw_kernel(DwArgs args) {
 
 // ================================================================ host side
 static int g_dw_debug = 0;
-void set_dw_debug(int flags) { g_dw_debug = flags; }
+static double g_dw_w1 = 8.0, g_dw_w2 = 8.0;
+void set_dw_debug(int flags) {
+  if (flags >= 1000) {  // tuning: flags = 1000 + 100 * w1 + w2
+    g_dw_w1 = double((flags - 1000) / 100);
+    g_dw_w2 = double((flags - 1000) % 100);
+    return;
+  }
+  g_dw_debug = flags;
+}
 
 int init_mlp_tc_bwd() {
   int rc = upload_tc_tables();
@@ -539,7 +547,10 @@ int nerf_bwd_tc(const float* P, const void* packed, int64_t m, void* ws, int64_t
   double wj[kDwMaxJobs];
   for (int j = 0; j < nj; ++j) {
     wj[j] = d.jobs[j].a_blocks + d.jobs[j].b_blocks;
-    if (d.jobs[j].extra == 2) wj[j] = 4;  // CUDA-core only job: bounded by its row loop, not by bytes
+    // the two jobs that also form a head gradient on the CUDA cores are bounded by that row
+    // loop, not by the bytes they stream (g_dw_w1 / g_dw_w2: tuning knobs, see lnrf_set_debug_flags)
+    if (d.jobs[j].extra == 1) wj[j] = g_dw_w1;
+    if (d.jobs[j].extra == 2) wj[j] = g_dw_w2;
     wsum += wj[j];
   }
   int begin = 0;
