@@ -167,13 +167,15 @@ int lnrf_hashgrid_bwd(const int64_t* level_offsets_host, const int32_t* grid_siz
 
 /* InstantNGPModel heads (instant_ngp.py:37,46-53) on a precomputed encoding:
  * enc[m,2L] (+ d[m,3] or ray mode) -> dens[m], rgb[m,3].  params: Dense_0..4
- * flat (kernel then bias each).  Workspace keeps activations for bwd.         */
+ * flat (kernel then bias each).  One fused kernel per direction; with
+ * save_for_backward the workspace keeps the layer inputs for lnrf_ngp_mlp_bwd
+ * (workspace may be NULL otherwise).                                          */
 int64_t lnrf_ngp_mlp_param_count(int32_t L); /* floats incl. 16-byte padding of each tensor */
 /* host out[10]: float offsets of kernel_i (out[2i]) and bias_i (out[2i+1]), i = 0..4. */
 int lnrf_ngp_mlp_param_offsets(int32_t L, int64_t* out_host);
 int lnrf_ngp_mlp_workspace_bytes(int64_t m, int32_t L, int64_t* bytes_out_host);
 int lnrf_ngp_mlp_fwd(const float* params, int32_t L, const float* enc, const float* d,
-                     const float* rays, int64_t n, int32_t T, void* workspace,
+                     const float* rays, int64_t n, int32_t T, int32_t save_for_backward, void* workspace,
                      int64_t workspace_bytes, float* dens, float* rgb, lnrf_stream_t stream);
 int lnrf_ngp_mlp_bwd(const float* params, int32_t L, const float* enc, int64_t m, void* workspace,
                      int64_t workspace_bytes, const float* dens, const float* rgb,

@@ -230,4 +230,99 @@ static int gemm_tn_acc(cudaStream_t st, int M, int N, const float* At, int lda, 
   return launch_sgemm<true, false, EPI_ATOMIC>(g, (int)splits, st);
 }
 
+// ---------------------------------------------------------------- small dW kernel
+// C[M,N] += At[K,M]^T @ B[K,N] and (optionally) db[N] += column sums of B, for M, N <= 64
+// (the Instant-NGP head layers).  One 64x64 tile per block, 4x4 accumulators per thread, the K
+// range (= samples) split over the grid and reduced with atomics.  M, N, lda, ldb multiples of 4.
+constexpr int SBK = 16;
+template <int UNUSED = 0>  // template only so that the definition can live in this header
+__global__ void __launch_bounds__(256)
+dw_small_kernel(const float* __restrict__ At, int lda, const float* __restrict__ B, int ldb, int M, int N,
+                int64_t K, int64_t k_per_block, float* __restrict__ C, int ldc, float* __restrict__ db) {
+  __shared__ __align__(16) float As[2][SBK][64 + 4];
+  __shared__ __align__(16) float Bs[2][SBK][64 + 4];
+  __shared__ float s_db[64];
+  const int t = threadIdx.x;
+  const int tx = t & 15, ty = t >> 4;        // output micro-tile: rows ty*4.., cols tx*4..
+  const int lk = t >> 4, lq = (t & 15) * 4;  // loader: row lk of the K tile, columns lq..lq+3
+  const int64_t kbeg = int64_t(blockIdx.x) * k_per_block;
+  const int64_t kend = min(kbeg + k_per_block, K);
+  if (t < 64) s_db[t] = 0.0f;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+  float4 ra, rb, bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto load = [&](int64_t k0) {
+    const int64_t k = k0 + lk;
+    ra = make_float4(0.f, 0.f, 0.f, 0.f);
+    rb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k < kend) {
+      if (lq < M) ra = __ldg(reinterpret_cast<const float4*>(At + k * lda + lq));
+      if (lq < N) rb = __ldg(reinterpret_cast<const float4*>(B + k * ldb + lq));
+    }
+    bsum.x += rb.x; bsum.y += rb.y; bsum.z += rb.z; bsum.w += rb.w;
+  };
+  auto store = [&](int buf) {
+    *reinterpret_cast<float4*>(&As[buf][lk][lq]) = ra;
+    *reinterpret_cast<float4*>(&Bs[buf][lk][lq]) = rb;
+  };
+  const int64_t nk = (kend - kbeg + SBK - 1) / SBK;
+  if (nk > 0) {
+    load(kbeg);
+    store(0);
+  }
+  __syncthreads();
+  for (int64_t kt = 0; kt < nk; ++kt) {
+    const int buf = int(kt & 1);
+    if (kt + 1 < nk) load(kbeg + (kt + 1) * SBK);
+#pragma unroll
+    for (int k = 0; k < SBK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) store(buf ^ 1);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = tx * 4 + j;
+      if (n < N) atomicAdd(C + int64_t(m) * ldc + n, acc[i][j]);
+    }
+  }
+  if (db != nullptr) {
+    if (lq < N) {
+      atomicAdd(&s_db[lq + 0], bsum.x);
+      atomicAdd(&s_db[lq + 1], bsum.y);
+      atomicAdd(&s_db[lq + 2], bsum.z);
+      atomicAdd(&s_db[lq + 3], bsum.w);
+    }
+    __syncthreads();
+    if (t < N) atomicAdd(db + t, s_db[t]);
+  }
+}
+
+static int gemm_tn_small(cudaStream_t st, int M, int N, const float* At, int lda, const float* B, int ldb,
+                         int64_t K, float* C, int ldc, float* db) {
+  LNRF_REQUIRE(M <= 64 && N <= 64 && M % 4 == 0 && N % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0, LNRF_E_UNSUPPORTED,
+               "gemm_tn_small: M=%d N=%d lda=%d ldb=%d", M, N, lda, ldb);
+  int64_t blocks = int64_t(sm_count()) * 4;
+  int64_t kpb = align_up(ceil_div(K, blocks), SBK);
+  if (kpb < 512) kpb = 512;
+  blocks = ceil_div(K, kpb);
+  dw_small_kernel<><<<(unsigned)blocks, 256, 0, st>>>(At, lda, B, ldb, M, N, K, kpb, C, ldc, db);
+  LNRF_LAUNCH_CHECK("dw_small_kernel");
+  return LNRF_OK;
+}
+
 }  // namespace lnrf

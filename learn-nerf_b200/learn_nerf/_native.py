@@ -72,7 +72,7 @@ _SIGS = {
                                                      c_void_p, c_void_p, c_void_p]),
     "lnrf_ngp_mlp_param_count": (c_int64, [c_int32]),
     "lnrf_ngp_mlp_workspace_bytes": (c_int32, [c_int64, c_int32, c_void_p]),
-    "lnrf_ngp_mlp_fwd": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
+    "lnrf_ngp_mlp_fwd": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32,
                                    c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "lnrf_ngp_mlp_bwd": (c_int32, [c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_int64] +
                          [c_void_p] * 7),
@@ -341,10 +341,11 @@ def ngp_mlp_workspace_bytes(m: int, L: int) -> int:
     return int(out.value)
 
 
-def ngp_mlp_fwd(flat, L, enc, d, rays, n, T, workspace, dens, rgb):
+def ngp_mlp_fwd(flat, L, enc, d, rays, n, T, save, workspace, dens, rgb):
     ensure_init(flat.device)
-    _check(load().lnrf_ngp_mlp_fwd(_p(flat), L, _p(enc), _p(d), _p(rays), n, T, _p(workspace),
-                                   workspace.numel(), _p(dens), _p(rgb), _stream()), "lnrf_ngp_mlp_fwd")
+    _check(load().lnrf_ngp_mlp_fwd(_p(flat), L, _p(enc), _p(d), _p(rays), n, T, int(save), _p(workspace),
+                                   0 if workspace is None else workspace.numel(), _p(dens), _p(rgb),
+                                   _stream()), "lnrf_ngp_mlp_fwd")
 
 
 def ngp_mlp_bwd(flat, L, enc, m, workspace, dens, rgb, d_dens, d_rgb, d_flat, d_enc):

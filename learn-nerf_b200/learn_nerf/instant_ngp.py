@@ -115,26 +115,26 @@ class InstantNGPModel(ModelBase):
         return {"params": tree}
 
     # ------------------------------------------------------------------ native calls
-    def _workspace(self, m: int, device, slot):
+    def _workspace(self, m: int, device, slot, save):
         cache = self.__dict__.setdefault("_ws_cache", {})
-        nbytes = _native.ngp_mlp_workspace_bytes(m, self.L)
-        ws = cache.get((str(device), slot))
+        nbytes = _native.ngp_mlp_workspace_bytes(m, self.L) if save else 0
+        ws = cache.get((str(device), slot, save))
         if ws is None or ws[0].numel() < nbytes or ws[1].shape[0] < m:
-            ws = (torch.empty(nbytes, dtype=torch.uint8, device=device),
+            ws = (torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device),
                   torch.empty(m, 2 * self.L, device=device))
-            cache[(str(device), slot)] = ws
+            cache[(str(device), slot, save)] = ws
         return ws
 
-    def _forward(self, tree, x, d, rays, ts, n, T, slot=None):
+    def _forward(self, tree, x, d, rays, ts, n, T, slot=None, save=False):
         spec = self.spec()
         dev = tree.flat.device
         m = n * T
-        ws, enc = self._workspace(m, dev, slot)
+        ws, enc = self._workspace(m, dev, slot, save)
         enc = enc[:m]
         _native.hashgrid_fwd(tree.flat, spec, x, rays, ts, n, T, enc)
         dens = torch.empty(m, device=dev)
         rgb = torch.empty(m, 3, device=dev)
-        _native.ngp_mlp_fwd(tree.flat, self.L, enc, d, rays, n, T, ws, dens, rgb)
+        _native.ngp_mlp_fwd(tree.flat, self.L, enc, d, rays, n, T, save, ws if save else None, dens, rgb)
         return dens, rgb, ws, enc
 
     def encode(self, params, x: torch.Tensor) -> torch.Tensor:
@@ -156,7 +156,7 @@ class InstantNGPModel(ModelBase):
         tree = self.flatten_params(params)
         n, T = ts.shape
         rays, ts = _native._f32c(rays, "rays"), _native._f32c(ts, "ts")
-        dens, rgb, ws, enc = self._forward(tree, None, None, rays, ts, n, T, slot if save else None)
+        dens, rgb, ws, enc = self._forward(tree, None, None, rays, ts, n, T, slot if save else None, save)
         ctx = dict(tree=tree, ws=ws, enc=enc, rays=rays, ts=ts, n=n, T=T, dens=dens, rgb=rgb) if save else None
         return dens.view(n, T), rgb.view(n, T, 3), {}, ctx
 
