@@ -524,6 +524,7 @@ int init_mlp_tc_fwd2();  // mlp_tc_fwd2.cu
 int nerf_fwd_pair(const void* packed, const float* x, const float* d, const float* rays, const float* ts,
                   int64_t m, int T, bool save, const TcStash& stash, float* dens, float* rgb, cudaStream_t st);
 void set_dw_debug(int flags);
+void set_fwd_debug(int flags);
 
 template <typename K>
 static int set_smem(K kernel, int bytes) {
@@ -630,6 +631,7 @@ int lnrf_set_tc_stages(int32_t stages) {
 // ablation switches for profiling the dW kernel (results are wrong when non-zero)
 int lnrf_set_debug_flags(int32_t flags) {
   lnrf::set_dw_debug(flags);
+  lnrf::set_fwd_debug(flags >= 1000 ? 0 : flags);
   return LNRF_OK;
 }
 

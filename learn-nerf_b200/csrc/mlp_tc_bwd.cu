@@ -553,10 +553,28 @@ int nerf_bwd_tc(const float* P, const void* packed, int64_t m, void* ws, int64_t
     if (d.jobs[j].extra == 2) wj[j] = g_dw_w2;
     wsum += wj[j];
   }
+  // largest-remainder apportionment so that every SM gets a CTA
+  int cnt[kDwMaxJobs];
+  double frac[kDwMaxJobs];
+  int used = 0;
+  for (int j = 0; j < nj; ++j) {
+    const double exact = total_ctas * wj[j] / wsum;
+    cnt[j] = int(exact);
+    if (cnt[j] < 1) cnt[j] = 1;
+    frac[j] = exact - cnt[j];
+    used += cnt[j];
+  }
+  while (used < total_ctas) {
+    int best = 0;
+    for (int j = 1; j < nj; ++j)
+      if (frac[j] > frac[best]) best = j;
+    ++cnt[best];
+    frac[best] -= 1.0;
+    ++used;
+  }
   int begin = 0;
   for (int j = 0; j < nj; ++j) {
-    int c = int(total_ctas * wj[j] / wsum);
-    if (c < 1) c = 1;
+    int c = cnt[j];
     if (int64_t(c) > tiles) c = int(tiles);
     d.jobs[j].cta_begin = begin;
     d.jobs[j].cta_count = c;

@@ -29,6 +29,7 @@ struct TcFwdArgs2 {
   float* dens;
   float* rgb;
   TcStash stash;
+  int debug;  // profiling ablations: 8 = skip the stash stores, 16 = alias all stash tiles onto the first 64
 };
 
 // sin/cos of a = x * 2^f with an explicit two-step Cody-Waite reduction to [-pi, pi] followed by
@@ -98,6 +99,8 @@ __device__ __forceinline__ void epi_layer(const TcFwdArgs2& args, int X, int r, 
                                           uint4* mask_row, const uint32_t (&de)[12]) {
   constexpr uint32_t par = TL & 1;  // ten layers per tile pair: the phase parity of layer TL is fixed
   uint32_t mw[4];
+  if (args.debug & 8) tile_ok = false;
+  if (args.debug & 16) tile &= 63;
   // ---- half 0: columns 0..127 -> A blocks 0,1
   mbar_wait(bars + PairSmem::acc0 + 8 * X, par);
   tc_fence_after();
@@ -147,7 +150,9 @@ __device__ __forceinline__ void epi_layer(const TcFwdArgs2& args, int X, int r, 
   mbar_arrive(bars + PairSmem::a_ready1 + 8 * X);
 }
 
-template <bool SAVE>
+// FULLN = lockstep schedule on full-N weight chunks (faster without the stash), else the N-half
+// pipelined schedule.
+template <bool SAVE, bool FULLN>
 __global__ void __launch_bounds__(kPairThreads, 1)
 nerf_fwd_pair_kernel(const __grid_constant__ TcFwdArgs2 args) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -167,7 +172,7 @@ nerf_fwd_pair_kernel(const __grid_constant__ TcFwdArgs2 args) {
   const int64_t my_pairs = (pairs > blockIdx.x) ? (pairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
   if (tid == 0) {
-    for (int s = 0; s < kPairStages; ++s) {
+    for (int s = 0; s < PairCfg<FULLN>::stages; ++s) {
       mbar_init(bars + PairSmem::full + 8 * s, 1);
       mbar_init(bars + PairSmem::empty + 8 * s, 1);
     }
@@ -190,9 +195,13 @@ nerf_fwd_pair_kernel(const __grid_constant__ TcFwdArgs2 args) {
   const uint32_t tmem = *tmem_slot_ptr;
 
   if (warp == 8) {
-    if (lane == 0) pair_producer(args.packed, c_chunks.f2, kF2Chunks, my_pairs, sW, bars);
+    if (lane == 0) {
+      if (FULLN) pair_producer<true>(args.packed, c_chunks.f, kTcChunks, my_pairs, sW, bars);
+      else pair_producer<false>(args.packed, c_chunks.f2, kF2Chunks, my_pairs, sW, bars);
+    }
   } else if (warp == 9) {
-    pair_mma(c_pair_meta.f2, kF2Chunks, my_pairs, sA0, sW, bars, tmem);
+    if (FULLN) pair_mma<true>(c_pair_meta.f_full, kTcChunks, my_pairs, sA0, sW, bars, tmem);
+    else pair_mma<false>(c_pair_meta.f2, kF2Chunks, my_pairs, sA0, sW, bars, tmem);
   } else {
     // ===== epilogue group X: thread r owns row r of tile X
     const int X = warp >> 2;
@@ -355,13 +364,16 @@ nerf_fwd_pair_kernel(const __grid_constant__ TcFwdArgs2 args) {
   if (warp == 8) tmem_dealloc(tmem, 512);
 }
 
+static int g_fwd_debug = 0;
+void set_fwd_debug(int flags) { g_fwd_debug = flags; }
+
 int init_mlp_tc_fwd2() {
   int rc = upload_tc_tables();
   if (rc) return rc;
   if ((rc = upload_pair_meta())) return rc;
-  LNRF_CUDA(cudaFuncSetAttribute(nerf_fwd_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  LNRF_CUDA(cudaFuncSetAttribute(nerf_fwd_pair_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)PairSmem::total));
-  LNRF_CUDA(cudaFuncSetAttribute(nerf_fwd_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  LNRF_CUDA(cudaFuncSetAttribute(nerf_fwd_pair_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)PairSmem::total));
   return LNRF_OK;
 }
@@ -372,12 +384,12 @@ int nerf_fwd_pair(const void* packed, const float* x, const float* d, const floa
   // this model's biases / rgb head -> constant bank (11 KB device-to-device, stream-ordered)
   LNRF_CUDA(cudaMemcpyToSymbolAsync(c_small, reinterpret_cast<const uint8_t*>(packed) + kSmallOffset,
                                     sizeof(SmallParams), 0, cudaMemcpyDeviceToDevice, st));
-  TcFwdArgs2 a{reinterpret_cast<const uint8_t*>(packed), x, d, rays, ts, T, m, dens, rgb, stash};
+  TcFwdArgs2 a{reinterpret_cast<const uint8_t*>(packed), x, d, rays, ts, T, m, dens, rgb, stash, g_fwd_debug};
   const int64_t pairs = (ceil_div(m, 128) + 1) / 2;
   int64_t grid = sm_count();
   if (grid > pairs) grid = pairs;
-  if (save) nerf_fwd_pair_kernel<true><<<(unsigned)grid, kPairThreads, PairSmem::total, st>>>(a);
-  else nerf_fwd_pair_kernel<false><<<(unsigned)grid, kPairThreads, PairSmem::total, st>>>(a);
+  if (save) nerf_fwd_pair_kernel<true, false><<<(unsigned)grid, kPairThreads, PairSmem::total, st>>>(a);
+  else nerf_fwd_pair_kernel<false, true><<<(unsigned)grid, kPairThreads, PairSmem::total, st>>>(a);
   LNRF_LAUNCH_CHECK("nerf_fwd_pair_kernel");
   return LNRF_OK;
 }

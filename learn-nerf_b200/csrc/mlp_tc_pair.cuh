@@ -16,19 +16,18 @@
 namespace lnrf {
 
 constexpr int kPairThreads = 320;
-constexpr int kPairStages = 4;
 constexpr uint32_t kPairTileBytes = 5 * kABlockBytes;  // 4 activation blocks + embedding block
 
 struct PairSmem {
   static constexpr uint32_t a_off = 0;                                     // tile A, then tile B
   static constexpr uint32_t w_off = 2 * kPairTileBytes;                    // 163,840
-  static constexpr uint32_t bar_off = w_off + kPairStages * kChunkBytes128;  // 229,376
+  static constexpr uint32_t bar_off = w_off + 4 * kChunkBytes128;          // 229,376 (64 KB ring)
   static constexpr uint32_t total = bar_off + 256;
   // barrier map (8 B each, relative to bar_off)
-  static constexpr uint32_t full = 0;                     // [kPairStages]
-  static constexpr uint32_t empty = 8 * kPairStages;      // [kPairStages]
+  static constexpr uint32_t full = 0;                     // [<= 4 stages]
+  static constexpr uint32_t empty = 32;                   // [<= 4 stages]
   // per tile X (8 X bytes further): epilogue -> MMA (128 arrivals each)
-  static constexpr uint32_t a_ready0 = 16 * kPairStages;  // A blocks 0,1 written, accumulator half 0 drained
+  static constexpr uint32_t a_ready0 = 64;                 // A blocks 0,1 written, accumulator half 0 drained
   static constexpr uint32_t a_ready1 = a_ready0 + 16;     // A blocks 2,3 (+ embedding block) written
   static constexpr uint32_t drained1 = a_ready1 + 16;     // accumulator half 1 read back
   // MMA -> epilogue (tcgen05.commit)
@@ -60,15 +59,18 @@ __device__ __forceinline__ void tmem_wait_ld_dep(uint32_t (&v)[32]) {
 }
 
 // Producer (one thread): stream `nchunks` weight chunks per tile pair through the ring.
+template <bool FULLN>
 __device__ __forceinline__ void pair_producer(const uint8_t* packed, const ChunkInfo* chunks, int nchunks,
                                               int64_t my_pairs, uint32_t sW, uint32_t bars) {
+  constexpr int kPairStages = PairCfg<FULLN>::stages;
+  constexpr uint32_t kPairSlotBytes = PairCfg<FULLN>::slot_bytes;
   uint32_t stage = 0, phase = 0;
   for (int64_t t = 0; t < my_pairs; ++t) {
     for (int ci = 0; ci < nchunks; ++ci) {
       const uint32_t bytes = uint32_t(chunks[ci].n) * 128u;
       ptx::mbar_wait(bars + PairSmem::empty + 8 * stage, phase ^ 1);
       ptx::mbar_arrive_expect_tx(bars + PairSmem::full + 8 * stage, bytes);
-      ptx::bulk_g2s(sW + stage * kChunkBytes128, packed + chunks[ci].offset, bytes,
+      ptx::bulk_g2s(sW + stage * kPairSlotBytes, packed + chunks[ci].offset, bytes,
                     bars + PairSmem::full + 8 * stage);
       if (++stage == kPairStages) { stage = 0; phase ^= 1; }
     }
@@ -80,6 +82,7 @@ __device__ __forceinline__ void pair_producer(const uint8_t* packed, const Chunk
 struct PairMeta {
   uint32_t f2[kF2Chunks];
   uint32_t b2[kB2Chunks];
+  uint32_t f_full[kTcChunks];  // full-N schedule over the chunks of table `f`
 };
 static __constant__ PairMeta c_pair_meta;
 
@@ -88,6 +91,7 @@ static int upload_pair_meta() {
   PairMeta m{};
   for (int i = 0; i < kF2Chunks; ++i) m.f2[i] = uint32_t(t.f2[i].last);
   for (int i = 0; i < kB2Chunks; ++i) m.b2[i] = uint32_t(t.b2[i].last);
+  for (int i = 0; i < kTcChunks; ++i) m.f_full[i] = uint32_t(t.f[i].last);
   LNRF_CUDA(cudaMemcpyToSymbol(c_pair_meta, &m, sizeof(m)));
   return LNRF_OK;
 }
@@ -118,21 +122,26 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, u
 // MMA issuer (the whole warp runs the loop so that every operand stays in uniform registers;
 // one elected lane issues): per chunk one group of four K=16 MMAs per tile, in the order and
 // with the waits/commits its control word prescribes (tc_common.cuh, emit_layer).
+template <bool FULLN>
 __device__ __forceinline__ void pair_mma(const uint32_t* meta, int nchunks, int64_t my_pairs, uint32_t sA,
                                          uint32_t sW, uint32_t bars, uint32_t tmem) {
   using namespace ptx;
+  constexpr int kPairStages = PairCfg<FULLN>::stages;
+  constexpr uint32_t kPairSlotBytes = PairCfg<FULLN>::slot_bytes;
   // descriptor words (see umma_desc_sw128_kmajor): lo = addr >> 4 | LBO(1) << 16; hi is constant
   const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
   const uint32_t a_lo0 = ((sA & 0x3FFFFu) >> 4) | (1u << 16);
   const uint32_t b_lo0 = ((sW & 0x3FFFFu) >> 4) | (1u << 16);
   const uint32_t idesc128 = umma_idesc_bf16(128, 128), idesc16 = umma_idesc_bf16(128, 16);
+  const uint32_t idesc256 = umma_idesc_bf16(128, 256), idesc144 = umma_idesc_bf16(128, kNColor);
   uint32_t stage = 0, phase = 0, ev = 0;
   for (int64_t t = 0; t < my_pairs; ++t) {
     for (int ci = 0; ci < nchunks; ++ci) {
       const uint32_t mt = meta[ci];
-      const uint32_t idesc = (mt & PM_SMALL) ? idesc16 : idesc128;
+      const uint32_t idesc = (mt & PM_FULL) ? ((mt & PM_SMALL) ? idesc144 : idesc256)
+                                            : ((mt & PM_SMALL) ? idesc16 : idesc128);
       const uint32_t a_lo = a_lo0 + (mt & 7u) * (kABlockBytes >> 4);
-      const uint32_t b_lo = b_lo0 + stage * (kChunkBytes128 >> 4);
+      const uint32_t b_lo = b_lo0 + stage * (kPairSlotBytes >> 4);
       const uint32_t d0 = tmem + ((mt & PM_HALF) << 4);  // + 128 columns for the second N half
       const uint32_t acc = (mt & PM_OVERWRITE) ? 0u : 1u;
       if (mt & PM_W0) ev ^= 1;  // first chunk of a layer: the layer's phase parity

@@ -32,12 +32,21 @@ constexpr int64_t kFwdPackedBytes = 34 * int64_t(kChunkBytes256) + 5 * int64_t(k
 //   forward  f2: per tensor layer, per K chunk, per N half (T9: 128 colour columns, then a
 //                16-row chunk carrying the density column)              -> 78 chunks
 //   backward b2: B0 (K = 128) and B1..B8 (K = 256), per K chunk, per N half -> 68 chunks
+// A second schedule ("full N") reuses the forward table `f` ([256 n x 64 k] chunks, 32 KB,
+// 2-slot ring): both accumulator halves complete together (lockstep epilogue) but every MMA is
+// N = 256, which needs 25 % less shared-memory operand bandwidth per FLOP than two N = 128
+// MMAs.  It is the faster one when nothing is stashed (rendering).
 constexpr int kF2Chunks = 78;
 constexpr int kB2Chunks = 68;
 constexpr uint32_t kChunkBytes128 = 128 * 128;
 constexpr uint32_t kChunkBytes16 = 16 * 128;
+template <bool FULLN>
+struct PairCfg {
+  static constexpr uint32_t slot_bytes = FULLN ? 2 * kChunkBytes128 : kChunkBytes128;
+  static constexpr int stages = FULLN ? 2 : 4;
+};
 constexpr int64_t kF2PackedBytes = 73 * int64_t(kChunkBytes128) + 5 * int64_t(kChunkBytes16);
-constexpr int64_t kB2PackedBytes = kB2Chunks * int64_t(kChunkBytes128);
+constexpr int64_t kB2PackedBytes = 68 * int64_t(kChunkBytes128);
 // Small fp32 parameters the epilogues read from the constant bank (biases of the ten tensor
 // layers, the rgb head): gathered by the pack kernel into the tail of the packed buffer and
 // copied from there into constant memory right before each launch (one stream-ordered D2D copy).
@@ -73,6 +82,7 @@ constexpr uint32_t PM_W0 = 128;        // wait: A blocks 0,1 written / accumulat
 constexpr uint32_t PM_W1 = 256;        // wait: A blocks 2,3 and the embedding block written
 constexpr uint32_t PM_WD = 512;        // wait: accumulator half 1 drained
 constexpr uint32_t PM_C1 = 1024;       // commit "accumulator half 1 complete"
+constexpr uint32_t PM_FULL = 2048;     // full-N chunk: N = 256 (with PM_SMALL: N = 144, the colour layer)
 struct ChunkTable {
   ChunkInfo f[kTcChunks];
   ChunkInfo b[kBwChunks];
@@ -171,6 +181,17 @@ static ChunkTable build_chunk_table() {
   //   h0k0 h0k1 h1k0 h1k1 | h0k2 h0k3 (h0 emb) -> half 0 complete | h1k2 h1k3 (h1 emb) -> half 1
   // `last` carries the control word of the MMA issuer (see PM_* below).
   struct Item { int k0, kvalid, ablock; };
+  // full-N control words for the chunks of an existing table (`f` / `b`), natural K order
+  auto full_meta = [&](ChunkInfo* tab, int& cnt, const Item* items, int ni, int n_half1) {
+    bool w1 = true;
+    for (int i = 0; i < ni; ++i) {
+      uint32_t m = uint32_t(items[i].ablock) | PM_FULL | (n_half1 == 16 ? PM_SMALL : 0u);
+      if (i == 0) m |= PM_W0 | PM_WD | PM_OVERWRITE;
+      if (w1 && (items[i].ablock >= 2 || i == ni - 1)) { m |= PM_W1; w1 = false; }
+      if (i == ni - 1) m |= PM_C0 | PM_C1;
+      tab[cnt++].last = int(m);
+    }
+  };
   auto emit_layer = [&](ChunkInfo* out, int& cnt, int layer, int tlayer, const Item* items, int ni, int transposed,
                         int n_half1) {
     // items: K chunks in order; the first min(2, ni) form group "lo" (blocks 0,1), the rest group "hi"
@@ -203,16 +224,20 @@ static ChunkTable build_chunk_table() {
     }
   };
   n = 0;
+  int nf = 0;
   {
     const Item emb_x{0, kXE, 4};
     emit_layer(t.f2, n, 0, 0, &emb_x, 1, 0, 128);
+    full_meta(t.f, nf, &emb_x, 1, 128);
     const Item plain[4] = {{0, 64, 0}, {64, 64, 1}, {128, 64, 2}, {192, 64, 3}};
-    for (int l = 1; l <= 4; ++l) emit_layer(t.f2, n, l, l, plain, 4, 0, 128);
+    for (int l = 1; l <= 4; ++l) { emit_layer(t.f2, n, l, l, plain, 4, 0, 128); full_meta(t.f, nf, plain, 4, 128); }
     const Item skip[5] = {{0, 64, 0}, {64, 64, 1}, {128, 64, 2}, {192, 64, 3}, {256, kXE, 4}};
     emit_layer(t.f2, n, 5, 5, skip, 5, 0, 128);
-    for (int l = 6; l <= 8; ++l) emit_layer(t.f2, n, l, l, plain, 4, 0, 128);
+    full_meta(t.f, nf, skip, 5, 128);
+    for (int l = 6; l <= 8; ++l) { emit_layer(t.f2, n, l, l, plain, 4, 0, 128); full_meta(t.f, nf, plain, 4, 128); }
     const Item colour[5] = {{0, 64, 0}, {64, 64, 1}, {128, 64, 2}, {192, 64, 3}, {256, kDE, 4}};
     emit_layer(t.f2, n, 10, 9, colour, 5, 0, 16);
+    full_meta(t.f, nf, colour, 5, 16);
   }
   n = 0;
   {
