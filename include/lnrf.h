@@ -207,6 +207,17 @@ int lnrf_refnerf_bwd(const float* params, const float* x, const float* d, const 
                      const float* d_rgb, const float* d_aux_normal_mse, const float* d_aux_neg_normal,
                      float* d_params, lnrf_stream_t stream);
 
+/* ---------------------------------------------------------------- ray generation / image assembly
+ * CameraView.bare_rays (dataset.py:52-78): rays of image rows [row0, row0+rows) of a width x height
+ * view in raster order, rays[rows*width, 2, 3] = (origin, normalised direction).  tan_half_x_fov /
+ * tan_half_y_fov are tan(fov/2) evaluated on the host in double precision (as math.tan at
+ * dataset.py:61,66) and rounded to fp32.  Bit-exact with the oracle restatement.            */
+int lnrf_bare_rays(const float* origin_host, const float* x_axis_host, const float* y_axis_host,
+                   const float* z_host, float tan_half_x_fov, float tan_half_y_fov, int32_t width,
+                   int32_t height, int32_t row0, int32_t rows, float* rays, lnrf_stream_t stream);
+/* ((colors + 1) * 127.5).astype(uint8) (render_nerf.py:93-96); colors are clamped to [-1, 1].   */
+int lnrf_rgb_to_u8(const float* colors, int64_t count, uint8_t* out, lnrf_stream_t stream);
+
 /* ---------------------------------------------------------------- diagnostics
  * Single 128xNxK bf16 GEMM tile on tcgen05 (A[128,K], B[N,K] both K-major,
  * D fp32 [128,N]) used by tests to pin the UMMA descriptor encodings.         */

@@ -55,6 +55,9 @@ _SIGS = {
     "lnrf_debug_umma_gemm": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "lnrf_debug_umma_gemm_tn": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "lnrf_set_tc_stages": (c_int32, [c_int32]),
+    "lnrf_bare_rays": (c_int32, [c_void_p] * 4 + [c_float, c_float, c_int32, c_int32, c_int32, c_int32, c_void_p,
+                                                   c_void_p]),
+    "lnrf_rgb_to_u8": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p]),
     "lnrf_refnerf_param_count": (c_int64, []),
     "lnrf_refnerf_param_floats": (c_int64, []),
     "lnrf_refnerf_param_offsets": (c_int32, [c_void_p]),
@@ -353,6 +356,26 @@ def ngp_mlp_bwd(flat, L, enc, m, workspace, dens, rgb, d_dens, d_rgb, d_flat, d_
     _check(load().lnrf_ngp_mlp_bwd(_p(flat), L, _p(enc), m, _p(workspace), workspace.numel(), _p(dens),
                                    _p(rgb), _p(_f32c(d_dens, "d_dens")), _p(_f32c(d_rgb, "d_rgb")),
                                    _p(d_flat), _p(d_enc), _stream()), "lnrf_ngp_mlp_bwd")
+
+
+# --------------------------------------------------------------------------- rays / images
+def bare_rays(origin, x_axis, y_axis, z, tan_half_x_fov, tan_half_y_fov, width, height, row0, rows, device):
+    device = torch.device(device)
+    ensure_init(device)
+    with torch.cuda.device(device):
+        rays = torch.empty(rows * width, 2, 3, device=device)
+        _check(load().lnrf_bare_rays(_host3(origin), _host3(x_axis), _host3(y_axis), _host3(z),
+                                     tan_half_x_fov, tan_half_y_fov, width, height, row0, rows, _p(rays),
+                                     _stream()), "lnrf_bare_rays")
+    return rays
+
+
+def rgb_to_u8(colors: torch.Tensor) -> torch.Tensor:
+    colors = _f32c(colors.contiguous(), "colors")
+    ensure_init(colors.device)
+    out = torch.empty(colors.shape, dtype=torch.uint8, device=colors.device)
+    _check(load().lnrf_rgb_to_u8(_p(colors), colors.numel(), _p(out), _stream()), "lnrf_rgb_to_u8")
+    return out
 
 
 # --------------------------------------------------------------------------- Ref-NeRF

@@ -215,3 +215,38 @@ class NeRFRenderer:
             return_samples["coarse"] = coarse_ts
             return_samples["fine"] = fine_ts
         return dict(coarse=coarse_out, fine=fine_out, coarse_aux=coarse_aux, fine_aux=fine_aux)
+
+
+# --------------------------------------------------------------------------- rays / images
+def bare_rays(camera_direction, camera_origin, x_axis, y_axis, x_fov, y_fov, width, height):
+    """CameraView.bare_rays, dataset.py:52-78 -> [H*W, 2, 3] fp32, raster order.
+
+    jnp.linspace(-1, 1, num) is restated as start + i * ((stop - start) / (num - 1)) in fp32 with
+    the last point set to stop [recalled]; math.tan(fov / 2) is a Python double that JAX rounds
+    to fp32 when it multiplies the fp32 array."""
+    import math
+    f = np.float32
+
+    def lin(num):
+        if num == 1:
+            return np.array([-1.0], f)
+        step = f(2.0) / f(num - 1)
+        out = (f(-1.0) + np.arange(num, dtype=f) * step).astype(f)
+        out[-1] = f(1.0)
+        return out
+
+    z = np.asarray(camera_direction, f)
+    ys = (f(math.tan(y_fov / 2)) * lin(height))[:, None, None] * np.asarray(y_axis, f)
+    xs = (f(math.tan(x_fov / 2)) * lin(width))[None, :, None] * np.asarray(x_axis, f)
+    directions = ((xs + ys) + z).reshape(-1, 3).astype(f)
+    sq = directions * directions
+    norm = np.sqrt((sq[:, 0] + sq[:, 1]) + sq[:, 2]).astype(f)
+    directions = (directions / norm[:, None]).astype(f)
+    origins = np.tile(np.asarray(camera_origin, f)[None], (height * width, 1))
+    return np.stack([origins, directions], axis=1)
+
+
+def rgb_to_u8(colors):
+    """render_nerf.py:93-96: ((colors + 1) * 127.5).astype(uint8), colours clamped to [-1, 1]."""
+    c = np.clip(np.asarray(colors, np.float32), -1.0, 1.0)
+    return ((c + np.float32(1.0)) * np.float32(127.5)).astype(np.uint8)

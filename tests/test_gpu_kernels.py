@@ -195,3 +195,49 @@ def test_adam_step(nat):
         np.testing.assert_allclose(norms.cpu().numpy(),
                                    [(g.astype(np.float64) ** 2).sum(), (p_before.astype(np.float64) ** 2).sum()],
                                    rtol=1e-5)
+
+
+def _camera():
+    import math
+    return dict(camera_direction=(0.1, -0.2, -0.97), camera_origin=(0.5, 1.0, 4.0), x_axis=(0.99, 0.05, 0.09),
+                y_axis=(0.04, -0.98, 0.2), x_fov=math.radians(60.0), y_fov=math.radians(45.0))
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (7, 5), (128, 128), (801, 333)])
+def test_bare_rays_bit_exact(w, h):
+    """CameraView.bare_rays (dataset.py:52-78) on the device vs the oracle restatement."""
+    from learn_nerf.dataset import CameraView
+    from oracle import render_np
+    cam = _camera()
+    ref = render_np.bare_rays(width=w, height=h, **cam)
+    view = CameraView(**cam)
+    got = view.bare_rays(w, h).cpu().numpy()
+    np.testing.assert_array_equal(got, ref)
+    # a row block equals the corresponding slice (how a view is sharded over GPUs)
+    if h >= 3:
+        part = view.bare_rays(w, h, row0=1, rows=h - 2).cpu().numpy()
+        np.testing.assert_array_equal(part, ref[w:(h - 1) * w])
+
+
+def test_rgb_to_u8_and_render_view():
+    from learn_nerf import _native
+    from learn_nerf.dataset import CameraView
+    from learn_nerf.model import NeRFModel
+    from learn_nerf.render import NeRFRenderer
+    from learn_nerf.scripts.render_nerf import render_view
+    from oracle import render_np
+    rs = np.random.RandomState(0)
+    c = np.concatenate([rs.uniform(-1.2, 1.2, 1000), [-1.0, 1.0, 0.0, -0.0, 0.999999]]).astype(F)
+    np.testing.assert_array_equal(_native.rgb_to_u8(dev(c)).cpu().numpy(), render_np.rgb_to_u8(c))
+    model = NeRFModel(precision="bf16")
+    params = model.init(3, device="cuda")["params"]
+    r = NeRFRenderer(coarse=model, fine=model, coarse_params=params, fine_params=params,
+                     background=torch.tensor([-1.0, -1.0, -1.0], device="cuda"), bbox_min=BBOX_MIN,
+                     bbox_max=BBOX_MAX, coarse_ts=64, fine_ts=128)
+    view = CameraView(camera_direction=(0.0, 0.0, -1.0), camera_origin=(0.0, 0.0, 4.0), x_axis=(1.0, 0.0, 0.0),
+                      y_axis=(0.0, -1.0, 0.0), x_fov=1.0, y_fov=1.0)
+    img = render_view(r, view, 40, 30, batch_size=512, key=1)
+    assert img.shape == (30, 40, 3) and img.dtype == torch.uint8
+    corner = img[0, 0].cpu().numpy()  # fov 1 rad at distance 4: the corner ray misses the unit bbox -> background
+    np.testing.assert_array_equal(corner, [0, 0, 0])
+    assert int(img[15, 20].sum()) > 0
