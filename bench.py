@@ -238,7 +238,24 @@ def run_ours(args):
 
     originals = {nm: getattr(_native, nm) for nm in dom_names}
 
+    if args.workload == "image":  # configs[4] / configs[0]: one W x H view, rows sharded over ranks
+        from learn_nerf.dataset import CameraView
+        from learn_nerf.scripts.render_nerf import render_view
+        import math
+        view = CameraView(camera_direction=(0.0, 0.0, -1.0), camera_origin=(0.0, 0.0, 4.0),
+                          x_axis=(1.0, 0.0, 0.0), y_axis=(0.0, -1.0, 0.0), x_fov=math.radians(60.0),
+                          y_fov=math.radians(60.0))
+        img_renderer = NeRFRenderer(coarse=coarse, fine=fine, coarse_params=loop.state.params["coarse"],
+                                    fine_params=loop.state.params["fine"],
+                                    background=loop.state.params["background"], bbox_min=bbox[0],
+                                    bbox_max=bbox[1], coarse_ts=64, fine_ts=128)
+        n = args.width * args.height // world  # rays per GPU (for the JSON line)
+
     def one_step(i, host=False):
+        if args.workload == "image":
+            img = render_view(img_renderer, view, args.width, args.height, batch_size=args.batch_size,
+                              key=1000 + i, device=dev)
+            return img.cpu() if host else img
         b = host_batch.to(dev, non_blocking=True) if host else batch
         if args.workload == "train":
             logs = step(1000 + i, b)
@@ -304,7 +321,7 @@ def run_ours(args):
     ms, e2e_ms, dom_ms = [float(x) for x in t.tolist()]
 
     if rank == 0:
-        total_rays = n * world
+        total_rays = n * world if args.workload != "image" else args.width * args.height
         value = total_rays / (ms * 1e-3)
         e2e_value = total_rays / (e2e_ms * 1e-3)
         train = args.workload == "train"
@@ -312,6 +329,8 @@ def run_ours(args):
                 "refnerf": "Ref-NeRF (sh_degree 4) coarse+fine"}[args.model]
         cfg_name = {("nerf", True): "configs[1]: ", ("ngp", True): "configs[2]: ", ("refnerf", True): "configs[3]: ",
                     ("nerf", False): "configs[4]-style: "}.get((args.model, train), "")
+        if args.workload == "image":
+            cfg_name = f"configs[4]: {args.width}x{args.height} view in chunks of {args.batch_size} rays, device-side ray generation and uint8 conversion, "
         if args.model in ("nerf", "refnerf"):
             if args.model == "nerf":
                 flop_per_sample = FLOP_TRAIN_PER_SAMPLE if train else FLOP_FWD_PER_SAMPLE
@@ -353,8 +372,8 @@ def run_ours(args):
                                        ", no collective")},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "rays/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": int(host_batch.numel() * 4),
-                    "d2h_bytes_per_step": 16 if train else int(n * 3 * 4)},
+                    "h2d_bytes_per_step": 0 if args.workload == "image" else int(host_batch.numel() * 4),
+                    "d2h_bytes_per_step": 16 if train else (int(n * 3) if args.workload == "image" else int(n * 3 * 4))},
             "gpu_launches": int(launches),
             "roofline": roofline,
         }
@@ -377,7 +396,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="train", choices=["train", "render"])
+    ap.add_argument("--workload", default="train", choices=["train", "render", "image"])
+    ap.add_argument("--width", type=int, default=800)
+    ap.add_argument("--height", type=int, default=800)
+    ap.add_argument("--batch_size", type=int, default=65536, help="rays per render_rays call (image workload)")
     ap.add_argument("--model", default="nerf", choices=["nerf", "ngp", "refnerf"])
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
                     help="NeRF MLP path: bf16 tcgen05 (2e-2) or fp32 FFMA (1e-5)")

@@ -2,11 +2,12 @@
 //   Dense_0: 2L -> 64 relu;  Dense_1: 64 -> 16 (col 0 -> exp -> density);
 //   [d_emb(24) | out(16)] -> Dense_2: 40 -> 64 relu;  Dense_3: 64 -> 64 relu;  Dense_4: 64 -> 3 tanh
 //
-// The five layers are far too small for tiled GEMMs (9,920 MAC per sample), so the forward and
-// the dX chain of the backward are each ONE fused kernel: a thread owns a sample and keeps the
-// 64-wide activations in registers, all weights (40 KB) sit in shared memory and are read as
-// warp-uniform 128-bit broadcasts.  Only what the weight gradients need (layer inputs and
-// per-layer dL/dpre-activation) goes to HBM; dW = act^T g runs on the split-K FFMA GEMM.
+// The five layers are tiny (9,920 MAC per sample), so the forward and the dX chain of the
+// backward are each ONE fused kernel: a block owns a tile of 128 samples, all weights (40 KB)
+// and the current activations sit in shared memory, and every layer is an 8x8 register-tiled
+// FFMA GEMM over that tile (64 FFMA per four 128-bit shared loads).  Only what the weight
+// gradients need (layer inputs and per-layer dL/dpre-activation) goes to HBM; dW = act^T g runs
+// on the 64x64 split-K kernel of sgemm.cuh.
 #include "embed.cuh"
 #include "lnrf_common.cuh"
 #include "lnrf_math.cuh"
@@ -66,38 +67,80 @@ static NgpWs carve_ngp(void* base, int64_t m) {
   return w;
 }
 
-__device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+// ---------------------------------------------------------------- tile GEMM chain
+// A block owns a tile of 128 samples.  Activations live in shared memory feature-major
+// (Xt[k][row], 8-row groups XOR-swizzled by k/8 so that both the 8x8 register-tile loads and the
+// transposed epilogue stores are bank-conflict free); thread (tx, ty) computes rows ty*8..+7 x
+// columns tx*8..+7 of each layer: per k two 128-bit loads of activations + two of weights feed
+// 64 FFMAs.
+constexpr int kTM = 128;  // samples per tile
+__device__ __forceinline__ int xoff(int k, int rowgrp) { return k * kTM + (((rowgrp ^ (k >> 3)) & 15) << 3); }
 
-// acc[0..N) += x * row[0..N)  (row in shared memory, warp-uniform address -> broadcast)
-template <int N>
-__device__ __forceinline__ void axpy_row(float x, const float* __restrict__ row, float (&acc)[N]) {
+template <int NCOLS>  // 64 or 16: threads with tx*8 >= NCOLS idle
+__device__ __forceinline__ void tile_gemm(const float* __restrict__ Xt, int K, const float* __restrict__ W, int ldw,
+                                          float (&acc)[8][8], int tx, int ty) {
 #pragma unroll
-  for (int j = 0; j < N; j += 4) {
-    const float4 w = lds4(row + j);
-    acc[j] = fmaf(x, w.x, acc[j]);
-    acc[j + 1] = fmaf(x, w.y, acc[j + 1]);
-    acc[j + 2] = fmaf(x, w.z, acc[j + 2]);
-    acc[j + 3] = fmaf(x, w.w, acc[j + 3]);
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+  if (tx * 8 >= NCOLS) return;
+#pragma unroll 4
+  for (int k = 0; k < K; ++k) {
+    const float* ap = Xt + xoff(k, ty);
+    const float4 a0 = *reinterpret_cast<const float4*>(ap), a1 = *reinterpret_cast<const float4*>(ap + 4);
+    const float* wp = W + k * ldw + tx * 8;
+    const float4 w0 = *reinterpret_cast<const float4*>(wp), w1 = *reinterpret_cast<const float4*>(wp + 4);
+    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
   }
 }
-// sum_j row[j] * g[j]
-template <int N>
-__device__ __forceinline__ float dot_row(const float* __restrict__ row, const float (&g)[N]) {
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+// registers (8 rows x 8 cols) -> feature-major smem at feature offset k0
+__device__ __forceinline__ void tile_store_smem(float* __restrict__ Yt, int k0, const float (&v)[8][8], int tx, int ty) {
 #pragma unroll
-  for (int j = 0; j < N; j += 4) {
-    const float4 w = lds4(row + j);
-    a0 = fmaf(w.x, g[j], a0);
-    a1 = fmaf(w.y, g[j + 1], a1);
-    a2 = fmaf(w.z, g[j + 2], a2);
-    a3 = fmaf(w.w, g[j + 3], a3);
+  for (int j = 0; j < 8; ++j) {
+    float* p = Yt + xoff(k0 + tx * 8 + j, ty);
+    *reinterpret_cast<float4*>(p) = make_float4(v[0][j], v[1][j], v[2][j], v[3][j]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4][j], v[5][j], v[6][j], v[7][j]);
   }
-  return (a0 + a1) + (a2 + a3);
 }
-template <int N>
-__device__ __forceinline__ void store_row(float* __restrict__ dst, const float (&v)[N]) {
+// registers -> row-major global [m, ld] at column offset c0 (each warp store covers 4 rows x 256 B)
+__device__ __forceinline__ void tile_store_global(float* __restrict__ dst, int ld, int c0, int64_t row0, int64_t m,
+                                                  const float (&v)[8][8], int tx, int ty, int ncols) {
+  if (tx * 8 >= ncols) return;
 #pragma unroll
-  for (int j = 0; j < N; j += 4) reinterpret_cast<float4*>(dst)[j >> 2] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  for (int i = 0; i < 8; ++i) {
+    const int64_t r = row0 + ty * 8 + i;
+    if (r >= m) continue;
+    float* p = dst + r * ld + c0 + tx * 8;
+    if (tx * 8 + 8 <= ncols) {
+      *reinterpret_cast<float4*>(p) = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
+      *reinterpret_cast<float4*>(p + 4) = make_float4(v[i][4], v[i][5], v[i][6], v[i][7]);
+    } else {  // ragged last column group (E = 12: columns 8..11)
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (tx * 8 + j < ncols) p[j] = v[i][j];
+    }
+  }
+}
+// v *= [h > 0] with h row-major in global [m, 64]
+__device__ __forceinline__ void tile_mask(const float* __restrict__ h, int64_t row0, int64_t m, float (&v)[8][8],
+                                          int tx, int ty) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t r = row0 + ty * 8 + i;
+    float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0;
+    if (r < m) {
+      h0 = __ldg(reinterpret_cast<const float4*>(h + r * kNgpHidden + tx * 8));
+      h1 = __ldg(reinterpret_cast<const float4*>(h + r * kNgpHidden + tx * 8) + 1);
+    }
+    const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[i][j] = hv[j] > 0.0f ? v[i][j] : 0.0f;
+  }
 }
 
 struct NgpFwdArgs {
@@ -114,89 +157,126 @@ struct NgpFwdArgs {
   float* rgb;
 };
 
+constexpr int kNgpXFloats = kNgpHidden * kTM;  // one feature-major activation buffer
+
 template <bool SAVE>
 __global__ void __launch_bounds__(kNgpThreads)
 ngp_mlp_fwd_kernel(const __grid_constant__ NgpFwdArgs a) {
-  extern __shared__ __align__(16) float sw[];
+  extern __shared__ __align__(16) float sm[];
+  float* sw = sm;                                   // all parameters, reference layout ([in][out])
+  float* Xa = sm + align_up(a.nl.total, 4);
+  float* Xb = Xa + kNgpXFloats;
   for (int i = threadIdx.x; i < int(a.nl.total); i += kNgpThreads) sw[i] = __ldg(a.P + i);
-  __syncthreads();
   const float* W0 = sw + a.nl.w[0]; const float* B0 = sw + a.nl.b[0];
   const float* W1 = sw + a.nl.w[1]; const float* B1 = sw + a.nl.b[1];
   const float* W2 = sw + a.nl.w[2]; const float* B2 = sw + a.nl.b[2];
   const float* W3 = sw + a.nl.w[3]; const float* B3 = sw + a.nl.b[3];
   const float* W4 = sw + a.nl.w[4]; const float* B4 = sw + a.nl.b[4];
-  for (int64_t s = int64_t(blockIdx.x) * kNgpThreads + threadIdx.x; s < a.m; s += int64_t(gridDim.x) * kNgpThreads) {
-    // ---- Dense_0 (2L -> 64) + relu                                         instant_ngp.py:46-47
-    float h[kNgpHidden];
-#pragma unroll
-    for (int j = 0; j < kNgpHidden; ++j) h[j] = B0[j];
-    const float4* erow = reinterpret_cast<const float4*>(a.enc + s * a.E);
-    for (int i4 = 0; i4 < a.E / 4; ++i4) {
-      const float4 x = __ldg(erow + i4);
-      axpy_row<kNgpHidden>(x.x, W0 + (i4 * 4 + 0) * kNgpHidden, h);
-      axpy_row<kNgpHidden>(x.y, W0 + (i4 * 4 + 1) * kNgpHidden, h);
-      axpy_row<kNgpHidden>(x.z, W0 + (i4 * 4 + 2) * kNgpHidden, h);
-      axpy_row<kNgpHidden>(x.w, W0 + (i4 * 4 + 3) * kNgpHidden, h);
-    }
-#pragma unroll
-    for (int j = 0; j < kNgpHidden; ++j) h[j] = fmaxf(h[j], 0.0f);
-    if (SAVE) store_row<kNgpHidden>(a.ws.h0 + s * kNgpHidden, h);
-    // ---- Dense_1 (64 -> 16); density = exp(out[0])                         :48-49
-    float in2[kNgpIn2];
+  const int t = threadIdx.x, tx = t & 7, ty = t >> 3;
+  const int64_t tiles = ceil_div(a.m, kTM);
+  float acc[8][8];
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int64_t row0 = tile * kTM;
+    const int64_t s = row0 + t;  // the sample this thread owns in the per-sample phases
+    const bool valid = s < a.m;
+    __syncthreads();  // previous tile's readers of Xa / Xb are done (also covers the weight load)
+    // ---- inputs: encoding -> Xa[k < E]; d_emb = sinusoidal_emb(d, 4) (:37) -> registers
     {
-      float o[kNgpDensity];
-#pragma unroll
-      for (int j = 0; j < kNgpDensity; ++j) o[j] = B1[j];
-#pragma unroll
-      for (int i = 0; i < kNgpHidden; ++i) axpy_row<kNgpDensity>(h[i], W1 + i * kNgpDensity, o);
-      a.dens[s] = expf(o[0]);
-#pragma unroll
-      for (int j = 0; j < kNgpDensity; ++j) in2[kNgpDE + j] = o[j];
+      const int rg = t >> 3, rl = t & 7;
+      for (int k4 = 0; k4 < a.E / 4; ++k4) {
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) x = __ldg(reinterpret_cast<const float4*>(a.enc + s * a.E) + k4);
+        Xa[xoff(k4 * 4 + 0, rg) + rl] = x.x;
+        Xa[xoff(k4 * 4 + 1, rg) + rl] = x.y;
+        Xa[xoff(k4 * 4 + 2, rg) + rl] = x.z;
+        Xa[xoff(k4 * 4 + 3, rg) + rl] = x.w;
+      }
     }
-    // ---- d_emb = sinusoidal_emb(d, 4)                                      :37
+    float de[kNgpDE];
     {
-      float dv[3];
+      float dv[3] = {0.f, 0.f, 0.f};
+      if (valid) {
 #pragma unroll
-      for (int k = 0; k < 3; ++k) dv[k] = a.d ? __ldg(a.d + s * 3 + k) : __ldg(a.rays + (s / a.T) * 6 + 3 + k);
+        for (int k = 0; k < 3; ++k) dv[k] = a.d ? __ldg(a.d + s * 3 + k) : __ldg(a.rays + (s / a.T) * 6 + 3 + k);
+      }
 #pragma unroll
       for (int dim = 0; dim < 3; ++dim)
 #pragma unroll
-        for (int f = 0; f < 4; ++f) {
-          float sn, cs;
-          sincosf(dv[dim] * float(1 << f), &sn, &cs);
-          in2[dim * 8 + f] = sn;
-          in2[dim * 8 + 4 + f] = cs;
+        for (int f = 0; f < 4; ++f) sincosf(dv[dim] * float(1 << f), &de[dim * 8 + f], &de[dim * 8 + 4 + f]);
+    }
+    __syncthreads();
+    // ---- Dense_0 (2L -> 64) + relu -> Xb                                   instant_ngp.py:46-47
+    tile_gemm<64>(Xa, a.E, W0, kNgpHidden, acc, tx, ty);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = fmaxf(acc[i][j] + B0[tx * 8 + j], 0.0f);
+    tile_store_smem(Xb, 0, acc, tx, ty);
+    if (SAVE) tile_store_global(a.ws.h0, kNgpHidden, 0, row0, a.m, acc, tx, ty, kNgpHidden);
+    __syncthreads();
+    // ---- Dense_1 (64 -> 16) -> Xa[24..39]; d_emb -> Xa[0..23]; density = exp(out[0])   :48-50
+    tile_gemm<16>(Xb, kNgpHidden, W1, kNgpDensity, acc, tx, ty);
+    if (tx < 2) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] += B1[tx * 8 + j];
+      tile_store_smem(Xa, kNgpDE, acc, tx, ty);
+      if (SAVE) tile_store_global(a.ws.in2, kNgpIn2, kNgpDE, row0, a.m, acc, tx, ty, kNgpDensity);
+      if (tx == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int64_t r = row0 + ty * 8 + i;
+          if (r < a.m) a.dens[r] = expf(acc[i][0]);
         }
+      }
     }
-    if (SAVE) store_row<kNgpIn2>(a.ws.in2 + s * kNgpIn2, in2);
-    // ---- Dense_2 (40 -> 64) + relu                                         :50-52
+    {
+      const int rg = t >> 3, rl = t & 7;
 #pragma unroll
-    for (int j = 0; j < kNgpHidden; ++j) h[j] = B2[j];
+      for (int k = 0; k < kNgpDE; ++k) Xa[xoff(k, rg) + rl] = de[k];
+      if (SAVE && valid) {
+        float4* dst = reinterpret_cast<float4*>(a.ws.in2 + s * kNgpIn2);
 #pragma unroll
-    for (int i = 0; i < kNgpIn2; ++i) axpy_row<kNgpHidden>(in2[i], W2 + i * kNgpHidden, h);
-#pragma unroll
-    for (int j = 0; j < kNgpHidden; ++j) h[j] = fmaxf(h[j], 0.0f);
-    if (SAVE) store_row<kNgpHidden>(a.ws.h2 + s * kNgpHidden, h);
-    // ---- Dense_3 (64 -> 64) + relu
-    float h3[kNgpHidden];
-#pragma unroll
-    for (int j = 0; j < kNgpHidden; ++j) h3[j] = B3[j];
-#pragma unroll
-    for (int i = 0; i < kNgpHidden; ++i) axpy_row<kNgpHidden>(h[i], W3 + i * kNgpHidden, h3);
-#pragma unroll
-    for (int j = 0; j < kNgpHidden; ++j) h3[j] = fmaxf(h3[j], 0.0f);
-    if (SAVE) store_row<kNgpHidden>(a.ws.h3 + s * kNgpHidden, h3);
-    // ---- Dense_4 (64 -> 3) + tanh                                          :53
-    float o0 = B4[0], o1 = B4[1], o2 = B4[2];
-#pragma unroll
-    for (int i = 0; i < kNgpHidden; ++i) {
-      o0 = fmaf(h3[i], W4[i * 3 + 0], o0);
-      o1 = fmaf(h3[i], W4[i * 3 + 1], o1);
-      o2 = fmaf(h3[i], W4[i * 3 + 2], o2);
+        for (int k4 = 0; k4 < kNgpDE / 4; ++k4) dst[k4] = make_float4(de[k4 * 4], de[k4 * 4 + 1], de[k4 * 4 + 2], de[k4 * 4 + 3]);
+      }
     }
-    a.rgb[s * 3 + 0] = tanhf(o0);
-    a.rgb[s * 3 + 1] = tanhf(o1);
-    a.rgb[s * 3 + 2] = tanhf(o2);
+    __syncthreads();
+    // ---- Dense_2 (40 -> 64) + relu -> Xb                                   :51-52
+    tile_gemm<64>(Xa, kNgpIn2, W2, kNgpHidden, acc, tx, ty);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = fmaxf(acc[i][j] + B2[tx * 8 + j], 0.0f);
+    tile_store_smem(Xb, 0, acc, tx, ty);  // readers of Xb (Dense_1) finished before the last barrier
+    if (SAVE) tile_store_global(a.ws.h2, kNgpHidden, 0, row0, a.m, acc, tx, ty, kNgpHidden);
+    __syncthreads();
+    // ---- Dense_3 (64 -> 64) + relu -> Xa
+    tile_gemm<64>(Xb, kNgpHidden, W3, kNgpHidden, acc, tx, ty);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = fmaxf(acc[i][j] + B3[tx * 8 + j], 0.0f);
+    tile_store_smem(Xa, 0, acc, tx, ty);  // readers of Xa (Dense_2) finished before the last barrier
+    if (SAVE) tile_store_global(a.ws.h3, kNgpHidden, 0, row0, a.m, acc, tx, ty, kNgpHidden);
+    __syncthreads();
+    // ---- Dense_4 (64 -> 3) + tanh: thread per sample                        :53
+    {
+      const int rg = t >> 3, rl = t & 7;
+      float o0 = B4[0], o1 = B4[1], o2 = B4[2];
+#pragma unroll 8
+      for (int k = 0; k < kNgpHidden; ++k) {
+        const float h = Xa[xoff(k, rg) + rl];
+        o0 = fmaf(h, W4[k * 3 + 0], o0);
+        o1 = fmaf(h, W4[k * 3 + 1], o1);
+        o2 = fmaf(h, W4[k * 3 + 2], o2);
+      }
+      if (valid) {
+        a.rgb[s * 3 + 0] = tanhf(o0);
+        a.rgb[s * 3 + 1] = tanhf(o1);
+        a.rgb[s * 3 + 2] = tanhf(o2);
+      }
+    }
   }
 }
 
@@ -213,90 +293,131 @@ struct NgpBwdArgs {
   float* d_enc;
 };
 
+// transposed weights in shared memory for the dX chain: Wt[j][i] = W[i][j]
+struct NgpBwdSmem {
+  int wt4, wt3, wt2o, wt1, wt0, x, total;  // float offsets
+  int epad;
+};
+__host__ __device__ inline NgpBwdSmem ngp_bwd_smem(int E) {
+  NgpBwdSmem s{};
+  s.epad = (E + 7) / 8 * 8;
+  int off = 0;
+  s.wt4 = off; off += 4 * kNgpHidden;              // [4 (3 used)][64]
+  s.wt3 = off; off += kNgpHidden * kNgpHidden;     // [64][64]
+  s.wt2o = off; off += kNgpHidden * kNgpDensity;   // [64][16]  (rows 24..39 of Dense_2)
+  s.wt1 = off; off += kNgpDensity * kNgpHidden;    // [16][64]
+  s.wt0 = off; off += kNgpHidden * s.epad;         // [64][epad]
+  s.x = off; off += 2 * kNgpXFloats;
+  s.total = off;
+  return s;
+}
+
 // dX chain: g3, g2, g_out1, g0 (written for the dW GEMMs) and d_enc.
 __global__ void __launch_bounds__(kNgpThreads)
 ngp_mlp_bwd_kernel(const __grid_constant__ NgpBwdArgs a) {
-  extern __shared__ __align__(16) float sw[];
-  for (int i = threadIdx.x; i < int(a.nl.total); i += kNgpThreads) sw[i] = __ldg(a.P + i);
-  __syncthreads();
-  const float* W0 = sw + a.nl.w[0];
-  const float* W1 = sw + a.nl.w[1];
-  const float* W2 = sw + a.nl.w[2];
-  const float* W3 = sw + a.nl.w[3];
-  const float* W4 = sw + a.nl.w[4];
-  for (int64_t s = int64_t(blockIdx.x) * kNgpThreads + threadIdx.x; s < a.m; s += int64_t(gridDim.x) * kNgpThreads) {
-    float dp[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const float y = __ldg(a.rgb + s * 3 + j);
-      dp[j] = __ldg(a.d_rgb + s * 3 + j) * (1.0f - y * y);  // tanh'
-    }
-    // g3 = (dp @ W4^T) * [h3 > 0]
-    float g3[kNgpHidden];
+  extern __shared__ __align__(16) float sm[];
+  const NgpBwdSmem L = ngp_bwd_smem(a.E);
+  float* Wt4 = sm + L.wt4; float* Wt3 = sm + L.wt3; float* Wt2o = sm + L.wt2o;
+  float* Wt1 = sm + L.wt1; float* Wt0 = sm + L.wt0;
+  float* Xa = sm + L.x;
+  float* Xb = Xa + kNgpXFloats;
+  const float* P = a.P;
+  for (int i = threadIdx.x; i < 4 * kNgpHidden; i += kNgpThreads) {  // Wt4[j][i] = W4[i][j]
+    const int j = i / kNgpHidden, ii = i % kNgpHidden;
+    Wt4[i] = j < 3 ? __ldg(P + a.nl.w[4] + ii * 3 + j) : 0.0f;
+  }
+  for (int i = threadIdx.x; i < kNgpHidden * kNgpHidden; i += kNgpThreads) {  // Wt3[j][i] = W3[i][j]
+    const int j = i / kNgpHidden, ii = i % kNgpHidden;
+    Wt3[i] = __ldg(P + a.nl.w[3] + ii * kNgpHidden + j);
+  }
+  for (int i = threadIdx.x; i < kNgpHidden * kNgpDensity; i += kNgpThreads) {  // Wt2o[j][i] = W2[24 + i][j]
+    const int j = i / kNgpDensity, ii = i % kNgpDensity;
+    Wt2o[i] = __ldg(P + a.nl.w[2] + (kNgpDE + ii) * kNgpHidden + j);
+  }
+  for (int i = threadIdx.x; i < kNgpDensity * kNgpHidden; i += kNgpThreads) {  // Wt1[j][i] = W1[i][j]
+    const int j = i / kNgpHidden, ii = i % kNgpHidden;
+    Wt1[i] = __ldg(P + a.nl.w[1] + ii * kNgpDensity + j);
+  }
+  for (int i = threadIdx.x; i < kNgpHidden * L.epad; i += kNgpThreads) {  // Wt0[j][i] = W0[i][j], zero padded
+    const int j = i / L.epad, ii = i % L.epad;
+    Wt0[i] = ii < a.E ? __ldg(P + a.nl.w[0] + ii * kNgpHidden + j) : 0.0f;
+  }
+  const int t = threadIdx.x, tx = t & 7, ty = t >> 3;
+  const int rg = t >> 3, rl = t & 7;
+  const int64_t tiles = ceil_div(a.m, kTM);
+  float acc[8][8];
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int64_t row0 = tile * kTM;
+    const int64_t s = row0 + t;
+    const bool valid = s < a.m;
+    __syncthreads();
+    // ---- dp = d_rgb * tanh' -> Xa[0..3]
     {
-      const float4* hrow = reinterpret_cast<const float4*>(a.ws.h3 + s * kNgpHidden);
+      float dp[4] = {0.f, 0.f, 0.f, 0.f};
+      if (valid) {
 #pragma unroll
-      for (int i4 = 0; i4 < kNgpHidden / 4; ++i4) {
-        const float4 hv = __ldg(hrow + i4);
-        const float hh[4] = {hv.x, hv.y, hv.z, hv.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int i = i4 * 4 + k;
-          const float t = dp[0] * W4[i * 3 + 0] + dp[1] * W4[i * 3 + 1] + dp[2] * W4[i * 3 + 2];
-          g3[i] = hh[k] > 0.0f ? t : 0.0f;
+        for (int j = 0; j < 3; ++j) {
+          const float y = __ldg(a.rgb + s * 3 + j);
+          dp[j] = __ldg(a.d_rgb + s * 3 + j) * (1.0f - y * y);
         }
       }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) Xa[xoff(j, rg) + rl] = dp[j];
     }
-    store_row<kNgpHidden>(a.ws.g3 + s * kNgpHidden, g3);
-    // g2 = (g3 @ W3^T) * [h2 > 0]
-    float g2[kNgpHidden];
-    {
-      const float4* hrow = reinterpret_cast<const float4*>(a.ws.h2 + s * kNgpHidden);
+    __syncthreads();
+    // ---- g3 = (dp @ W4^T) * [h3 > 0] -> Xb, global
+    tile_gemm<64>(Xa, 4, Wt4, kNgpHidden, acc, tx, ty);
+    tile_mask(a.ws.h3, row0, a.m, acc, tx, ty);
+    tile_store_smem(Xb, 0, acc, tx, ty);
+    tile_store_global(a.ws.g3, kNgpHidden, 0, row0, a.m, acc, tx, ty, kNgpHidden);
+    __syncthreads();
+    // ---- g2 = (g3 @ W3^T) * [h2 > 0] -> Xa, global
+    tile_gemm<64>(Xb, kNgpHidden, Wt3, kNgpHidden, acc, tx, ty);
+    tile_mask(a.ws.h2, row0, a.m, acc, tx, ty);
+    tile_store_smem(Xa, 0, acc, tx, ty);
+    tile_store_global(a.ws.g2, kNgpHidden, 0, row0, a.m, acc, tx, ty, kNgpHidden);
+    __syncthreads();
+    // ---- g_out1 = g2 @ W2[24:40]^T, + d_dens * density on column 0 -> Xb[0..15], global
+    tile_gemm<16>(Xa, kNgpHidden, Wt2o, kNgpDensity, acc, tx, ty);
+    if (tx < 2) {
+      if (tx == 0) {
 #pragma unroll
-      for (int i4 = 0; i4 < kNgpHidden / 4; ++i4) {
-        const float4 hv = __ldg(hrow + i4);
-        const float hh[4] = {hv.x, hv.y, hv.z, hv.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int i = i4 * 4 + k;
-          const float t = dot_row<kNgpHidden>(W3 + i * kNgpHidden, g3);
-          g2[i] = hh[k] > 0.0f ? t : 0.0f;
+        for (int i = 0; i < 8; ++i) {
+          const int64_t r = row0 + ty * 8 + i;
+          if (r < a.m) acc[i][0] += __ldg(a.d_dens + r) * __ldg(a.dens + r);
         }
       }
+      tile_store_smem(Xb, 0, acc, tx, ty);
+      tile_store_global(a.ws.go1, kNgpDensity, 0, row0, a.m, acc, tx, ty, kNgpDensity);
     }
-    store_row<kNgpHidden>(a.ws.g2 + s * kNgpHidden, g2);
-    // g_out1 = g2 @ W2[24:40]^T, plus dL/d out[0] += d_dens * density  (density = exp(out[0]))
-    float go1[kNgpDensity];
+    __syncthreads();
+    // ---- g0 = (g_out1 @ W1^T) * [h0 > 0] -> Xa, global
+    tile_gemm<64>(Xb, kNgpDensity, Wt1, kNgpHidden, acc, tx, ty);
+    tile_mask(a.ws.h0, row0, a.m, acc, tx, ty);
+    tile_store_smem(Xa, 0, acc, tx, ty);
+    tile_store_global(a.ws.g0, kNgpHidden, 0, row0, a.m, acc, tx, ty, kNgpHidden);
+    __syncthreads();
+    // ---- d_enc = g0 @ W0^T -> global [m, E]
+    if (tx * 8 < L.epad) {
+      // epad <= 32: the first epad/8 column groups are active
 #pragma unroll
-    for (int i = 0; i < kNgpDensity; ++i) go1[i] = dot_row<kNgpHidden>(W2 + (kNgpDE + i) * kNgpHidden, g2);
-    go1[0] += __ldg(a.d_dens + s) * __ldg(a.dens + s);
-    store_row<kNgpDensity>(a.ws.go1 + s * kNgpDensity, go1);
-    // g0 = (g_out1 @ W1^T) * [h0 > 0]
-    float g0[kNgpHidden];
-    {
-      const float4* hrow = reinterpret_cast<const float4*>(a.ws.h0 + s * kNgpHidden);
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int i4 = 0; i4 < kNgpHidden / 4; ++i4) {
-        const float4 hv = __ldg(hrow + i4);
-        const float hh[4] = {hv.x, hv.y, hv.z, hv.w};
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+#pragma unroll 4
+      for (int k = 0; k < kNgpHidden; ++k) {
+        const float* ap = Xa + xoff(k, ty);
+        const float4 a0 = *reinterpret_cast<const float4*>(ap), a1 = *reinterpret_cast<const float4*>(ap + 4);
+        const float* wp = Wt0 + k * L.epad + tx * 8;
+        const float4 w0 = *reinterpret_cast<const float4*>(wp), w1 = *reinterpret_cast<const float4*>(wp + 4);
+        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int i = i4 * 4 + k;
-          const float t = dot_row<kNgpDensity>(W1 + i * kNgpDensity, go1);
-          g0[i] = hh[k] > 0.0f ? t : 0.0f;
-        }
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
       }
-    }
-    store_row<kNgpHidden>(a.ws.g0 + s * kNgpHidden, g0);
-    // d_enc = g0 @ W0^T
-    float4* drow = reinterpret_cast<float4*>(a.d_enc + s * a.E);
-    for (int i4 = 0; i4 < a.E / 4; ++i4) {
-      float4 o;
-      o.x = dot_row<kNgpHidden>(W0 + (i4 * 4 + 0) * kNgpHidden, g0);
-      o.y = dot_row<kNgpHidden>(W0 + (i4 * 4 + 1) * kNgpHidden, g0);
-      o.z = dot_row<kNgpHidden>(W0 + (i4 * 4 + 2) * kNgpHidden, g0);
-      o.w = dot_row<kNgpHidden>(W0 + (i4 * 4 + 3) * kNgpHidden, g0);
-      drow[i4] = o;
+      tile_store_global(a.d_enc, a.E, 0, row0, a.m, acc, tx, ty, a.E);
     }
   }
 }
@@ -343,10 +464,11 @@ ngp_dw4_kernel(const float* __restrict__ h3, const float* __restrict__ rgb, cons
 }
 
 static int ngp_grid(int64_t m) {
-  int64_t blocks = ceil_div(m, kNgpThreads);
-  const int64_t cap = int64_t(sm_count()) * 3;
+  int64_t blocks = ceil_div(m, kTM);
+  const int64_t cap = int64_t(sm_count()) * 2;  // two ~100 KB blocks per SM, persistent over tiles
   return int(blocks < cap ? blocks : cap);
 }
+static size_t ngp_fwd_smem(const NgpLayout& nl) { return size_t(align_up(nl.total, 4) + 2 * kNgpXFloats) * sizeof(float); }
 
 }  // namespace lnrf
 
@@ -392,12 +514,12 @@ int lnrf_ngp_mlp_fwd(const float* params, int32_t L, const float* enc, const flo
   }
   const NgpLayout nl = ngp_layout(L);
   NgpFwdArgs a{params, nl, 2 * L, enc, d, rays, T, m, w, dens, rgb};
-  const size_t smem = size_t(nl.total) * sizeof(float);
+  const size_t smem = ngp_fwd_smem(nl);
   static bool configured = false;
   if (!configured) {
-    LNRF_CUDA(cudaFuncSetAttribute(ngp_mlp_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    LNRF_CUDA(cudaFuncSetAttribute(ngp_mlp_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    LNRF_CUDA(cudaFuncSetAttribute(ngp_mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    LNRF_CUDA(cudaFuncSetAttribute(ngp_mlp_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    LNRF_CUDA(cudaFuncSetAttribute(ngp_mlp_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    LNRF_CUDA(cudaFuncSetAttribute(ngp_mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     configured = true;
   }
   if (save) ngp_mlp_fwd_kernel<true><<<ngp_grid(m), kNgpThreads, smem, as_stream(stream)>>>(a);
@@ -422,7 +544,7 @@ int lnrf_ngp_mlp_bwd(const float* params, int32_t L, const float* enc, int64_t m
   cudaStream_t st = as_stream(stream);
   float* G = d_params;
   NgpBwdArgs a{params, nl, 2 * L, m, w, dens, rgb, d_dens, d_rgb, d_enc};
-  ngp_mlp_bwd_kernel<<<ngp_grid(m), kNgpThreads, size_t(nl.total) * sizeof(float), st>>>(a);
+  ngp_mlp_bwd_kernel<<<ngp_grid(m), kNgpThreads, size_t(ngp_bwd_smem(2 * L).total) * sizeof(float), st>>>(a);
   LNRF_LAUNCH_CHECK("ngp_mlp_bwd_kernel");
   // weight / bias gradients: dW_l = input_l^T g_l (split-K FFMA GEMM), db_l = column sums
   int rc;
