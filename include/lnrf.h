@@ -218,6 +218,10 @@ int lnrf_bare_rays(const float* origin_host, const float* x_axis_host, const flo
 /* ((colors + 1) * 127.5).astype(uint8) (render_nerf.py:93-96); colors are clamped to [-1, 1].   */
 int lnrf_rgb_to_u8(const float* colors, int64_t count, uint8_t* out, lnrf_stream_t stream);
 
+/* jax.random.uniform(key, [n]) in fp32 (render.py:142): Threefry-2x32 over iota(n) as JAX's
+ * non-partitionable threefry does, 23 mantissa bits; key = the two uint32 words of the key.  */
+int lnrf_threefry_uniform(uint32_t key0, uint32_t key1, int64_t n, float* out, lnrf_stream_t stream);
+
 /* ---------------------------------------------------------------- diagnostics
  * Single 128xNxK bf16 GEMM tile on tcgen05 (A[128,K], B[N,K] both K-major,
  * D fp32 [128,N]) used by tests to pin the UMMA descriptor encodings.         */

@@ -58,6 +58,7 @@ _SIGS = {
     "lnrf_bare_rays": (c_int32, [c_void_p] * 4 + [c_float, c_float, c_int32, c_int32, c_int32, c_int32, c_void_p,
                                                    c_void_p]),
     "lnrf_rgb_to_u8": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "lnrf_threefry_uniform": (c_int32, [ctypes.c_uint32, ctypes.c_uint32, c_int64, c_void_p, c_void_p]),
     "lnrf_refnerf_param_count": (c_int64, []),
     "lnrf_refnerf_param_floats": (c_int64, []),
     "lnrf_refnerf_param_offsets": (c_int32, [c_void_p]),
@@ -368,6 +369,16 @@ def bare_rays(origin, x_axis, y_axis, z, tan_half_x_fov, tan_half_y_fov, width, 
                                      tan_half_x_fov, tan_half_y_fov, width, height, row0, rows, _p(rays),
                                      _stream()), "lnrf_bare_rays")
     return rays
+
+
+def threefry_uniform(key0: int, key1: int, shape, device) -> torch.Tensor:
+    device = torch.device(device)
+    ensure_init(device)
+    with torch.cuda.device(device):
+        out = torch.empty(tuple(shape), device=device)
+        _check(load().lnrf_threefry_uniform(key0, key1, out.numel(), _p(out), _stream()),
+               "lnrf_threefry_uniform")
+    return out
 
 
 def rgb_to_u8(colors: torch.Tensor) -> torch.Tensor:

@@ -1,28 +1,67 @@
-"""Counter-style PRNG keys standing in for jax.random keys.
+"""jax.random-style keys for the host mirror (render.py:55,142; train.py:137).
 
-The reference threads ``jax.random`` keys through render_rays/step_fn
-(render.py:55,142; train.py:137).  JAX's threefry2x32 stream is not reproduced
-(needs a real JAX to validate), so a key -> uniforms mapping here
-is deterministic but NOT bit-identical to JAX's.  Parity with the oracle is always
-established through the explicit-uniforms entry points instead.
-
-``uniform`` matches jax.random.uniform's fp32 construction: 23 random mantissa bits,
-i.e. multiples of 2^-23 in [0, 1).
+``PRNGKey``, ``split``, ``fold_in`` and ``uniform`` follow JAX's (non-partitionable)
+Threefry-2x32 construction, so an integer seed produces the uniforms JAX would produce --
+as far as that can be established without JAX: the construction is [recalled] and pinned by the
+Random123 known-answer vectors and JAX's documented ``split(PRNGKey(0))`` / ``uniform(PRNGKey(0))``
+values (tests/test_oracle.py).  Key bookkeeping runs on the host in Python integers (a handful of
+32-bit operations per split); the uniforms themselves are generated on the device
+(lnrf_threefry_uniform).  Parity tests keep using explicit uniforms.
 """
 from dataclasses import dataclass
 from typing import Tuple, Union
 
 import torch
 
-_MASK = (1 << 63) - 1
+_M32 = 0xFFFFFFFF
+_ROT = ((13, 15, 26, 6), (17, 29, 16, 24))
+
+
+def _threefry_pair(k0: int, k1: int, x0: int, x1: int) -> Tuple[int, int]:
+    ks = (k0, k1, k0 ^ k1 ^ 0x1BD11BDA)
+    x0 = (x0 + ks[0]) & _M32
+    x1 = (x1 + ks[1]) & _M32
+    for i in range(5):
+        for r in _ROT[i % 2]:
+            x0 = (x0 + x1) & _M32
+            x1 = ((x1 << r) | (x1 >> (32 - r))) & _M32
+            x1 ^= x0
+        x0 = (x0 + ks[(i + 1) % 3]) & _M32
+        x1 = (x1 + ks[(i + 2) % 3] + i + 1) & _M32
+    return x0, x1
+
+
+def _threefry_2x32(k0: int, k1: int, counts):
+    counts = list(counts)
+    n = len(counts)
+    if n % 2:
+        counts.append(0)
+    half = len(counts) // 2
+    a, b = [], []
+    for j in range(half):
+        y0, y1 = _threefry_pair(k0, k1, counts[j], counts[half + j])
+        a.append(y0)
+        b.append(y1)
+    return (a + b)[:n]
 
 
 @dataclass(frozen=True)
 class PRNGKey:
-    seed: int
+    """``PRNGKey(seed)`` as jax.random.PRNGKey: words (seed >> 32, seed & 0xFFFFFFFF)."""
+
+    k0: int
+    k1: int = None
 
     def __post_init__(self):
-        object.__setattr__(self, "seed", int(self.seed) & _MASK)
+        if self.k1 is None:  # constructed from a seed
+            seed = int(self.k0)
+            object.__setattr__(self, "k0", (seed >> 32) & _M32)
+            object.__setattr__(self, "k1", seed & _M32)
+
+    @property
+    def seed(self) -> int:
+        """One integer identifying the key (used to seed torch generators for weight init)."""
+        return ((self.k0 << 32) | self.k1) & ((1 << 63) - 1)
 
 
 KeyLike = Union[PRNGKey, int]
@@ -32,21 +71,20 @@ def _as_key(key: KeyLike) -> PRNGKey:
     return key if isinstance(key, PRNGKey) else PRNGKey(int(key))
 
 
-def _mix(x: int) -> int:  # splitmix64 finaliser
-    x = (x + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
-    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
-    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
-    return x ^ (x >> 31)
-
-
 def split(key: KeyLike, num: int = 2) -> Tuple[PRNGKey, ...]:
     k = _as_key(key)
-    return tuple(PRNGKey(_mix(k.seed * 0x100000001B3 + i + 1)) for i in range(num))
+    bits = _threefry_2x32(k.k0, k.k1, range(2 * num))
+    return tuple(PRNGKey(bits[2 * i], bits[2 * i + 1]) for i in range(num))
+
+
+def fold_in(key: KeyLike, data: int) -> PRNGKey:
+    k = _as_key(key)
+    y = _threefry_2x32(k.k0, k.k1, [0, int(data) & _M32])
+    return PRNGKey(y[0], y[1])
 
 
 def uniform(key: KeyLike, shape, device) -> torch.Tensor:
-    """fp32 uniforms k * 2^-23, k in [0, 2^23), generated on `device`."""
-    gen = torch.Generator(device=device)
-    gen.manual_seed(_as_key(key).seed)
-    bits = torch.randint(0, 1 << 23, tuple(shape), generator=gen, device=device, dtype=torch.int32)
-    return bits.to(torch.float32) * (2.0 ** -23)
+    """fp32 uniforms in [0, 1) (multiples of 2^-23) generated on ``device`` (CUDA only)."""
+    from . import _native
+    k = _as_key(key)
+    return _native.threefry_uniform(k.k0, k.k1, shape, device)

@@ -120,7 +120,7 @@ class TrainLoop:
         """Per-chunk key: explicit uniforms are sliced, PRNG keys are re-split."""
         if isinstance(key, (tuple, list)) and isinstance(key[0], torch.Tensor):
             return (key[0][a:b].contiguous(), key[1][a:b].contiguous())
-        return key if (a == 0 and b == n) else prng.split(key, 2 + a)[-1]
+        return key if (a == 0 and b == n) else prng.fold_in(key, a)
 
     def _step(self, key, bmin, bmax, batch: torch.Tensor) -> Dict[str, torch.Tensor]:
         st = self.state

@@ -55,14 +55,18 @@ def test_product_never_imports_oracle():
 
 
 def test_prng_keys():
+    """Host key bookkeeping equals the numpy threefry oracle (and with it JAX's documented values)."""
     from learn_nerf import prng
-    a, b = prng.split(7)
-    assert a != b and prng.split(7) == (a, b)
-    u = prng.uniform(a, (4, 8), "cpu")
-    assert u.dtype == torch.float32 and float(u.min()) >= 0.0 and float(u.max()) < 1.0
-    k = (u * 2 ** 23)
-    assert torch.equal(k, k.round())  # multiples of 2^-23 like jax.random.uniform
-    assert torch.equal(u, prng.uniform(a, (4, 8), "cpu"))
+    from oracle import prng_np
+    a, b = prng.split(0)
+    assert (a.k0, a.k1, b.k0, b.k1) == (4146024105, 967050713, 2718843009, 1272950319)
+    for seed in (0, 7, 2 ** 40 + 3):
+        ref = prng_np.split(prng_np.prng_key(seed), 3)
+        got = prng.split(seed, 3)
+        assert [(k.k0, k.k1) for k in got] == [tuple(int(x) for x in r) for r in ref]
+        f = prng.fold_in(seed, 1234)
+        assert (f.k0, f.k1) == tuple(int(x) for x in prng_np.fold_in(prng_np.prng_key(seed), 1234))
+    assert prng.split(7) == prng.split(prng.PRNGKey(7))
 
 
 def test_shard_bounds_cover_and_balance():

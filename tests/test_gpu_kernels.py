@@ -241,3 +241,14 @@ def test_rgb_to_u8_and_render_view():
     corner = img[0, 0].cpu().numpy()  # fov 1 rad at distance 4: the corner ray misses the unit bbox -> background
     np.testing.assert_array_equal(corner, [0, 0, 0])
     assert int(img[15, 20].sum()) > 0
+
+
+@pytest.mark.parametrize("shape", [(1,), (5, 7), (4096, 64), (333, 128)])
+def test_threefry_uniform_bit_exact(shape):
+    """Device uniforms from a key equal the numpy threefry oracle bit for bit."""
+    from learn_nerf import prng
+    from oracle import prng_np
+    key = prng.split(11)[1]
+    got = prng.uniform(key, shape, "cuda").cpu().numpy()
+    ref = prng_np.uniform(np.array([key.k0, key.k1], np.uint32), shape)
+    np.testing.assert_array_equal(got, ref)

@@ -188,3 +188,17 @@ def test_golden_fine_sampling_fixture_bit_exact():
     out, idx = s.fine_sampling(128, g["u"], g["densities"], return_indices=True)
     np.testing.assert_array_equal(out.ts, g["fine_ts"])
     np.testing.assert_array_equal(idx, g["idx"])
+
+
+def test_threefry_known_answers():
+    """Random123 Threefry-2x32 vectors (also used by JAX's own tests) and JAX's documented outputs."""
+    from oracle import prng_np as P
+    h = lambda a: [int(x) for x in a]
+    assert h(P.threefry_2x32([0, 0], [0, 0])) == [0x6B200159, 0x99BA4EFE]
+    assert h(P.threefry_2x32([0xFFFFFFFF] * 2, [0xFFFFFFFF] * 2)) == [0x1CB996FC, 0xBB002BE7]
+    assert h(P.threefry_2x32([0x13198A2E, 0x03707344], [0x243F6A88, 0x85A308D3])) == [0xC4923A9C, 0x483DF7A0]
+    assert P.split(P.prng_key(0)).tolist() == [[4146024105, 967050713], [2718843009, 1272950319]]
+    assert abs(float(P.uniform(P.prng_key(0), ())) - 0.41845703) < 1e-8
+    u = P.uniform(P.prng_key(3), (5, 7))
+    assert u.dtype == np.float32 and (u >= 0).all() and (u < 1).all()
+    assert np.all(u * 2 ** 23 == np.round(u * 2 ** 23))
