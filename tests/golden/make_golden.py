@@ -59,7 +59,45 @@ def main():
     np.savez_compressed(os.path.join(HERE, "fine_sampling_small.npz"), ts=cs.ts, t_min=t_min,
                         t_max=t_max, mask=mask, densities=dens, u=u, fine_ts=fs.ts, idx=idx,
                         new_ts=new_only.ts, rays=rays)
+    models_fixture()
     print("wrote fixtures to", HERE)
+
+
+def models_case():
+    """Inputs and seeded oracle models shared by make_golden.py and the tests."""
+    import torch
+    rs = np.random.RandomState(31)
+    x = rs.uniform(-1.1, 1.1, (64, 3)).astype(F)
+    d = rs.randn(64, 3).astype(F)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    ngp = M.InstantNGPModel([2 ** 18] * 16, [2 ** (4 + i // 2) for i in range(16)], BBOX_MIN, BBOX_MAX)
+    p_ngp = ngp.init(torch.Generator().manual_seed(41))
+    for leaf in p_ngp["MultiresHashTableEncoding_0"].values():
+        leaf["table"] *= 1e4  # O(1) tables so that the encoding matters
+    ref = M.RefNERFModel()
+    p_ref = ref.init(torch.Generator().manual_seed(42))
+    for i, leaf in enumerate(p_ref.values()):
+        leaf["bias"] = torch.from_numpy((0.1 * np.random.RandomState(50 + i).randn(*leaf["bias"].shape)).astype(F))
+    cam = dict(camera_direction=(0.1, -0.2, -0.97), camera_origin=(0.5, 1.0, 4.0), x_axis=(0.99, 0.05, 0.09),
+               y_axis=(0.04, -0.98, 0.2), x_fov=1.0471975511965976, y_fov=0.7853981633974483)
+    return x, d, ngp, p_ngp, ref, p_ref, cam
+
+
+def models_fixture():
+    import torch
+    from oracle import prng_np
+    x, d, ngp, p_ngp, ref, p_ref, cam = models_case()
+    with torch.no_grad():
+        nd, nrgb, _ = ngp.apply(p_ngp, torch.from_numpy(x), torch.from_numpy(d))
+        nenc = ngp.encode(p_ngp, torch.from_numpy(x))
+    rd, rrgb, raux = ref.apply(p_ref, torch.from_numpy(x), torch.from_numpy(d), create_graph=False)
+    rays = render_np.bare_rays(width=7, height=5, **cam)
+    key = prng_np.split(prng_np.prng_key(123))[1]
+    np.savez_compressed(
+        os.path.join(HERE, "models_small.npz"), x=x, d=d, ngp_enc=nenc.numpy(), ngp_dens=nd.numpy(),
+        ngp_rgb=nrgb.numpy(), ref_dens=rd.numpy(), ref_rgb=rrgb.numpy(),
+        ref_normal_mse=raux["normal_mse"].numpy(), ref_neg_normal=raux["neg_normal"].numpy(), rays_7x5=rays,
+        key=key, uniforms_5x7=prng_np.uniform(key, (5, 7)))
 
 
 if __name__ == "__main__":

@@ -168,3 +168,37 @@ def test_ngp_train_step_vs_oracle():
     worst.sort(reverse=True)
     print("worst NGP grad rel-L2 (gpu-vs-fp64, cpu32-vs-fp64, gpu-vs-cpu32):", worst[:4])
     assert worst[0][0] < 2 * scale + 1e-5, worst[:4]
+
+
+def test_golden_models_fixture_gpu():
+    """The CUDA NGP / Ref-NeRF / ray-generation / PRNG paths against tests/golden/models_small.npz."""
+    import importlib.util
+    import os
+    from learn_nerf import prng
+    from learn_nerf.dataset import CameraView
+    from learn_nerf.instant_ngp import InstantNGPModel
+    from learn_nerf.ref_nerf import RefNERFModel
+    golden = os.path.join(os.path.dirname(__file__), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(golden, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    g = np.load(os.path.join(golden, "models_small.npz"))
+    x, d, ongp, p_ngp, oref, p_ref, cam = mg.models_case()
+    cu = lambda t: {k: cu(v) if isinstance(v, dict) else v.cuda() for k, v in t.items()}
+    ngp = InstantNGPModel(table_sizes=[2 ** 18] * 16, grid_sizes=[2 ** (4 + i // 2) for i in range(16)],
+                          bbox_min=BBOX_MIN, bbox_max=BBOX_MAX)
+    tree = ngp.flatten_params(cu(p_ngp))
+    np.testing.assert_allclose(ngp.encode(tree, dev(x)).cpu().numpy(), g["ngp_enc"], atol=2e-5)
+    dens, rgb, _ = ngp.apply(dict(params=tree), dev(x), dev(d))
+    np.testing.assert_allclose(dens.cpu().numpy(), g["ngp_dens"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(rgb.cpu().numpy(), g["ngp_rgb"], atol=2e-5)
+    ref = RefNERFModel()
+    rtree = ref.flatten_params(cu(p_ref))
+    dens, rgb, aux = ref.apply(dict(params=rtree), dev(x), dev(d))
+    np.testing.assert_allclose(dens.cpu().numpy(), g["ref_dens"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(rgb.cpu().numpy(), g["ref_rgb"], atol=1e-5)
+    np.testing.assert_allclose(aux["neg_normal"].cpu().numpy(), g["ref_neg_normal"], atol=1e-5)
+    assert np.median(np.abs(aux["normal_mse"].cpu().numpy() - g["ref_normal_mse"])) < 1e-5
+    np.testing.assert_array_equal(CameraView(**cam).bare_rays(7, 5).cpu().numpy(), g["rays_7x5"])
+    key = prng.PRNGKey(int(g["key"][0]), int(g["key"][1]))
+    np.testing.assert_array_equal(prng.uniform(key, (5, 7), "cuda").cpu().numpy(), g["uniforms_5x7"])

@@ -202,3 +202,27 @@ def test_threefry_known_answers():
     u = P.uniform(P.prng_key(3), (5, 7))
     assert u.dtype == np.float32 and (u >= 0).all() and (u < 1).all()
     assert np.all(u * 2 ** 23 == np.round(u * 2 ** 23))
+
+
+def test_golden_models_fixture():
+    """Regression of the NGP / Ref-NeRF / ray-generation / PRNG restatements against the committed
+    fixture (generated by tests/golden/make_golden.py from this oracle; the GPU tests compare the
+    CUDA path with the same file)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLDEN, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    from oracle import prng_np
+    g = np.load(os.path.join(GOLDEN, "models_small.npz"))
+    x, d, ngp, p_ngp, ref, p_ref, cam = mg.models_case()
+    np.testing.assert_array_equal(x, g["x"])
+    with torch.no_grad():
+        nd, nrgb, _ = ngp.apply(p_ngp, torch.from_numpy(x), torch.from_numpy(d))
+    np.testing.assert_allclose(nd.numpy(), g["ngp_dens"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(nrgb.numpy(), g["ngp_rgb"], atol=1e-5)
+    rd, rrgb, raux = ref.apply(p_ref, torch.from_numpy(x), torch.from_numpy(d), create_graph=False)
+    np.testing.assert_allclose(rd.numpy(), g["ref_dens"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(rrgb.numpy(), g["ref_rgb"], atol=1e-5)
+    np.testing.assert_allclose(raux["neg_normal"].numpy(), g["ref_neg_normal"], atol=1e-5)
+    np.testing.assert_array_equal(render_np.bare_rays(width=7, height=5, **cam), g["rays_7x5"])
+    np.testing.assert_array_equal(prng_np.uniform(g["key"], (5, 7)), g["uniforms_5x7"])
