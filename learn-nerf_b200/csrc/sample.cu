@@ -208,6 +208,187 @@ sample_fine_kernel(const float* __restrict__ ts_c, const float* __restrict__ den
   }
 }
 
+
+// ------------------------------------------------------------------ K4, default sizes (64 + 128)
+// Same arithmetic as sample_fine_kernel (bit-exact), organised for throughput: every lane keeps
+// its two coarse samples in registers, the two strictly sequential cumulative sums run as
+// warp-synchronous shuffle loops (every lane carries the same running sum, no shared-memory
+// round trips), and the final jnp.sort of [coarse | new] is a rank-based two-way merge (each
+// element's position = its index + its rank in the other list) whenever both lists are already
+// sorted -- which is checked per ray; otherwise (an fp32 rounding inversion) the bitonic network
+// of the generic kernel runs.  A sorted array is unique, so both give the same bits.
+constexpr int kF64Smem = 66 + 66 + 64 + 128 + 256;  // xs, ys, a, b, out (floats per warp)
+
+__global__ void __launch_bounds__(256)
+sample_fine64_kernel(const float* __restrict__ ts_c, const float* __restrict__ dens_c,
+                     const float* __restrict__ t_min_in, const float* __restrict__ t_max_in,
+                     const float* __restrict__ u, int64_t n, float eps, float* __restrict__ ts_out,
+                     int32_t* __restrict__ idx_out, float* __restrict__ new_ts_out) {
+  constexpr int Tc = 64, Tf = 128, T2 = 192;
+  __shared__ float smem[8 * kF64Smem];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float* s_xs = smem + wib * kF64Smem;
+  float* s_ys = s_xs + 66;
+  float* s_a = s_ys + 66;
+  float* s_b = s_a + 64;
+  float* s_out = s_b + 128;
+  const unsigned full = 0xffffffffu;
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  const float ubin = __fdiv_rn(__fsub_rn(1.0f, 0.0f), float(Tf));
+  for (int64_t r = warp; r < n; r += nwarps) {
+    const float t_min = __ldg(t_min_in + r), t_max = __ldg(t_max_in + r);
+    const float ts0 = __ldg(ts_c + r * Tc + lane), ts1 = __ldg(ts_c + r * Tc + 32 + lane);
+    const float de0 = __ldg(dens_c + r * Tc + lane), de1 = __ldg(dens_c + r * Tc + 32 + lane);
+    float uq[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) uq[q] = __ldg(u + r * Tf + q * 32 + lane);
+    // neighbours of the lane's two samples i = lane and i = 32 + lane
+    float prev0 = __shfl_up_sync(full, ts0, 1), next0 = __shfl_down_sync(full, ts0, 1);
+    float prev1 = __shfl_up_sync(full, ts1, 1), next1 = __shfl_down_sync(full, ts1, 1);
+    const float ts1_first = __shfl_sync(full, ts1, 0), ts0_last = __shfl_sync(full, ts0, 31);
+    if (lane == 31) next0 = ts1_first;
+    if (lane == 0) prev1 = ts0_last;
+    // starts/ends/deltas (render.py:259-268), density_dt (:271)
+    const float start0 = lane == 0 ? t_min : __fdiv_rn(__fadd_rn(ts0, prev0), 2.0f);
+    const float end0 = __fdiv_rn(__fadd_rn(next0, ts0), 2.0f);
+    const float start1 = __fdiv_rn(__fadd_rn(ts1, prev1), 2.0f);
+    const float end1 = lane == 31 ? t_max : __fdiv_rn(__fadd_rn(next1, ts1), 2.0f);
+    const float ddt0 = __fmul_rn(de0, __fsub_rn(end0, start0));
+    const float ddt1 = __fmul_rn(de1, __fsub_rn(end1, start1));
+    // cumsum(density_dt), strictly sequential (:275): exclusive prefixes of the lane's samples
+    float acc = 0.0f, accp0 = 0.0f, accp1 = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float v = __shfl_sync(full, ddt0, i);
+      if (lane == i) accp0 = acc;
+      acc = __fadd_rn(acc, v);
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float v = __shfl_sync(full, ddt1, i);
+      if (lane == i) accp1 = acc;
+      acc = __fadd_rn(acc, v);
+    }
+    // w = surv * term + eps (:279-287, :232)
+    const float w0 = __fadd_rn(__fmul_rn(lnrf_expf(-accp0), __fsub_rn(1.0f, lnrf_expf(-ddt0))), eps);
+    const float w1 = __fadd_rn(__fmul_rn(lnrf_expf(-accp1), __fsub_rn(1.0f, lnrf_expf(-ddt1))), eps);
+    // xs = [0, cumsum(w)] (:235-236), sequential; then / total (:237)
+    float xa0 = 0.0f, xa1 = 0.0f;
+    acc = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      acc = __fadd_rn(acc, __shfl_sync(full, w0, i));
+      if (lane == i) xa0 = acc;
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      acc = __fadd_rn(acc, __shfl_sync(full, w1, i));
+      if (lane == i) xa1 = acc;
+    }
+    const float total = acc;
+    __syncwarp();  // the previous ray's readers of the shared arrays are done
+    if (lane == 0) {
+      s_xs[0] = __fdiv_rn(0.0f, total);
+      s_ys[0] = t_min;  // ys = [t_min, ends()] (:238-241)
+    }
+    s_xs[1 + lane] = __fdiv_rn(xa0, total);
+    s_xs[33 + lane] = __fdiv_rn(xa1, total);
+    s_ys[1 + lane] = end0;
+    s_ys[33 + lane] = end1;
+    s_a[lane] = ts0;
+    s_a[32 + lane] = ts1;
+    __syncwarp();
+    // inverse CDF at stratified points: vmap(jnp.interp) (:251)
+    const float xp_first = s_xs[0], xp_last = s_xs[Tc];
+    const float fp_first = s_ys[0], fp_last = s_ys[Tc];
+    float fq[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j = q * 32 + lane;
+      const float x = __fadd_rn(__fmul_rn(float(j), ubin), __fmul_rn(uq[q], ubin));
+      int lo = 0, hi = Tc + 1;  // searchsorted(xs, x, side='right') over Tc + 1 entries
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (s_xs[mid] <= x) lo = mid + 1; else hi = mid;
+      }
+      const int i = min(max(lo, 1), Tc);
+      const float df = __fsub_rn(s_ys[i], s_ys[i - 1]);
+      const float dx = __fsub_rn(s_xs[i], s_xs[i - 1]);
+      const float delta = __fsub_rn(x, s_xs[i - 1]);
+      const bool dx0 = fabsf(dx) <= 1.4210854715202004e-14f;  // np.spacing(finfo(f32).eps)
+      const float ratio = __fdiv_rn(delta, dx0 ? 1.0f : dx);
+      float f = dx0 ? s_ys[i - 1] : __fadd_rn(s_ys[i - 1], __fmul_rn(ratio, df));
+      if (x < xp_first) f = fp_first;
+      if (x > xp_last) f = fp_last;
+      fq[q] = f;
+      s_b[j] = f;
+      if (idx_out) idx_out[r * Tf + j] = i;
+      if (new_ts_out) new_ts_out[r * Tf + j] = f;
+    }
+    // ---- jnp.sort(concat[ts, new_ts]) (:253-255)
+    bool ok = (ts0 <= next0) && (lane == 31 || ts1 <= next1);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float nx = __shfl_down_sync(full, fq[q], 1);
+      const float wrap = __shfl_sync(full, fq[(q + 1) & 3], 0);
+      if (lane == 31) nx = wrap;
+      if (!(q == 3 && lane == 31)) ok = ok && (fq[q] <= nx);
+    }
+    __syncwarp();
+    if (__all_sync(full, ok)) {
+      // two-way merge by ranks: a[i] goes to i + #{b < a[i]}, b[j] goes to j + #{a <= b[j]}
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float v = h ? ts1 : ts0;
+        int lo = 0, hi = Tf;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (s_b[mid] < v) lo = mid + 1; else hi = mid;
+        }
+        s_out[h * 32 + lane + lo] = v;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float v = fq[q];
+        int lo = 0, hi = Tc;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (s_a[mid] <= v) lo = mid + 1; else hi = mid;
+        }
+        s_out[q * 32 + lane + lo] = v;
+      }
+      __syncwarp();
+    } else {
+      s_out[lane] = ts0;
+      s_out[32 + lane] = ts1;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) s_out[64 + q * 32 + lane] = fq[q];
+      s_out[192 + lane] = CUDART_INF_F;
+      s_out[224 + lane] = CUDART_INF_F;
+      __syncwarp();
+      for (int k = 2; k <= 256; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int i = lane; i < 256; i += 32) {
+            const int l = i ^ j;
+            if (l > i) {
+              const float x = s_out[i], y = s_out[l];
+              const bool up = (i & k) == 0;
+              if (up ? (x > y) : (x < y)) {
+                s_out[i] = y;
+                s_out[l] = x;
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) ts_out[r * T2 + k * 32 + lane] = s_out[k * 32 + lane];
+  }
+}
+
 }  // namespace lnrf
 
 extern "C" {
@@ -260,6 +441,15 @@ int lnrf_sample_fine(const float* ts_c, const float* dens_c, const float* t_min,
   if (n == 0) return LNRF_OK;
   LNRF_REQUIRE(ts_c && dens_c && t_min && t_max && u && ts_out, LNRF_E_INVALID,
                "lnrf_sample_fine: null pointer");
+  if (Tc == 64 && Tf == 128) {  // the reference's default sample counts: the fast kernel
+    int64_t blocks = lnrf::ceil_div(n, 8);
+    const int64_t cap = int64_t(lnrf::sm_count()) * 8;
+    if (blocks > cap) blocks = cap;
+    lnrf::sample_fine64_kernel<<<(unsigned)blocks, 256, 0, lnrf::as_stream(stream)>>>(
+        ts_c, dens_c, t_min, t_max, u, n, eps, ts_out, idx_out, new_ts_out);
+    LNRF_LAUNCH_CHECK("sample_fine64_kernel");
+    return LNRF_OK;
+  }
   int P = 2;
   while (P < Tc + Tf) P <<= 1;
   const int warps = 8, threads = warps * 32;

@@ -116,6 +116,29 @@ def test_sample_fine_random_bit_exact(nat, Tc, Tf):
     assert bool((out[:, 1:] >= out[:, :-1]).all())
 
 
+def test_sample_fine_unsorted_inputs_take_the_sort_path(nat):
+    """The 64+128 kernel merges two sorted lists; rays whose coarse samples are NOT sorted (possible
+    through fp32 rounding, forced here) must fall back to the full sort and still equal np.sort."""
+    from oracle import render_np
+    n = 64
+    rays = make_rays(n, seed=15, with_targets=False)
+    t_min, t_max, mask = render_np.ray_t_range(BBOX_MIN, BBOX_MAX, rays)
+    cs = render_np.RaySamples.stratified_sampling(t_min, t_max, mask, 64, make_uniforms(n, 64, 19))
+    rs = np.random.RandomState(14)
+    ts = cs.ts.copy()
+    for r in range(0, n, 2):  # every other ray: one or three 1-ulp inversions, as rounding could produce
+        for i in rs.choice(63, 3 if r % 4 == 0 else 1, replace=False):
+            ts[r, i + 1] = np.nextafter(ts[r, i], np.float32(-np.inf))
+    assert (np.diff(ts, axis=1) < 0).any()
+    cs2 = render_np.RaySamples(t_min=t_min, t_max=t_max, mask=mask, ts=ts)
+    dens = rs.gamma(0.5, 4.0, (n, 64)).astype(F)
+    u = make_uniforms(n, 128, 20)
+    o, o_idx = cs2.fine_sampling(128, u, dens, return_indices=True)
+    out, idx, _ = nat.sample_fine(dev(ts), dev(dens), dev(t_min), dev(t_max), dev(u), debug=True)
+    np.testing.assert_array_equal(idx.cpu().numpy(), o_idx)
+    np.testing.assert_array_equal(out.cpu().numpy().view(np.uint32), o.ts.view(np.uint32))
+
+
 # ------------------------------------------------------------------ K3 / K5
 def _composite_case(n, T, seed, miss=0.25):
     from oracle import render_np
