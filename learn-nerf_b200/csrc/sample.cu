@@ -47,30 +47,45 @@ __device__ __forceinline__ void ray_t_range(const float* __restrict__ ray, const
   t_max = mask ? max_t_clipped : min_t_range;
 }
 
+// One thread per 4 consecutive samples of a ray (T % 4 == 0) or per sample: flat, fully coalesced
+// 128-bit loads/stores of u / ts.  The slab test is recomputed by every thread of a ray (six
+// divisions, far cheaper than staging it); the thread of sample 0 writes the ray's bounds.
+template <int V>
 __global__ void __launch_bounds__(256)
 sample_coarse_kernel(const float* __restrict__ rays, int64_t n, BBox bb, float min_t_range,
                      float epsilon, const float* __restrict__ u, int T, float* __restrict__ t_min_out,
                      float* __restrict__ t_max_out, uint8_t* __restrict__ mask_out,
                      float* __restrict__ ts_out) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
-  for (int64_t r = warp; r < n; r += nwarps) {
+  const int per_ray = T / V;
+  const int64_t items = n * per_ray;
+  for (int64_t it = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; it < items;
+       it += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = it / per_ray;
+    const int i0 = int(it - r * per_ray) * V;
     float t_min, t_max;
     bool mask;
     ray_t_range(rays + r * 6, bb, min_t_range, epsilon, t_min, t_max, mask);
-    if (lane == 0) {
+    if (i0 == 0) {
       t_min_out[r] = t_min;
       t_max_out[r] = t_max;
       mask_out[r] = mask ? 1 : 0;
     }
     // stratified_sampling, render.py:138-143
     const float bin = __fdiv_rn(__fsub_rn(t_max, t_min), float(T));
-    for (int i = lane; i < T; i += 32) {
-      float start = __fadd_rn(__fmul_rn(float(i), bin), t_min);
-      float rnd = __fmul_rn(__ldg(u + r * T + i), bin);
-      ts_out[r * T + i] = __fadd_rn(start, rnd);
+    float uv[V], out[V];
+    if (V == 4) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(u + r * T + i0));
+      uv[0] = q.x; uv[1 % V] = q.y; uv[2 % V] = q.z; uv[3 % V] = q.w;
+    } else {
+      uv[0] = __ldg(u + r * T + i0);
     }
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const float start = __fadd_rn(__fmul_rn(float(i0 + k), bin), t_min);
+      out[k] = __fadd_rn(start, __fmul_rn(uv[k], bin));
+    }
+    if (V == 4) *reinterpret_cast<float4*>(ts_out + r * T + i0) = make_float4(out[0], out[1 % V], out[2 % V], out[3 % V]);
+    else ts_out[r * T + i0] = out[0];
   }
 }
 
@@ -407,11 +422,16 @@ int lnrf_sample_coarse(const float* rays, int64_t n, const float* bbox_min_host,
     bb.hi[a] = bbox_max_host[a];
   }
   const int threads = 256;
-  int64_t blocks = lnrf::ceil_div(n, threads / 32);
-  int64_t cap = int64_t(lnrf::sm_count()) * 8;
+  const bool vec = (T % 4 == 0) && ((uintptr_t)u % 16 == 0) && ((uintptr_t)ts % 16 == 0);
+  int64_t blocks = lnrf::ceil_div(n * (vec ? T / 4 : T), threads);
+  int64_t cap = int64_t(lnrf::sm_count()) * 32;
   if (blocks > cap) blocks = cap;
-  lnrf::sample_coarse_kernel<<<(unsigned)blocks, threads, 0, lnrf::as_stream(stream)>>>(
-      rays, n, bb, min_t_range, epsilon, u, T, t_min, t_max, mask, ts);
+  if (vec)
+    lnrf::sample_coarse_kernel<4><<<(unsigned)blocks, threads, 0, lnrf::as_stream(stream)>>>(
+        rays, n, bb, min_t_range, epsilon, u, T, t_min, t_max, mask, ts);
+  else
+    lnrf::sample_coarse_kernel<1><<<(unsigned)blocks, threads, 0, lnrf::as_stream(stream)>>>(
+        rays, n, bb, min_t_range, epsilon, u, T, t_min, t_max, mask, ts);
   LNRF_LAUNCH_CHECK("sample_coarse_kernel");
   return LNRF_OK;
 }
