@@ -254,7 +254,7 @@ int nerf_bwd_fp32(const float* P, int64_t m, void* ws_base, int64_t ws_bytes, co
                                               G + kNerf.b[9]);
   LNRF_LAUNCH_CHECK("density_head_bwd_kernel");
   int rc;
-  const unsigned cb = ew_blocks(m, 2048);
+  const unsigned cb = ew_blocks(m, 512);  // >= 1k blocks at training sizes
   // colour layer Dense_10: input [z8 | d_emb]
   rc = gemm_tn_acc(st, kH, kHC, w.h[8], kH, w.dc, kHC, m, G + kNerf.w[10], kHC);
   if (rc) return rc;

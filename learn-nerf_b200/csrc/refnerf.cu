@@ -592,7 +592,7 @@ int lnrf_refnerf_bwd(const float* params, const float* x, const float* d, const 
   cudaStream_t st = as_stream(stream);
   const float* P = params;
   float* G = d_params;
-  const unsigned cb = ew_blocks(m, 2048);
+  const unsigned cb = ew_blocks(m, 512);  // >= 1k blocks at training sizes
   int rc;
   // ---- directional block
   ref_out_bwd_kernel<<<ew_blocks(m, 8 * 16), 256, 0, st>>>(w.h[8], w.o, w.c, d_rgb, P + kRef.w[10], m, w.d_o,

@@ -34,7 +34,7 @@ struct GemmArgs {
 constexpr int GBM = 128, GBN = 128, GBK = 8, GPAD = 4;
 
 template <bool ATRANS, bool BTRANS, int EPI>
-__global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g) {
+__global__ void __launch_bounds__(256, 2) sgemm_kernel(GemmArgs g) {  // <= 128 registers: two blocks per SM
   __shared__ __align__(16) float As[2][GBK][GBM + GPAD];
   __shared__ __align__(16) float Bs[2][GBK][GBN + GPAD];
   const int t = threadIdx.x;
@@ -169,25 +169,38 @@ __global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g) {
   }
 }
 
-// db[n] += sum_m G[m,n]; N must divide 256 (bias gradients).  Template only so that the
-// definition can live in this header.
+// db[n] += sum_m G[m,n] (bias gradients); N a multiple of 4 with N/4 dividing 256.  128-bit
+// coalesced row loads, one block per row range, a shared-memory fold and one atomic per column.
+// Template only so that the definition can live in this header.
 template <int UNUSED = 0>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ G, int64_t m, int N, float* __restrict__ db) {
-  const int col = threadIdx.x % N;
-  const int rsub = threadIdx.x / N, rstep = blockDim.x / N;
+  const int n4 = N >> 2;                    // float4 per row
+  const int c4 = threadIdx.x % n4;
+  const int rsub = threadIdx.x / n4, rstep = blockDim.x / n4;
   const int64_t rows_per_block = ceil_div(m, gridDim.x);
   const int64_t r0 = int64_t(blockIdx.x) * rows_per_block;
   const int64_t r1 = min(r0 + rows_per_block, m);
-  float acc = 0.0f;
-  for (int64_t r = r0 + rsub; r < r1; r += rstep) acc += __ldg(G + r * N + col);
-  __shared__ float s[256];
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* Gv = reinterpret_cast<const float4*>(G);
+#pragma unroll 4
+  for (int64_t r = r0 + rsub; r < r1; r += rstep) {
+    const float4 v = __ldg(Gv + r * n4 + c4);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  __shared__ float4 s[256];
   s[threadIdx.x] = acc;
   __syncthreads();
-  if (threadIdx.x < N) {
-    float t = 0.0f;
-    for (int k = 0; k < rstep; ++k) t += s[k * N + threadIdx.x];
-    atomicAdd(db + threadIdx.x, t);
+  if (threadIdx.x < n4) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < rstep; ++k) {
+      const float4 v = s[k * n4 + threadIdx.x];
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    atomicAdd(db + threadIdx.x * 4 + 0, t.x);
+    atomicAdd(db + threadIdx.x * 4 + 1, t.y);
+    atomicAdd(db + threadIdx.x * 4 + 2, t.z);
+    atomicAdd(db + threadIdx.x * 4 + 3, t.w);
   }
 }
 
