@@ -343,6 +343,7 @@ nerf_bwd_dw_kernel(DwArgs args) {
         }
         mbar_arrive_expect_tx(bar_full + 8 * stage, uint32_t(job.a_blocks + job.b_blocks) * kHalfBlock);
         const uint32_t sa = smem_base + stage * kDwStageBytes, sb = sa + 4 * kHalfBlock;
+        // (an L2 evict_first hint on these read-once loads was measured: no gain, 6.10 vs 6.04 ms/step)
         for (int b = 0; b < job.a_blocks; ++b)
           bulk_g2s(sa + b * kHalfBlock, job.A + (tile * job.a_blocks + b) * int64_t(kABlockBytes) + half,
                    kHalfBlock, bar_full + 8 * stage);
