@@ -521,6 +521,7 @@ static int g_tc_stages = 0;  // 0 = pair kernel (default); 1 / 4 = single-tile k
 
 int init_mlp_tc_bwd();  // mlp_tc_bwd.cu
 int init_mlp_tc_fwd2();  // mlp_tc_fwd2.cu
+int init_mlp_tc_bwd2();  // mlp_tc_bwd2.cu
 int nerf_fwd_pair(const void* packed, const float* x, const float* d, const float* rays, const float* ts,
                   int64_t m, int T, bool save, const TcStash& stash, float* dens, float* rgb, cudaStream_t st);
 void set_dw_debug(int flags);
@@ -545,6 +546,7 @@ int init_mlp_tc() {
   if ((rc = set_smem(debug_umma_gemm_tn_kernel, 200 * 1024))) return rc;
   if ((rc = init_mlp_tc_bwd())) return rc;
   if ((rc = init_mlp_tc_fwd2())) return rc;
+  if ((rc = init_mlp_tc_bwd2())) return rc;
   g_tc_ready = true;
   return LNRF_OK;
 }

@@ -18,21 +18,10 @@ namespace lnrf {
 using namespace ptx;
 
 bool tc_ready();
+int nerf_bwd_dx_pair(const TcBwdArgs& a, cudaStream_t st);  // mlp_tc_bwd2.cu
 int64_t tc_workspace_bytes(int64_t m, bool save);
 
 // ================================================================ dX chain
-struct TcBwdArgs {
-  const uint8_t* packed;
-  const float* P;
-  const float* dens;    // forward outputs [m], [m,3]
-  const float* rgb;
-  const float* d_dens;  // upstream gradients [m], [m,3]
-  const float* d_rgb;
-  int64_t m;
-  TcStash stash;
-  float* G;             // flat parameter gradient (for the two head biases)
-};
-
 constexpr uint32_t kBwdABytes = 4 * kABlockBytes;
 struct BwdSmem {
   static constexpr uint32_t a_off = 0;
@@ -519,10 +508,15 @@ int nerf_bwd_tc(const float* P, const void* packed, int64_t m, void* ws, int64_t
   const int64_t tiles = ceil_div(m, 128);
 
   TcBwdArgs a{reinterpret_cast<const uint8_t*>(packed), P, dens, rgb, d_dens, d_rgb, m, s, G};
-  int64_t grid = int64_t(sm_count()) * 2;
-  if (grid > tiles) grid = tiles;
-  nerf_bwd_dx_kernel<<<(unsigned)grid, kTcThreads, BwdSmem::total, st>>>(a);
-  LNRF_LAUNCH_CHECK("nerf_bwd_dx_kernel");
+  if (g_dw_debug & 512) {  // A/B switch: the single-tile dX kernel (two CTAs per SM)
+    int64_t grid = int64_t(sm_count()) * 2;
+    if (grid > tiles) grid = tiles;
+    nerf_bwd_dx_kernel<<<(unsigned)grid, kTcThreads, BwdSmem::total, st>>>(a);
+    LNRF_LAUNCH_CHECK("nerf_bwd_dx_kernel");
+  } else {
+    const int rc = nerf_bwd_dx_pair(a, st);
+    if (rc) return rc;
+  }
 
   // ---- dW jobs; CTAs are shared out in proportion to the bytes each job streams per tile
   DwArgs d{};

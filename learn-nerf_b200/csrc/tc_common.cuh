@@ -137,6 +137,19 @@ inline TcStash carve_stash(void* base, int64_t m) {
   return s;
 }
 
+// arguments of the dX-chain kernels (mlp_tc_bwd.cu, mlp_tc_bwd2.cu)
+struct TcBwdArgs {
+  const uint8_t* packed;
+  const float* P;
+  const float* dens;    // forward outputs [m], [m,3]
+  const float* rgb;
+  const float* d_dens;  // upstream gradients [m], [m,3]
+  const float* d_rgb;
+  int64_t m;
+  TcStash stash;
+  float* G;             // flat parameter gradient (for the two head biases)
+};
+
 // ---------------------------------------------------------------- device helpers
 // 16-byte store of 8 bf16 into chunk `chunk` (0..7) of row `row` of an SW128 block
 __device__ __forceinline__ void store_row_chunk(uint32_t block_base, int row, int chunk, uint32_t a,
