@@ -42,9 +42,6 @@ class TrainLoop:
                  fine_ts: int, adam_b1: float = 0.9, adam_b2: float = 0.999, adam_eps: float = 1e-7,
                  loss_weights: Dict[str, float] = None, density_penalty: Optional[float] = None,
                  density_penalty_batch_size: int = 128, device=None, ray_chunk: Optional[int] = None):
-        if density_penalty is not None:
-            raise NotImplementedError("density_penalty (train.py:153-184) is default-off in the "
-                                      "reference and not part of the native hot path yet")
         self.coarse, self.fine = coarse, fine
         self.coarse_ts, self.fine_ts = coarse_ts, fine_ts
         self.lr, self.b1, self.b2, self.eps = lr, adam_b1, adam_b2, adam_eps
@@ -115,6 +112,36 @@ class TrainLoop:
                             bbox_min=bmin, bbox_max=bmax, coarse_ts=self.coarse_ts,
                             fine_ts=self.fine_ts)
 
+    # ------------------------------------------------------------------ density penalty
+    def _density_points(self, density_key, bmin, bmax):
+        """train.py:174-180: coords = U[0,1)^3 * (bbox_max - bbox_min) + bbox_min and unit
+        directions, both drawn from ``density_key``.  ``density_key`` may also be an explicit
+        ``(coords[B,3], dirs[B,3])`` pair (the parity entry point).  The directions only reach
+        the colour head, so they never influence the penalty or its gradient."""
+        if isinstance(density_key, (tuple, list)) and isinstance(density_key[0], torch.Tensor):
+            coords, dirs = density_key
+            return (_native._f32c(coords.contiguous(), "coords"), _native._f32c(dirs.contiguous(), "dirs"))
+        bs = self.density_penalty_batch_size
+        u = prng.uniform(density_key, (bs, 3), self.device)
+        lo = torch.tensor(bmin, device=self.device, dtype=torch.float32)
+        hi = torch.tensor(bmax, device=self.device, dtype=torch.float32)
+        coords = u * (hi - lo) + lo
+        # jax.random.normal(key) = sqrt(2) * erfinv(uniform(key, minval=nextafter(-1, 0), maxval=1))
+        lo1 = float(np.nextafter(np.float32(-1.0), np.float32(0.0)))
+        z = math.sqrt(2.0) * torch.erfinv(torch.clamp(u * (1.0 - lo1) + lo1, min=lo1))
+        dirs = z / z.norm(dim=-1, keepdim=True)
+        return coords.contiguous(), dirs.contiguous()
+
+    def average_density(self, key, model: ModelBase, params, bbox_min, bbox_max, _save=False):
+        """train.py:166-184: mean density of ``model`` at random points of the bounding box.
+        The points go through the renderer's fused seam as zero-length rays (x = o + d * 0)."""
+        coords, dirs = self._density_points(key, _vec3(bbox_min), _vec3(bbox_max))
+        rays = torch.stack([coords, dirs], dim=1).contiguous()
+        ts = torch.zeros(coords.shape[0], 1, device=coords.device)
+        dens, rgb, _, ctx = model.apply_rays(params, rays, ts, save=_save, slot="density_penalty")
+        mean = dens.mean()
+        return (mean, dens, rgb, ctx) if _save else mean
+
     @staticmethod
     def _split_key(key, n, tc, tf, a, b):
         """Per-chunk key: explicit uniforms are sliced, PRNG keys are re-split."""
@@ -127,8 +154,11 @@ class TrainLoop:
         batch = _native._f32c(batch.contiguous(), "batch")
         n = batch.shape[0]
         world = parallel.world()[1]
-        if not isinstance(key, (tuple, list)):
-            key, _density_key = prng.split(key)  # train.py:137
+        density_key = None
+        if isinstance(key, (tuple, list)) and len(key) == 3:  # (u_coarse, u_fine, (coords, dirs))
+            key, density_key = (key[0], key[1]), key[2]
+        elif not isinstance(key, (tuple, list)):
+            key, density_key = prng.split(key)  # train.py:137
         g = self._grads
         g.zero_()
         self._scalars.zero_()
@@ -172,6 +202,19 @@ class TrainLoop:
                     d_dens = d_dens + d_dens_aux
                     d_aux = {name: d_cols[..., i].contiguous() for i, name in enumerate(names)}
                 model.backward_rays(lv["_ctx"], d_dens, d_rgb, g[sl[0]:sl[1]], d_aux=d_aux)
+        penalties: Dict[str, torch.Tensor] = {}
+        if self.density_penalty is not None:
+            # train.py:153-163: total += density_penalty * mean(density(model, random points)),
+            # fine model first.  Every rank draws the same points, so after the all-reduce and
+            # Adam's 1/world the gradient is that of the single-device loss.
+            if density_key is None:
+                raise ValueError("density_penalty needs a PRNG key or explicit (coords, dirs) points")
+            for prefix, model, sl in (("fine", self.fine, sf), ("coarse", self.coarse, sc)):
+                mean, dens, rgb, ctx = self.average_density(density_key, model, st.params[prefix], bmin, bmax,
+                                                            _save=True)
+                penalties[f"{prefix}_density"] = mean
+                d_dens = torch.full_like(dens, self.density_penalty / dens.numel())
+                model.backward_rays(ctx, d_dens, torch.zeros_like(rgb), g[sl[0]:sl[1]])
         if world > 1:
             parallel.allreduce_sum_(g)  # one NCCL sum over NVLink; 1/world is folded into Adam
             parallel.allreduce_sum_(self._scalars[:2])
@@ -190,6 +233,7 @@ class TrainLoop:
                 parallel.mean_scalars_(vals)
             for i, k in enumerate(names):
                 logs[k] = vals[i]
+        logs.update(penalties)
         logs["grad_norm"] = torch.sqrt(s[2])
         logs["param_norm"] = torch.sqrt(s[3])
         return logs
@@ -198,8 +242,11 @@ class TrainLoop:
         """train.py:114-165 (forward only) -> (total_loss, loss_dict)."""
         batch = _native._f32c(batch.contiguous(), "batch")
         n = batch.shape[0]
-        if not isinstance(key, (tuple, list)):
-            key, _density_key = prng.split(key)
+        density_key = None
+        if isinstance(key, (tuple, list)) and len(key) == 3:
+            key, density_key = (key[0], key[1]), key[2]
+        elif not isinstance(key, (tuple, list)):
+            key, density_key = prng.split(key)
         renderer = self._renderer(_vec3(bbox_min), _vec3(bbox_max), params)
         out = renderer.render_rays(key, batch[:, :2].contiguous())
         sums = torch.zeros(2, device=batch.device)
@@ -211,4 +258,9 @@ class TrainLoop:
             for name, loss in out[f"{prefix}_aux"].items():
                 loss_dict[f"{prefix}_{name}"] = loss
                 total = total + self.loss_weights[name] * loss
+        if self.density_penalty is not None:  # :153-163
+            for prefix, model in (("fine", self.fine), ("coarse", self.coarse)):
+                penalty = self.average_density(density_key, model, params[prefix], bbox_min, bbox_max)
+                loss_dict[f"{prefix}_density"] = penalty
+                total = total + self.density_penalty * penalty
         return total, loss_dict

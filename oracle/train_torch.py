@@ -2,8 +2,8 @@
 
 TEST INFRASTRUCTURE (see oracle/__init__.py).  PARITY UNPINNED (no JAX here).
 
-``losses`` follows train.py:114-165 (density-penalty branch :153-163 excluded:
-default off).  ``adam_update`` restates optax.adam as used at train.py:59
+``losses`` follows train.py:114-165; the density-penalty branch (:153-184) takes its random
+points as explicit inputs (``density_points = (coords[B,3], dirs[B,3])``), like the uniforms.  ``adam_update`` restates optax.adam as used at train.py:59
 [recalled: optax is absent]: m <- b1 m + (1-b1) g; v <- b2 v + (1-b2) g^2;
 theta <- theta - lr * (m / (1-b1^t)) / (sqrt(v / (1-b2^t)) + eps), t from 1.
 Sample positions come from oracle.render_np (bit-exact fp32 stage); the
@@ -33,7 +33,8 @@ def init_params(coarse, fine, seed: int):
 def losses(coarse, fine, params, bbox_min, bbox_max, batch: np.ndarray, u_coarse: np.ndarray,
            u_fine: np.ndarray, coarse_ts: int, fine_ts: int,
            loss_weights: Optional[Dict[str, float]] = None, dtype=torch.float32,
-           fixed_fine_ts: Optional[np.ndarray] = None):
+           fixed_fine_ts: Optional[np.ndarray] = None, density_penalty: Optional[float] = None,
+           density_points=None):
     """-> (total_loss tensor, loss_dict, render_out).  ``batch`` [N,3,3] numpy fp32.
 
     ``fixed_fine_ts`` lets a test inject fine sample positions computed elsewhere
@@ -70,6 +71,14 @@ def losses(coarse, fine, params, bbox_min, bbox_max, batch: np.ndarray, u_coarse
     for name, l in f_aux.items():  # :149-151
         loss_dict[f"fine_{name}"] = l
         total = total + loss_weights[name] * l
+    if density_penalty is not None:  # :153-163, fine model first
+        coords = torch.from_numpy(np.asarray(density_points[0], np.float32)).to(dtype)
+        dirs = torch.from_numpy(np.asarray(density_points[1], np.float32)).to(dtype)
+        for prefix, model in (("fine", fine), ("coarse", coarse)):
+            densities, _, _ = model.apply(p[prefix], coords, dirs)  # :182
+            penalty = torch.mean(densities)  # :183
+            loss_dict[f"{prefix}_density"] = penalty
+            total = total + density_penalty * penalty
     render_out = dict(coarse=c_out, fine=f_out, coarse_aux=c_aux, fine_aux=f_aux,
                       coarse_ts=cs.ts, fine_ts=f_ts, t_min=t_min, t_max=t_max, mask=mask)
     return total, loss_dict, (p, render_out)

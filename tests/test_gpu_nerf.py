@@ -161,11 +161,11 @@ def test_render_key_api_and_masked_rays():
                                   out["coarse"]["densities"].cpu().numpy())
 
 
-def _train_loop(precision, params, ray_chunk=None, lr=1e-4):
+def _train_loop(precision, params, ray_chunk=None, lr=1e-4, **kwargs):
     from learn_nerf.model import NeRFModel
     from learn_nerf.train import TrainLoop
     coarse, fine = NeRFModel(precision=precision), NeRFModel(precision=precision)
-    loop = TrainLoop(coarse, fine, init_rng=0, lr=lr, coarse_ts=64, fine_ts=128, ray_chunk=ray_chunk)
+    loop = TrainLoop(coarse, fine, init_rng=0, lr=lr, coarse_ts=64, fine_ts=128, ray_chunk=ray_chunk, **kwargs)
     for name in ("coarse", "fine"):
         for lname, leaf in params[name].items():
             for k in ("kernel", "bias"):
@@ -364,6 +364,54 @@ def test_train_step_bf16_vs_oracle():
     worst.sort(reverse=True)
     print("worst bf16 grad rel-L2:", worst[:5])
     assert worst[0][0] < 5e-2, worst[:5]
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 5e-3), ("bf16", 1e-1)])
+def test_density_penalty_vs_oracle(precision, tol):
+    """train.py:153-184: total += density_penalty * mean(density(model, random bbox points)) for
+    the fine and the coarse model.  Explicit points (coords, dirs) are the parity entry point;
+    logged penalties and the per-tensor gradients are checked against fp64 autograd (fp32 path
+    rel-L2 5e-3; bf16 path 1e-1: 128 points + 256 rays is a small batch for Dense_0, measured 6e-2)."""
+    M, T, nerf, params = oracle_setup()
+    n, bs, w = 256, 128, 0.05
+    batch, uc, uf = _render_case(n, 270)
+    rs = np.random.RandomState(5)
+    coords = rs.uniform(-1, 1, (bs, 3)).astype(F)
+    dirs = rs.randn(bs, 3).astype(F)
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    loop = _train_loop(precision, params, density_penalty=w, density_penalty_batch_size=bs)
+    step = loop.step_fn(BBOX_MIN, BBOX_MAX)
+    fine_ts = loop._renderer(list(BBOX_MIN), list(BBOX_MAX), loop.state.params).render_rays(
+        (dev(uc), dev(uf)), dev(batch[:, :2]), _save=True)["fine"]["_ts"].ts.cpu().numpy()
+    g, ld, _ = T.grads(nerf, nerf, params, BBOX_MIN, BBOX_MAX, batch, uc, uf, 64, 128,
+                       fixed_fine_ts=fine_ts, dtype=torch.float64, density_penalty=w,
+                       density_points=(coords, dirs))
+    g0, _, _ = T.grads(nerf, nerf, params, BBOX_MIN, BBOX_MAX, batch, uc, uf, 64, 128,
+                       fixed_fine_ts=fine_ts, dtype=torch.float64)
+    logs = step((dev(uc), dev(uf), (dev(coords), dev(dirs))), dev(batch))
+    assert {"fine_density", "coarse_density"} <= set(logs)
+    rtol = 1e-4 if precision == "fp32" else 2e-2
+    np.testing.assert_allclose(float(logs["fine_density"]), ld["fine_density"], rtol=rtol)
+    np.testing.assert_allclose(float(logs["coarse_density"]), ld["coarse_density"], rtol=rtol)
+    grads = loop._grads
+    worst, moved = [], 0.0
+    for name in ("coarse", "fine"):
+        gt = getattr(loop, name).bind(grads[loop._slices[name][0]:loop._slices[name][1]])
+        for lname, leaf in g[name].items():
+            for k in ("kernel", "bias"):
+                worst.append((rel_l2(gt[lname][k].cpu().numpy(), leaf[k].numpy()), name, lname, k))
+                moved = max(moved, rel_l2(g0[name][lname][k].numpy(), leaf[k].numpy()))
+    worst.sort(reverse=True)
+    print("worst grad rel-L2 with density penalty:", worst[:4], "penalty moved the gradient by", moved)
+    assert moved > 0.2  # the penalty term is a visible part of the gradient in this case
+    assert worst[0][0] < tol, worst[:4]
+    # losses(): forward-only total including the penalty
+    total, loss_dict = loop.losses((dev(uc), dev(uf), (dev(coords), dev(dirs))), BBOX_MIN, BBOX_MAX,
+                                   dev(batch), loop.state.params)
+    assert "fine_density" in loss_dict and float(total) > 0
+    # PRNG-key entry point: points drawn on the device from the key (train.py:137,174-180)
+    logs = step(7, dev(batch))
+    assert np.isfinite(float(logs["fine_density"])) and float(logs["fine_density"]) > 0
 
 
 def test_train_bf16_loss_decreases():

@@ -226,3 +226,32 @@ def test_golden_models_fixture():
     np.testing.assert_allclose(raux["neg_normal"].numpy(), g["ref_neg_normal"], atol=1e-5)
     np.testing.assert_array_equal(render_np.bare_rays(width=7, height=5, **cam), g["rays_7x5"])
     np.testing.assert_array_equal(prng_np.uniform(g["key"], (5, 7)), g["uniforms_5x7"])
+
+
+def test_density_penalty_branch():
+    """train.py:153-184 restated in oracle.train_torch.losses: with weight w the total grows by
+    w * (mean density of the fine model + of the coarse model) at the given points, and the
+    gradient of that term only reaches the density branch (the rgb head gets none)."""
+    from oracle import models_torch as M
+    from oracle import train_torch as T
+    nerf = M.NeRFModel()
+    params = T.init_params(nerf, nerf, 3)
+    rs = np.random.RandomState(0)
+    batch = make_rays(8, seed=2)
+    uc, uf = make_uniforms(8, 64, 3), make_uniforms(8, 128, 4)
+    coords = rs.uniform(-1, 1, (16, 3)).astype(np.float32)
+    dirs = rs.randn(16, 3).astype(np.float32)
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    t0, ld0, _ = T.losses(nerf, nerf, params, BBOX_MIN, BBOX_MAX, batch, uc, uf, 64, 128)
+    t1, ld1, _ = T.losses(nerf, nerf, params, BBOX_MIN, BBOX_MAX, batch, uc, uf, 64, 128,
+                          density_penalty=0.25, density_points=(coords, dirs))
+    with torch.no_grad():
+        df = nerf.apply(params["fine"], torch.from_numpy(coords), torch.from_numpy(dirs))[0].mean()
+        dc = nerf.apply(params["coarse"], torch.from_numpy(coords), torch.from_numpy(dirs))[0].mean()
+    assert list(ld1)[-2:] == ["fine_density", "coarse_density"]  # fine first (:154)
+    np.testing.assert_allclose(float(ld1["fine_density"]), float(df), rtol=1e-6)
+    np.testing.assert_allclose(float(t1 - t0), 0.25 * float(df + dc), rtol=1e-4)
+    # the directions do not matter for the penalty
+    t2, _, _ = T.losses(nerf, nerf, params, BBOX_MIN, BBOX_MAX, batch, uc, uf, 64, 128,
+                        density_penalty=0.25, density_points=(coords, -dirs))
+    assert float(t2) == float(t1)
