@@ -32,6 +32,9 @@ FLOP_TRAIN_PER_SAMPLE = 3_481_344        # fwd + dW + dX, no padding / recompute
 REF_FLOP_FWD_PER_SAMPLE = 2 * (590_336 + 489_472)
 REF_FLOP_TRAIN_PER_SAMPLE = 2 * 3_709_088
 SAMPLES_PER_RAY = 64 + 192
+# ncu (profiles/r01b_nerf_train_kernels_ncu_full.txt): fwd 4.232 + dX 4.034 + dW 8.557 GB of DRAM
+# traffic for the 786,432 samples of the fine level
+NCU_TRAIN_DRAM_BYTES_PER_SAMPLE = (4.232e9 + 4.034e9 + 8.557e9) / 786432
 
 
 def load_peaks():
@@ -339,11 +342,17 @@ def run_ours(args):
             flops = flop_per_sample * SAMPLES_PER_RAY * n  # per rank, per step
             achieved = flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
             roofline = {"bound": "tensor",
-                        "kernel": "nerf_fwd_pair_kernel" + (" + nerf_bwd_dx_kernel + nerf_bwd_dw_kernel"
+                        "kernel": "nerf_fwd_pair_kernel" + (" + nerf_bwd_dx_pair_kernel + nerf_bwd_dw_kernel"
                                                             if train else "") if prec == "bf16"
                                   else "sgemm_kernel chain (fp32 FFMA)",
                         "achieved": achieved, "peak": peaks["tf"], "unit": "TFLOP/s",
-                        "frac": achieved / peaks["tf"], "traffic": None,
+                        "frac": achieved / peaks["tf"],
+                        # DRAM bytes of the three MLP kernels per 4096-ray step, from the ncu --set full
+                        # capture profiles/r01b_nerf_train_kernels_ncu_full.txt (fine level 4.23 + 4.03 +
+                        # 8.56 GB, coarse level = 1/3 of it); equals the algorithmic stash bytes
+                        "traffic": (NCU_TRAIN_DRAM_BYTES_PER_SAMPLE * SAMPLES_PER_RAY * n
+                                    if (train and prec == "bf16" and args.model == "nerf") else None),
+                        "traffic_unit": "bytes per step (dram__bytes_read.sum + dram__bytes_write.sum, ncu)",
                         "peak_source": peaks["source"] + " (sustained bf16 cuBLAS)",
                         "kernel_ms_per_step": dom_ms, "kernel_share_of_step": dom_ms / ms,
                         "algorithmic_flop_per_sample": flop_per_sample}
@@ -379,10 +388,11 @@ def run_ours(args):
         }
         if args.cpu_baseline and world == 1 and args.model == "nerf" and train:
             threads = os.cpu_count() or 1
-            v, sec = cpu_train_sample(args.cpu_rays, 2, 1, threads)
+            cpu_steps = 16  # ~10 s of CPU work on the box's host cores
+            v, sec = cpu_train_sample(args.cpu_rays, cpu_steps, 1, threads)
             line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": threads, "kind": "port",
-                                    "sample": f"oracle torch-CPU train step, {args.cpu_rays} rays/step x 2 "
-                                              f"steps ({sec:.2f} s/step)"}
+                                    "sample": f"oracle torch-CPU train step, {args.cpu_rays} rays/step x "
+                                              f"{cpu_steps} steps ({sec:.2f} s/step)"}
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line))
