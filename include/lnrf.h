@@ -146,6 +146,16 @@ int lnrf_nerf_mlp_bwd(const float* params, const void* packed, int64_t m, int32_
 int lnrf_adam_step(float* params, const float* grads, float* m, float* v, int64_t count,
                    float lr, float b1, float b2, float eps, int32_t step, float grad_scale,
                    float* norms_out, lnrf_stream_t stream);
+/* Data-parallel variant (the reference is single-device, train.py:85-106): fused
+ * all-reduce + Adam.  peer_grads is a HOST array of `world` device addresses, one flat gradient
+ * buffer per rank (NVLink peer / symmetric-memory mappings, own rank included), each holding
+ * count + extra floats.  Gradients are summed in rank order and scaled by grad_scale inside the
+ * optimiser pass; the `extra` trailing floats (per-rank loss sums) are summed into extra_out.
+ * The caller brackets the call with cross-rank barriers.                                      */
+int lnrf_adam_step_peers(float* params, const uint64_t* peer_grads, int32_t world, float* m, float* v,
+                         int64_t count, int32_t extra, float lr, float b1, float b2, float eps,
+                         int32_t step, float grad_scale, float* norms_out, float* extra_out,
+                         lnrf_stream_t stream);
 
 /* ---------------------------------------------------------------- K7/K8 hash grid
  * MultiresHashTableEncoding / HashTableEncoding / hash_table_lookup

@@ -34,6 +34,45 @@ def shard_rays(batch: torch.Tensor) -> torch.Tensor:
     return batch[a:b]
 
 
+class PeerGrads:
+    """The flat gradient buffer of every rank, mapped into this process over NVLink
+    (torch symmetric memory is only the allocator / rendezvous: plumbing).  ``buffer`` is this
+    rank's own gradient tensor, ``ptrs`` the device addresses of all ranks' buffers in rank
+    order, ``barrier()`` a cross-rank barrier enqueued on the current stream."""
+
+    def __init__(self, numel: int, device: torch.device):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.buffer = symm_mem.empty(numel, dtype=torch.float32, device=device)
+        self.buffer.zero_()
+        self._hdl = symm_mem.rendezvous(self.buffer, dist.group.WORLD.group_name)
+        self.ptrs = [int(p) for p in self._hdl.buffer_ptrs]
+        if len(self.ptrs) != dist.get_world_size() or any(p == 0 for p in self.ptrs):
+            raise RuntimeError("symmetric-memory rendezvous returned no peer mappings")
+
+    def barrier(self):
+        self._hdl.barrier()
+
+
+def peer_grads(numel: int, device: torch.device):
+    """PeerGrads when the job is multi-GPU over NCCL and peer mappings are available, else None
+    (single GPU, the gloo CPU tests, LNRF_ALLREDUCE=nccl, or no NVLink P2P): the caller then
+    uses ncclAllReduce followed by the plain Adam kernel."""
+    import os
+    if world()[1] <= 1 or device.type != "cuda" or dist.get_backend() != "nccl":
+        return None
+    if os.environ.get("LNRF_ALLREDUCE", "peer").lower() in ("nccl", "none"):
+        return None
+    try:
+        pg = PeerGrads(numel, device)
+        ok = torch.ones(1, device=device)
+    except Exception as e:  # noqa: BLE001  (every rank must agree on the path: vote below)
+        import warnings
+        warnings.warn(f"peer gradient mapping unavailable ({e!r}); using ncclAllReduce")
+        pg, ok = None, torch.zeros(1, device=device)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    return pg if float(ok) > 0 else None
+
+
 def allreduce_sum_(flat: torch.Tensor) -> torch.Tensor:
     """In-place sum over ranks of the flat gradient buffer (no-op for world 1).  Returns the
     buffer; the caller scales by 1/world (lnrf_adam_step's grad_scale)."""

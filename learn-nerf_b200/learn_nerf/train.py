@@ -65,7 +65,14 @@ class TrainLoop:
             params=dict(coarse=coarse_vars["params"], fine=fine_vars["params"],
                         background=flat[nc + nf: nc + nf + 3]),
             flat=flat)
-        self._grads = torch.zeros_like(flat)
+        # gradients: same layout as the params, followed by the two per-rank loss sums so that ONE
+        # exchange per step covers everything that is summed over ranks
+        self._n_params = nc + nf + 4
+        self._peers = parallel.peer_grads(self._n_params + 4, device)  # None: single GPU / NCCL path
+        self._grads_all = self._peers.buffer if self._peers is not None else torch.zeros(
+            self._n_params + 4, device=device)
+        self._grads = self._grads_all[:self._n_params]
+        self._loss_sums = self._grads_all[self._n_params:self._n_params + 2]
         self._scalars = torch.zeros(4, device=device)  # loss_c, loss_f, |g|^2, |p|^2
         self._zero3 = torch.zeros(3, device=device)
         self._scratch3 = torch.zeros(3, device=device)
@@ -160,7 +167,7 @@ class TrainLoop:
         elif not isinstance(key, (tuple, list)):
             key, density_key = prng.split(key)  # train.py:137
         g = self._grads
-        g.zero_()
+        self._grads_all.zero_()
         self._scalars.zero_()
         aux_sums: Dict[str, torch.Tensor] = {}
         renderer = self._renderer(bmin, bmax, st.params)
@@ -179,7 +186,7 @@ class TrainLoop:
                 lv = out[level]
                 d_out = torch.empty_like(lv["outputs"])
                 _native.mse_loss(lv["outputs"], targets, 9, b - a, inv_count,
-                                 self._scalars[li:li + 1], d_out)
+                                 self._loss_sums[li:li + 1], d_out)
                 ts: RaySamples = lv["_ts"]
                 d_dens, d_rgb = _native.composite_bwd(ts.ts, ts.t_min, ts.t_max, ts._mask_u8(),
                                                       lv["densities"], lv["rgbs"],
@@ -215,12 +222,21 @@ class TrainLoop:
                 penalties[f"{prefix}_density"] = mean
                 d_dens = torch.full_like(dens, self.density_penalty / dens.numel())
                 model.backward_rays(ctx, d_dens, torch.zeros_like(rgb), g[sl[0]:sl[1]])
-        if world > 1:
-            parallel.allreduce_sum_(g)  # one NCCL sum over NVLink; 1/world is folded into Adam
-            parallel.allreduce_sum_(self._scalars[:2])
         st.step += 1
-        _native.adam_step(st.flat, g, st.m, st.v, self.lr, self.b1, self.b2, self.eps, st.step,
-                          1.0 / world, self._scalars[2:4])
+        if self._peers is not None:
+            # fused all-reduce + Adam: every rank reads all ranks' gradients over NVLink inside the
+            # optimiser kernel (rank-order sum, 1/world folded in); barriers fence the peer reads
+            self._peers.barrier()
+            _native.adam_step_peers(st.flat, self._peers.ptrs, st.m, st.v, self._n_params, 2, self.lr,
+                                    self.b1, self.b2, self.eps, st.step, 1.0 / world, self._scalars[2:4],
+                                    self._scalars[0:2])
+            self._peers.barrier()
+        else:
+            if world > 1 and os.environ.get("LNRF_ALLREDUCE") != "none":  # one NCCL sum (gradients + loss sums); 1/world is folded into Adam
+                parallel.allreduce_sum_(self._grads_all)
+            self._scalars[0:2].copy_(self._loss_sums)
+            _native.adam_step(st.flat, g, st.m, st.v, self.lr, self.b1, self.b2, self.eps, st.step,
+                              1.0 / world, self._scalars[2:4])
         for name in ("coarse", "fine"):
             st.params[name].mark_updated()
         s = self._scalars
