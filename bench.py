@@ -370,14 +370,17 @@ def run_ours(args):
             "metric": f"rays/sec ({dict(nerf='NeRF', ngp='Instant-NGP', refnerf='Ref-NeRF')[args.model]} "
                       f"{'train step fwd+bwd+Adam' if train else 'render'})",
             "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            # train / render: fixed rays per GPU (weak); image: one fixed view split over the ranks (strong)
+            "scaling": "strong" if args.workload == "image" else "weak",
             "vs_baseline": None, "dtype": prec, "data": "synthetic",
             "config": {"workload": cfg_name + what + (" train step" if train else " render") +
                                    ", 64+128 samples/ray, random-init weights, bbox [-1,1]^3",
                        "rays_per_gpu": n, "mlp_precision": prec, "ray_chunk": args.ray_chunk,
                        "l2": "256 MiB flush between timed steps; per-step working set >> 126 MB L2",
                        "parallelism": f"ray-sharded dp{world}" +
-                                      (", one NCCL all-reduce of the flat gradient per step" if train else
+                                      (", one exchange of the flat gradient per step (fused NVLink peer "
+                                       "all-reduce + Adam; NCCL fallback)" if train else
                                        ", no collective")},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "rays/s", "ms_per_step": e2e_ms,
