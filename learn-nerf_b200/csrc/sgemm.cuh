@@ -249,7 +249,7 @@ static int gemm_tn_acc(cudaStream_t st, int M, int N, const float* At, int lda, 
 // range (= samples) split over the grid and reduced with atomics.  M, N, lda, ldb multiples of 4.
 constexpr int SBK = 16;
 template <int UNUSED = 0>  // template only so that the definition can live in this header
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)  // <= 64 registers: four blocks per SM (34.6 -> 32.1 ms/step)
 dw_small_kernel(const float* __restrict__ At, int lda, const float* __restrict__ B, int ldb, int M, int N,
                 int64_t K, int64_t k_per_block, float* __restrict__ C, int ldc, float* __restrict__ db) {
   __shared__ __align__(16) float As[2][SBK][64 + 4];
