@@ -183,6 +183,12 @@ def build_models(args, dev):
     if args.model == "refnerf":
         from learn_nerf.ref_nerf import RefNERFModel
         return RefNERFModel(sh_degree=4), RefNERFModel(sh_degree=4), {}
+    if args.model == "ngpref":  # train_nerf.py:141-170 with --instant_ngp --ref_nerf
+        from learn_nerf.instant_ngp import InstantNGPRefNERFModel
+        mk = lambda L: InstantNGPRefNERFModel(table_sizes=[2 ** 18] * L,
+                                              grid_sizes=[2 ** (4 + i // 2) for i in range(L)],
+                                              bbox_min=[-1.0] * 3, bbox_max=[1.0] * 3)
+        return mk(6), mk(16), dict(adam_eps=1e-15, adam_b1=0.9, adam_b2=0.99)
     from learn_nerf.model import NeRFModel
     return NeRFModel(precision=args.precision), NeRFModel(precision=args.precision), {}
 
@@ -211,7 +217,7 @@ def run_ours(args):
     peaks = load_peaks()
     if args.tc_stages is not None:
         _native.set_tc_stages(args.tc_stages)
-    n = args.rays or (32768 if args.model == "ngp" else 4096)
+    n = args.rays or (32768 if args.model in ("ngp", "ngpref") else 4096)
     prec = args.precision if args.model == "nerf" else "fp32"
     if args.model == "refnerf" and args.ray_chunk is None and n > 2048:
         args.ray_chunk = 2048  # 24 KB of saved activations per sample: keep the workspace near 10 GB
@@ -226,6 +232,7 @@ def run_ours(args):
 
     # the dominant kernels, timed with CUDA events on the launching (current) stream
     dom_names = {"ngp": ["hashgrid_fwd", "hashgrid_bwd"], "refnerf": ["refnerf_fwd", "refnerf_bwd"],
+                 "ngpref": ["ngpref_fwd", "ngpref_bwd"],
                  "nerf": ["nerf_mlp_fwd", "nerf_mlp_bwd"]}[args.model]
     dom_events = []
 
@@ -329,12 +336,18 @@ def run_ours(args):
         e2e_value = total_rays / (e2e_ms * 1e-3)
         train = args.workload == "train"
         what = {"nerf": "NeRF coarse+fine", "ngp": "Instant-NGP coarse (L=6) + fine (L=16)",
+                "ngpref": "Instant-NGP Ref-NeRF (smooth hash grid, sh_degree 4) coarse (L=6) + fine (L=16)",
                 "refnerf": "Ref-NeRF (sh_degree 4) coarse+fine"}[args.model]
         cfg_name = {("nerf", True): "configs[1]: ", ("ngp", True): "configs[2]: ", ("refnerf", True): "configs[3]: ",
                     ("nerf", False): "configs[4]-style: "}.get((args.model, train), "")
         if args.workload == "image":
             cfg_name = f"configs[4]: {args.width}x{args.height} view in chunks of {args.batch_size} rays, device-side ray generation and uint8 conversion, "
-        if args.model in ("nerf", "refnerf"):
+        if args.model == "ngpref":
+            roofline = {"bound": "hbm", "kernel": "lnrf_ngpref_fwd" + (" + lnrf_ngpref_bwd" if train else ""),
+                        "achieved": None, "peak": peaks["hbm"], "unit": "GB/s", "frac": None, "traffic": None,
+                        "kernel_ms_per_step": dom_ms, "kernel_share_of_step": dom_ms / ms,
+                        "note": "hash-grid gathers + 64-wide fp32 GEMM chain; no single dominant kernel yet"}
+        elif args.model in ("nerf", "refnerf"):
             if args.model == "nerf":
                 flop_per_sample = FLOP_TRAIN_PER_SAMPLE if train else FLOP_FWD_PER_SAMPLE
             else:
@@ -367,7 +380,7 @@ def run_ours(args):
                         "kernel_ms_per_step": dom_ms, "kernel_share_of_step": dom_ms / ms,
                         "algorithmic_bytes_per_ray": ngp_grid_bytes_per_ray(train)}
         line = {
-            "metric": f"rays/sec ({dict(nerf='NeRF', ngp='Instant-NGP', refnerf='Ref-NeRF')[args.model]} "
+            "metric": f"rays/sec ({dict(nerf='NeRF', ngp='Instant-NGP', refnerf='Ref-NeRF', ngpref='Instant-NGP Ref-NeRF')[args.model]} "
                       f"{'train step fwd+bwd+Adam' if train else 'render'})",
             "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -413,7 +426,7 @@ def main():
     ap.add_argument("--width", type=int, default=800)
     ap.add_argument("--height", type=int, default=800)
     ap.add_argument("--batch_size", type=int, default=65536, help="rays per render_rays call (image workload)")
-    ap.add_argument("--model", default="nerf", choices=["nerf", "ngp", "refnerf"])
+    ap.add_argument("--model", default="nerf", choices=["nerf", "ngp", "refnerf", "ngpref"])
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
                     help="NeRF MLP path: bf16 tcgen05 (2e-2) or fp32 FFMA (1e-5)")
     ap.add_argument("--rays", type=int, default=None, help="rays per GPU per step (4096 NeRF, 32768 NGP)")

@@ -241,6 +241,26 @@ int lnrf_debug_umma_gemm(const float* a, const float* b, int32_t N, int32_t K, f
  * MN-major views of [128 x 64] SW128 block images; M in {128,256}, N in {64,128,192,256}. */
 int lnrf_debug_umma_gemm_tn(const float* at, const float* bt, int32_t M, int32_t N, float* d_out,
                             lnrf_stream_t stream);
+/* ---- InstantNGPRefNERFModel (instant_ngp.py:57-89 on RefNERFBase, ref_nerf.py:34-77): Ref-NeRF
+ * heads on a SMOOTH multiresolution hash grid.  Flat parameter layout: Dense_0 [2L,64], Dense_1
+ * [64,16], Dense_2 [36 rows (33 used),64], Dense_3 [64,64], Dense_4 [64,3] at
+ * lnrf_ngpref_param_offsets (w0,b0,..,w4,b4), then the tables at level_offsets (floats from the
+ * start of `params`, as for lnrf_hashgrid_fwd).  Outputs / aux losses as lnrf_refnerf_fwd; the
+ * backward includes the second-order term through the hash grid's input Jacobian.            */
+int64_t lnrf_ngpref_mlp_param_floats(int32_t L);
+int lnrf_ngpref_param_offsets(int32_t L, int64_t* out_host);
+int lnrf_ngpref_workspace_bytes(int64_t m, int32_t L, int32_t save_for_backward, int64_t* bytes_out_host);
+int lnrf_ngpref_fwd(const float* params, const int64_t* level_offsets_host, const int32_t* grid_sizes_host,
+                    const int32_t* table_sizes_host, int32_t L, const float* bbox_min_host,
+                    const float* bbox_max_host, const float* x, const float* d, const float* rays, const float* ts,
+                    int64_t n, int32_t T, int32_t save_for_backward, void* workspace, int64_t workspace_bytes,
+                    float* dens, float* rgb, float* aux_normal_mse, float* aux_neg_normal, lnrf_stream_t stream);
+int lnrf_ngpref_bwd(const float* params, const int64_t* level_offsets_host, const int32_t* grid_sizes_host,
+                    const int32_t* table_sizes_host, int32_t L, const float* bbox_min_host,
+                    const float* bbox_max_host, const float* x, const float* d, const float* rays, const float* ts,
+                    int64_t n, int32_t T, void* workspace, int64_t workspace_bytes, const float* d_dens,
+                    const float* d_rgb, const float* d_aux_normal_mse, const float* d_aux_neg_normal,
+                    float* d_params, lnrf_stream_t stream);
 /* Tuning knob of the fused bf16 kernel: 1 = one weight-ring stage and two CTAs
  * per SM (default); >= 2 = four stages, one CTA per SM.                       */
 int lnrf_set_tc_stages(int32_t stages);

@@ -126,6 +126,118 @@ hashgrid_bwd_kernel(GridLevels g, const float* __restrict__ x, const float* __re
   }
 }
 
+// ---------------------------------------------------------------- input Jacobian (InstantNGPRefNERFModel)
+// RefNERFBase differentiates the spatial block w.r.t. x (ref_nerf.py:38-43); with a hash-grid
+// spatial block (instant_ngp.py:69-82) that needs d enc / d x.  Per axis a and corner c:
+//   d w_c / d x_a = sign_a(c) * s_a * prod_{b != a} w_b(c),
+//   s_a = [0 <= frac_raw <= 1] / (hi_a - lo_a) * (G - 2 or G - 1) * (smooth ? 6 cf (1 - cf) : 1)
+// (clip -> affine -> fi - floor(fi) -> smoothstep -> cf or 1 - cf), floor / min have zero gradient.
+struct CornersD {
+  uint32_t idx[8];
+  float dw[8][3];  // d w_c / d x_a
+};
+__device__ __forceinline__ CornersD level_corners_dx(const GridLevels& g, int l, const float x[3]) {
+  const int G = g.grid[l];
+  uint32_t base[3];
+  float cf[3], sa[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float raw = (x[a] - g.lo[a]) / (g.hi[a] - g.lo[a]);
+    const float inside = (raw >= 0.0f && raw <= 1.0f) ? 1.0f : 0.0f;
+    const float frac = fminf(fmaxf(raw, 0.0f), 1.0f);
+    const float fi = g.smooth ? __fadd_rn(0.5f, __fmul_rn(float(G - 2), frac)) : float(G - 1) * frac;
+    const float fl = fminf(floorf(fi), float(G - 2));
+    float c = fi - fl;
+    float dc = 1.0f;
+    if (g.smooth) {
+      dc = 6.0f * c * (1.0f - c);
+      c = (c * c) * (3.0f - 2.0f * c);
+    }
+    cf[a] = c;
+    sa[a] = inside / (g.hi[a] - g.lo[a]) * float(g.smooth ? G - 2 : G - 1) * dc;
+    base[a] = uint32_t(fl);
+  }
+  CornersD out;
+  int k = 0;
+#pragma unroll
+  for (int xo = 0; xo < 2; ++xo)
+#pragma unroll
+    for (int yo = 0; yo < 2; ++yo)
+#pragma unroll
+      for (int zo = 0; zo < 2; ++zo, ++k) {
+        const uint32_t cx = base[0] + xo, cy = base[1] + yo, cz = base[2] + zo;
+        const float wx = xo ? cf[0] : 1.0f - cf[0];
+        const float wy = yo ? cf[1] : 1.0f - cf[1];
+        const float wz = zo ? cf[2] : 1.0f - cf[2];
+        out.dw[k][0] = (xo ? sa[0] : -sa[0]) * (wy * wz);
+        out.dw[k][1] = (yo ? sa[1] : -sa[1]) * (wx * wz);
+        out.dw[k][2] = (zo ? sa[2] : -sa[2]) * (wx * wy);
+        if (g.hashed[l]) out.idx[k] = (cx ^ (19349663u * cy) ^ (83492791u * cz)) % g.rows[l];
+        else out.idx[k] = cx + uint32_t(G) * (cy + uint32_t(G) * cz);
+      }
+  return out;
+}
+
+// out[s, a] = sum_{l,f} vec[s, 2l+f] * d enc[s, 2l+f] / d x_a  (= J^T vec), [m,4] (3 used).
+// One thread per point, levels in order: deterministic, no atomics.
+__global__ void __launch_bounds__(256)
+hashgrid_jtv_kernel(const float* __restrict__ tables, GridLevels g, const float* __restrict__ x,
+                    const float* __restrict__ rays, const float* __restrict__ ts, int T, int64_t m,
+                    const float* __restrict__ vec, float* __restrict__ out) {
+  for (int64_t s = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; s < m; s += int64_t(gridDim.x) * blockDim.x) {
+    float p[3];
+    load_point(x, rays, ts, T, s, p);
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (int l = 0; l < g.L; ++l) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(vec + s * 2 * g.L) + l);
+      const CornersD c = level_corners_dx(g, l, p);
+      const float2* tab = reinterpret_cast<const float2*>(tables + g.offset[l]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float2 t = __ldg(tab + c.idx[k]);
+        const float tv = t.x * v.x + t.y * v.y;
+        acc[0] = fmaf(c.dw[k][0], tv, acc[0]);
+        acc[1] = fmaf(c.dw[k][1], tv, acc[1]);
+        acc[2] = fmaf(c.dw[k][2], tv, acc[2]);
+      }
+    }
+    reinterpret_cast<float4*>(out)[s] = make_float4(acc[0], acc[1], acc[2], 0.0f);
+  }
+}
+
+// Backward of out = J^T vec along u = dL/dout [m,4]:  tvec[s, 2l+f] = (J u)[s, 2l+f] = dL/dvec, and
+// d_table[idx_c][f] += (u . d w_c / d x) * vec[s, 2l+f].  One thread per (point, level).
+__global__ void __launch_bounds__(256)
+hashgrid_jtv_bwd_kernel(const float* __restrict__ tables, GridLevels g, const float* __restrict__ x,
+                        const float* __restrict__ rays, const float* __restrict__ ts, int T, int64_t m,
+                        const float* __restrict__ vec, const float* __restrict__ u, float* __restrict__ tvec,
+                        float* __restrict__ d_tables) {
+  const int64_t total = m * g.L;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t s = i / g.L;
+    const int l = int(i - s * g.L);
+    const float4 uu = __ldg(reinterpret_cast<const float4*>(u) + s);
+    const float2 v = __ldg(reinterpret_cast<const float2*>(vec) + i);
+    float p[3];
+    load_point(x, rays, ts, T, s, p);
+    const CornersD c = level_corners_dx(g, l, p);
+    const float2* tab = reinterpret_cast<const float2*>(tables + g.offset[l]);
+    float2* dtab = reinterpret_cast<float2*>(d_tables + g.offset[l]);
+    float2 acc = make_float2(0.f, 0.f);
+    const bool live = (uu.x != 0.0f || uu.y != 0.0f || uu.z != 0.0f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float du = c.dw[k][0] * uu.x + c.dw[k][1] * uu.y + c.dw[k][2] * uu.z;
+      const float2 t = __ldg(tab + c.idx[k]);
+      acc.x = fmaf(du, t.x, acc.x);
+      acc.y = fmaf(du, t.y, acc.y);
+      if (live && du != 0.0f) atomicAdd(dtab + c.idx[k], make_float2(du * v.x, du * v.y));
+    }
+    reinterpret_cast<float2*>(tvec)[i] = acc;
+  }
+}
+
 static int make_levels(GridLevels& g, const int64_t* level_offsets, const int32_t* grid_sizes,
                        const int32_t* table_sizes, int L, const float* bmin, const float* bmax,
                        int smooth, const char* who) {
@@ -148,6 +260,39 @@ static int make_levels(GridLevels& g, const int64_t* level_offsets, const int32_
     g.grid[l] = int(G);
     g.hashed[l] = (G * G * G > int64_t(table_sizes[l])) ? 1 : 0;
     g.rows[l] = g.hashed[l] ? uint32_t(table_sizes[l]) : uint32_t(G * G * G);
+  }
+  return LNRF_OK;
+}
+
+// internal entry points used by the InstantNGPRefNERFModel path (refnerf.cu)
+int hashgrid_launch(int which, const float* tables, const int64_t* level_offsets, const int32_t* grid_sizes,
+                    const int32_t* table_sizes, int L, const float* bmin, const float* bmax, int smooth,
+                    const float* x, const float* rays, const float* ts, int T, int64_t m, const float* in0,
+                    const float* in1, float* out0, float* out1, cudaStream_t st) {
+  GridLevels g;
+  int rc = make_levels(g, level_offsets, grid_sizes, table_sizes, L, bmin, bmax, smooth, "hashgrid_launch");
+  if (rc) return rc;
+  if (m == 0) return LNRF_OK;
+  switch (which) {
+    case 0:  // enc = encode(x)
+      hashgrid_fwd_kernel<<<ew_blocks(m * L, 256), 256, 0, st>>>(tables, g, x, rays, ts, T, m, out0);
+      LNRF_LAUNCH_CHECK("hashgrid_fwd_kernel");
+      break;
+    case 1:  // d_tables += scatter(d_enc = in0)
+      hashgrid_bwd_kernel<<<ew_blocks(m * L, 256), 256, 0, st>>>(g, x, rays, ts, T, m, in0, out0);
+      LNRF_LAUNCH_CHECK("hashgrid_bwd_kernel");
+      break;
+    case 2:  // out0[m,4] = J^T in0
+      hashgrid_jtv_kernel<<<ew_blocks(m, 256), 256, 0, st>>>(tables, g, x, rays, ts, T, m, in0, out0);
+      LNRF_LAUNCH_CHECK("hashgrid_jtv_kernel");
+      break;
+    case 3:  // out0 = J in1(u), d_tables(out1) += second-order scatter with vec = in0
+      hashgrid_jtv_bwd_kernel<<<ew_blocks(m * L, 256), 256, 0, st>>>(tables, g, x, rays, ts, T, m, in0, in1, out0,
+                                                                     out1);
+      LNRF_LAUNCH_CHECK("hashgrid_jtv_bwd_kernel");
+      break;
+    default:
+      return LNRF_E_INVALID;
   }
   return LNRF_OK;
 }

@@ -123,12 +123,13 @@ __device__ __forceinline__ void load_pos(const float* __restrict__ x, const floa
 // ---------------------------------------------------------------- normal chain helpers
 // Gn_7[s, j] = -W_8[j, 0] * [h_7[s, j] > 0]    (seed of the VJP of -z8[:, 0])
 __global__ void __launch_bounds__(256)
-ref_seed_kernel(const float* __restrict__ h7, const float* __restrict__ w8, int64_t m, float* __restrict__ gn7) {
-  const int64_t total = m * kH;
+ref_seed_kernel(const float* __restrict__ h7, const float* __restrict__ w8, int64_t m, float* __restrict__ gn7,
+                int width = kH, int ldw = kH) {  // width = hidden units (power of two), ldw = columns of the last kernel
+  const int64_t total = m * width;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += int64_t(gridDim.x) * blockDim.x) {
-    const int j = int(i & (kH - 1));
-    gn7[i] = __ldg(h7 + i) > 0.0f ? -__ldg(w8 + int64_t(j) * kH) : 0.0f;
+    const int j = int(i & (width - 1));
+    gn7[i] = __ldg(h7 + i) > 0.0f ? -__ldg(w8 + int64_t(j) * ldw) : 0.0f;
   }
 }
 
@@ -183,14 +184,15 @@ ref_temb_kernel(const float* __restrict__ x, const float* __restrict__ rays, con
 
 // dW_8[:, 0] -= sum_s T_7[s, :]   (the tangent network's last layer is column 0 of Dense_8)
 __global__ void __launch_bounds__(256)
-ref_w8col_kernel(const float* __restrict__ t7, int64_t m, float* __restrict__ dw8) {
-  const int col = threadIdx.x;  // 256 threads = 256 input units
+ref_w8col_kernel(const float* __restrict__ t7, int64_t m, float* __restrict__ dw8, int ldw = kH) {
+  const int col = threadIdx.x;  // one thread per input unit (blockDim.x = hidden width)
+  const int width = blockDim.x;
   const int64_t rows_per_block = ceil_div(m, gridDim.x);
   const int64_t r0 = int64_t(blockIdx.x) * rows_per_block;
   const int64_t r1 = min(r0 + rows_per_block, m);
   float acc = 0.0f;
-  for (int64_t r = r0; r < r1; ++r) acc += __ldg(t7 + r * kH + col);
-  atomicAdd(dw8 + int64_t(col) * kH, -acc);
+  for (int64_t r = r0; r < r1; ++r) acc += __ldg(t7 + r * width + col);
+  atomicAdd(dw8 + int64_t(col) * ldw, -acc);
 }
 
 // ---------------------------------------------------------------- per-sample head
@@ -225,11 +227,11 @@ __device__ __forceinline__ RefHead ref_head(const float z[9], const float d[3], 
 __global__ void __launch_bounds__(256)
 ref_head_fwd1_kernel(const float* __restrict__ z8, const float* __restrict__ d, const float* __restrict__ rays,
                      int T, const float* __restrict__ nraw, int64_t m, float* __restrict__ dens,
-                     float* __restrict__ E, float* __restrict__ aux_mse, float* __restrict__ aux_neg) {
+                     float* __restrict__ E, float* __restrict__ aux_mse, float* __restrict__ aux_neg, int ldz = kH) {
   for (int64_t s = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; s < m; s += int64_t(gridDim.x) * blockDim.x) {
     float z[9], dv[3], nr[3];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) z[i] = __ldg(z8 + s * kH + i);
+    for (int i = 0; i < 9; ++i) z[i] = __ldg(z8 + s * ldz + i);
     load_dir(d, rays, T, s, dv);
 #pragma unroll
     for (int i = 0; i < 3; ++i) nr[i] = __ldg(nraw + s * 4 + i);
@@ -259,12 +261,13 @@ __device__ __forceinline__ float srgb_df(float c) {
 
 // forward part 2: o = directional_block output [m,4] -> rgb (:65-71)
 __global__ void __launch_bounds__(256)
-ref_head_fwd2_kernel(const float* __restrict__ z8, const float* __restrict__ o, int64_t m, float* __restrict__ rgb) {
+ref_head_fwd2_kernel(const float* __restrict__ z8, const float* __restrict__ o, int64_t m, float* __restrict__ rgb,
+                     int ldz = kH) {
   for (int64_t s = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; s < m; s += int64_t(gridDim.x) * blockDim.x) {
-    const float spec = sigmoid_f(__ldg(z8 + s * kH + 4));
+    const float spec = sigmoid_f(__ldg(z8 + s * ldz + 4));
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      const float dif = sigmoid_f(__ldg(z8 + s * kH + 1 + i) - 1.0986122886681098f);
+      const float dif = sigmoid_f(__ldg(z8 + s * ldz + 1 + i) - 1.0986122886681098f);
       const float lin = sigmoid_f(__ldg(o + s * 4 + i)) * spec + dif;
       const float cl = fminf(fmaxf(lin, 0.0f), 1.0f);  // _leaky_clip forward value (:320-326)
       rgb[s * 3 + i] = srgb_f(cl) * 2.0f - 1.0f;
@@ -272,24 +275,35 @@ ref_head_fwd2_kernel(const float* __restrict__ z8, const float* __restrict__ o, 
   }
 }
 
-// Dense_10 (128 -> 3): o = c @ W10 + b10, warp per sample (o is [m,4], 3 used)
+// Dense_10 (128 -> 3) / the 64 -> 3 layer of the hash-grid variant: o = c @ W + b, warp per sample
+// (o is [m,4], 3 used); a lane owns PER = width / 32 consecutive hidden units.
+__device__ __forceinline__ void load_per(const float* p, float (&v)[4]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+__device__ __forceinline__ void load_per(const float* p, float (&v)[2]) {
+  const float2 a = __ldg(reinterpret_cast<const float2*>(p));
+  v[0] = a.x; v[1] = a.y;
+}
+template <int PER>
 __global__ void __launch_bounds__(256)
 ref_out_fwd_kernel(const float* __restrict__ c, const float* __restrict__ w10, const float* __restrict__ b10,
                    int64_t m, float* __restrict__ o) {
+  constexpr int kW = PER * 32;
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
-  float w[4][3];
+  float w[PER][3];
 #pragma unroll
-  for (int k = 0; k < 4; ++k)
+  for (int k = 0; k < PER; ++k)
 #pragma unroll
-    for (int j = 0; j < 3; ++j) w[k][j] = __ldg(w10 + (lane * 4 + k) * 3 + j);
+    for (int j = 0; j < 3; ++j) w[k][j] = __ldg(w10 + (lane * PER + k) * 3 + j);
   for (int64_t s = warp; s < m; s += nwarps) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(c + s * kHC) + lane);
-    const float av[4] = {a.x, a.y, a.z, a.w};
+    float av[PER];
+    load_per(c + s * kW + lane * PER, av);
     float acc[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
+    for (int k = 0; k < PER; ++k)
 #pragma unroll
       for (int j = 0; j < 3; ++j) acc[j] = fmaf(av[k], w[k][j], acc[j]);
 #pragma unroll
@@ -300,28 +314,30 @@ ref_out_fwd_kernel(const float* __restrict__ c, const float* __restrict__ w10, c
 
 // backward part 1: d o (gradient w.r.t. the directional block's output) from d rgb; then
 // Dense_10 backward: gc = (d_o @ W10^T) * [c > 0], dW10 += c^T d_o, db10 += sum d_o.
+template <int PER>
 __global__ void __launch_bounds__(256)
 ref_out_bwd_kernel(const float* __restrict__ z8, const float* __restrict__ o, const float* __restrict__ c,
                    const float* __restrict__ d_rgb, const float* __restrict__ w10, int64_t m,
                    float* __restrict__ d_o, float* __restrict__ gc, float* __restrict__ dw10,
-                   float* __restrict__ db10) {
+                   float* __restrict__ db10, int ldz) {
+  constexpr int kW = PER * 32;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
-  float w[4][3], gw[4][3], gb[3] = {0.f, 0.f, 0.f};
+  float w[PER][3], gw[PER][3], gb[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-  for (int k = 0; k < 4; ++k)
+  for (int k = 0; k < PER; ++k)
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      w[k][j] = __ldg(w10 + (lane * 4 + k) * 3 + j);
+      w[k][j] = __ldg(w10 + (lane * PER + k) * 3 + j);
       gw[k][j] = 0.0f;
     }
   for (int64_t s = warp; s < m; s += nwarps) {
-    const float spec = sigmoid_f(__ldg(z8 + s * kH + 4));
+    const float spec = sigmoid_f(__ldg(z8 + s * ldz + 4));
     float dov[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      const float dif = sigmoid_f(__ldg(z8 + s * kH + 1 + i) - 1.0986122886681098f);
+      const float dif = sigmoid_f(__ldg(z8 + s * ldz + 1 + i) - 1.0986122886681098f);
       const float sc = sigmoid_f(__ldg(o + s * 4 + i));
       const float lin = sc * spec + dif;
       const float cl = fminf(fmaxf(lin, 0.0f), 1.0f);
@@ -330,25 +346,26 @@ ref_out_bwd_kernel(const float* __restrict__ z8, const float* __restrict__ o, co
       gb[i] += dov[i];
     }
     if (lane < 3) d_o[s * 4 + lane] = lane == 0 ? dov[0] : (lane == 1 ? dov[1] : dov[2]);
-    const float4 a = __ldg(reinterpret_cast<const float4*>(c + s * kHC) + lane);
-    const float av[4] = {a.x, a.y, a.z, a.w};
-    float g4[4];
+    float av[PER];
+    load_per(c + s * kW + lane * PER, av);
+    float g4[PER];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < PER; ++k) {
       const float t = dov[0] * w[k][0] + dov[1] * w[k][1] + dov[2] * w[k][2];
       g4[k] = av[k] > 0.0f ? t : 0.0f;
 #pragma unroll
       for (int j = 0; j < 3; ++j) gw[k][j] = fmaf(av[k], dov[j], gw[k][j]);
     }
-    reinterpret_cast<float4*>(gc + s * kHC)[lane] = make_float4(g4[0], g4[1], g4[2], g4[3]);
+#pragma unroll
+    for (int k = 0; k < PER; ++k) gc[s * kW + lane * PER + k] = g4[k];
   }
-  __shared__ float s_gw[8][kHC * 3];
+  __shared__ float s_gw[8][kW * 3];
 #pragma unroll
-  for (int k = 0; k < 4; ++k)
+  for (int k = 0; k < PER; ++k)
 #pragma unroll
-    for (int j = 0; j < 3; ++j) s_gw[wib][(lane * 4 + k) * 3 + j] = gw[k][j];
+    for (int j = 0; j < 3; ++j) s_gw[wib][(lane * PER + k) * 3 + j] = gw[k][j];
   __syncthreads();
-  for (int i = threadIdx.x; i < kHC * 3; i += blockDim.x) {
+  for (int i = threadIdx.x; i < kW * 3; i += blockDim.x) {
     float t = 0.0f;
     for (int ww = 0; ww < 8; ++ww) t += s_gw[ww][i];
     atomicAdd(dw10 + i, t);
@@ -367,11 +384,12 @@ ref_head_bwd_kernel(const float* __restrict__ z8, const float* __restrict__ d, c
                     int T, const float* __restrict__ nraw, const float* __restrict__ o,
                     const float* __restrict__ d_dens, const float* __restrict__ d_rgb,
                     const float* __restrict__ d_mse, const float* __restrict__ d_neg,
-                    const float* __restrict__ dE, int64_t m, float* __restrict__ g8, float* __restrict__ u) {
+                    const float* __restrict__ dE, int64_t m, float* __restrict__ g8, float* __restrict__ u,
+                    int ldz = kH) {
   for (int64_t s = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; s < m; s += int64_t(gridDim.x) * blockDim.x) {
     float z[9], dv[3], nr[3];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) z[i] = __ldg(z8 + s * kH + i);
+    for (int i = 0; i < 9; ++i) z[i] = __ldg(z8 + s * ldz + i);
     load_dir(d, rays, T, s, dv);
 #pragma unroll
     for (int i = 0; i < 3; ++i) nr[i] = __ldg(nraw + s * 4 + i);
@@ -429,7 +447,7 @@ ref_head_bwd_kernel(const float* __restrict__ z8, const float* __restrict__ d, c
       u[s * 4 + 3] = 0.0f;
     }
 #pragma unroll
-    for (int i = 0; i < 9; ++i) g8[s * kH + i] += dz[i];
+    for (int i = 0; i < 9; ++i) g8[s * ldz + i] += dz[i];
   }
 }
 
@@ -486,6 +504,85 @@ static RefWs carve_ref(void* base, int64_t m, bool save) {
   w.bytes = off;
   return w;
 }
+
+// ================================================================ InstantNGPRefNERFModel
+// instant_ngp.py:57-89 on RefNERFBase (ref_nerf.py:34-77): spatial_block = smooth multiresolution
+// hash grid (E = 2L features) -> Dense_0 (E -> 64) ReLU -> Dense_1 (64 -> 16); the 16 outputs are
+// split exactly like z8[:, :9] above; directional_block = Dense_2 (16 + 16 + 1 = 33 -> 64) ReLU ->
+// Dense_3 (64 -> 64) ReLU -> Dense_4 (64 -> 3).  real_normal needs d(-out[:,0])/dx THROUGH the hash
+// grid: vec = Gn_0 W_0^T with Gn_0 = -W_1[:,0] * [h_0 > 0], then n_raw = J^T vec with J = d enc / d x
+// (hashgrid.cu).  The backward adds, along u = dL/dn_raw: T_enc = J u, dW_0 += T_enc^T Gn_0,
+// dW_1[:,0] -= sum (T_enc W_0) * [h_0 > 0], and the table gradient (u . d w_c/dx) vec.
+constexpr int kNrHidden = 64, kNrOut = 16;
+constexpr int kNrDirRows = kNrOut + kRefE;  // 36 kernel rows in the flat buffer (33 used, 3 zero pads)
+struct NgpRefLayout {
+  int in[5], rows[5], out[5];
+  int64_t w[5], b[5], total;
+};
+static NgpRefLayout ngpref_layout(int L) {
+  NgpRefLayout n{};
+  const int ins[5] = {2 * L, kNrHidden, kNrOut + kRefEnc + 1, kNrHidden, kNrHidden};
+  const int rows[5] = {2 * L, kNrHidden, kNrDirRows, kNrHidden, kNrHidden};
+  const int outs[5] = {kNrHidden, kNrOut, kNrHidden, kNrHidden, 3};
+  int64_t off = 0;
+  for (int i = 0; i < 5; ++i) {
+    n.in[i] = ins[i];
+    n.rows[i] = rows[i];
+    n.out[i] = outs[i];
+    n.w[i] = off;
+    off = align_up(off + int64_t(rows[i]) * outs[i], 4);
+    n.b[i] = off;
+    off = align_up(off + outs[i], 4);
+  }
+  n.total = off;
+  return n;
+}
+
+struct NgpRefWs {
+  float *enc, *h0, *z, *gn0, *vec, *nraw, *E, *c1, *c2, *o;       // forward
+  float *d_o, *gc2, *gc1, *g, *dE, *u, *g0, *d_enc, *tenc, *t0;   // backward only
+  int64_t bytes;
+};
+static NgpRefWs carve_ngpref(void* base, int64_t m, int E, bool save) {
+  NgpRefWs w{};
+  char* p = reinterpret_cast<char*>(base);
+  int64_t off = 0;
+  auto take = [&](int64_t floats) {
+    float* r = reinterpret_cast<float*>(p + off);
+    off += align_up(floats * 4, 256);
+    return r;
+  };
+  w.enc = take(m * E);
+  w.h0 = take(m * kNrHidden);
+  w.z = take(m * kNrOut);
+  w.gn0 = take(m * kNrHidden);
+  w.vec = take(m * E);
+  w.nraw = take(m * 4);
+  w.E = take(m * kRefE);
+  w.c1 = take(m * kNrHidden);
+  w.c2 = take(m * kNrHidden);
+  w.o = take(m * 4);
+  if (save) {
+    w.d_o = take(m * 4);
+    w.gc2 = take(m * kNrHidden);
+    w.gc1 = take(m * kNrHidden);
+    w.g = take(m * kNrOut);
+    w.dE = take(m * kRefE);
+    w.u = take(m * 4);
+    w.g0 = take(m * kNrHidden);
+    w.d_enc = take(m * E);
+    w.tenc = take(m * E);
+    w.t0 = take(m * kNrHidden);
+  }
+  w.bytes = off;
+  return w;
+}
+
+// hashgrid.cu: 0 = encode, 1 = scatter d_enc, 2 = J^T vec, 3 = J u + second-order table scatter
+int hashgrid_launch(int which, const float* tables, const int64_t* level_offsets, const int32_t* grid_sizes,
+                    const int32_t* table_sizes, int L, const float* bmin, const float* bmax, int smooth,
+                    const float* x, const float* rays, const float* ts, int T, int64_t m, const float* in0,
+                    const float* in1, float* out0, float* out1, cudaStream_t st);
 
 }  // namespace lnrf
 
@@ -567,7 +664,7 @@ int lnrf_refnerf_fwd(const float* params, const float* x, const float* d, const 
   LNRF_LAUNCH_CHECK("ref_head_fwd1_kernel");
   if ((rc = gemm_nn<EPI_BIAS_RELU>(st, m, kHC, w.h[8], kH, kH, w.E, kRefE, kRefE, P + kRef.w[9], kHC, w.c, kHC,
                                    P + kRef.b[9]))) return rc;  // directional_block :105-106
-  ref_out_fwd_kernel<<<ew_blocks(m, 8), 256, 0, st>>>(w.c, P + kRef.w[10], P + kRef.b[10], m, w.o);  // :107
+  ref_out_fwd_kernel<4><<<ew_blocks(m, 8), 256, 0, st>>>(w.c, P + kRef.w[10], P + kRef.b[10], m, w.o);  // :107
   LNRF_LAUNCH_CHECK("ref_out_fwd_kernel");
   ref_head_fwd2_kernel<<<ew_blocks(m, 256), 256, 0, st>>>(w.h[8], w.o, m, rgb);
   LNRF_LAUNCH_CHECK("ref_head_fwd2_kernel");
@@ -595,8 +692,8 @@ int lnrf_refnerf_bwd(const float* params, const float* x, const float* d, const 
   const unsigned cb = ew_blocks(m, 512);  // >= 1k blocks at training sizes
   int rc;
   // ---- directional block
-  ref_out_bwd_kernel<<<ew_blocks(m, 8 * 16), 256, 0, st>>>(w.h[8], w.o, w.c, d_rgb, P + kRef.w[10], m, w.d_o,
-                                                            w.gc, G + kRef.w[10], G + kRef.b[10]);
+  ref_out_bwd_kernel<4><<<ew_blocks(m, 8 * 16), 256, 0, st>>>(w.h[8], w.o, w.c, d_rgb, P + kRef.w[10], m, w.d_o,
+                                                               w.gc, G + kRef.w[10], G + kRef.b[10], kH);
   LNRF_LAUNCH_CHECK("ref_out_bwd_kernel");
   if ((rc = gemm_tn_acc(st, kH, kHC, w.h[8], kH, w.gc, kHC, m, G + kRef.w[9], kHC))) return rc;
   if ((rc = gemm_tn_acc(st, kRefE, kHC, w.E, kRefE, w.gc, kHC, m, G + kRef.w[9] + int64_t(kH) * kHC, kHC))) return rc;
@@ -645,6 +742,141 @@ int lnrf_refnerf_bwd(const float* params, const float* x, const float* d, const 
     float* t = tc; tc = tn; tn = t;
   }
   ref_w8col_kernel<<<cb, 256, 0, st>>>(tc, m, G + kRef.w[8]);  // dW_8[:, 0] -= sum T_7
+  LNRF_LAUNCH_CHECK("ref_w8col_kernel");
+  return LNRF_OK;
+}
+
+// ---------------------------------------------------------------- InstantNGPRefNERFModel entries
+int64_t lnrf_ngpref_mlp_param_floats(int32_t L) { return lnrf::ngpref_layout(L).total; }
+int lnrf_ngpref_param_offsets(int32_t L, int64_t* out_host) {
+  LNRF_REQUIRE(out_host && L >= 1 && L <= 16, LNRF_E_INVALID, "lnrf_ngpref_param_offsets: bad args");
+  const lnrf::NgpRefLayout n = lnrf::ngpref_layout(L);
+  for (int i = 0; i < 5; ++i) {
+    out_host[2 * i] = n.w[i];
+    out_host[2 * i + 1] = n.b[i];
+  }
+  return LNRF_OK;
+}
+int lnrf_ngpref_workspace_bytes(int64_t m, int32_t L, int32_t save_for_backward, int64_t* bytes_out_host) {
+  LNRF_REQUIRE(m >= 0 && L >= 1 && L <= 16 && bytes_out_host, LNRF_E_INVALID, "lnrf_ngpref_workspace_bytes: bad args");
+  *bytes_out_host = lnrf::carve_ngpref(nullptr, m, 2 * L, save_for_backward != 0).bytes;
+  return LNRF_OK;
+}
+
+int lnrf_ngpref_fwd(const float* params, const int64_t* level_offsets_host, const int32_t* grid_sizes_host,
+                    const int32_t* table_sizes_host, int32_t L, const float* bbox_min_host,
+                    const float* bbox_max_host, const float* x, const float* d, const float* rays, const float* ts,
+                    int64_t n, int32_t T, int32_t save_for_backward, void* workspace, int64_t workspace_bytes,
+                    float* dens, float* rgb, float* aux_normal_mse, float* aux_neg_normal, lnrf_stream_t stream) {
+  using namespace lnrf;
+  LNRF_REQUIRE(n >= 0 && T >= 1 && L >= 1 && L <= 16, LNRF_E_INVALID, "lnrf_ngpref_fwd: n=%lld T=%d L=%d", (long long)n, T, L);
+  const int64_t m = n * T;
+  if (m == 0) return LNRF_OK;
+  LNRF_REQUIRE(params && workspace && dens && rgb && aux_normal_mse && aux_neg_normal, LNRF_E_INVALID,
+               "lnrf_ngpref_fwd: null pointer");
+  LNRF_REQUIRE((x && d && !rays && !ts) || (!x && !d && rays && ts), LNRF_E_INVALID,
+               "lnrf_ngpref_fwd: pass either (x,d) or (rays,ts)");
+  LNRF_REQUIRE(m < (int64_t(1) << 31), LNRF_E_UNSUPPORTED, "lnrf_ngpref_fwd: %lld samples per call; chunk the batch",
+               (long long)m);
+  const int E = 2 * L;
+  const bool save = save_for_backward != 0;
+  LNRF_REQUIRE(workspace_bytes >= carve_ngpref(nullptr, m, E, save).bytes, LNRF_E_WORKSPACE,
+               "lnrf_ngpref_fwd: workspace %lld < %lld bytes", (long long)workspace_bytes,
+               (long long)carve_ngpref(nullptr, m, E, save).bytes);
+  const NgpRefWs w = carve_ngpref(workspace, m, E, save);
+  const NgpRefLayout nl = ngpref_layout(L);
+  cudaStream_t st = as_stream(stream);
+  const float* P = params;
+  int rc;
+#define LNRF_GRID(which, in0, in1, out0, out1)                                                                  \
+  hashgrid_launch(which, P, level_offsets_host, grid_sizes_host, table_sizes_host, L, bbox_min_host, bbox_max_host, \
+                  1, x, rays, ts, T, m, in0, in1, out0, out1, st)
+  // ---- spatial_block (instant_ngp.py:69-82): smooth hash grid -> Dense_0 ReLU -> Dense_1
+  if ((rc = LNRF_GRID(0, nullptr, nullptr, w.enc, nullptr))) return rc;
+  if ((rc = gemm_nn<EPI_BIAS_RELU>(st, m, kNrHidden, w.enc, E, E, nullptr, 0, 0, P + nl.w[0], kNrHidden, w.h0,
+                                   kNrHidden, P + nl.b[0]))) return rc;
+  if ((rc = gemm_nn<EPI_BIAS>(st, m, kNrOut, w.h0, kNrHidden, kNrHidden, nullptr, 0, 0, P + nl.w[1], kNrOut, w.z,
+                              kNrOut, P + nl.b[1]))) return rc;
+  // ---- real_normal (ref_nerf.py:38-43): Gn_0 = -W_1[:,0] [h_0 > 0]; vec = Gn_0 W_0^T; n_raw = J^T vec
+  ref_seed_kernel<<<ew_blocks(m * kNrHidden, 256), 256, 0, st>>>(w.h0, P + nl.w[1], m, w.gn0, kNrHidden, kNrOut);
+  LNRF_LAUNCH_CHECK("ref_seed_kernel");
+  if ((rc = gemm_nt<EPI_STORE>(st, m, E, w.gn0, kNrHidden, kNrHidden, P + nl.w[0], kNrHidden, w.vec, E))) return rc;
+  if ((rc = LNRF_GRID(2, w.vec, nullptr, w.nraw, nullptr))) return rc;
+  // ---- heads (ref_nerf.py:45-75)
+  ref_head_fwd1_kernel<<<ew_blocks(m, 256), 256, 0, st>>>(w.z, d, rays, T, w.nraw, m, dens, w.E, aux_normal_mse,
+                                                          aux_neg_normal, kNrOut);
+  LNRF_LAUNCH_CHECK("ref_head_fwd1_kernel");
+  // ---- directional_block (instant_ngp.py:84-89): [spatial_out | IDE | n.(-d)] -> 64 -> 64 -> 3
+  if ((rc = gemm_nn<EPI_BIAS_RELU>(st, m, kNrHidden, w.z, kNrOut, kNrOut, w.E, kRefE, kRefE, P + nl.w[2], kNrHidden,
+                                   w.c1, kNrHidden, P + nl.b[2]))) return rc;
+  if ((rc = gemm_nn<EPI_BIAS_RELU>(st, m, kNrHidden, w.c1, kNrHidden, kNrHidden, nullptr, 0, 0, P + nl.w[3],
+                                   kNrHidden, w.c2, kNrHidden, P + nl.b[3]))) return rc;
+  ref_out_fwd_kernel<2><<<ew_blocks(m, 8), 256, 0, st>>>(w.c2, P + nl.w[4], P + nl.b[4], m, w.o);
+  LNRF_LAUNCH_CHECK("ref_out_fwd_kernel");
+  ref_head_fwd2_kernel<<<ew_blocks(m, 256), 256, 0, st>>>(w.z, w.o, m, rgb, kNrOut);
+  LNRF_LAUNCH_CHECK("ref_head_fwd2_kernel");
+  return LNRF_OK;
+}
+
+int lnrf_ngpref_bwd(const float* params, const int64_t* level_offsets_host, const int32_t* grid_sizes_host,
+                    const int32_t* table_sizes_host, int32_t L, const float* bbox_min_host,
+                    const float* bbox_max_host, const float* x, const float* d, const float* rays, const float* ts,
+                    int64_t n, int32_t T, void* workspace, int64_t workspace_bytes, const float* d_dens,
+                    const float* d_rgb, const float* d_aux_normal_mse, const float* d_aux_neg_normal,
+                    float* d_params, lnrf_stream_t stream) {
+  using namespace lnrf;
+  LNRF_REQUIRE(n >= 0 && T >= 1 && L >= 1 && L <= 16, LNRF_E_INVALID, "lnrf_ngpref_bwd: n=%lld T=%d L=%d", (long long)n, T, L);
+  const int64_t m = n * T;
+  if (m == 0) return LNRF_OK;
+  LNRF_REQUIRE(params && workspace && d_dens && d_rgb && d_aux_normal_mse && d_aux_neg_normal && d_params,
+               LNRF_E_INVALID, "lnrf_ngpref_bwd: null pointer");
+  LNRF_REQUIRE((x && d && !rays && !ts) || (!x && !d && rays && ts), LNRF_E_INVALID,
+               "lnrf_ngpref_bwd: pass either (x,d) or (rays,ts)");
+  LNRF_REQUIRE((uintptr_t)d_params % 16 == 0, LNRF_E_INVALID, "lnrf_ngpref_bwd: d_params not 16-byte aligned");
+  const int E = 2 * L;
+  LNRF_REQUIRE(workspace_bytes >= carve_ngpref(nullptr, m, E, true).bytes, LNRF_E_WORKSPACE,
+               "lnrf_ngpref_bwd: workspace too small");
+  const NgpRefWs w = carve_ngpref(workspace, m, E, true);
+  const NgpRefLayout nl = ngpref_layout(L);
+  cudaStream_t st = as_stream(stream);
+  const float* P = params;
+  float* G = d_params;
+  int rc;
+  // ---- directional block: Dense_4, Dense_3, Dense_2
+  ref_out_bwd_kernel<2><<<ew_blocks(m, 8 * 16), 256, 0, st>>>(w.z, w.o, w.c2, d_rgb, P + nl.w[4], m, w.d_o, w.gc2,
+                                                               G + nl.w[4], G + nl.b[4], kNrOut);
+  LNRF_LAUNCH_CHECK("ref_out_bwd_kernel");
+  if ((rc = gemm_tn_small(st, kNrHidden, kNrHidden, w.c1, kNrHidden, w.gc2, kNrHidden, m, G + nl.w[3], kNrHidden,
+                          G + nl.b[3]))) return rc;
+  if ((rc = gemm_nt<EPI_MASK>(st, m, kNrHidden, w.gc2, kNrHidden, kNrHidden, P + nl.w[3], kNrHidden, w.gc1, kNrHidden,
+                              w.c1, kNrHidden))) return rc;
+  if ((rc = gemm_tn_small(st, kNrOut, kNrHidden, w.z, kNrOut, w.gc1, kNrHidden, m, G + nl.w[2], kNrHidden,
+                          G + nl.b[2]))) return rc;
+  if ((rc = gemm_tn_small(st, kRefE, kNrHidden, w.E, kRefE, w.gc1, kNrHidden, m,
+                          G + nl.w[2] + int64_t(kNrOut) * kNrHidden, kNrHidden, nullptr))) return rc;
+  if ((rc = gemm_nt<EPI_STORE>(st, m, kNrOut, w.gc1, kNrHidden, kNrHidden, P + nl.w[2], kNrHidden, w.g, kNrOut))) return rc;
+  if ((rc = gemm_nt<EPI_STORE>(st, m, kRefE, w.gc1, kNrHidden, kNrHidden, P + nl.w[2] + int64_t(kNrOut) * kNrHidden,
+                               kNrHidden, w.dE, kRefE))) return rc;
+  // ---- heads: adds dL/dspatial_out[:, :9] into g, produces u = dL/dn_raw
+  ref_head_bwd_kernel<<<ew_blocks(m, 256), 256, 0, st>>>(w.z, d, rays, T, w.nraw, w.o, d_dens, d_rgb, d_aux_normal_mse,
+                                                         d_aux_neg_normal, w.dE, m, w.g, w.u, kNrOut);
+  LNRF_LAUNCH_CHECK("ref_head_bwd_kernel");
+  // ---- first-order chain through the spatial block and the hash grid
+  if ((rc = gemm_tn_small(st, kNrHidden, kNrOut, w.h0, kNrHidden, w.g, kNrOut, m, G + nl.w[1], kNrOut, G + nl.b[1]))) return rc;
+  if ((rc = gemm_nt<EPI_MASK>(st, m, kNrHidden, w.g, kNrOut, kNrOut, P + nl.w[1], kNrOut, w.g0, kNrHidden, w.h0,
+                              kNrHidden))) return rc;
+  if ((rc = gemm_tn_small(st, E, kNrHidden, w.enc, E, w.g0, kNrHidden, m, G + nl.w[0], kNrHidden, G + nl.b[0]))) return rc;
+  if ((rc = gemm_nt<EPI_STORE>(st, m, E, w.g0, kNrHidden, kNrHidden, P + nl.w[0], kNrHidden, w.d_enc, E))) return rc;
+#define LNRF_GRID_B(which, in0, in1, out0, out1)                                                                \
+  hashgrid_launch(which, P, level_offsets_host, grid_sizes_host, table_sizes_host, L, bbox_min_host, bbox_max_host, \
+                  1, x, rays, ts, T, m, in0, in1, out0, out1, st)
+  if ((rc = LNRF_GRID_B(1, w.d_enc, nullptr, G, nullptr))) return rc;
+  // ---- second-order term through real_normal: tangent pass along u
+  if ((rc = LNRF_GRID_B(3, w.vec, w.u, w.tenc, G))) return rc;                                   // T_enc = J u; tables
+  if ((rc = gemm_tn_small(st, E, kNrHidden, w.tenc, E, w.gn0, kNrHidden, m, G + nl.w[0], kNrHidden, nullptr))) return rc;
+  if ((rc = gemm_nn<EPI_MASK>(st, m, kNrHidden, w.tenc, E, E, nullptr, 0, 0, P + nl.w[0], kNrHidden, w.t0, kNrHidden,
+                              nullptr, w.h0, kNrHidden))) return rc;                               // T_0
+  ref_w8col_kernel<<<ew_blocks(m, 512), kNrHidden, 0, st>>>(w.t0, m, G + nl.w[1], kNrOut);         // dW_1[:,0] -= sum T_0
   LNRF_LAUNCH_CHECK("ref_w8col_kernel");
   return LNRF_OK;
 }

@@ -70,6 +70,13 @@ _SIGS = {
                          [c_void_p] * 5),
     "lnrf_refnerf_bwd": (c_int32, [c_void_p] * 5 + [c_int64, c_int32, c_void_p, c_int64] + [c_void_p] * 6),
     "lnrf_set_debug_flags": (c_int32, [c_int32]),
+    "lnrf_ngpref_mlp_param_floats": (c_int64, [c_int32]),
+    "lnrf_ngpref_param_offsets": (c_int32, [c_int32, c_void_p]),
+    "lnrf_ngpref_workspace_bytes": (c_int32, [c_int64, c_int32, c_int32, c_void_p]),
+    "lnrf_ngpref_fwd": (c_int32, [c_void_p] * 4 + [c_int32, c_void_p, c_void_p] + [c_void_p] * 4 +
+                        [c_int64, c_int32, c_int32, c_void_p, c_int64] + [c_void_p] * 5),
+    "lnrf_ngpref_bwd": (c_int32, [c_void_p] * 4 + [c_int32, c_void_p, c_void_p] + [c_void_p] * 4 +
+                        [c_int64, c_int32, c_void_p, c_int64] + [c_void_p] * 6),
     "lnrf_ngp_mlp_param_offsets": (c_int32, [c_int32, c_void_p]),
     "lnrf_hashgrid_fwd": (c_int32, [c_void_p] * 4 + [c_int32, c_void_p, c_void_p, c_int32,
                                                      c_void_p, c_void_p, c_void_p, c_int64, c_int32,
@@ -341,6 +348,37 @@ def hashgrid_bwd(spec: GridSpec, x, rays, ts, n, T, d_enc, d_tables_flat):
     _check(load().lnrf_hashgrid_bwd(spec._off, spec._grid, spec._tab, spec.L, spec._lo, spec._hi,
                                     spec.smooth, _p(x), _p(rays), _p(ts), n, T, _p(_f32c(d_enc, "d_enc")),
                                     _p(d_tables_flat), _stream()), "lnrf_hashgrid_bwd")
+
+
+def ngpref_mlp_param_floats(L: int) -> int:
+    return int(load().lnrf_ngpref_mlp_param_floats(L))
+
+
+def ngpref_param_offsets(L: int):
+    buf = (c_int64 * 10)()
+    _check(load().lnrf_ngpref_param_offsets(L, buf), "lnrf_ngpref_param_offsets")
+    return [int(v) for v in buf]
+
+
+def ngpref_workspace_bytes(m: int, L: int, save: bool) -> int:
+    out = c_int64(0)
+    _check(load().lnrf_ngpref_workspace_bytes(m, L, int(save), ctypes.byref(out)), "lnrf_ngpref_workspace_bytes")
+    return int(out.value)
+
+
+def ngpref_fwd(flat, spec: GridSpec, x, d, rays, ts, n, T, save, workspace, dens, rgb, aux_mse, aux_neg):
+    ensure_init(flat.device)
+    _check(load().lnrf_ngpref_fwd(_p(flat), spec._off, spec._grid, spec._tab, spec.L, spec._lo, spec._hi, _p(x),
+                                  _p(d), _p(rays), _p(ts), n, T, int(save), _p(workspace), workspace.numel(),
+                                  _p(dens), _p(rgb), _p(aux_mse), _p(aux_neg), _stream()), "lnrf_ngpref_fwd")
+
+
+def ngpref_bwd(flat, spec: GridSpec, x, d, rays, ts, n, T, workspace, d_dens, d_rgb, d_mse, d_neg, d_flat):
+    ensure_init(flat.device)
+    _check(load().lnrf_ngpref_bwd(_p(flat), spec._off, spec._grid, spec._tab, spec.L, spec._lo, spec._hi, _p(x),
+                                  _p(d), _p(rays), _p(ts), n, T, _p(workspace), workspace.numel(),
+                                  _p(_f32c(d_dens, "d_dens")), _p(_f32c(d_rgb, "d_rgb")), _p(_f32c(d_mse, "d_mse")),
+                                  _p(_f32c(d_neg, "d_neg")), _p(d_flat), _stream()), "lnrf_ngpref_bwd")
 
 
 def ngp_mlp_param_floats(L: int) -> int:

@@ -4,6 +4,8 @@ Same constructor fields as the reference (instant_ngp.py:16-31); parameters keep
 names (``Dense_0..4`` and ``MultiresHashTableEncoding_0/HashTableEncoding_l/table``) as
 views into one flat fp32 buffer ``[MLP | table_0 | table_1 | ...]``.  The arithmetic runs
 in liblnrf.so: lnrf_hashgrid_fwd/_bwd (K7/K8) and lnrf_ngp_mlp_fwd/_bwd.
+``InstantNGPRefNERFModel`` (instant_ngp.py:57-89) is the Ref-NeRF variant on a smooth hash grid
+(lnrf_ngpref_fwd/_bwd).
 """
 import math
 from dataclasses import dataclass, field
@@ -167,3 +169,129 @@ class InstantNGPModel(ModelBase):
         _native.ngp_mlp_bwd(tree.flat, self.L, ctx["enc"], m, ctx["ws"], ctx["dens"], ctx["rgb"],
                             d_dens.reshape(-1), d_rgb.reshape(-1, 3), d_flat, d_enc)
         _native.hashgrid_bwd(self.spec(), None, ctx["rays"], ctx["ts"], ctx["n"], ctx["T"], d_enc, d_flat)
+
+
+@dataclass
+class InstantNGPRefNERFModel(ModelBase):
+    """instant_ngp.py:57-89 on RefNERFBase (ref_nerf.py:19-77, sh_degree = 4): smooth hash grid ->
+    Dense(64) ReLU -> Dense(16) as the spatial block, Dense(64) ReLU x2 -> Dense(3) as the
+    directional block.  Same model contract as RefNERFModel:
+    ``(x[N,3], d[N,3]) -> (density[N,1], rgb[N,3], {"normal_mse": [N], "neg_normal": [N]})``."""
+
+    table_sizes: List[int]
+    grid_sizes: List[int]
+    bbox_min: Any
+    bbox_max: Any
+    sh_degree: int = 4
+    table_feature_dim: int = 2
+    d_freqs: int = 4
+    hidden_dim: int = 64
+    density_dim: int = 16
+    density_layers: int = 1
+    color_layers: int = 2
+    precision: str = "fp32"
+    _spec: Optional[_native.GridSpec] = field(default=None, repr=False, compare=False)
+
+    aux_names = ("normal_mse", "neg_normal")
+
+    def _check_arch(self):
+        assert 1 <= self.sh_degree <= 8  # ref_nerf.py:154
+        if (self.sh_degree, self.table_feature_dim, self.hidden_dim, self.density_dim, self.density_layers,
+                self.color_layers) != (4, 2, 64, 16, 1, 2):
+            raise _native.LnrfError("liblnrf implements InstantNGPRefNERFModel(sh_degree=4) with the default "
+                                    "head sizes only (F=2, hidden 64, density_dim 16, 1 + 2 layers)")
+        if len(self.grid_sizes) != len(self.table_sizes) or not 1 <= len(self.grid_sizes) <= 16:
+            raise _native.LnrfError("1..16 levels supported")
+        if self.precision != "fp32":
+            raise _native.LnrfError("InstantNGPRefNERFModel runs on the fp32 path only")
+
+    @property
+    def L(self) -> int:
+        return len(self.grid_sizes)
+
+    def spec(self) -> _native.GridSpec:
+        if self._spec is None:
+            self._check_arch()
+            def v3(v):
+                return [float(x) for x in (v.tolist() if hasattr(v, "tolist") else v)]
+            self._spec = _native.GridSpec(self.table_sizes, self.grid_sizes, v3(self.bbox_min), v3(self.bbox_max),
+                                          True, base_offset=_native.ngpref_mlp_param_floats(self.L))  # smooth=True :79
+        return self._spec
+
+    def layer_dims(self):
+        return [(2 * self.L, 64), (64, 16), (16 + 16 + 1, 64), (64, 64), (64, 3)]
+
+    def param_floats(self) -> int:
+        return self.spec().end
+
+    def param_count(self) -> int:
+        return sum(a * b + b for a, b in self.layer_dims()) + sum(r * 2 for r in self.spec().rows)
+
+    def bind(self, flat: torch.Tensor) -> ParamTree:
+        spec = self.spec()
+        offs = _native.ngpref_param_offsets(self.L)
+        tree = ParamTree()
+        for i, (a, b) in enumerate(self.layer_dims()):  # Dense_2 owns 36 rows in the buffer: 3 zero pads follow
+            tree[f"Dense_{i}"] = dict(kernel=flat[offs[2 * i]: offs[2 * i] + a * b].view(a, b),
+                                      bias=flat[offs[2 * i + 1]: offs[2 * i + 1] + b])
+        tree["MultiresHashTableEncoding_0"] = {
+            f"HashTableEncoding_{l}": dict(table=flat[o: o + r * 2].view(r, 2))
+            for l, (o, r) in enumerate(zip(spec.offsets, spec.rows))}
+        tree.flat = flat
+        return tree
+
+    flatten_params = InstantNGPModel.flatten_params
+    init = InstantNGPModel.init
+
+    # ------------------------------------------------------------------ native calls
+    def _workspace(self, m: int, save: bool, device, slot=None) -> torch.Tensor:
+        nbytes = _native.ngpref_workspace_bytes(m, self.L, save)
+        cache = self.__dict__.setdefault("_ws_cache", {})
+        key = (str(device), bool(save), slot)
+        ws = cache.get(key)
+        if ws is None or ws.numel() < nbytes:
+            raw = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+            shift = (-raw.data_ptr()) % 256
+            ws = raw[shift: shift + nbytes]
+            cache[key] = ws
+        return ws
+
+    def _forward(self, tree, x, d, rays, ts, n, T, save, slot=None):
+        dev = tree.flat.device
+        m = n * T
+        dens = torch.empty(m, device=dev)
+        rgb = torch.empty(m, 3, device=dev)
+        aux_mse = torch.empty(m, device=dev)
+        aux_neg = torch.empty(m, device=dev)
+        ws = self._workspace(m, save, dev, slot)
+        _native.ngpref_fwd(tree.flat, self.spec(), x, d, rays, ts, n, T, save, ws, dens, rgb, aux_mse, aux_neg)
+        return dens, rgb, aux_mse, aux_neg, ws
+
+    def apply(self, variables, x: torch.Tensor, d: torch.Tensor):
+        tree = self.flatten_params(variables["params"])
+        x = _native._f32c(x.contiguous(), "x")
+        d = _native._f32c(d.contiguous(), "d")
+        dens, rgb, a1, a2, _ = self._forward(tree, x, d, None, None, x.shape[0], 1, save=False)
+        return dens[:, None], rgb, dict(normal_mse=a1, neg_normal=a2)
+
+    def apply_rays(self, params, rays, ts, save: bool = False, slot=None):
+        tree = self.flatten_params(params)
+        n, T = ts.shape
+        rays, ts = _native._f32c(rays, "rays"), _native._f32c(ts, "ts")
+        dens, rgb, a1, a2, ws = self._forward(tree, None, None, rays, ts, n, T, save, slot)
+        ctx = dict(tree=tree, ws=ws, rays=rays, ts=ts, n=n, T=T) if save else None
+        return dens.view(n, T), rgb.view(n, T, 3), dict(normal_mse=a1.view(n, T), neg_normal=a2.view(n, T)), ctx
+
+    def backward_rays(self, ctx, d_dens, d_rgb, d_flat, d_aux=None):
+        m = ctx["n"] * ctx["T"]
+        zeros = None
+        def aux(name):
+            nonlocal zeros
+            if d_aux is not None and name in d_aux:
+                return d_aux[name].reshape(-1).contiguous()
+            if zeros is None:
+                zeros = torch.zeros(m, device=d_flat.device)
+            return zeros
+        _native.ngpref_bwd(ctx["tree"].flat, self.spec(), None, None, ctx["rays"], ctx["ts"], ctx["n"], ctx["T"],
+                           ctx["ws"], d_dens.reshape(-1).contiguous(), d_rgb.reshape(-1, 3).contiguous(),
+                           aux("normal_mse"), aux("neg_normal"), d_flat)

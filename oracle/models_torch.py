@@ -317,6 +317,60 @@ class RefNERFModel:
         return density, full, aux
 
 
+class InstantNGPRefNERFModel(RefNERFModel):
+    """instant_ngp.py:57-89: RefNERFBase.__call__ (RefNERFModel.apply above) with a smooth hash-grid
+    spatial block (:69-82) and a 2 x 64 directional block (:84-89).  Flax creation order inside
+    __call__: MultiresHashTableEncoding_0, Dense_0, Dense_1 (spatial), Dense_2..4 (directional)."""
+
+    def __init__(self, table_sizes: Sequence[int], grid_sizes: Sequence[int], bbox_min, bbox_max, sh_degree=4,
+                 table_feature_dim=2, d_freqs=4, hidden_dim=64, density_dim=16, density_layers=1,
+                 color_layers=2):
+        self.sh_degree = sh_degree
+        self.table_sizes, self.grid_sizes = list(table_sizes), list(grid_sizes)
+        self.bbox_min = torch.as_tensor(bbox_min, dtype=torch.float32)
+        self.bbox_max = torch.as_tensor(bbox_max, dtype=torch.float32)
+        self.F, self.d_freqs = table_feature_dim, d_freqs
+        self.hidden_dim, self.density_dim = hidden_dim, density_dim
+        self.density_layers, self.color_layers = density_layers, color_layers
+
+    def layer_dims(self):
+        dims, cur = [], self.F * len(self.grid_sizes)
+        for _ in range(self.density_layers):
+            dims.append((cur, self.hidden_dim)); cur = self.hidden_dim
+        dims.append((cur, self.density_dim))
+        cur = self.density_dim + sum(HARMONIC_COUNTS[: self.sh_degree]) + 1  # ref_nerf.py:63
+        for _ in range(self.color_layers):
+            dims.append((cur, self.hidden_dim)); cur = self.hidden_dim
+        dims.append((cur, 3))
+        return dims
+
+    def init(self, gen: torch.Generator) -> Params:
+        p = {f"Dense_{i}": dense_init(gen, a, b) for i, (a, b) in enumerate(self.layer_dims())}
+        enc = {}
+        for l, (t, g) in enumerate(zip(self.table_sizes, self.grid_sizes)):
+            u = torch.rand((hash_level_rows(t, g), self.F), generator=gen)
+            enc[f"HashTableEncoding_{l}"] = dict(table=(1e-4 * (u * 2 - 1)).float())
+        p["MultiresHashTableEncoding_0"] = enc
+        return p
+
+    def spatial_block(self, params: Params, x: torch.Tensor) -> torch.Tensor:  # :69-82
+        enc = params["MultiresHashTableEncoding_0"]
+        outs = []
+        for l, (t, g) in enumerate(zip(self.table_sizes, self.grid_sizes)):
+            outs.append(hash_table_encoding(enc[f"HashTableEncoding_{l}"]["table"], x, t, g,
+                                            self.bbox_min.to(x.dtype), self.bbox_max.to(x.dtype), smooth=True))
+        z, li = torch.cat(outs, dim=1), 0
+        for _ in range(self.density_layers):
+            z = torch.relu(dense(params[f"Dense_{li}"], z)); li += 1
+        return dense(params[f"Dense_{li}"], z)
+
+    def directional_block(self, params: Params, x: torch.Tensor) -> torch.Tensor:  # :84-89
+        li = self.density_layers + 1
+        for _ in range(self.color_layers):
+            x = torch.relu(dense(params[f"Dense_{li}"], x)); li += 1
+        return dense(params[f"Dense_{li}"], x)
+
+
 # --------------------------------------------------------------------------- helpers
 def tree_map(fn, tree):
     if isinstance(tree, dict):

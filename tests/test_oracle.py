@@ -255,3 +255,39 @@ def test_density_penalty_branch():
     t2, _, _ = T.losses(nerf, nerf, params, BBOX_MIN, BBOX_MAX, batch, uc, uf, 64, 128,
                         density_penalty=0.25, density_points=(coords, -dirs))
     assert float(t2) == float(t1)
+
+
+def test_ngp_refnerf_oracle_normals_match_finite_differences():
+    """InstantNGPRefNERFModel (instant_ngp.py:57-89): the spatial block's input gradient (what
+    RefNERFBase takes with jax.grad, ref_nerf.py:38-43) equals a central finite difference of
+    -spatial_out[:, 0] in fp64 through the SMOOTH hash grid, and the aux loss normal_mse is
+    |normalize(out[6:9]) - normalize(grad)|^2."""
+    from oracle import models_torch as M
+    L = 6
+    o = M.InstantNGPRefNERFModel([2 ** 12] * L, [2 ** (2 + i // 2) for i in range(L)], BBOX_MIN, BBOX_MAX)
+    assert o.layer_dims() == [(12, 64), (64, 16), (33, 64), (64, 64), (64, 3)]
+    p = o.init(torch.Generator().manual_seed(1))
+    for leaf in p["MultiresHashTableEncoding_0"].values():
+        leaf["table"] *= 1e4
+    p64 = M.tree_map(lambda t: t.double(), p)
+    rs = np.random.RandomState(2)
+    x = torch.from_numpy(rs.uniform(-0.9, 0.9, (40, 3)))
+    d = torch.from_numpy(rs.randn(40, 3))
+    d = d / d.norm(dim=1, keepdim=True)
+    xg = x.clone().requires_grad_(True)
+    out = o.spatial_block(p64, xg)
+    (grad,) = torch.autograd.grad(-out[:, 0].sum(), xg)
+    h = 1e-6
+    fd = torch.zeros_like(x)
+    for a in range(3):
+        e = torch.zeros(3, dtype=torch.float64)
+        e[a] = h
+        with torch.no_grad():
+            fd[:, a] = -(o.spatial_block(p64, x + e)[:, 0] - o.spatial_block(p64, x - e)[:, 0]) / (2 * h)
+    ok = (grad - fd).abs().max(dim=1).values < 1e-5 * (1 + grad.abs().max())
+    assert ok.float().mean() > 0.9  # the rest straddle a cell face or a ReLU kink within +-h
+    _, _, aux = o.apply(p64, x, d, create_graph=False)
+    n = out[:, 6:9].detach()
+    n = n / torch.sqrt((n ** 2).sum(1, keepdim=True) + 1e-10)
+    rn = grad / torch.sqrt((grad ** 2).sum(1, keepdim=True) + 1e-10)
+    np.testing.assert_allclose(aux["normal_mse"].numpy(), ((n - rn) ** 2).sum(1).numpy(), rtol=1e-9, atol=1e-12)
