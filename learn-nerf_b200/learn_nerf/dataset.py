@@ -1,17 +1,25 @@
-"""Host-side mirror of the ray-generation part of learn_nerf/dataset.py: CameraView.
+"""Host-side mirror of learn_nerf/dataset.py: CameraView / NeRFView / NeRFDataset and the
+pre-shuffled on-disk ray feeder.
 
-Only what feeds the render path is mirrored (camera JSON I/O and ``bare_rays``,
-dataset.py:15-78); image loading and the on-disk shuffle are host I/O outside the hot path.
 ``bare_rays`` runs on the device (lnrf_bare_rays) and is bit-exact with the oracle restatement.
+The feeder (``NeRFDataset.iterate_batches`` / ``ShuffledDataset``, dataset.py:130-263) keeps the
+reference's two-stage shuffle and its shard file format (raw float32 ``[N,3,3]`` records, a
+``done`` marker), so shard directories are interchangeable; the shard assignment and the
+permutations come from the Threefry streams in ``prng`` (restated from memory: the ORDER may differ
+from what a given JAX version produces, the reference's own test properties hold,
+tests/test_cpu_host.py).  With a CUDA ``device`` the batches are staged through pinned buffers
+and copied on a side stream one batch ahead of the consumer.
 """
 import json
 import math
+import os
 from dataclasses import dataclass
-from typing import Tuple
+from typing import Iterator, List, Optional, Tuple
 
+import numpy as np
 import torch
 
-from . import _native
+from . import _native, prng
 
 Vec3 = Tuple[float, float, float]
 
@@ -47,3 +55,174 @@ class CameraView:
         return _native.bare_rays(self.camera_origin, self.x_axis, self.y_axis, self.camera_direction,
                                  math.tan(self.x_fov / 2), math.tan(self.y_fov / 2), width, height, row0,
                                  rows, device)
+
+
+@dataclass
+class NeRFView(CameraView):
+    """dataset.py:81-101."""
+
+    def image(self) -> np.ndarray:
+        """[H, W, 3] uint8 RGB."""
+        raise NotImplementedError
+
+    def rays(self, device="cuda") -> torch.Tensor:
+        """[N,3,3] rows (origin, direction, colour in [-1,1]), raster order (dataset.py:88-101)."""
+        img = np.asarray(self.image())
+        bare = self.bare_rays(img.shape[1], img.shape[0], device=device)
+        colors = torch.from_numpy(img.reshape(-1, 3).astype(np.float32) / np.float32(127.5) - np.float32(1.0))
+        return torch.cat([bare, colors.to(bare.device)[:, None]], dim=1)
+
+
+@dataclass
+class FileNeRFView(NeRFView):
+    """dataset.py:104-111."""
+
+    image_path: str = ""
+
+    def image(self) -> np.ndarray:
+        from PIL import Image
+        rgba = np.array(Image.open(self.image_path).convert("RGBA"))
+        # premultiplied alpha (:109-111); np.round == jnp.round (half to even)
+        return np.round(rgba[:, :, :3] * (rgba[:, :, 3:] / 255)).astype(np.uint8)
+
+
+@dataclass
+class ModelMetadata:
+    """dataset.py:114-127."""
+
+    bbox_min: Vec3
+    bbox_max: Vec3
+
+    @classmethod
+    def from_json(cls, path: str) -> "ModelMetadata":
+        with open(path, "rb") as f:
+            metadata = json.load(f)
+        return cls(bbox_min=tuple(metadata["min"]), bbox_max=tuple(metadata["max"]))
+
+
+@dataclass
+class NeRFDataset:
+    """dataset.py:130-160."""
+
+    metadata: ModelMetadata
+    views: List[NeRFView]
+
+    def iterate_batches(self, dir_path: str, key, batch_size: int, repeat: bool = True, num_shards: int = 32,
+                        device=None, ray_device="cuda") -> Iterator[torch.Tensor]:
+        """Shuffled [N,3,3] ray batches (dataset.py:134-160).  ``device``: where the batches are
+        delivered (None = CPU tensors; a CUDA device = pinned staging + one-batch-ahead copies);
+        ``ray_device``: where ``view.rays()`` is evaluated while the shards are first written."""
+        with ShuffledDataset(dir_path, self, key, num_shards=num_shards, ray_device=ray_device) as sd:
+            yield from sd.iterate_batches(batch_size, repeat=repeat, device=device)
+
+
+class ShuffledDataset:
+    """dataset.py:163-263: the two-stage shuffle (random shard assignment on write, a random shard
+    order plus a permutation inside each shard on read)."""
+
+    def __init__(self, dir_path: str, dataset: NeRFDataset, key, num_shards: int = 32, ray_device="cuda"):
+        self.num_shards = num_shards
+        self.shard_key, self.shuffle_key = prng.split(key)
+        if not os.path.exists(dir_path):
+            os.mkdir(dir_path)
+        done_path = os.path.join(dir_path, "done")
+        if os.path.exists(done_path):
+            self.fds = [open(os.path.join(dir_path, f"{i}"), "rb") for i in range(num_shards)]
+        else:
+            self.fds = [open(os.path.join(dir_path, f"{i}"), "wb+") for i in range(num_shards)]
+            self._create_shards(dataset, ray_device)
+            with open(done_path, "wb+") as f:
+                f.write(b"done\n")
+
+    def _host_batches(self, batch_size: int, repeat: bool) -> Iterator[np.ndarray]:
+        key = self.shuffle_key
+        cur = None
+        while True:
+            key, this_key = prng.split(key)
+            for shard in prng.permutation_host(this_key, self.num_shards).tolist():
+                key, this_key = prng.split(key)
+                rays = self._read_shard(shard)
+                rays = rays[prng.permutation_host(this_key, rays.shape[0])]
+                cur = rays if cur is None else np.concatenate([cur, rays], axis=0)
+                while cur.shape[0] >= batch_size:
+                    yield cur[:batch_size]
+                    cur = cur[batch_size:]
+            if not repeat:
+                break
+        if cur is not None and cur.shape[0]:
+            yield cur
+
+    def iterate_batches(self, batch_size: int, repeat: bool = False, device=None) -> Iterator[torch.Tensor]:
+        dev = torch.device(device) if device is not None else None
+        if dev is None or dev.type != "cuda":
+            for b in self._host_batches(batch_size, repeat):
+                yield torch.from_numpy(np.ascontiguousarray(b))
+            return
+        # GPU prefetch: two pinned staging buffers, copies on a side stream, one batch in flight
+        stream = torch.cuda.Stream(device=dev)
+        pinned = [torch.empty(batch_size, 3, 3).pin_memory() for _ in range(2)]
+        copied = [None, None]  # per staging buffer: event of the last copy that read it
+        pending = None         # (device tensor, event) of the batch in flight
+
+        def deliver(item):
+            t, ev = item
+            cur = torch.cuda.current_stream(dev)
+            cur.wait_event(ev)      # the consumer's stream sees the finished copy
+            t.record_stream(cur)
+            return t
+
+        for i, b in enumerate(self._host_batches(batch_size, repeat)):
+            if copied[i & 1] is not None:
+                copied[i & 1].synchronize()  # the copy that last read this pinned buffer has finished
+            buf = pinned[i & 1][: b.shape[0]]
+            buf.copy_(torch.from_numpy(np.ascontiguousarray(b)))
+            with torch.cuda.stream(stream):
+                t = buf.to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(stream)
+            copied[i & 1] = ev
+            if pending is not None:
+                yield deliver(pending)
+            pending = (t, ev)
+        if pending is not None:
+            yield deliver(pending)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *args):
+        for fd in self.fds:
+            fd.close()
+
+    def _create_shards(self, dataset: NeRFDataset, ray_device):
+        key = self.shard_key
+        for view in dataset.views:
+            rays = view.rays(device=ray_device) if _takes_device(view) else view.rays()
+            rays = rays.detach().cpu().numpy() if isinstance(rays, torch.Tensor) else np.asarray(rays)
+            key, this_key = prng.split(key)
+            assignments = prng.randint_host(this_key, rays.shape[0], 0, self.num_shards)
+            for shard in range(self.num_shards):
+                sub = rays[assignments == shard]
+                if sub.shape[0]:
+                    self.fds[shard].write(sub.astype(np.float32).tobytes())
+
+    def _read_shard(self, shard: int) -> np.ndarray:
+        f = self.fds[shard]
+        f.seek(0)
+        return np.frombuffer(f.read(), dtype=np.float32).reshape([-1, 3, 3])
+
+
+def _takes_device(view) -> bool:
+    import inspect
+    return "device" in inspect.signature(view.rays).parameters
+
+
+def load_dataset(directory: str) -> NeRFDataset:
+    """dataset.py:266-288: X.png + X.json per view, metadata.json with the bounding box."""
+    dataset = NeRFDataset(metadata=ModelMetadata.from_json(os.path.join(directory, "metadata.json")), views=[])
+    for img_name in sorted(os.listdir(directory)):
+        if img_name.startswith(".") or not img_name.endswith(".png"):
+            continue
+        img_path = os.path.join(directory, img_name)
+        dataset.views.append(FileNeRFView.from_json(img_path[: -len(".png")] + ".json", image_path=img_path))
+    return dataset

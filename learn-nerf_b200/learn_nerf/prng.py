@@ -88,3 +88,59 @@ def uniform(key: KeyLike, shape, device) -> torch.Tensor:
     from . import _native
     k = _as_key(key)
     return _native.threefry_uniform(k.k0, k.k1, shape, device)
+
+
+# ---------------------------------------------------------------------------- host-side streams
+# Vectorised (numpy) Threefry for the dataset feeder (dataset.py:206-248), where whole arrays of
+# random bits are needed on the host.  Same stream as the device kernel / the scalar code above.
+def random_bits_host(key: KeyLike, size: int):
+    """uint32[size] = threefry_2x32(key, arange(size)) (jax.random.bits for 32-bit words)."""
+    import numpy as np
+    k = _as_key(key)
+    count = np.arange(size, dtype=np.uint32)
+    if size % 2:
+        count = np.concatenate([count, np.zeros(1, np.uint32)])
+    half = count.size // 2
+    x0, x1 = count[:half].copy(), count[half:].copy()
+    ks = [np.uint32(k.k0), np.uint32(k.k1), np.uint32(k.k0 ^ k.k1 ^ 0x1BD11BDA)]
+    with np.errstate(over="ignore"):
+        x0 += ks[0]
+        x1 += ks[1]
+        for i in range(5):
+            for r in _ROT[i % 2]:
+                x0 += x1
+                x1 = (x1 << np.uint32(r)) | (x1 >> np.uint32(32 - r))
+                x1 ^= x0
+            x0 += ks[(i + 1) % 3]
+            x1 += ks[(i + 2) % 3] + np.uint32(i + 1)
+    return np.concatenate([x0, x1])[:size]
+
+
+def randint_host(key: KeyLike, size: int, minval: int, maxval: int):
+    """jax.random.randint(key, [size], minval, maxval) [recalled from jax/_src/random.py, 0.4 series;
+    not verifiable here]: two 32-bit draws hi, lo from split(key);
+    offset = ((hi % span) * (2^32 % span) + lo % span) % span, i.e. a 64-bit draw modulo span."""
+    import numpy as np
+    k1, k2 = split(key)
+    span = np.uint32(maxval - minval)
+    hi, lo = random_bits_host(k1, size), random_bits_host(k2, size)
+    mult = np.uint32((int(2 ** 16 % int(span)) ** 2) % int(span))
+    with np.errstate(over="ignore"):
+        off = ((hi % span) * mult + (lo % span)) % span
+    return (off.astype(np.int64) + minval).astype(np.int32)
+
+
+def permutation_host(key: KeyLike, n: int):
+    """Index permutation in the manner of jax.random.permutation / _shuffle [recalled; not
+    verifiable here]: ceil(3 ln n / ln(2^32 - 1)) rounds, each a stable sort by fresh 32-bit keys."""
+    import math
+    import numpy as np
+    idx = np.arange(n)
+    if n <= 1:
+        return idx
+    rounds = int(math.ceil(3 * math.log(max(1, n)) / math.log(2 ** 32 - 1)))
+    k = _as_key(key)
+    for _ in range(rounds):
+        k, sub = split(k)
+        idx = idx[np.argsort(random_bits_host(sub, n), kind="stable")]
+    return idx

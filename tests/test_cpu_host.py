@@ -125,3 +125,66 @@ def test_data_parallel_recipe_two_gloo_processes(tmp_path):
     outs = [p.communicate(timeout=300)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(outs)
     assert "DP_OK" in outs[0]
+
+
+def test_nerf_dataset_iterate_batches(tmp_path):
+    """The reference's own test of the ray feeder (learn_nerf/test_dataset.py:19-86) restated for
+    the host mirror: two 10x10 dummy views, batch_size 51 without repeat -> 4 batches, the last one
+    of 200 - 3 * 51 rays; every view contributes exactly its pixel count of rays with its origin,
+    their mean direction is the camera axis and their mean colour the image mean; plus: the shard
+    directory is reusable (same stream on a second pass), and ``repeat`` keeps going past one epoch.
+    (bare_rays is a device kernel: the dummy views take their rays from the oracle restatement.)"""
+    from dataclasses import dataclass
+    import math
+    from learn_nerf.dataset import ModelMetadata, NeRFDataset, NeRFView, ShuffledDataset
+    from oracle import render_np
+
+    @dataclass
+    class DummyView(NeRFView):
+        dummy_image: np.ndarray = None
+
+        def image(self):
+            return self.dummy_image
+
+        def bare_rays(self, width, height, device="cpu", row0=0, rows=None):
+            return torch.from_numpy(render_np.bare_rays(self.camera_direction, self.camera_origin, self.x_axis,
+                                                        self.y_axis, self.x_fov, self.y_fov, width, height))
+
+    rs = np.random.RandomState(1337)
+    views = [DummyView(camera_direction=(0.0, 1.0, 0.0), camera_origin=(2.0, 2.0, 2.0), x_axis=(-1.0, 0.0, 0.0),
+                       y_axis=(0.0, 0.0, 1.0), x_fov=math.radians(60.0), y_fov=math.radians(60.0),
+                       dummy_image=rs.randint(0, 256, (10, 10, 3)).astype(np.uint8)),
+             DummyView(camera_direction=(1.0, 0.0, 0.0), camera_origin=(-2.0, 2.0, 2.0), x_axis=(-0.0, 0.0, -1.0),
+                       y_axis=(0.0, 1.0, 0.0), x_fov=math.radians(60.0), y_fov=math.radians(60.0),
+                       dummy_image=rs.randint(0, 256, (10, 10, 3)).astype(np.uint8))]
+    dataset = NeRFDataset(metadata=ModelMetadata(bbox_min=(0.0, 0.0, 0.0), bbox_max=(1.0, 1.0, 1.0)), views=views)
+    shard_dir = str(tmp_path / "shards")
+    batches = list(dataset.iterate_batches(shard_dir, 1234, batch_size=51, repeat=False, ray_device="cpu"))
+    assert len(batches) == 4, "unexpected number of batches"
+    assert batches[-1].shape[0] == 200 - 51 * 3, "unexpected last batch size"
+    assert all(b.shape[1:] == (3, 3) and b.dtype == torch.float32 for b in batches)
+    combined = torch.cat(batches, dim=0).numpy()
+    for view in views:
+        origin = np.asarray(view.camera_origin, np.float32)
+        mask = np.abs(combined[:, 0] - origin).sum(-1) < 1e-5
+        assert int(mask.sum()) == 100, f"unexpected number of samples with origin {origin}"
+        rays = combined[mask]
+        mean_dir = rays[:, 1].mean(0)
+        mean_dir /= np.linalg.norm(mean_dir)
+        assert abs(float((mean_dir * np.asarray(view.camera_direction, np.float32)).sum()) - 1) < 1e-5
+        want = (view.dummy_image.astype(np.float32) / 127.5 - 1).mean(axis=(0, 1))
+        assert float(np.abs(rays[:, 2].mean(0) - want).mean()) < 1e-5, "invalid colors for rays"
+    # the rays are shuffled (not in raster order), every ray appears exactly once
+    ref = np.concatenate([v.rays(device="cpu").numpy() for v in views])
+    assert not np.array_equal(combined, ref)
+    key = lambda a: sorted(map(bytes, a.reshape(len(a), -1)))
+    assert key(combined) == key(ref)
+    # second pass over the finished shard directory: identical stream; shard files are raw fp32 [N,3,3]
+    again = torch.cat(list(dataset.iterate_batches(shard_dir, 1234, batch_size=51, repeat=False, ray_device="cpu")))
+    assert np.array_equal(again.numpy(), combined)
+    assert os.path.exists(os.path.join(shard_dir, "done"))
+    assert sum(os.path.getsize(os.path.join(shard_dir, str(i))) for i in range(32)) == 200 * 36
+    with ShuffledDataset(shard_dir, dataset, 1234) as sd:
+        it = sd.iterate_batches(64, repeat=True)
+        got = [next(it) for _ in range(5)]  # 320 rays > one epoch of 200
+    assert all(b.shape == (64, 3, 3) for b in got)

@@ -275,3 +275,40 @@ def test_threefry_uniform_bit_exact(shape):
     got = prng.uniform(key, shape, "cuda").cpu().numpy()
     ref = prng_np.uniform(np.array([key.k0, key.k1], np.uint32), shape)
     np.testing.assert_array_equal(got, ref)
+
+
+def test_dataset_feeder_gpu_prefetch(tmp_path):
+    """load_dataset (PNG + JSON views, dataset.py:266-288) -> ShuffledDataset -> batches delivered
+    to the GPU through pinned staging buffers on a side stream: same batches, same order as the
+    host path; colours are the premultiplied-alpha image mapped to [-1, 1]."""
+    import json
+    import math
+    from PIL import Image
+    from learn_nerf.dataset import load_dataset
+    rs = np.random.RandomState(0)
+    d = tmp_path / "scene"
+    d.mkdir()
+    (d / "metadata.json").write_text(json.dumps({"min": [-1, -1, -1], "max": [1, 1, 1]}))
+    imgs = {}
+    for i in range(3):
+        rgba = rs.randint(0, 256, (12, 16, 4)).astype(np.uint8)
+        Image.fromarray(rgba, "RGBA").save(d / f"v{i}.png")
+        imgs[f"v{i}"] = rgba
+        ang = 2 * math.pi * i / 3
+        (d / f"v{i}.json").write_text(json.dumps(dict(
+            origin=[4 * math.cos(ang), 4 * math.sin(ang), 0.5], z=[-math.cos(ang), -math.sin(ang), 0.0],
+            x=[-math.sin(ang), math.cos(ang), 0.0], y=[0.0, 0.0, -1.0], x_fov=1.0, y_fov=0.8)))
+    ds = load_dataset(str(d))
+    assert len(ds.views) == 3 and ds.metadata.bbox_max == (1, 1, 1)
+    v0 = ds.views[0]
+    rays = v0.rays().cpu().numpy()
+    assert rays.shape == (12 * 16, 3, 3)
+    rgba = imgs["v0"].astype(np.float64)
+    want = np.round(rgba[:, :, :3] * (rgba[:, :, 3:] / 255)).astype(np.uint8).reshape(-1, 3)
+    np.testing.assert_array_equal(rays[:, 2], want.astype(F) / F(127.5) - F(1.0))
+    np.testing.assert_array_equal(rays[:, :2], v0.bare_rays(16, 12).cpu().numpy())
+    host = list(ds.iterate_batches(str(tmp_path / "s"), 7, batch_size=100, repeat=False))
+    gpu = list(ds.iterate_batches(str(tmp_path / "s"), 7, batch_size=100, repeat=False, device="cuda"))
+    assert len(host) == len(gpu) == 6 and gpu[0].is_cuda and gpu[-1].shape[0] == 3 * 192 - 500
+    for a, b in zip(host, gpu):
+        assert torch.equal(a, b.cpu())
