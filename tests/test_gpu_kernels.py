@@ -312,3 +312,35 @@ def test_dataset_feeder_gpu_prefetch(tmp_path):
     assert len(host) == len(gpu) == 6 and gpu[0].is_cuda and gpu[-1].shape[0] == 3 * 192 - 500
     for a, b in zip(host, gpu):
         assert torch.equal(a, b.cpu())
+
+
+def test_train_script_mirror_end_to_end(tmp_path):
+    """scripts/train_nerf.train (train_nerf.py:72-133): dataset directory -> shuffled feeder with GPU
+    prefetch -> TrainLoop.step_fn -> checkpoint, for two of create_model's four families; the loss
+    on a constant-colour scene falls."""
+    import json
+    import math
+    from PIL import Image
+    from learn_nerf.dataset import load_dataset
+    from learn_nerf.scripts.train_nerf import create_model, train
+    d = tmp_path / "scene"
+    d.mkdir()
+    (d / "metadata.json").write_text(json.dumps({"min": [-1, -1, -1], "max": [1, 1, 1]}))
+    for i in range(4):
+        Image.fromarray(np.full((24, 24, 4), 255, np.uint8) * np.array([1, 0, 0, 1], np.uint8), "RGBA").save(d / f"v{i}.png")
+        ang = 2 * math.pi * i / 4
+        (d / f"v{i}.json").write_text(json.dumps(dict(
+            origin=[4 * math.cos(ang), 4 * math.sin(ang), 0.0], z=[-math.cos(ang), -math.sin(ang), 0.0],
+            x=[-math.sin(ang), math.cos(ang), 0.0], y=[0.0, 0.0, -1.0], x_fov=0.5, y_fov=0.5)))
+    data = load_dataset(str(d))
+    kinds = [type(m).__name__ for kw in (dict(), dict(ref_nerf=True), dict(instant_ngp=True),
+                                        dict(instant_ngp=True, ref_nerf=True))
+             for m in create_model(data.metadata, **kw)[:1]]
+    assert kinds == ["NeRFModel", "RefNERFModel", "InstantNGPModel", "InstantNGPRefNERFModel"]
+    for kw in (dict(precision="bf16"), dict(instant_ngp=True)):
+        logs = []
+        ck = str(tmp_path / ("ck_" + "_".join(kw) + ".pkl"))
+        loop = train(data, ck, key=3, lr=2e-3, batch_size=512, max_steps=12, save_interval=5, log=logs.append, **kw)
+        fine = [float(l.split(" fine=")[1].split()[0]) for l in logs if l.startswith("step")]
+        assert len(fine) == 12 and fine[-1] < fine[0], fine
+        assert os.path.exists(ck) and loop.state.step == 12
