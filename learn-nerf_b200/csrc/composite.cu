@@ -35,6 +35,11 @@ __device__ __forceinline__ float warp_excl_suffix(float v, int lane) {
   return inc - v;
 }
 
+// With ts in s_ts and the densities in s_a: fills delta / a = dens*delta / acc_prev.
+// Returns the ray's total optical depth.
+__device__ __forceinline__ float stage_ray_smem(int T, float t_min, float t_max, int lane, int c0, int c1,
+                                                float* s_ts, float* s_delta, float* s_a, float* s_acc);
+
 // Loads one ray's samples into smem and fills delta / a = dens*delta / acc_prev.
 // Returns the ray's total optical depth.
 __device__ __forceinline__ float stage_ray(const float* __restrict__ ts, const float* __restrict__ dens,
@@ -46,6 +51,11 @@ __device__ __forceinline__ float stage_ray(const float* __restrict__ ts, const f
     s_a[i] = __ldg(dens + r * T + i);
   }
   __syncwarp();
+  return stage_ray_smem(T, t_min, t_max, lane, c0, c1, s_ts, s_delta, s_a, s_acc);
+}
+
+__device__ __forceinline__ float stage_ray_smem(int T, float t_min, float t_max, int lane, int c0, int c1,
+                                                float* s_ts, float* s_delta, float* s_a, float* s_acc) {
   float local = 0.0f;
   for (int i = c0; i < c1; ++i) {  // starts/ends/deltas render.py:259-268, density_dt :271
     float t = s_ts[i];
@@ -100,6 +110,130 @@ composite_fwd_kernel(const float* __restrict__ rays, const float* __restrict__ t
       o[k] = __ldg(rays + r * 6 + k);
       d[k] = __ldg(rays + r * 6 + 3 + k);
     }
+    float c_rgb[3] = {0.f, 0.f, 0.f}, c_xyz[3] = {0.f, 0.f, 0.f};
+    for (int i = c0; i < c1; ++i) {
+      float p = lnrf_expf(-s_acc[i]) * (1.0f - lnrf_expf(-s_a[i]));  // :279-287
+      float t = s_ts[i];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        c_rgb[k] += p * s_rgb[i * 3 + k];
+        c_xyz[k] += p * __fadd_rn(o[k], __fmul_rn(d[k], t));  // points, :153
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      c_rgb[k] = warp_sum(c_rgb[k]);
+      c_xyz[k] = warp_sum(c_xyz[k]);
+    }
+    const float p_esc = lnrf_expf(-total);  // last column of termination_probs
+    if (lane == 0) {
+      outputs[r * 3 + 0] = c_rgb[0] + p_esc * bg0;
+      outputs[r * 3 + 1] = c_rgb[1] + p_esc * bg1;
+      outputs[r * 3 + 2] = c_rgb[2] + p_esc * bg2;
+      if (alphas) alphas[r] = 1.0f - p_esc;
+      if (coords) {
+        coords[r * 3 + 0] = c_xyz[0];
+        coords[r * 3 + 1] = c_xyz[1];
+        coords[r * 3 + 2] = c_xyz[2];
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// Register-prefetching variants for T <= 32 C (C = 2: the 64 coarse samples, C = 6: the 192 fine
+// samples): the next ray's ts / densities / colours and per-ray scalars are requested before the
+// current ray is processed, so a warp always has one ray of loads (1.3 / 3.9 KB) in flight behind
+// its arithmetic.  The generic kernels above were latency-bound (25 - 45 % of the HBM copy peak).
+template <int C>
+struct RayRegs {
+  float ts[C], dens[C], rgb[3 * C];
+  float tmin, tmax;
+  int mask;
+};
+template <int C>
+__device__ __forceinline__ void ray_prefetch(RayRegs<C>& q, const float* __restrict__ ts, const float* __restrict__ dens,
+                                             const float* __restrict__ rgb, const float* __restrict__ t_min_in,
+                                             const float* __restrict__ t_max_in, const uint8_t* __restrict__ mask_in,
+                                             int64_t r, int T, int lane) {
+  q.mask = mask_in[r];
+  q.tmin = __ldg(t_min_in + r);
+  q.tmax = __ldg(t_max_in + r);
+#pragma unroll
+  for (int j = 0; j < C; ++j) {
+    const int i = lane + 32 * j;
+    q.ts[j] = i < T ? __ldg(ts + r * T + i) : 0.0f;
+    q.dens[j] = i < T ? __ldg(dens + r * T + i) : 0.0f;
+  }
+#pragma unroll
+  for (int j = 0; j < 3 * C; ++j) {
+    const int i = lane + 32 * j;
+    q.rgb[j] = i < 3 * T ? __ldg(rgb + r * 3 * T + i) : 0.0f;
+  }
+}
+template <int C>
+__device__ __forceinline__ void ray_to_smem(const RayRegs<C>& q, int T, int lane, float* s_ts, float* s_a, float* s_rgb) {
+#pragma unroll
+  for (int j = 0; j < C; ++j) {
+    const int i = lane + 32 * j;
+    if (i < T) {
+      s_ts[i] = q.ts[j];
+      s_a[i] = q.dens[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 3 * C; ++j) {
+    const int i = lane + 32 * j;
+    if (i < 3 * T) s_rgb[i] = q.rgb[j];
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(kCompWarps * 32)
+composite_fwd_pf_kernel(const float* __restrict__ rays, const float* __restrict__ ts,
+                        const float* __restrict__ t_min_in, const float* __restrict__ t_max_in,
+                        const uint8_t* __restrict__ mask_in, const float* __restrict__ dens,
+                        const float* __restrict__ rgb, const float* __restrict__ background, int64_t n,
+                        int T, float* __restrict__ outputs, float* __restrict__ alphas,
+                        float* __restrict__ coords) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float* s_ts = smem + size_t(wib) * 7 * T;
+  float* s_delta = s_ts + T;
+  float* s_a = s_delta + T;
+  float* s_acc = s_a + T;
+  float* s_rgb = s_acc + T;  // 3T
+  const int CH = (T + 31) / 32;
+  const int c0 = min(lane * CH, T), c1 = min(c0 + CH, T);
+  const float bg0 = __ldg(background), bg1 = __ldg(background + 1), bg2 = __ldg(background + 2);
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  RayRegs<C> q;
+  float od[6];
+  if (warp < n) {
+    ray_prefetch<C>(q, ts, dens, rgb, t_min_in, t_max_in, mask_in, warp, T, lane);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) od[k] = __ldg(rays + warp * 6 + k);
+  }
+  for (int64_t r = warp; r < n; r += nwarps) {
+    const int mask = q.mask;
+    const float t_min = q.tmin, t_max = q.tmax;
+    float o[3] = {od[0], od[1], od[2]}, d[3] = {od[3], od[4], od[5]};
+    if (mask) ray_to_smem<C>(q, T, lane, s_ts, s_a, s_rgb);
+    if (r + nwarps < n) {  // next ray's loads go out before this ray's arithmetic
+      ray_prefetch<C>(q, ts, dens, rgb, t_min_in, t_max_in, mask_in, r + nwarps, T, lane);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) od[k] = __ldg(rays + (r + nwarps) * 6 + k);
+    }
+    if (!mask) {  // render.py:174-176, :190: masked rays show the background
+      if (lane < 3) outputs[r * 3 + lane] = lane == 0 ? bg0 : (lane == 1 ? bg1 : bg2);
+      if (lane == 0 && alphas) alphas[r] = 0.0f;
+      if (lane < 3 && coords) coords[r * 3 + lane] = 0.0f;
+      continue;
+    }
+    __syncwarp();
+    float total = stage_ray_smem(T, t_min, t_max, lane, c0, c1, s_ts, s_delta, s_a, s_acc);
+    __syncwarp();
     float c_rgb[3] = {0.f, 0.f, 0.f}, c_xyz[3] = {0.f, 0.f, 0.f};
     for (int i = c0; i < c1; ++i) {
       float p = lnrf_expf(-s_acc[i]) * (1.0f - lnrf_expf(-s_a[i]));  // :279-287
@@ -205,6 +339,87 @@ composite_bwd_kernel(const float* __restrict__ ts, const float* __restrict__ t_m
   }
 }
 
+template <int C>
+__global__ void __launch_bounds__(kCompWarps * 32)
+composite_bwd_pf_kernel(const float* __restrict__ ts, const float* __restrict__ t_min_in,
+                        const float* __restrict__ t_max_in, const uint8_t* __restrict__ mask_in,
+                        const float* __restrict__ dens, const float* __restrict__ rgb,
+                        const float* __restrict__ background, const float* __restrict__ d_outputs,
+                        int64_t n, int T, float* __restrict__ d_dens, float* __restrict__ d_rgb,
+                        float* __restrict__ d_background) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float* s_ts = smem + size_t(wib) * 7 * T;
+  float* s_delta = s_ts + T;
+  float* s_a = s_delta + T;
+  float* s_acc = s_a + T;
+  float* s_rgb = s_acc + T;  // 3T
+  const int CH = (T + 31) / 32;
+  const int c0 = min(lane * CH, T), c1 = min(c0 + CH, T);
+  const float bg0 = __ldg(background), bg1 = __ldg(background + 1), bg2 = __ldg(background + 2);
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  float dbg[3] = {0.f, 0.f, 0.f};  // lane 0 accumulates this warp's d_background
+  RayRegs<C> q;
+  float gq[3];
+  if (warp < n) {
+    ray_prefetch<C>(q, ts, dens, rgb, t_min_in, t_max_in, mask_in, warp, T, lane);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) gq[k] = __ldg(d_outputs + warp * 3 + k);
+  }
+  for (int64_t r = warp; r < n; r += nwarps) {
+    const int mask = q.mask;
+    const float t_min = q.tmin, t_max = q.tmax;
+    const float g0 = gq[0], g1 = gq[1], g2 = gq[2];
+    if (mask) ray_to_smem<C>(q, T, lane, s_ts, s_a, s_rgb);
+    if (r + nwarps < n) {
+      ray_prefetch<C>(q, ts, dens, rgb, t_min_in, t_max_in, mask_in, r + nwarps, T, lane);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) gq[k] = __ldg(d_outputs + (r + nwarps) * 3 + k);
+    }
+    if (!mask) {
+      for (int i = lane; i < T; i += 32) d_dens[r * T + i] = 0.0f;
+      for (int i = lane; i < 3 * T; i += 32) d_rgb[r * 3 * T + i] = 0.0f;
+      dbg[0] += g0; dbg[1] += g1; dbg[2] += g2;
+      continue;
+    }
+    __syncwarp();
+    float total = stage_ray_smem(T, t_min, t_max, lane, c0, c1, s_ts, s_delta, s_a, s_acc);
+    __syncwarp();
+    const float p_esc = lnrf_expf(-total);
+    const float g_bg = bg0 * g0 + bg1 * g1 + bg2 * g2;
+    float local = 0.0f;
+    for (int i = c0; i < c1; ++i) {
+      float p = lnrf_expf(-s_acc[i]) * (1.0f - lnrf_expf(-s_a[i]));
+      float gk = s_rgb[i * 3] * g0 + s_rgb[i * 3 + 1] * g1 + s_rgb[i * 3 + 2] * g2;
+      s_ts[i] = p;
+      local += p * gk;
+    }
+    float suffix = warp_excl_suffix(local, lane) + p_esc * g_bg;  // sum over later lanes + bg term
+    for (int i = c1 - 1; i >= c0; --i) {
+      float p = s_ts[i];
+      float gk = s_rgb[i * 3] * g0 + s_rgb[i * 3 + 1] * g1 + s_rgb[i * 3 + 2] * g2;
+      float t_next = lnrf_expf(-(s_acc[i] + s_a[i]));  // T_{k+1}
+      float dla = t_next * gk - suffix;
+      suffix += p * gk;
+      s_a[i] = dla * s_delta[i];  // d_dens
+      s_rgb[i * 3] = p * g0;      // d_rgb
+      s_rgb[i * 3 + 1] = p * g1;
+      s_rgb[i * 3 + 2] = p * g2;
+    }
+    __syncwarp();
+    for (int i = lane; i < T; i += 32) d_dens[r * T + i] = s_a[i];
+    for (int i = lane; i < 3 * T; i += 32) d_rgb[r * 3 * T + i] = s_rgb[i];
+    dbg[0] += p_esc * g0; dbg[1] += p_esc * g1; dbg[2] += p_esc * g2;
+    __syncwarp();
+  }
+  if (lane == 0 && (dbg[0] != 0.f || dbg[1] != 0.f || dbg[2] != 0.f)) {
+    atomicAdd(d_background + 0, dbg[0]);
+    atomicAdd(d_background + 1, dbg[1]);
+    atomicAdd(d_background + 2, dbg[2]);
+  }
+}
+
 // train.py:140-142: per-level MSE and its gradient.
 __global__ void __launch_bounds__(256)
 mse_loss_kernel(const float* __restrict__ outputs, const float* __restrict__ targets,
@@ -260,9 +475,16 @@ int lnrf_composite_fwd(const float* rays, const float* ts, const float* t_min, c
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  lnrf::composite_fwd_kernel<<<(unsigned)blocks, lnrf::kCompWarps * 32, smem,
-                               lnrf::as_stream(stream)>>>(rays, ts, t_min, t_max, mask, dens, rgb,
-                                                          background, n, T, outputs, alphas, coords);
+  if (T <= 64)
+    lnrf::composite_fwd_pf_kernel<2><<<(unsigned)blocks, lnrf::kCompWarps * 32, smem, lnrf::as_stream(stream)>>>(
+        rays, ts, t_min, t_max, mask, dens, rgb, background, n, T, outputs, alphas, coords);
+  else if (T <= 192)
+    lnrf::composite_fwd_pf_kernel<6><<<(unsigned)blocks, lnrf::kCompWarps * 32, smem, lnrf::as_stream(stream)>>>(
+        rays, ts, t_min, t_max, mask, dens, rgb, background, n, T, outputs, alphas, coords);
+  else
+    lnrf::composite_fwd_kernel<<<(unsigned)blocks, lnrf::kCompWarps * 32, smem,
+                                 lnrf::as_stream(stream)>>>(rays, ts, t_min, t_max, mask, dens, rgb,
+                                                            background, n, T, outputs, alphas, coords);
   LNRF_LAUNCH_CHECK("composite_fwd_kernel");
   return LNRF_OK;
 }
@@ -286,10 +508,17 @@ int lnrf_composite_bwd(const float* ts, const float* t_min, const float* t_max, 
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  lnrf::composite_bwd_kernel<<<(unsigned)blocks, lnrf::kCompWarps * 32, smem,
-                               lnrf::as_stream(stream)>>>(ts, t_min, t_max, mask, dens, rgb,
-                                                          background, d_outputs, n, T, d_dens, d_rgb,
-                                                          d_background);
+  if (T <= 64)
+    lnrf::composite_bwd_pf_kernel<2><<<(unsigned)blocks, lnrf::kCompWarps * 32, smem, lnrf::as_stream(stream)>>>(
+        ts, t_min, t_max, mask, dens, rgb, background, d_outputs, n, T, d_dens, d_rgb, d_background);
+  else if (T <= 192)
+    lnrf::composite_bwd_pf_kernel<6><<<(unsigned)blocks, lnrf::kCompWarps * 32, smem, lnrf::as_stream(stream)>>>(
+        ts, t_min, t_max, mask, dens, rgb, background, d_outputs, n, T, d_dens, d_rgb, d_background);
+  else
+    lnrf::composite_bwd_kernel<<<(unsigned)blocks, lnrf::kCompWarps * 32, smem,
+                                 lnrf::as_stream(stream)>>>(ts, t_min, t_max, mask, dens, rgb,
+                                                            background, d_outputs, n, T, d_dens, d_rgb,
+                                                            d_background);
   LNRF_LAUNCH_CHECK("composite_bwd_kernel");
   return LNRF_OK;
 }
