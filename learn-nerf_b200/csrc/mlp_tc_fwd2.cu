@@ -375,6 +375,8 @@ int init_mlp_tc_fwd2() {
                                  (int)PairSmem::total));
   LNRF_CUDA(cudaFuncSetAttribute(nerf_fwd_pair_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)PairSmem::total));
+  LNRF_CUDA(cudaFuncSetAttribute(nerf_fwd_pair_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)PairSmem::total));
   return LNRF_OK;
 }
 
@@ -389,6 +391,7 @@ int nerf_fwd_pair(const void* packed, const float* x, const float* d, const floa
   int64_t grid = sm_count();
   if (grid > pairs) grid = pairs;
   if (save) nerf_fwd_pair_kernel<true, false><<<(unsigned)grid, kPairThreads, PairSmem::total, st>>>(a);
+  else if (g_fwd_debug & 64) nerf_fwd_pair_kernel<false, false><<<(unsigned)grid, kPairThreads, PairSmem::total, st>>>(a);
   else nerf_fwd_pair_kernel<false, true><<<(unsigned)grid, kPairThreads, PairSmem::total, st>>>(a);
   LNRF_LAUNCH_CHECK("nerf_fwd_pair_kernel");
   return LNRF_OK;

@@ -21,6 +21,9 @@ def timeit(fn, reps=5):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
 print("fwd(nosave) ms", timeit(lambda: m.apply_rays(tree, rays, ts, save=False)))
+_native.load().lnrf_set_debug_flags(64)
+print("fwd(nosave, N-half schedule) ms", timeit(lambda: m.apply_rays(tree, rays, ts, save=False)))
+_native.load().lnrf_set_debug_flags(0)
 for flags in [int(x) for x in os.environ.get("FLAGS", "0,8,16").split(",")]:
     _native.load().lnrf_set_debug_flags(flags)
     print(f"fwd(save) flags={flags} ms", timeit(lambda: m.apply_rays(tree, rays, ts, save=True, slot="a")))

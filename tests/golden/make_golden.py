@@ -100,5 +100,39 @@ def models_fixture():
         key=key, uniforms_5x7=prng_np.uniform(key, (5, 7)))
 
 
+def ngpref_case():
+    """Seeded InstantNGPRefNERFModel (instant_ngp.py:57-89) and a density-penalty case (train.py:153-184)."""
+    import torch
+    rs = np.random.RandomState(61)
+    x = rs.uniform(-1.05, 1.05, (48, 3)).astype(F)
+    d = rs.randn(48, 3).astype(F)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    o = M.InstantNGPRefNERFModel([2 ** 14] * 16, [2 ** (4 + i // 2) for i in range(16)], BBOX_MIN, BBOX_MAX)
+    p = o.init(torch.Generator().manual_seed(62))
+    for leaf in p["MultiresHashTableEncoding_0"].values():
+        leaf["table"] *= 0.5e4
+    for i in range(5):
+        leaf = p[f"Dense_{i}"]
+        leaf["bias"] = torch.from_numpy((0.1 * np.random.RandomState(70 + i).randn(*leaf["bias"].shape)).astype(F))
+    return x, d, o, p
+
+
+def ngpref_fixture():
+    """Separate file so that the older fixtures stay byte-identical: python -c
+    'import make_golden as m; m.ngpref_fixture()' from tests/golden/."""
+    import torch
+    x, d, o, p = ngpref_case()
+    de, rgb, aux = o.apply(p, torch.from_numpy(x), torch.from_numpy(d), create_graph=False)
+    nerf = M.NeRFModel()
+    params = T.init_params(nerf, nerf, 7)
+    batch, uc, uf = make_rays(8, seed=63), make_uniforms(8, 64, 64), make_uniforms(8, 128, 65)
+    total, ld, _ = T.losses(nerf, nerf, params, BBOX_MIN, BBOX_MAX, batch, uc, uf, 64, 128, density_penalty=0.1,
+                            density_points=(x, d))
+    np.savez_compressed(os.path.join(HERE, "ngpref_small.npz"), x=x, d=d, dens=de.numpy(), rgb=rgb.numpy(),
+                        normal_mse=aux["normal_mse"].numpy(), neg_normal=aux["neg_normal"].numpy(),
+                        penalty_total=np.float32(total), penalty_fine=np.float32(ld["fine_density"]),
+                        penalty_coarse=np.float32(ld["coarse_density"]))
+
+
 if __name__ == "__main__":
     main()

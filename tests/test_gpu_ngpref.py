@@ -189,3 +189,23 @@ def test_ngpref_train_step_vs_oracle():
     print("worst NGP-Ref train grad rel-L2 (gpu, cpu-fp32):", worst[:4])
     assert worst[0][0] < 2e-2, worst[:4]
     assert worst[0][0] < 3 * max(w[1] for w in worst) + 1e-5, worst[:4]
+
+
+def test_golden_ngpref_fixture_gpu():
+    """The CUDA InstantNGPRefNERFModel path against the committed fixture tests/golden/ngpref_small.npz."""
+    import importlib.util
+    import os
+    from learn_nerf.instant_ngp import InstantNGPRefNERFModel
+    golden = os.path.join(os.path.dirname(__file__), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(golden, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    g = np.load(os.path.join(golden, "ngpref_small.npz"))
+    x, d, o, p = mg.ngpref_case()
+    n = InstantNGPRefNERFModel(table_sizes=[2 ** 14] * 16, grid_sizes=[2 ** (4 + i // 2) for i in range(16)],
+                               bbox_min=BBOX_MIN, bbox_max=BBOX_MAX)
+    dens, rgb, aux = n.apply(dict(params=to_native(n, p)), dev(x), dev(d))
+    np.testing.assert_allclose(dens.cpu().numpy(), g["dens"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(rgb.cpu().numpy(), g["rgb"], atol=2e-5)
+    np.testing.assert_allclose(aux["neg_normal"].cpu().numpy(), g["neg_normal"], atol=2e-5)
+    assert np.median(np.abs(aux["normal_mse"].cpu().numpy() - g["normal_mse"])) < 2e-5

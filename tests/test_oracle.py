@@ -291,3 +291,27 @@ def test_ngp_refnerf_oracle_normals_match_finite_differences():
     n = n / torch.sqrt((n ** 2).sum(1, keepdim=True) + 1e-10)
     rn = grad / torch.sqrt((grad ** 2).sum(1, keepdim=True) + 1e-10)
     np.testing.assert_allclose(aux["normal_mse"].numpy(), ((n - rn) ** 2).sum(1).numpy(), rtol=1e-9, atol=1e-12)
+
+
+def test_golden_ngpref_fixture():
+    """Regression of the InstantNGPRefNERFModel restatement and of the density-penalty branch
+    against tests/golden/ngpref_small.npz (generated by make_golden.ngpref_fixture from this oracle)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLDEN, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    g = np.load(os.path.join(GOLDEN, "ngpref_small.npz"))
+    x, d, o, p = mg.ngpref_case()
+    np.testing.assert_array_equal(x, g["x"])
+    de, rgb, aux = o.apply(p, torch.from_numpy(x), torch.from_numpy(d), create_graph=False)
+    np.testing.assert_allclose(de.numpy(), g["dens"], rtol=1e-5)
+    np.testing.assert_allclose(rgb.numpy(), g["rgb"], atol=1e-6)
+    np.testing.assert_allclose(aux["normal_mse"].numpy(), g["normal_mse"], atol=1e-5)
+    np.testing.assert_allclose(aux["neg_normal"].numpy(), g["neg_normal"], atol=1e-6)
+    nerf = M.NeRFModel()
+    params = T.init_params(nerf, nerf, 7)
+    batch, uc, uf = make_rays(8, seed=63), make_uniforms(8, 64, 64), make_uniforms(8, 128, 65)
+    total, ld, _ = T.losses(nerf, nerf, params, BBOX_MIN, BBOX_MAX, batch, uc, uf, 64, 128, density_penalty=0.1,
+                            density_points=(x, d))
+    np.testing.assert_allclose(float(total), float(g["penalty_total"]), rtol=1e-5)
+    np.testing.assert_allclose(float(ld["fine_density"]), float(g["penalty_fine"]), rtol=1e-5)
