@@ -236,13 +236,13 @@ def run_ours(args):
                  "nerf": ["nerf_mlp_fwd", "nerf_mlp_bwd"]}[args.model]
     dom_events = []
 
-    def timed(fn):
+    def timed(fn, name):
         def wrapper(*a, **k):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             r = fn(*a, **k)
             e1.record()
-            dom_events.append((e0, e1))
+            dom_events.append((e0, e1, name))
             return r
         return wrapper
 
@@ -290,7 +290,7 @@ def run_ours(args):
 
     # ---- timed region 1: device-resident inputs, per-step CUDA events, L2 flushed between steps
     for nm in dom_names:
-        setattr(_native, nm, timed(originals[nm]))
+        setattr(_native, nm, timed(originals[nm], nm))
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = _native.launch_count()
@@ -309,7 +309,8 @@ def run_ours(args):
     for nm in dom_names:
         setattr(_native, nm, originals[nm])
     step_ms = [a.elapsed_time(b) for a, b in evs]
-    dom_ms = sum(a.elapsed_time(b) for a, b in dom_events) / max(args.steps, 1)
+    dom_ms = sum(a.elapsed_time(b) for a, b, _ in dom_events) / max(args.steps, 1)
+    part_ms = {nm: sum(a.elapsed_time(b) for a, b, k in dom_events if k == nm) / max(args.steps, 1) for nm in dom_names}
     ms = float(np.mean(step_ms))
 
     # ---- timed region 2 (e2e): host pinned batch -> H2D -> step -> D2H of the logged scalars
@@ -369,6 +370,15 @@ def run_ours(args):
                         "peak_source": peaks["source"] + " (sustained bf16 cuBLAS)",
                         "kernel_ms_per_step": dom_ms, "kernel_share_of_step": dom_ms / ms,
                         "algorithmic_flop_per_sample": flop_per_sample}
+            if args.model == "nerf":  # per C-ABI call: forward kernel vs dX + dW kernels
+                fl = {"nerf_mlp_fwd": FLOP_FWD_PER_SAMPLE, "nerf_mlp_bwd": FLOP_TRAIN_PER_SAMPLE - FLOP_FWD_PER_SAMPLE}
+                names = {"nerf_mlp_fwd": "nerf_fwd_pair_kernel",
+                         "nerf_mlp_bwd": "nerf_bwd_dx_pair_kernel + nerf_bwd_dw_kernel"}
+                roofline["parts"] = [
+                    {"kernel": names[nm] if prec == "bf16" else nm + " (fp32 FFMA chain)", "ms_per_step": part_ms[nm],
+                     "achieved": fl[nm] * SAMPLES_PER_RAY * n / (part_ms[nm] * 1e-3) / 1e12,
+                     "frac": fl[nm] * SAMPLES_PER_RAY * n / (part_ms[nm] * 1e-3) / 1e12 / peaks["tf"]}
+                    for nm in dom_names if part_ms.get(nm, 0) > 0]
         else:
             nbytes = ngp_grid_bytes_per_ray(train) * n
             achieved = nbytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
