@@ -117,42 +117,75 @@ class NeRFDataset:
 
 
 class ShuffledDataset:
-    """dataset.py:163-263: the two-stage shuffle (random shard assignment on write, a random shard
-    order plus a permutation inside each shard on read)."""
+    """Pre-shuffled rays of a NeRFDataset on disk (dataset.py:163-263): a two-stage shuffle.  Stage
+    one scatters every view's rays over ``num_shards`` files with a random shard id per ray; stage
+    two, at read time, visits the shards in a random order and permutes the rays inside each.
+    Files ``<dir>/0 .. <dir>/<num_shards-1>`` hold raw float32 ``[N,3,3]`` records and ``<dir>/done``
+    marks a finished directory, exactly as the reference writes them."""
+
+    RECORD_FLOATS = 9
 
     def __init__(self, dir_path: str, dataset: NeRFDataset, key, num_shards: int = 32, ray_device="cuda"):
         self.num_shards = num_shards
         self.shard_key, self.shuffle_key = prng.split(key)
-        if not os.path.exists(dir_path):
-            os.mkdir(dir_path)
-        done_path = os.path.join(dir_path, "done")
-        if os.path.exists(done_path):
-            self.fds = [open(os.path.join(dir_path, f"{i}"), "rb") for i in range(num_shards)]
-        else:
-            self.fds = [open(os.path.join(dir_path, f"{i}"), "wb+") for i in range(num_shards)]
-            self._create_shards(dataset, ray_device)
-            with open(done_path, "wb+") as f:
+        self._paths = [os.path.join(dir_path, str(i)) for i in range(num_shards)]
+        os.makedirs(dir_path, exist_ok=True)
+        marker = os.path.join(dir_path, "done")
+        if not os.path.exists(marker):
+            self._write_shards(dataset, ray_device)
+            with open(marker, "wb") as f:
                 f.write(b"done\n")
+
+    # ---- stage one
+    def _write_shards(self, dataset: NeRFDataset, ray_device):
+        key = self.shard_key
+        files = [open(p, "wb") for p in self._paths]
+        try:
+            for view in dataset.views:
+                rays = view.rays(device=ray_device) if _takes_device(view) else view.rays()
+                rays = rays.detach().cpu().numpy() if isinstance(rays, torch.Tensor) else np.asarray(rays)
+                rays = np.ascontiguousarray(rays, dtype=np.float32)
+                key, view_key = prng.split(key)
+                shard_of = prng.randint_host(view_key, rays.shape[0], 0, self.num_shards)
+                order = np.argsort(shard_of, kind="stable")  # rays of one shard stay in raster order
+                counts = np.bincount(shard_of, minlength=self.num_shards)
+                start = 0
+                for shard, count in enumerate(counts.tolist()):
+                    if count:
+                        files[shard].write(rays[order[start:start + count]].tobytes())
+                    start += count
+        finally:
+            for f in files:
+                f.close()
+
+    # ---- stage two
+    def _read_shard(self, shard: int) -> np.ndarray:
+        return np.fromfile(self._paths[shard], dtype=np.float32).reshape(-1, 3, 3)
 
     def _host_batches(self, batch_size: int, repeat: bool) -> Iterator[np.ndarray]:
         key = self.shuffle_key
-        cur = None
+        carry: List[np.ndarray] = []  # rays not yet handed out, oldest first
+        carried = 0
         while True:
-            key, this_key = prng.split(key)
-            for shard in prng.permutation_host(this_key, self.num_shards).tolist():
-                key, this_key = prng.split(key)
+            key, order_key = prng.split(key)
+            for shard in prng.permutation_host(order_key, self.num_shards).tolist():
+                key, perm_key = prng.split(key)
                 rays = self._read_shard(shard)
-                rays = rays[prng.permutation_host(this_key, rays.shape[0])]
-                cur = rays if cur is None else np.concatenate([cur, rays], axis=0)
-                while cur.shape[0] >= batch_size:
-                    yield cur[:batch_size]
-                    cur = cur[batch_size:]
+                carry.append(rays[prng.permutation_host(perm_key, rays.shape[0])])
+                carried += rays.shape[0]
+                if carried >= batch_size:
+                    pool = np.concatenate(carry, axis=0) if len(carry) > 1 else carry[0]
+                    full = (carried // batch_size) * batch_size
+                    for a in range(0, full, batch_size):
+                        yield pool[a:a + batch_size]
+                    carry, carried = ([pool[full:]] if full < carried else []), carried - full
             if not repeat:
                 break
-        if cur is not None and cur.shape[0]:
-            yield cur
+        if carried:
+            yield np.concatenate(carry, axis=0) if len(carry) > 1 else carry[0]
 
     def iterate_batches(self, batch_size: int, repeat: bool = False, device=None) -> Iterator[torch.Tensor]:
+        """Batches of ``batch_size`` rays (the last one may be short when ``repeat`` is False)."""
         dev = torch.device(device) if device is not None else None
         if dev is None or dev.type != "cuda":
             for b in self._host_batches(batch_size, repeat):
@@ -191,25 +224,7 @@ class ShuffledDataset:
         return self
 
     def __exit__(self, *args):
-        for fd in self.fds:
-            fd.close()
-
-    def _create_shards(self, dataset: NeRFDataset, ray_device):
-        key = self.shard_key
-        for view in dataset.views:
-            rays = view.rays(device=ray_device) if _takes_device(view) else view.rays()
-            rays = rays.detach().cpu().numpy() if isinstance(rays, torch.Tensor) else np.asarray(rays)
-            key, this_key = prng.split(key)
-            assignments = prng.randint_host(this_key, rays.shape[0], 0, self.num_shards)
-            for shard in range(self.num_shards):
-                sub = rays[assignments == shard]
-                if sub.shape[0]:
-                    self.fds[shard].write(sub.astype(np.float32).tobytes())
-
-    def _read_shard(self, shard: int) -> np.ndarray:
-        f = self.fds[shard]
-        f.seek(0)
-        return np.frombuffer(f.read(), dtype=np.float32).reshape([-1, 3, 3])
+        return None  # shard files are opened per read
 
 
 def _takes_device(view) -> bool:
