@@ -220,6 +220,40 @@ def test_adam_step(nat):
                                    rtol=1e-5)
 
 
+def test_adam_step_peers_single_process(nat):
+    """lnrf_adam_step_peers (fused peer all-reduce + Adam) with the 'peers' being three gradient
+    buffers of this one GPU: rank-order sum, 1/world scaling, the trailing loss sums, norms and the
+    update against the oracle's optax.adam restatement fed with the mean gradient.  (The real
+    multi-GPU exchange is covered by tests/mgpu_check.py under torchrun.)"""
+    from oracle import train_torch as T
+    rs = np.random.RandomState(1)
+    n, extra, world = 10007, 2, 3
+    p0 = rs.randn(n).astype(F)
+    params = dict(w=torch.from_numpy(p0.copy()))
+    st = T.AdamState(params)
+    p, m, v = dev(p0.copy()), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    # 16-byte aligned per-rank buffers of n + extra (+ pad) floats
+    bufs = [torch.zeros(n + extra + 3, device="cuda") for _ in range(world)]
+    for step in range(1, 4):
+        gs = [rs.randn(n + extra).astype(F) for _ in range(world)]
+        for b, g in zip(bufs, gs):
+            b[: n + extra].copy_(dev(g))
+        norms, sums = torch.zeros(2, device="cuda"), torch.zeros(extra, device="cuda")
+        p_before = p.cpu().numpy().copy()
+        nat.adam_step_peers(p, [b.data_ptr() for b in bufs], m, v, n, extra, 1e-3, 0.9, 0.999, 1e-7, step,
+                            1.0 / world, norms, sums)
+        gsum = gs[0].astype(np.float32).copy()
+        for g in gs[1:]:
+            gsum = gsum + g  # rank order, fp32
+        gmean = gsum[:n] * np.float32(1.0 / world)
+        params = T.adam_update(params, dict(w=torch.from_numpy(gmean.copy())), st, 1e-3, eps=1e-7)
+        np.testing.assert_allclose(p.cpu().numpy(), params["w"].numpy(), rtol=2e-6, atol=1e-7)
+        np.testing.assert_array_equal(sums.cpu().numpy(), gsum[n:])
+        np.testing.assert_allclose(norms.cpu().numpy(),
+                                   [(gmean.astype(np.float64) ** 2).sum(), (p_before.astype(np.float64) ** 2).sum()],
+                                   rtol=1e-5)
+
+
 def _camera():
     import math
     return dict(camera_direction=(0.1, -0.2, -0.97), camera_origin=(0.5, 1.0, 4.0), x_axis=(0.99, 0.05, 0.09),
