@@ -32,9 +32,9 @@ FLOP_TRAIN_PER_SAMPLE = 3_481_344        # fwd + dW + dX, no padding / recompute
 REF_FLOP_FWD_PER_SAMPLE = 2 * (590_336 + 489_472)
 REF_FLOP_TRAIN_PER_SAMPLE = 2 * 3_709_088
 SAMPLES_PER_RAY = 64 + 192
-# ncu (profiles/r01b_nerf_train_kernels_ncu_full.txt): fwd 4.232 + dX 4.034 + dW 8.557 GB of DRAM
+# ncu (profiles/r01d_nerf_train_kernels_ncu_full.txt): fwd 4.230 + dX 4.035 + dW 8.539 GB of DRAM
 # traffic for the 786,432 samples of the fine level
-NCU_TRAIN_DRAM_BYTES_PER_SAMPLE = (4.232e9 + 4.034e9 + 8.557e9) / 786432
+NCU_TRAIN_DRAM_BYTES_PER_SAMPLE = (4.230e9 + 4.035e9 + 8.539e9) / 786432
 
 
 def load_peaks():
@@ -362,7 +362,7 @@ def run_ours(args):
                         "achieved": achieved, "peak": peaks["tf"], "unit": "TFLOP/s",
                         "frac": achieved / peaks["tf"],
                         # DRAM bytes of the three MLP kernels per 4096-ray step, from the ncu --set full
-                        # capture profiles/r01b_nerf_train_kernels_ncu_full.txt (fine level 4.23 + 4.03 +
+                        # capture profiles/r01d_nerf_train_kernels_ncu_full.txt (fine level 4.23 + 4.03 +
                         # 8.56 GB, coarse level = 1/3 of it); equals the algorithmic stash bytes
                         "traffic": (NCU_TRAIN_DRAM_BYTES_PER_SAMPLE * SAMPLES_PER_RAY * n
                                     if (train and prec == "bf16" and args.model == "nerf") else None),

@@ -264,8 +264,12 @@ int lnrf_ngpref_bwd(const float* params, const int64_t* level_offsets_host, cons
 /* Tuning knob of the fused bf16 kernel: 1 = one weight-ring stage and two CTAs
  * per SM (default); >= 2 = four stages, one CTA per SM.                       */
 int lnrf_set_tc_stages(int32_t stages);
-/* Profiling ablations of the bf16 dW kernel (1 skip loads, 2 skip MMAs, 4 skip worker math);
- * results are WRONG while non-zero.  Default 0.                                  */
+/* Profiling / tuning switches of the bf16 tcgen05 kernels (used by profiles/ablate_*.py and
+ * profiles/with_flags.py only; default 0).  Bit flags: 1 / 2 / 4 = dW kernel without loads / MMAs /
+ * worker math and 8 / 16 = forward without stash stores / with all stash tiles aliased onto the
+ * first 64 (results are WRONG with these five); 64 = the other forward schedule (full-N with the
+ * stash, N-half without); 512 = the single-tile dX kernel instead of the pair kernel.  Values
+ * >= 2000 set the dW kernel's CTA waves (2000 + waves), 1000..1999 its job weights.          */
 int lnrf_set_debug_flags(int32_t flags);
 
 #ifdef __cplusplus
