@@ -313,7 +313,14 @@ def run_ours(args):
     part_ms = {nm: sum(a.elapsed_time(b) for a, b, k in dom_events if k == nm) / max(args.steps, 1) for nm in dom_names}
     ms = float(np.mean(step_ms))
 
-    # ---- timed region 2 (e2e): host pinned batch -> H2D -> step -> D2H of the logged scalars
+    # ---- timed region 2 (e2e): host pinned batch -> H2D -> step -> D2H of the logged scalars.
+    # The train step is replayed as a CUDA graph here (TrainLoop(cuda_graph=True), the setting a user
+    # would train with on one GPU); region 1 stays eager because it times individual C-ABI calls.
+    graph_e2e = bool(args.cuda_graph and args.workload == "train" and world == 1)
+    if graph_e2e:
+        loop.cuda_graph = True
+        one_step(0, host=True)  # captures the graph (untimed)
+        graph_e2e = loop._cg is not None  # e.g. Ref-NeRF with a ray_chunk stays eager
     barrier()
     t_e2e = []
     for i in range(args.steps):
@@ -406,7 +413,7 @@ def run_ours(args):
                                        "all-reduce + Adam; NCCL fallback)" if train else
                                        ", no collective")},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "rays/s", "ms_per_step": e2e_ms,
+            "e2e": {"value": e2e_value, "unit": "rays/s", "ms_per_step": e2e_ms, "cuda_graph": graph_e2e,
                     "h2d_bytes_per_step": 0 if args.workload == "image" else int(host_batch.numel() * 4),
                     "d2h_bytes_per_step": 16 if train else (int(n * 3) if args.workload == "image" else int(n * 3 * 4))},
             "gpu_launches": int(launches),
@@ -444,6 +451,8 @@ def main():
     ap.add_argument("--cpu_rays", type=int, default=512, help="rays per step of the CPU sample")
     ap.add_argument("--tc_stages", type=int, default=None, help="bf16 kernel tuning knob")
     ap.add_argument("--no_cpu_baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--no_cuda_graph", dest="cuda_graph", action="store_false",
+                    help="run the end-to-end region with the eager step instead of the CUDA-graph replay")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

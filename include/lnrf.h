@@ -146,6 +146,13 @@ int lnrf_nerf_mlp_bwd(const float* params, const void* packed, int64_t m, int32_
 int lnrf_adam_step(float* params, const float* grads, float* m, float* v, int64_t count,
                    float lr, float b1, float b2, float eps, int32_t step, float grad_scale,
                    float* norms_out, lnrf_stream_t stream);
+/* Variants for CUDA-graph replays (captured once, replayed every step): the two inputs that change
+ * from step to step are read from device memory.  inv_bias_corr_dev = {1/(1-b1^t), 1/(1-b2^t)}
+ * (what lnrf_adam_step derives from `step` on the host); key_dev = the two Threefry key words. */
+int lnrf_adam_step_dk(float* params, const float* grads, float* m, float* v, int64_t count,
+                      float lr, float b1, float b2, float eps, const float* inv_bias_corr_dev,
+                      float grad_scale, float* norms_out, lnrf_stream_t stream);
+int lnrf_threefry_uniform_dk(const uint32_t* key_dev, int64_t n, float* out, lnrf_stream_t stream);
 /* Data-parallel variant (the reference is single-device, train.py:85-106): fused
  * all-reduce + Adam.  peer_grads is a HOST array of `world` device addresses, one flat gradient
  * buffer per rank (NVLink peer / symmetric-memory mappings, own rank included), each holding

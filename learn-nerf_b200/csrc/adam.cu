@@ -8,7 +8,12 @@ namespace lnrf {
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ params, const float* __restrict__ grads, float* __restrict__ m,
             float* __restrict__ v, int64_t count, float lr, float b1, float b2, float eps,
-            float inv_bc1, float inv_bc2, float grad_scale, float* __restrict__ norms_out) {
+            float inv_bc1, float inv_bc2, float grad_scale, float* __restrict__ norms_out,
+            const float* __restrict__ bc_dev = nullptr) {
+  if (bc_dev) {  // CUDA-graph replays: the step-dependent bias corrections live in device memory
+    inv_bc1 = __ldg(bc_dev);
+    inv_bc2 = __ldg(bc_dev + 1);
+  }
   float gsq = 0.0f, psq = 0.0f;
   const int64_t nvec = count >> 2;
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
@@ -168,6 +173,24 @@ extern "C" int lnrf_adam_step_peers(float* params, const uint64_t* peer_grads, i
       params, pp, world, m, v, count, extra, lr, b1, b2, eps, (float)(1.0 / bc1), (float)(1.0 / bc2), grad_scale,
       norms_out, extra_out);
   LNRF_LAUNCH_CHECK("adam_peers_kernel");
+  return LNRF_OK;
+}
+
+extern "C" int lnrf_adam_step_dk(float* params, const float* grads, float* m, float* v, int64_t count,
+                                 float lr, float b1, float b2, float eps, const float* inv_bias_corr_dev,
+                                 float grad_scale, float* norms_out, lnrf_stream_t stream) {
+  LNRF_REQUIRE(count >= 0, LNRF_E_INVALID, "lnrf_adam_step_dk: count=%lld", (long long)count);
+  if (count == 0) return LNRF_OK;
+  LNRF_REQUIRE(params && grads && m && v && inv_bias_corr_dev, LNRF_E_INVALID, "lnrf_adam_step_dk: null pointer");
+  LNRF_REQUIRE(((uintptr_t)params | (uintptr_t)grads | (uintptr_t)m | (uintptr_t)v) % 16 == 0,
+               LNRF_E_INVALID, "lnrf_adam_step_dk: buffers must be 16-byte aligned");
+  int64_t blocks = lnrf::ceil_div(lnrf::ceil_div(count, 4), 256);
+  int64_t cap = int64_t(lnrf::sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  lnrf::adam_kernel<<<(unsigned)blocks, 256, 0, lnrf::as_stream(stream)>>>(
+      params, grads, m, v, count, lr, b1, b2, eps, 0.0f, 0.0f, grad_scale, norms_out, inv_bias_corr_dev);
+  LNRF_LAUNCH_CHECK("adam_kernel");
   return LNRF_OK;
 }
 

@@ -47,9 +47,35 @@ threefry_uniform_kernel(uint32_t k0, uint32_t k1, int64_t n, float* __restrict__
   }
 }
 
+// same stream with the key read from device memory (CUDA-graph replays: the key changes every step)
+__global__ void __launch_bounds__(256)
+threefry_uniform_dk_kernel(const uint32_t* __restrict__ key, int64_t n, float* __restrict__ out) {
+  const uint32_t k0 = __ldg(key), k1 = __ldg(key + 1);
+  const int64_t half = (n + 1) / 2;
+  for (int64_t j = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < half; j += int64_t(gridDim.x) * blockDim.x) {
+    uint32_t x0 = uint32_t(j);
+    uint32_t x1 = (half + j < n) ? uint32_t(half + j) : 0u;
+    threefry2x32(k0, k1, x0, x1);
+    out[j] = bits_to_uniform(x0);
+    if (half + j < n) out[half + j] = bits_to_uniform(x1);
+  }
+}
+
 }  // namespace lnrf
 
 extern "C" {
+
+int lnrf_threefry_uniform_dk(const uint32_t* key_dev, int64_t n, float* out, lnrf_stream_t stream) {
+  LNRF_REQUIRE(n >= 0 && n < (int64_t(1) << 32), LNRF_E_INVALID, "lnrf_threefry_uniform_dk: n=%lld", (long long)n);
+  if (n == 0) return LNRF_OK;
+  LNRF_REQUIRE(out && key_dev, LNRF_E_INVALID, "lnrf_threefry_uniform_dk: null pointer");
+  int64_t blocks = lnrf::ceil_div((n + 1) / 2, 256);
+  const int64_t cap = int64_t(lnrf::sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  lnrf::threefry_uniform_dk_kernel<<<(unsigned)blocks, 256, 0, lnrf::as_stream(stream)>>>(key_dev, n, out);
+  LNRF_LAUNCH_CHECK("threefry_uniform_dk_kernel");
+  return LNRF_OK;
+}
 
 int lnrf_threefry_uniform(uint32_t key0, uint32_t key1, int64_t n, float* out, lnrf_stream_t stream) {
   LNRF_REQUIRE(n >= 0 && n < (int64_t(1) << 32), LNRF_E_INVALID, "lnrf_threefry_uniform: n=%lld", (long long)n);

@@ -52,6 +52,9 @@ _SIGS = {
                           [c_void_p] * 6),
     "lnrf_adam_step": (c_int32, [c_void_p] * 4 + [c_int64, c_float, c_float, c_float, c_float,
                                                   c_int32, c_float, c_void_p, c_void_p]),
+    "lnrf_adam_step_dk": (c_int32, [c_void_p] * 4 + [c_int64, c_float, c_float, c_float, c_float, c_void_p,
+                                     c_float, c_void_p, c_void_p]),
+    "lnrf_threefry_uniform_dk": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p]),
     "lnrf_adam_step_peers": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_int32,
                                        c_float, c_float, c_float, c_float, c_int32, c_float, c_void_p,
                                        c_void_p, c_void_p]),
@@ -282,6 +285,23 @@ def adam_step(params, grads, m, v, lr, b1, b2, eps, step, grad_scale, norms_out)
     _check(load().lnrf_adam_step(_p(_f32c(params, "params")), _p(_f32c(grads, "grads")), _p(m), _p(v),
                                  params.numel(), lr, b1, b2, eps, step, grad_scale, _p(norms_out),
                                  _stream()), "lnrf_adam_step")
+
+
+def adam_step_dk(params, grads, m, v, lr, b1, b2, eps, inv_bias_corr_dev, grad_scale, norms_out):
+    """lnrf_adam_step with the bias corrections {1/(1-b1^t), 1/(1-b2^t)} in device memory."""
+    ensure_init(params.device)
+    _check(load().lnrf_adam_step_dk(_p(_f32c(params, "params")), _p(_f32c(grads, "grads")), _p(m), _p(v),
+                                    params.numel(), lr, b1, b2, eps, _p(inv_bias_corr_dev), grad_scale,
+                                    _p(norms_out), _stream()), "lnrf_adam_step_dk")
+
+
+def threefry_uniform_dk(key_dev: torch.Tensor, shape) -> torch.Tensor:
+    """Uniforms from a Threefry key held in device memory (int32/uint32 tensor of 2 words)."""
+    ensure_init(key_dev.device)
+    out = torch.empty(tuple(shape), device=key_dev.device)
+    _check(load().lnrf_threefry_uniform_dk(_p(key_dev), out.numel(), _p(out), _stream()),
+           "lnrf_threefry_uniform_dk")
+    return out
 
 
 def adam_step_peers(params, peer_ptrs, m, v, count, extra, lr, b1, b2, eps, step, grad_scale, norms_out,

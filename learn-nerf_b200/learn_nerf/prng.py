@@ -64,6 +64,16 @@ class PRNGKey:
         return ((self.k0 << 32) | self.k1) & ((1 << 63) - 1)
 
 
+class DeviceKey:
+    """A Threefry key whose two words live in DEVICE memory (an int32 tensor of 2 elements): the
+    form a CUDA-graph replay needs, where the host rewrites the words before every replay.  Only
+    ``uniform`` accepts it; splitting is done on the host before the words are uploaded."""
+
+    def __init__(self, words: torch.Tensor):
+        assert words.numel() == 2 and words.is_cuda and words.dtype in (torch.int32, torch.uint32)
+        self.words = words
+
+
 KeyLike = Union[PRNGKey, int]
 
 
@@ -86,6 +96,8 @@ def fold_in(key: KeyLike, data: int) -> PRNGKey:
 def uniform(key: KeyLike, shape, device) -> torch.Tensor:
     """fp32 uniforms in [0, 1) (multiples of 2^-23) generated on ``device`` (CUDA only)."""
     from . import _native
+    if isinstance(key, DeviceKey):
+        return _native.threefry_uniform_dk(key.words, shape)
     k = _as_key(key)
     return _native.threefry_uniform(k.k0, k.k1, shape, device)
 

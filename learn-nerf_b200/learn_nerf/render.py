@@ -44,8 +44,8 @@ class NeRFRenderer:
     def render_rays(self, key, batch: torch.Tensor, _save: bool = False) -> Dict[str, Dict[str, torch.Tensor]]:
         """render.py:39-91.  ``key``: PRNG key / seed, or a pair (u_coarse[N,Tc], u_fine[N,Tf])."""
         batch = _native._f32c(batch.contiguous(), "batch")
-        if isinstance(key, (tuple, list)) and isinstance(key[0], torch.Tensor):
-            coarse_key, fine_key = key
+        if isinstance(key, (tuple, list)) and isinstance(key[0], (torch.Tensor, prng.DeviceKey)):
+            coarse_key, fine_key = key  # explicit uniforms, or pre-split device-resident keys
         else:
             coarse_key, fine_key = prng.split(key)  # :55
         # t_range (:53) and stratified_sampling (:57-63) are one fused launch (K1)

@@ -41,7 +41,8 @@ class TrainLoop:
     def __init__(self, coarse: ModelBase, fine: ModelBase, init_rng, lr: float, coarse_ts: int,
                  fine_ts: int, adam_b1: float = 0.9, adam_b2: float = 0.999, adam_eps: float = 1e-7,
                  loss_weights: Dict[str, float] = None, density_penalty: Optional[float] = None,
-                 density_penalty_batch_size: int = 128, device=None, ray_chunk: Optional[int] = None):
+                 density_penalty_batch_size: int = 128, device=None, ray_chunk: Optional[int] = None,
+                 cuda_graph: bool = False):
         self.coarse, self.fine = coarse, fine
         self.coarse_ts, self.fine_ts = coarse_ts, fine_ts
         self.lr, self.b1, self.b2, self.eps = lr, adam_b1, adam_b2, adam_eps
@@ -49,6 +50,11 @@ class TrainLoop:
         self.density_penalty = density_penalty
         self.density_penalty_batch_size = density_penalty_batch_size
         self.ray_chunk = ray_chunk
+        # cuda_graph: capture the whole step (19 launches for NeRF) once per batch size and replay it;
+        # the per-step PRNG keys and Adam bias corrections are uploaded to device memory before each
+        # replay.  Single GPU, PRNG-key entry point, no density penalty; anything else runs eagerly.
+        self.cuda_graph = cuda_graph
+        self._cg = None
         device = torch.device(device or "cuda")
         if device.type == "cuda" and device.index is None:
             device = torch.device("cuda", torch.cuda.current_device())
@@ -109,6 +115,8 @@ class TrainLoop:
         bmin, bmax = _vec3(bbox_min), _vec3(bbox_max)
 
         def in_place_step(key, batch: torch.Tensor) -> Dict[str, torch.Tensor]:
+            if self.cuda_graph and self._graphable(key, batch):
+                return self._step_graphed(key, bmin, bmax, batch)
             return self._step(key, bmin, bmax, batch)
 
         return in_place_step
@@ -156,7 +164,66 @@ class TrainLoop:
             return (key[0][a:b].contiguous(), key[1][a:b].contiguous())
         return key if (a == 0 and b == n) else prng.fold_in(key, a)
 
-    def _step(self, key, bmin, bmax, batch: torch.Tensor) -> Dict[str, torch.Tensor]:
+    # ------------------------------------------------------------------ CUDA-graph replay of the step
+    def _graphable(self, key, batch) -> bool:
+        return (parallel.world()[1] == 1 and self.density_penalty is None and not isinstance(key, (tuple, list))
+                and (self.ray_chunk is None or self.ray_chunk >= batch.shape[0]) and batch.shape[0] > 0)
+
+    def _step_graphed(self, key, bmin, bmax, batch: torch.Tensor) -> Dict[str, torch.Tensor]:
+        st = self.state
+        n = batch.shape[0]
+        cg = self._cg
+        if cg is None or cg["n"] != n or cg["bbox"] != (tuple(bmin), tuple(bmax)):
+            cg = self._cg = self._capture(n, bmin, bmax)
+        # host side of the step: key bookkeeping (train.py:137, render.py:55) and Adam's step count
+        key, _density_key = prng.split(key)
+        kc, kf = prng.split(key)
+        st.step += 1
+        words = cg["host_words"]
+        words[0], words[1], words[2], words[3] = kc.k0, kc.k1, kf.k0, kf.k1
+        cg["host_bc"][0] = 1.0 / (1.0 - self.b1 ** st.step)
+        cg["host_bc"][1] = 1.0 / (1.0 - self.b2 ** st.step)
+        cg["dev_scalars"].copy_(cg["host_scalars"], non_blocking=True)
+        cg["batch"].copy_(batch, non_blocking=True)
+        cg["graph"].replay()
+        for name in ("coarse", "fine"):  # eager users (losses(), a renderer) must re-pack the new weights
+            st.params[name].mark_updated()
+        return cg["logs"]
+
+    def _capture(self, n: int, bmin, bmax):
+        st = self.state
+        dev = self.device
+        host = torch.zeros(6, dtype=torch.int32).pin_memory()  # 4 key words | 2 fp32 bias corrections
+        dev_scalars = torch.zeros(6, dtype=torch.int32, device=dev)
+        cg = dict(n=n, bbox=(tuple(bmin), tuple(bmax)), host_scalars=host, dev_scalars=dev_scalars,
+                  host_words=host[:4].numpy().view(np.uint32), host_bc=host[4:6].numpy().view(np.float32),
+                  batch=torch.zeros(n, 3, 3, device=dev))
+        keys = (prng.DeviceKey(dev_scalars[0:2]), prng.DeviceKey(dev_scalars[2:4]))
+        bc_dev = dev_scalars[4:6].view(torch.float32)
+        # warm-up on a side stream (lazy allocations, workspace caches), then capture; neither may
+        # leave a trace in the training state
+        saved = (st.flat.clone(), st.m.clone(), st.v.clone())
+        cg["host_bc"][:] = 1.0
+        dev_scalars.copy_(host)
+        torch.cuda.synchronize(dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._step(keys, bmin, bmax, cg["batch"], _graph_bc=bc_dev)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            cg["logs"] = self._step(keys, bmin, bmax, cg["batch"], _graph_bc=bc_dev)
+        for dst, src in zip((st.flat, st.m, st.v), saved):
+            dst.copy_(src)
+        for name in ("coarse", "fine"):
+            st.params[name].mark_updated()
+        cg["graph"] = graph
+        return cg
+
+    def _step(self, key, bmin, bmax, batch: torch.Tensor, _graph_bc=None) -> Dict[str, torch.Tensor]:
         st = self.state
         batch = _native._f32c(batch.contiguous(), "batch")
         n = batch.shape[0]
@@ -222,8 +289,13 @@ class TrainLoop:
                 penalties[f"{prefix}_density"] = mean
                 d_dens = torch.full_like(dens, self.density_penalty / dens.numel())
                 model.backward_rays(ctx, d_dens, torch.zeros_like(rgb), g[sl[0]:sl[1]])
-        st.step += 1
-        if self._peers is not None:
+        if _graph_bc is None:
+            st.step += 1
+        if _graph_bc is not None:  # graph capture / replay: the caller owns the step count
+            self._scalars[0:2].copy_(self._loss_sums)
+            _native.adam_step_dk(st.flat, g, st.m, st.v, self.lr, self.b1, self.b2, self.eps, _graph_bc,
+                                 1.0 / world, self._scalars[2:4])
+        elif self._peers is not None:
             # fused all-reduce + Adam: every rank reads all ranks' gradients over NVLink inside the
             # optimiser kernel (rank-order sum, 1/world folded in); barriers fence the peer reads
             self._peers.barrier()

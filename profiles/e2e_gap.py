@@ -36,3 +36,7 @@ ts = []
 for i in range(30):
     torch.cuda.synchronize(); e0.record(); step(200 + i, dev); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
 print(f"CUDA-event time of the same step (first launch -> last kernel end): {np.mean(ts):6.3f} ms")
+loop.cuda_graph = True
+step(0, dev)  # capture
+run("CUDA graph: device batch, no readback", lambda i: step(100 + i, dev))
+run("CUDA graph: H2D + step + float() per scalar", lambda i: [float(v) for v in step(100 + i, host.to("cuda", non_blocking=True)).values()])
