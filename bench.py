@@ -264,7 +264,7 @@ def run_ours(args):
     def one_step(i, host=False):
         if args.workload == "image":
             img = render_view(img_renderer, view, args.width, args.height, batch_size=args.batch_size,
-                              key=1000 + i, device=dev)
+                              key=1000 + i, device=dev, cuda_graph=args.cuda_graph)
             return img.cpu() if host else img
         b = host_batch.to(dev, non_blocking=True) if host else batch
         if args.workload == "train":

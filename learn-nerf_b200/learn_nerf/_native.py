@@ -287,6 +287,31 @@ def adam_step(params, grads, m, v, lr, b1, b2, eps, step, grad_scale, norms_out)
                                  _stream()), "lnrf_adam_step")
 
 
+class PinnedRing:
+    """Race-free asynchronous upload of a few words per step (CUDA-graph replays): a ring of pinned
+    staging buffers, each guarded by the event of the copy that last read it, so the host never
+    rewrites a buffer whose H2D copy has not executed yet and never waits unless it runs ``depth``
+    steps ahead of the GPU."""
+
+    def __init__(self, words: int, depth: int = 8):
+        self.bufs = [torch.zeros(words, dtype=torch.int32).pin_memory() for _ in range(depth)]
+        self.views = [b.numpy() for b in self.bufs]
+        self.events = [None] * depth
+        self.i = 0
+
+    def upload(self, values, dst: torch.Tensor):
+        """values: int32 numpy array of ``words`` elements; dst: int32 device tensor."""
+        j = self.i
+        self.i = (j + 1) % len(self.bufs)
+        if self.events[j] is not None:
+            self.events[j].synchronize()
+        self.views[j][:] = values
+        dst.copy_(self.bufs[j], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dst.device))
+        self.events[j] = ev
+
+
 def adam_step_dk(params, grads, m, v, lr, b1, b2, eps, inv_bias_corr_dev, grad_scale, norms_out):
     """lnrf_adam_step with the bias corrections {1/(1-b1^t), 1/(1-b2^t)} in device memory."""
     ensure_init(params.device)

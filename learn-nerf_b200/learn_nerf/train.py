@@ -179,11 +179,11 @@ class TrainLoop:
         key, _density_key = prng.split(key)
         kc, kf = prng.split(key)
         st.step += 1
-        words = cg["host_words"]
-        words[0], words[1], words[2], words[3] = kc.k0, kc.k1, kf.k0, kf.k1
-        cg["host_bc"][0] = 1.0 / (1.0 - self.b1 ** st.step)
-        cg["host_bc"][1] = 1.0 / (1.0 - self.b2 ** st.step)
-        cg["dev_scalars"].copy_(cg["host_scalars"], non_blocking=True)
+        scalars = np.empty(6, dtype=np.int32)
+        scalars[:4] = np.array([kc.k0, kc.k1, kf.k0, kf.k1], dtype=np.uint32).view(np.int32)
+        scalars[4:6] = np.array([1.0 / (1.0 - self.b1 ** st.step), 1.0 / (1.0 - self.b2 ** st.step)],
+                                dtype=np.float32).view(np.int32)
+        cg["ring"].upload(scalars, cg["dev_scalars"])  # pinned ring: asynchronous and race-free
         cg["batch"].copy_(batch, non_blocking=True)
         cg["graph"].replay()
         for name in ("coarse", "fine"):  # eager users (losses(), a renderer) must re-pack the new weights
@@ -193,18 +193,15 @@ class TrainLoop:
     def _capture(self, n: int, bmin, bmax):
         st = self.state
         dev = self.device
-        host = torch.zeros(6, dtype=torch.int32).pin_memory()  # 4 key words | 2 fp32 bias corrections
-        dev_scalars = torch.zeros(6, dtype=torch.int32, device=dev)
-        cg = dict(n=n, bbox=(tuple(bmin), tuple(bmax)), host_scalars=host, dev_scalars=dev_scalars,
-                  host_words=host[:4].numpy().view(np.uint32), host_bc=host[4:6].numpy().view(np.float32),
+        dev_scalars = torch.zeros(6, dtype=torch.int32, device=dev)  # 4 key words | 2 fp32 bias corrections
+        cg = dict(n=n, bbox=(tuple(bmin), tuple(bmax)), dev_scalars=dev_scalars, ring=_native.PinnedRing(6),
                   batch=torch.zeros(n, 3, 3, device=dev))
         keys = (prng.DeviceKey(dev_scalars[0:2]), prng.DeviceKey(dev_scalars[2:4]))
         bc_dev = dev_scalars[4:6].view(torch.float32)
         # warm-up on a side stream (lazy allocations, workspace caches), then capture; neither may
         # leave a trace in the training state
         saved = (st.flat.clone(), st.m.clone(), st.v.clone())
-        cg["host_bc"][:] = 1.0
-        dev_scalars.copy_(host)
+        dev_scalars[4:6] = torch.tensor([1.0, 1.0]).view(torch.int32).to(dev)  # valid corrections for the warm-up
         torch.cuda.synchronize(dev)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))

@@ -300,6 +300,26 @@ def test_rgb_to_u8_and_render_view():
     assert int(img[15, 20].sum()) > 0
 
 
+def test_render_view_cuda_graph_matches_eager():
+    """render_view(cuda_graph=True): chunks replayed from one captured render_rays give the same
+    image as the eager loop (same keys -> same uniforms -> identical uint8 pixels), including a
+    ragged last chunk, on the bf16 path."""
+    from learn_nerf.dataset import CameraView
+    from learn_nerf.model import NeRFModel
+    from learn_nerf.render import NeRFRenderer
+    from learn_nerf.scripts.render_nerf import render_view
+    coarse, fine = NeRFModel(precision="bf16"), NeRFModel(precision="bf16")
+    r = NeRFRenderer(coarse=coarse, fine=fine, coarse_params=coarse.init(1, device="cuda")["params"],
+                     fine_params=fine.init(2, device="cuda")["params"], background=torch.tensor([-1.0, 0.0, 1.0]).cuda(),
+                     bbox_min=BBOX_MIN, bbox_max=BBOX_MAX, coarse_ts=64, fine_ts=128)
+    view = CameraView(**_camera())
+    eager = render_view(r, view, 50, 41, batch_size=512, key=9)          # 2050 rays: 4 chunks + 2 rays
+    graph = render_view(r, view, 50, 41, batch_size=512, key=9, cuda_graph=True)
+    again = render_view(r, view, 50, 41, batch_size=512, key=9, cuda_graph=True)  # cached graph
+    assert eager.shape == (41, 50, 3) and eager.dtype == torch.uint8
+    assert torch.equal(eager, graph) and torch.equal(graph, again)
+
+
 @pytest.mark.parametrize("shape", [(1,), (5, 7), (4096, 64), (333, 128)])
 def test_threefry_uniform_bit_exact(shape):
     """Device uniforms from a key equal the numpy threefry oracle bit for bit."""

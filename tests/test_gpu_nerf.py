@@ -448,8 +448,14 @@ def test_cuda_graph_step_matches_eager(precision):
         tol = 2e-3 if precision == "bf16" else 1e-4
         for k in la:
             assert abs(la[k] - lb[k]) <= tol * max(1.0, abs(lb[k])), (i, k, la[k], lb[k])
-    assert a.state.step == b.state.step == 5 and a._cg is not None and a._cg["n"] == 384
-    assert float((a.state.flat - b.state.flat).abs().max()) <= 2 * 5 * 1e-4  # <= 2 * steps * lr
+    # back-to-back replays without any host sync in between (the per-step key / bias-correction
+    # upload must not be overtaken by the next step's values)
+    batch = dev(make_rays(384, seed=80))
+    for i in range(6):
+        la, lb = sa(950 + i, batch), sb(950 + i, batch)
+    assert abs(float(la["fine"]) - float(lb["fine"])) <= tol * max(1.0, abs(float(lb["fine"])))
+    assert a.state.step == b.state.step == 11 and a._cg is not None and a._cg["n"] == 384
+    assert float((a.state.flat - b.state.flat).abs().max()) <= 2 * 11 * 1e-4  # <= 2 * steps * lr
     batch = dev(make_rays(256, seed=70))
     ta, _ = a.losses(5, BBOX_MIN, BBOX_MAX, batch, a.state.params)
     tb, _ = b.losses(5, BBOX_MIN, BBOX_MAX, batch, b.state.params)
@@ -457,4 +463,4 @@ def test_cuda_graph_step_matches_eager(precision):
     # entry points the graph does not cover fall back to the eager step
     uc, uf = dev(make_uniforms(256, 64, 1)), dev(make_uniforms(256, 128, 2))
     logs = sa((uc, uf), batch)
-    assert np.isfinite(float(logs["fine"])) and a.state.step == 6
+    assert np.isfinite(float(logs["fine"])) and a.state.step == 12
