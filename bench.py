@@ -316,7 +316,7 @@ def run_ours(args):
     # ---- timed region 2 (e2e): host pinned batch -> H2D -> step -> D2H of the logged scalars.
     # The train step is replayed as a CUDA graph here (TrainLoop(cuda_graph=True), the setting a user
     # would train with on one GPU); region 1 stays eager because it times individual C-ABI calls.
-    graph_e2e = bool(args.cuda_graph and args.workload == "train" and world == 1)
+    graph_e2e = bool(args.cuda_graph and args.workload == "train" and (world == 1 or loop._peers is not None))
     if graph_e2e:
         loop.cuda_graph = True
         one_step(0, host=True)  # captures the graph (untimed)

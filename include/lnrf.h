@@ -162,6 +162,7 @@ int lnrf_threefry_uniform_dk(const uint32_t* key_dev, int64_t n, float* out, lnr
 int lnrf_adam_step_peers(float* params, const uint64_t* peer_grads, int32_t world, float* m, float* v,
                          int64_t count, int32_t extra, float lr, float b1, float b2, float eps,
                          int32_t step, float grad_scale, float* norms_out, float* extra_out,
+                         const float* inv_bias_corr_dev /* nullable: overrides `step`, see lnrf_adam_step_dk */,
                          lnrf_stream_t stream);
 
 /* ---------------------------------------------------------------- K7/K8 hash grid

@@ -88,7 +88,12 @@ __global__ void __launch_bounds__(256)
 adam_peers_kernel(float* __restrict__ params, const __grid_constant__ PeerPtrs peers, int world,
                   float* __restrict__ m, float* __restrict__ v, int64_t count, int extra, float lr, float b1,
                   float b2, float eps, float inv_bc1, float inv_bc2, float grad_scale,
-                  float* __restrict__ norms_out, float* __restrict__ extra_out) {
+                  float* __restrict__ norms_out, float* __restrict__ extra_out,
+                  const float* __restrict__ bc_dev) {
+  if (bc_dev) {  // CUDA-graph replays: the step-dependent bias corrections live in device memory
+    inv_bc1 = __ldg(bc_dev);
+    inv_bc2 = __ldg(bc_dev + 1);
+  }
   float gsq = 0.0f, psq = 0.0f;
   const int64_t nvec = count >> 2;
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
@@ -149,7 +154,7 @@ adam_peers_kernel(float* __restrict__ params, const __grid_constant__ PeerPtrs p
 extern "C" int lnrf_adam_step_peers(float* params, const uint64_t* peer_grads, int32_t world, float* m, float* v,
                                     int64_t count, int32_t extra, float lr, float b1, float b2, float eps,
                                     int32_t step, float grad_scale, float* norms_out, float* extra_out,
-                                    lnrf_stream_t stream) {
+                                    const float* inv_bias_corr_dev, lnrf_stream_t stream) {
   LNRF_REQUIRE(count > 0 && step >= 1 && extra >= 0, LNRF_E_INVALID, "lnrf_adam_step_peers: count=%lld step=%d",
                (long long)count, step);
   LNRF_REQUIRE(world >= 1 && world <= lnrf::kMaxPeers, LNRF_E_UNSUPPORTED, "lnrf_adam_step_peers: world=%d (max %d)",
@@ -171,7 +176,7 @@ extern "C" int lnrf_adam_step_peers(float* params, const uint64_t* peer_grads, i
   if (blocks < 1) blocks = 1;
   lnrf::adam_peers_kernel<<<(unsigned)blocks, 256, 0, lnrf::as_stream(stream)>>>(
       params, pp, world, m, v, count, extra, lr, b1, b2, eps, (float)(1.0 / bc1), (float)(1.0 / bc2), grad_scale,
-      norms_out, extra_out);
+      norms_out, extra_out, inv_bias_corr_dev);
   LNRF_LAUNCH_CHECK("adam_peers_kernel");
   return LNRF_OK;
 }

@@ -57,7 +57,7 @@ _SIGS = {
     "lnrf_threefry_uniform_dk": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p]),
     "lnrf_adam_step_peers": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_int32,
                                        c_float, c_float, c_float, c_float, c_int32, c_float, c_void_p,
-                                       c_void_p, c_void_p]),
+                                       c_void_p, c_void_p, c_void_p]),
     "lnrf_debug_umma_gemm": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "lnrf_debug_umma_gemm_tn": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "lnrf_set_tc_stages": (c_int32, [c_int32]),
@@ -330,14 +330,15 @@ def threefry_uniform_dk(key_dev: torch.Tensor, shape) -> torch.Tensor:
 
 
 def adam_step_peers(params, peer_ptrs, m, v, count, extra, lr, b1, b2, eps, step, grad_scale, norms_out,
-                    extra_out):
+                    extra_out, inv_bias_corr_dev=None):
     """Fused all-reduce + Adam over NVLink peer mappings of every rank's flat gradient buffer.
     ``peer_ptrs``: device addresses (ints), one per rank, rank order."""
     ensure_init(params.device)
     arr = (ctypes.c_uint64 * len(peer_ptrs))(*[int(x) for x in peer_ptrs])
     _check(load().lnrf_adam_step_peers(_p(_f32c(params, "params")), ctypes.cast(arr, c_void_p), len(peer_ptrs),
                                        _p(m), _p(v), count, extra, lr, b1, b2, eps, step, grad_scale,
-                                       _p(norms_out), _p(extra_out), _stream()), "lnrf_adam_step_peers")
+                                       _p(norms_out), _p(extra_out), _p(inv_bias_corr_dev), _stream()),
+           "lnrf_adam_step_peers")
 
 
 def debug_umma_gemm(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:

@@ -52,7 +52,8 @@ class TrainLoop:
         self.ray_chunk = ray_chunk
         # cuda_graph: capture the whole step (19 launches for NeRF) once per batch size and replay it;
         # the per-step PRNG keys and Adam bias corrections are uploaded to device memory before each
-        # replay.  Single GPU, PRNG-key entry point, no density penalty; anything else runs eagerly.
+        # replay.  PRNG-key entry point, no density penalty, one GPU or the peer gradient exchange;
+        # anything else runs eagerly.
         self.cuda_graph = cuda_graph
         self._cg = None
         device = torch.device(device or "cuda")
@@ -166,7 +167,9 @@ class TrainLoop:
 
     # ------------------------------------------------------------------ CUDA-graph replay of the step
     def _graphable(self, key, batch) -> bool:
-        return (parallel.world()[1] == 1 and self.density_penalty is None and not isinstance(key, (tuple, list))
+        # multi-GPU: only with the peer exchange (its barriers and the fused kernel are plain launches)
+        multi_ok = parallel.world()[1] == 1 or self._peers is not None
+        return (multi_ok and self.density_penalty is None and not isinstance(key, (tuple, list))
                 and (self.ray_chunk is None or self.ray_chunk >= batch.shape[0]) and batch.shape[0] > 0)
 
     def _step_graphed(self, key, bmin, bmax, batch: torch.Tensor) -> Dict[str, torch.Tensor]:
@@ -288,7 +291,7 @@ class TrainLoop:
                 model.backward_rays(ctx, d_dens, torch.zeros_like(rgb), g[sl[0]:sl[1]])
         if _graph_bc is None:
             st.step += 1
-        if _graph_bc is not None:  # graph capture / replay: the caller owns the step count
+        if _graph_bc is not None and self._peers is None:  # graph capture / replay: the caller owns the step count
             self._scalars[0:2].copy_(self._loss_sums)
             _native.adam_step_dk(st.flat, g, st.m, st.v, self.lr, self.b1, self.b2, self.eps, _graph_bc,
                                  1.0 / world, self._scalars[2:4])
@@ -297,8 +300,8 @@ class TrainLoop:
             # optimiser kernel (rank-order sum, 1/world folded in); barriers fence the peer reads
             self._peers.barrier()
             _native.adam_step_peers(st.flat, self._peers.ptrs, st.m, st.v, self._n_params, 2, self.lr,
-                                    self.b1, self.b2, self.eps, st.step, 1.0 / world, self._scalars[2:4],
-                                    self._scalars[0:2])
+                                    self.b1, self.b2, self.eps, max(st.step, 1), 1.0 / world, self._scalars[2:4],
+                                    self._scalars[0:2], inv_bias_corr_dev=_graph_bc)
             self._peers.barrier()
         else:
             if world > 1 and os.environ.get("LNRF_ALLREDUCE") != "none":  # one NCCL sum (gradients + loss sums); 1/world is folded into Adam

@@ -94,6 +94,24 @@ def main():
         assert torch.equal(ref, peer.state.flat), f"{precision}: rank {rank} drifted from rank 0"
         if rank == 0:
             print(f"MGPU_OK {precision} world={world} max|peer-nccl|={diff:.3g} fine_loss={float(lp['fine']):.6f}")
+    # ---- 3. the CUDA-graph step on the peer path (cross-rank barriers and the fused kernel inside the graph)
+    if True:
+        os.environ["LNRF_ALLREDUCE"] = "peer"
+        mk = lambda graph: TrainLoop(NeRFModel(precision="bf16"), NeRFModel(precision="bf16"), init_rng=3, lr=5e-4,
+                                     coarse_ts=64, fine_ts=128, device=dev, cuda_graph=graph)
+        gl, el = mk(True), mk(False)
+        sg, se = gl.step_fn([-1.0] * 3, [1.0] * 3), el.step_fn([-1.0] * 3, [1.0] * 3)
+        for i in range(4):
+            lg, le = sg(300 + i, batch[a:b]), se(300 + i, batch[a:b])
+        for k in lg:
+            assert abs(float(lg[k]) - float(le[k])) <= 2e-3 * max(1.0, abs(float(le[k]))), (k, float(lg[k]), float(le[k]))
+        assert gl._cg is not None, "the graph path was not taken"
+        torch.cuda.synchronize()
+        ref = gl.state.flat.clone()
+        dist.broadcast(ref, src=0)
+        assert torch.equal(ref, gl.state.flat), f"graph path: rank {rank} drifted from rank 0"
+        if rank == 0:
+            print(f"MGPU_GRAPH_OK world={world} fine_loss={float(lg['fine']):.6f}")
     dist.destroy_process_group()
 
 
