@@ -180,3 +180,32 @@ def test_ngp_32768_rays_properties():
     assert all(np.isfinite(float(v)) for v in logs.values())
     gnorm = float(loop._grads.double().norm())
     assert abs(float(logs["grad_norm"]) - gnorm) <= 1e-4 * gnorm and gnorm > 0
+
+
+@pytest.mark.parametrize("family", ["nerf-bf16", "nerf-fp32", "ngp", "refnerf", "ngpref"])
+def test_empty_and_tiny_batches(family):
+    """The other end of the size range: 0, 1 and 3 rays through render_rays and (n > 0) a train step,
+    for every model family -- empty launches are skipped inside the library, a single ray fills one
+    partial 128-sample tile pair."""
+    from learn_nerf.instant_ngp import InstantNGPModel, InstantNGPRefNERFModel
+    from learn_nerf.model import NeRFModel
+    from learn_nerf.ref_nerf import RefNERFModel
+    from learn_nerf.train import TrainLoop
+    grids = lambda L: [2 ** (4 + i // 2) for i in range(L)]
+    kw = lambda L: dict(table_sizes=[2 ** 14] * L, grid_sizes=grids(L), bbox_min=BBOX_MIN, bbox_max=BBOX_MAX)
+    mk = {"nerf-bf16": lambda: (NeRFModel(precision="bf16"), NeRFModel(precision="bf16")),
+          "nerf-fp32": lambda: (NeRFModel(), NeRFModel()),
+          "ngp": lambda: (InstantNGPModel(**kw(6)), InstantNGPModel(**kw(16))),
+          "refnerf": lambda: (RefNERFModel(), RefNERFModel()),
+          "ngpref": lambda: (InstantNGPRefNERFModel(**kw(6)), InstantNGPRefNERFModel(**kw(16)))}[family]
+    for n in (0, 1, 3):
+        c, f = mk()
+        loop = TrainLoop(c, f, init_rng=1, lr=1e-4, coarse_ts=64, fine_ts=128)
+        batch = dev(make_rays(max(n, 1), seed=1)[:n])
+        r = loop._renderer(list(BBOX_MIN), list(BBOX_MAX), loop.state.params)
+        out = r.render_rays(3, batch[:, :2].contiguous())
+        assert out["fine"]["outputs"].shape == (n, 3) and out["coarse"]["densities"].shape == (n, 64)
+        assert bool(torch.isfinite(out["fine"]["outputs"]).all())
+        if n > 0:
+            logs = loop.step_fn(BBOX_MIN, BBOX_MAX)(4, batch)
+            assert all(np.isfinite(float(v)) for v in logs.values()), logs
