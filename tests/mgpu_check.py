@@ -84,7 +84,7 @@ def main():
         for i in range(3):
             lp, ln = sp(100 + i, batch[a:b]), sn(100 + i, batch[a:b])
             for k in lp:
-                assert abs(float(lp[k]) - float(ln[k])) <= 1e-5 * max(1.0, abs(float(ln[k]))), (k, float(lp[k]), float(ln[k]))
+                assert abs(float(lp[k]) - float(ln[k])) <= 1e-4 * max(1.0, abs(float(ln[k]))), (k, float(lp[k]), float(ln[k]))
         torch.cuda.synchronize()
         diff = float((peer.state.flat - nccl.state.flat).abs().max())
         assert diff <= 2 * 3 * 5e-4, f"{precision}: peer vs NCCL parameters differ by {diff} (> 2 * steps * lr)"

@@ -445,7 +445,7 @@ def test_cuda_graph_step_matches_eager(precision):
         la = {k: float(v) for k, v in sa(900 + i, batch).items()}
         lb = {k: float(v) for k, v in sb(900 + i, batch).items()}
         assert set(la) == set(lb) == {"coarse", "fine", "grad_norm", "param_norm"}
-        tol = 2e-3 if precision == "bf16" else 1e-4
+        tol = 2e-3 if precision == "bf16" else 5e-4  # two runs: atomic reordering noise, amplified by Adam's first steps
         for k in la:
             assert abs(la[k] - lb[k]) <= tol * max(1.0, abs(lb[k])), (i, k, la[k], lb[k])
     # back-to-back replays without any host sync in between (the per-step key / bias-correction
