@@ -18,7 +18,12 @@ namespace lnrf {
 constexpr int kNgpMaxLevels = 16;
 constexpr int kNgpHidden = 64, kNgpDensity = 16, kNgpDE = 24;
 constexpr int kNgpIn2 = kNgpDE + kNgpDensity;  // 40
-constexpr int kNgpThreads = 128;
+// A tile of 128 samples x 64 columns is covered by (64 / CW) x 16 threads, each owning an 8 (rows) x
+// CW (cols) register tile.  Forward: CW = 8 on 128 threads (64 FFMA per four 128-bit shared loads);
+// backward: CW = 4 on 256 threads (twice the warps hide the mask loads and the five dependent GEMMs:
+// train step 31.3 -> 30.3 ms; the forward is 4 % slower that way and keeps CW = 8).
+constexpr int kFwdCW = 8, kBwdCW = 4;
+constexpr int kNgpFwdThreads = 16 * 64 / kFwdCW, kNgpBwdThreads = 16 * 64 / kBwdCW;
 
 struct NgpLayout {
   int in[5], out[5];
@@ -76,70 +81,85 @@ static NgpWs carve_ngp(void* base, int64_t m) {
 constexpr int kTM = 128;  // samples per tile
 __device__ __forceinline__ int xoff(int k, int rowgrp) { return k * kTM + (((rowgrp ^ (k >> 3)) & 15) << 3); }
 
-template <int NCOLS>  // 64 or 16: threads with tx*8 >= NCOLS idle
+// kCW consecutive floats (kCW = 4 or 8) with 128-bit loads / stores
+template <int kCW>
+__device__ __forceinline__ void load_cols(const float* p, float (&v)[kCW]) {
+#pragma unroll
+  for (int q = 0; q < kCW / 4; ++q) {
+    const float4 x = *reinterpret_cast<const float4*>(p + 4 * q);
+    v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+  }
+}
+template <int kCW>
+__device__ __forceinline__ void store_cols(float* p, const float (&v)[kCW]) {
+#pragma unroll
+  for (int q = 0; q < kCW / 4; ++q)
+    *reinterpret_cast<float4*>(p + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+
+template <int NCOLS, int kCW>  // NCOLS = 64 or 16: threads with tx * kCW >= NCOLS idle
 __device__ __forceinline__ void tile_gemm(const float* __restrict__ Xt, int K, const float* __restrict__ W, int ldw,
-                                          float (&acc)[8][8], int tx, int ty) {
+                                          float (&acc)[8][kCW], int tx, int ty) {
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
-  if (tx * 8 >= NCOLS) return;
+    for (int j = 0; j < kCW; ++j) acc[i][j] = 0.0f;
+  if (tx * kCW >= NCOLS) return;
 #pragma unroll 4
   for (int k = 0; k < K; ++k) {
     const float* ap = Xt + xoff(k, ty);
     const float4 a0 = *reinterpret_cast<const float4*>(ap), a1 = *reinterpret_cast<const float4*>(ap + 4);
-    const float* wp = W + k * ldw + tx * 8;
-    const float4 w0 = *reinterpret_cast<const float4*>(wp), w1 = *reinterpret_cast<const float4*>(wp + 4);
+    float wv[kCW];
+    load_cols<kCW>(W + k * ldw + tx * kCW, wv);
     const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+      for (int j = 0; j < kCW; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
   }
 }
 // registers (8 rows x 8 cols) -> feature-major smem at feature offset k0
-__device__ __forceinline__ void tile_store_smem(float* __restrict__ Yt, int k0, const float (&v)[8][8], int tx, int ty) {
+template <int kCW>
+__device__ __forceinline__ void tile_store_smem(float* __restrict__ Yt, int k0, const float (&v)[8][kCW], int tx, int ty) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float* p = Yt + xoff(k0 + tx * 8 + j, ty);
+  for (int j = 0; j < kCW; ++j) {
+    float* p = Yt + xoff(k0 + tx * kCW + j, ty);
     *reinterpret_cast<float4*>(p) = make_float4(v[0][j], v[1][j], v[2][j], v[3][j]);
     *reinterpret_cast<float4*>(p + 4) = make_float4(v[4][j], v[5][j], v[6][j], v[7][j]);
   }
 }
-// registers -> row-major global [m, ld] at column offset c0 (each warp store covers 4 rows x 256 B)
+// registers -> row-major global [m, ld] at column offset c0
+template <int kCW>
 __device__ __forceinline__ void tile_store_global(float* __restrict__ dst, int ld, int c0, int64_t row0, int64_t m,
-                                                  const float (&v)[8][8], int tx, int ty, int ncols) {
-  if (tx * 8 >= ncols) return;
+                                                  const float (&v)[8][kCW], int tx, int ty, int ncols) {
+  if (tx * kCW >= ncols) return;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int64_t r = row0 + ty * 8 + i;
     if (r >= m) continue;
-    float* p = dst + r * ld + c0 + tx * 8;
-    if (tx * 8 + 8 <= ncols) {
-      *reinterpret_cast<float4*>(p) = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
-      *reinterpret_cast<float4*>(p + 4) = make_float4(v[i][4], v[i][5], v[i][6], v[i][7]);
-    } else {  // ragged last column group (E = 12: columns 8..11)
+    float* p = dst + r * ld + c0 + tx * kCW;
+    if (tx * kCW + kCW <= ncols) {
+      store_cols<kCW>(p, v[i]);
+    } else {  // ragged last column group (E = 12 with 8 columns per thread: columns 8..11)
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (tx * 8 + j < ncols) p[j] = v[i][j];
+      for (int j = 0; j < kCW; ++j)
+        if (tx * kCW + j < ncols) p[j] = v[i][j];
     }
   }
 }
 // v *= [h > 0] with h row-major in global [m, 64]
-__device__ __forceinline__ void tile_mask(const float* __restrict__ h, int64_t row0, int64_t m, float (&v)[8][8],
+template <int kCW>
+__device__ __forceinline__ void tile_mask(const float* __restrict__ h, int64_t row0, int64_t m, float (&v)[8][kCW],
                                           int tx, int ty) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int64_t r = row0 + ty * 8 + i;
-    float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0;
-    if (r < m) {
-      h0 = __ldg(reinterpret_cast<const float4*>(h + r * kNgpHidden + tx * 8));
-      h1 = __ldg(reinterpret_cast<const float4*>(h + r * kNgpHidden + tx * 8) + 1);
-    }
-    const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+    float hv[kCW];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[i][j] = hv[j] > 0.0f ? v[i][j] : 0.0f;
+    for (int j = 0; j < kCW; ++j) hv[j] = 0.0f;
+    if (r < m) load_cols<kCW>(h + r * kNgpHidden + tx * kCW, hv);
+#pragma unroll
+    for (int j = 0; j < kCW; ++j) v[i][j] = hv[j] > 0.0f ? v[i][j] : 0.0f;
   }
 }
 
@@ -160,28 +180,30 @@ struct NgpFwdArgs {
 constexpr int kNgpXFloats = kNgpHidden * kTM;  // one feature-major activation buffer
 
 template <bool SAVE>
-__global__ void __launch_bounds__(kNgpThreads)
+__global__ void __launch_bounds__(kNgpFwdThreads, 2)
 ngp_mlp_fwd_kernel(const __grid_constant__ NgpFwdArgs a) {
   extern __shared__ __align__(16) float sm[];
   float* sw = sm;                                   // all parameters, reference layout ([in][out])
   float* Xa = sm + align_up(a.nl.total, 4);
   float* Xb = Xa + kNgpXFloats;
-  for (int i = threadIdx.x; i < int(a.nl.total); i += kNgpThreads) sw[i] = __ldg(a.P + i);
+  for (int i = threadIdx.x; i < int(a.nl.total); i += kNgpFwdThreads) sw[i] = __ldg(a.P + i);
   const float* W0 = sw + a.nl.w[0]; const float* B0 = sw + a.nl.b[0];
   const float* W1 = sw + a.nl.w[1]; const float* B1 = sw + a.nl.b[1];
   const float* W2 = sw + a.nl.w[2]; const float* B2 = sw + a.nl.b[2];
   const float* W3 = sw + a.nl.w[3]; const float* B3 = sw + a.nl.b[3];
   const float* W4 = sw + a.nl.w[4]; const float* B4 = sw + a.nl.b[4];
-  const int t = threadIdx.x, tx = t & 7, ty = t >> 3;
+  constexpr int kCW = kFwdCW;
+  const int t = threadIdx.x, tx = t % (64 / kCW), ty = t / (64 / kCW);
   const int64_t tiles = ceil_div(a.m, kTM);
-  float acc[8][8];
+  float acc[8][kCW];
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int64_t row0 = tile * kTM;
-    const int64_t s = row0 + t;  // the sample this thread owns in the per-sample phases
-    const bool valid = s < a.m;
+    const bool owner = t < kTM;   // the first 128 threads each own one sample in the per-sample phases
+    const int64_t s = row0 + t;
+    const bool valid = owner && s < a.m;
     __syncthreads();  // previous tile's readers of Xa / Xb are done (also covers the weight load)
     // ---- inputs: encoding -> Xa[k < E]; d_emb = sinusoidal_emb(d, 4) (:37) -> registers
-    {
+    if (owner) {
       const int rg = t >> 3, rl = t & 7;
       for (int k4 = 0; k4 < a.E / 4; ++k4) {
         float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -193,7 +215,7 @@ ngp_mlp_fwd_kernel(const __grid_constant__ NgpFwdArgs a) {
       }
     }
     float de[kNgpDE];
-    {
+    if (owner) {
       float dv[3] = {0.f, 0.f, 0.f};
       if (valid) {
 #pragma unroll
@@ -210,17 +232,17 @@ ngp_mlp_fwd_kernel(const __grid_constant__ NgpFwdArgs a) {
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = fmaxf(acc[i][j] + B0[tx * 8 + j], 0.0f);
+      for (int j = 0; j < kCW; ++j) acc[i][j] = fmaxf(acc[i][j] + B0[tx * kCW + j], 0.0f);
     tile_store_smem(Xb, 0, acc, tx, ty);
     if (SAVE) tile_store_global(a.ws.h0, kNgpHidden, 0, row0, a.m, acc, tx, ty, kNgpHidden);
     __syncthreads();
     // ---- Dense_1 (64 -> 16) -> Xa[24..39]; d_emb -> Xa[0..23]; density = exp(out[0])   :48-50
     tile_gemm<16>(Xb, kNgpHidden, W1, kNgpDensity, acc, tx, ty);
-    if (tx < 2) {
+    if (tx * kCW < kNgpDensity) {
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] += B1[tx * 8 + j];
+        for (int j = 0; j < kCW; ++j) acc[i][j] += B1[tx * kCW + j];
       tile_store_smem(Xa, kNgpDE, acc, tx, ty);
       if (SAVE) tile_store_global(a.ws.in2, kNgpIn2, kNgpDE, row0, a.m, acc, tx, ty, kNgpDensity);
       if (tx == 0) {
@@ -231,7 +253,7 @@ ngp_mlp_fwd_kernel(const __grid_constant__ NgpFwdArgs a) {
         }
       }
     }
-    {
+    if (owner) {
       const int rg = t >> 3, rl = t & 7;
 #pragma unroll
       for (int k = 0; k < kNgpDE; ++k) Xa[xoff(k, rg) + rl] = de[k];
@@ -247,7 +269,7 @@ ngp_mlp_fwd_kernel(const __grid_constant__ NgpFwdArgs a) {
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = fmaxf(acc[i][j] + B2[tx * 8 + j], 0.0f);
+      for (int j = 0; j < kCW; ++j) acc[i][j] = fmaxf(acc[i][j] + B2[tx * kCW + j], 0.0f);
     tile_store_smem(Xb, 0, acc, tx, ty);  // readers of Xb (Dense_1) finished before the last barrier
     if (SAVE) tile_store_global(a.ws.h2, kNgpHidden, 0, row0, a.m, acc, tx, ty, kNgpHidden);
     __syncthreads();
@@ -256,12 +278,12 @@ ngp_mlp_fwd_kernel(const __grid_constant__ NgpFwdArgs a) {
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = fmaxf(acc[i][j] + B3[tx * 8 + j], 0.0f);
+      for (int j = 0; j < kCW; ++j) acc[i][j] = fmaxf(acc[i][j] + B3[tx * kCW + j], 0.0f);
     tile_store_smem(Xa, 0, acc, tx, ty);  // readers of Xa (Dense_2) finished before the last barrier
     if (SAVE) tile_store_global(a.ws.h3, kNgpHidden, 0, row0, a.m, acc, tx, ty, kNgpHidden);
     __syncthreads();
     // ---- Dense_4 (64 -> 3) + tanh: thread per sample                        :53
-    {
+    if (owner) {
       const int rg = t >> 3, rl = t & 7;
       float o0 = B4[0], o1 = B4[1], o2 = B4[2];
 #pragma unroll 8
@@ -313,7 +335,7 @@ __host__ __device__ inline NgpBwdSmem ngp_bwd_smem(int E) {
 }
 
 // dX chain: g3, g2, g_out1, g0 (written for the dW GEMMs) and d_enc.
-__global__ void __launch_bounds__(kNgpThreads)
+__global__ void __launch_bounds__(kNgpBwdThreads, 2)
 ngp_mlp_bwd_kernel(const __grid_constant__ NgpBwdArgs a) {
   extern __shared__ __align__(16) float sm[];
   const NgpBwdSmem L = ngp_bwd_smem(a.E);
@@ -322,37 +344,39 @@ ngp_mlp_bwd_kernel(const __grid_constant__ NgpBwdArgs a) {
   float* Xa = sm + L.x;
   float* Xb = Xa + kNgpXFloats;
   const float* P = a.P;
-  for (int i = threadIdx.x; i < 4 * kNgpHidden; i += kNgpThreads) {  // Wt4[j][i] = W4[i][j]
+  for (int i = threadIdx.x; i < 4 * kNgpHidden; i += kNgpBwdThreads) {  // Wt4[j][i] = W4[i][j]
     const int j = i / kNgpHidden, ii = i % kNgpHidden;
     Wt4[i] = j < 3 ? __ldg(P + a.nl.w[4] + ii * 3 + j) : 0.0f;
   }
-  for (int i = threadIdx.x; i < kNgpHidden * kNgpHidden; i += kNgpThreads) {  // Wt3[j][i] = W3[i][j]
+  for (int i = threadIdx.x; i < kNgpHidden * kNgpHidden; i += kNgpBwdThreads) {  // Wt3[j][i] = W3[i][j]
     const int j = i / kNgpHidden, ii = i % kNgpHidden;
     Wt3[i] = __ldg(P + a.nl.w[3] + ii * kNgpHidden + j);
   }
-  for (int i = threadIdx.x; i < kNgpHidden * kNgpDensity; i += kNgpThreads) {  // Wt2o[j][i] = W2[24 + i][j]
+  for (int i = threadIdx.x; i < kNgpHidden * kNgpDensity; i += kNgpBwdThreads) {  // Wt2o[j][i] = W2[24 + i][j]
     const int j = i / kNgpDensity, ii = i % kNgpDensity;
     Wt2o[i] = __ldg(P + a.nl.w[2] + (kNgpDE + ii) * kNgpHidden + j);
   }
-  for (int i = threadIdx.x; i < kNgpDensity * kNgpHidden; i += kNgpThreads) {  // Wt1[j][i] = W1[i][j]
+  for (int i = threadIdx.x; i < kNgpDensity * kNgpHidden; i += kNgpBwdThreads) {  // Wt1[j][i] = W1[i][j]
     const int j = i / kNgpHidden, ii = i % kNgpHidden;
     Wt1[i] = __ldg(P + a.nl.w[1] + ii * kNgpDensity + j);
   }
-  for (int i = threadIdx.x; i < kNgpHidden * L.epad; i += kNgpThreads) {  // Wt0[j][i] = W0[i][j], zero padded
+  for (int i = threadIdx.x; i < kNgpHidden * L.epad; i += kNgpBwdThreads) {  // Wt0[j][i] = W0[i][j], zero padded
     const int j = i / L.epad, ii = i % L.epad;
     Wt0[i] = ii < a.E ? __ldg(P + a.nl.w[0] + ii * kNgpHidden + j) : 0.0f;
   }
-  const int t = threadIdx.x, tx = t & 7, ty = t >> 3;
+  constexpr int kCW = kBwdCW;
+  const int t = threadIdx.x, tx = t % (64 / kCW), ty = t / (64 / kCW);
   const int rg = t >> 3, rl = t & 7;
   const int64_t tiles = ceil_div(a.m, kTM);
-  float acc[8][8];
+  float acc[8][kCW];
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int64_t row0 = tile * kTM;
+    const bool owner = t < kTM;  // the first 128 threads each own one sample in the per-sample phase
     const int64_t s = row0 + t;
-    const bool valid = s < a.m;
+    const bool valid = owner && s < a.m;
     __syncthreads();
     // ---- dp = d_rgb * tanh' -> Xa[0..3]
-    {
+    if (owner) {
       float dp[4] = {0.f, 0.f, 0.f, 0.f};
       if (valid) {
 #pragma unroll
@@ -379,7 +403,7 @@ ngp_mlp_bwd_kernel(const __grid_constant__ NgpBwdArgs a) {
     __syncthreads();
     // ---- g_out1 = g2 @ W2[24:40]^T, + d_dens * density on column 0 -> Xb[0..15], global
     tile_gemm<16>(Xa, kNgpHidden, Wt2o, kNgpDensity, acc, tx, ty);
-    if (tx < 2) {
+    if (tx * kCW < kNgpDensity) {
       if (tx == 0) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -398,24 +422,23 @@ ngp_mlp_bwd_kernel(const __grid_constant__ NgpBwdArgs a) {
     tile_store_global(a.ws.g0, kNgpHidden, 0, row0, a.m, acc, tx, ty, kNgpHidden);
     __syncthreads();
     // ---- d_enc = g0 @ W0^T -> global [m, E]
-    if (tx * 8 < L.epad) {
-      // epad <= 32: the first epad/8 column groups are active
+    if (tx * kCW < L.epad) {
+      // epad <= 32: the first epad / 4 column groups are active
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+        for (int j = 0; j < kCW; ++j) acc[i][j] = 0.0f;
 #pragma unroll 4
       for (int k = 0; k < kNgpHidden; ++k) {
         const float* ap = Xa + xoff(k, ty);
         const float4 a0 = *reinterpret_cast<const float4*>(ap), a1 = *reinterpret_cast<const float4*>(ap + 4);
-        const float* wp = Wt0 + k * L.epad + tx * 8;
-        const float4 w0 = *reinterpret_cast<const float4*>(wp), w1 = *reinterpret_cast<const float4*>(wp + 4);
+        float wv[kCW];
+        load_cols<kCW>(Wt0 + k * L.epad + tx * kCW, wv);
         const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+          for (int j = 0; j < kCW; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
       }
       tile_store_global(a.d_enc, a.E, 0, row0, a.m, acc, tx, ty, a.E);
     }
@@ -522,8 +545,8 @@ int lnrf_ngp_mlp_fwd(const float* params, int32_t L, const float* enc, const flo
     LNRF_CUDA(cudaFuncSetAttribute(ngp_mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     configured = true;
   }
-  if (save) ngp_mlp_fwd_kernel<true><<<ngp_grid(m), kNgpThreads, smem, as_stream(stream)>>>(a);
-  else ngp_mlp_fwd_kernel<false><<<ngp_grid(m), kNgpThreads, smem, as_stream(stream)>>>(a);
+  if (save) ngp_mlp_fwd_kernel<true><<<ngp_grid(m), kNgpFwdThreads, smem, as_stream(stream)>>>(a);
+  else ngp_mlp_fwd_kernel<false><<<ngp_grid(m), kNgpFwdThreads, smem, as_stream(stream)>>>(a);
   LNRF_LAUNCH_CHECK("ngp_mlp_fwd_kernel");
   return LNRF_OK;
 }
@@ -544,7 +567,7 @@ int lnrf_ngp_mlp_bwd(const float* params, int32_t L, const float* enc, int64_t m
   cudaStream_t st = as_stream(stream);
   float* G = d_params;
   NgpBwdArgs a{params, nl, 2 * L, m, w, dens, rgb, d_dens, d_rgb, d_enc};
-  ngp_mlp_bwd_kernel<<<ngp_grid(m), kNgpThreads, size_t(ngp_bwd_smem(2 * L).total) * sizeof(float), st>>>(a);
+  ngp_mlp_bwd_kernel<<<ngp_grid(m), kNgpBwdThreads, size_t(ngp_bwd_smem(2 * L).total) * sizeof(float), st>>>(a);
   LNRF_LAUNCH_CHECK("ngp_mlp_bwd_kernel");
   // weight / bias gradients: dW_l = input_l^T g_l (split-K FFMA GEMM), db_l = column sums
   int rc;
