@@ -215,8 +215,6 @@ def run_ours(args):
     from learn_nerf.train import TrainLoop
 
     peaks = load_peaks()
-    if args.tc_stages is not None:
-        _native.set_tc_stages(args.tc_stages)
     n = args.rays or (32768 if args.model in ("ngp", "ngpref") else 4096)
     prec = args.precision if args.model == "nerf" else "fp32"
     if args.model == "refnerf" and args.ray_chunk is None and n > 2048:
@@ -455,7 +453,6 @@ def main():
     ap.add_argument("--rays", type=int, default=None, help="rays per GPU per step (4096 NeRF, 32768 NGP)")
     ap.add_argument("--ray_chunk", type=int, default=None)
     ap.add_argument("--cpu_rays", type=int, default=512, help="rays per step of the CPU sample")
-    ap.add_argument("--tc_stages", type=int, default=None, help="bf16 kernel tuning knob")
     ap.add_argument("--no_cpu_baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no_cuda_graph", dest="cuda_graph", action="store_false",
                     help="run the end-to-end region with the eager step instead of the CUDA-graph replay")

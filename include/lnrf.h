@@ -73,6 +73,16 @@ int lnrf_sample_fine(const float* ts_c, const float* dens_c, const float* t_min,
                      float eps, float* ts_out, int32_t* idx_out, float* new_ts_out,
                      lnrf_stream_t stream);
 
+/* RaySamples.starts / ends / deltas (render.py:259-268): each [n,T]; any of the three outputs may
+ * be NULL.  Bit-exact with the oracle.                                         */
+int lnrf_ray_intervals(const float* ts, const float* t_min, const float* t_max, int64_t n, int32_t T,
+                       float* starts, float* ends, float* deltas, lnrf_stream_t stream);
+/* RaySamples.termination_probs (render.py:270-287): probs[n,T+1], the last column is the
+ * probability of escaping to the background.  Strictly sequential fp32 cumsum and the shared
+ * deterministic exp, as inside lnrf_sample_fine: bit-exact with the oracle.  T <= 1024.        */
+int lnrf_termination_probs(const float* ts, const float* t_min, const float* t_max, const float* dens,
+                           int64_t n, int32_t T, float* probs, lnrf_stream_t stream);
+
 /* ---------------------------------------------------------------- K3 compositing
  * termination_probs + RaySamples.render_rays / render_alpha and the coords
  * render (render.py:155-190, 270-287, 329-331).  dens [n,T]; rgb [n,T,3];
@@ -236,6 +246,13 @@ int lnrf_bare_rays(const float* origin_host, const float* x_axis_host, const flo
 /* ((colors + 1) * 127.5).astype(uint8) (render_nerf.py:93-96); colors are clamped to [-1, 1].   */
 int lnrf_rgb_to_u8(const float* colors, int64_t count, uint8_t* out, lnrf_stream_t stream);
 
+/* Depth image of scripts/render_new_dataset.py:96-133 from the fine level's coords[n,3] / alphas[n]:
+ * z = clip(where(alpha > 0.9, ((coords - origin) . direction) / (alpha + 1e-8), max_depth), 0, max_depth)
+ * / max_depth -> z_out[n] (nullable) and depth_u32_out[n] = (z * 0xFFFF) truncated (nullable).     */
+int lnrf_z_depth(const float* coords, const float* alphas, const float* camera_origin_host,
+                 const float* camera_direction_host, float max_depth, int64_t n, float* z_out,
+                 uint32_t* depth_u32_out, lnrf_stream_t stream);
+
 /* jax.random.uniform(key, [n]) in fp32 (render.py:142): Threefry-2x32 over iota(n) as JAX's
  * non-partitionable threefry does, 23 mantissa bits; key = the two uint32 words of the key.  */
 int lnrf_threefry_uniform(uint32_t key0, uint32_t key1, int64_t n, float* out, lnrf_stream_t stream);
@@ -269,17 +286,6 @@ int lnrf_ngpref_bwd(const float* params, const int64_t* level_offsets_host, cons
                     int64_t n, int32_t T, void* workspace, int64_t workspace_bytes, const float* d_dens,
                     const float* d_rgb, const float* d_aux_normal_mse, const float* d_aux_neg_normal,
                     float* d_params, lnrf_stream_t stream);
-/* Tuning knob of the fused bf16 kernel: 1 = one weight-ring stage and two CTAs
- * per SM (default); >= 2 = four stages, one CTA per SM.                       */
-int lnrf_set_tc_stages(int32_t stages);
-/* Profiling / tuning switches of the bf16 tcgen05 kernels (used by profiles/ablate_*.py and
- * profiles/with_flags.py only; default 0).  Bit flags: 1 / 2 / 4 = dW kernel without loads / MMAs /
- * worker math and 8 / 16 = forward without stash stores / with all stash tiles aliased onto the
- * first 64 (results are WRONG with these five); 64 = the other forward schedule (full-N with the
- * stash, N-half without); 512 = the single-tile dX kernel instead of the pair kernel.  Values
- * >= 2000 set the dW kernel's CTA waves (2000 + waves), 1000..1999 its job weights.          */
-int lnrf_set_debug_flags(int32_t flags);
-
 #ifdef __cplusplus
 }
 #endif

@@ -469,12 +469,9 @@ int lnrf_composite_fwd(const float* rays, const float* ts, const float* t_min, c
   int64_t blocks;
   size_t smem;
   lnrf::comp_launch_dims(n, T, blocks, smem);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem > 48 * 1024)  // the attribute is per device: set it per call (cheap, idempotent), no process state
     LNRF_CUDA(cudaFuncSetAttribute(lnrf::composite_fwd_kernel,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
   if (T <= 64)
     lnrf::composite_fwd_pf_kernel<2><<<(unsigned)blocks, lnrf::kCompWarps * 32, smem, lnrf::as_stream(stream)>>>(
         rays, ts, t_min, t_max, mask, dens, rgb, background, n, T, outputs, alphas, coords);
@@ -502,12 +499,9 @@ int lnrf_composite_bwd(const float* ts, const float* t_min, const float* t_max, 
   int64_t blocks;
   size_t smem;
   lnrf::comp_launch_dims(n, T, blocks, smem);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem > 48 * 1024)  // the attribute is per device: set it per call (cheap, idempotent), no process state
     LNRF_CUDA(cudaFuncSetAttribute(lnrf::composite_bwd_kernel,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
   if (T <= 64)
     lnrf::composite_bwd_pf_kernel<2><<<(unsigned)blocks, lnrf::kCompWarps * 32, smem, lnrf::as_stream(stream)>>>(
         ts, t_min, t_max, mask, dens, rgb, background, d_outputs, n, T, d_dens, d_rgb, d_background);

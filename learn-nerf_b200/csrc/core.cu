@@ -7,7 +7,7 @@
 namespace lnrf {
 
 static thread_local char g_err[512] = "";
-static int g_sm_count = 0;
+static int g_sm_count[64] = {0};  // per device ordinal, filled by lnrf_init / on first use
 static unsigned long long g_launches = 0;
 
 void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
@@ -24,19 +24,19 @@ int cuda_fail(cudaError_t e, const char* what) {
   return static_cast<int>(e);
 }
 
-int sm_count() {
-  if (g_sm_count == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      g_sm_count = n;
-    else
-      return 148;
+int sm_count() {  // SMs of the CURRENT device
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int n = __atomic_load_n(&g_sm_count[dev], __ATOMIC_RELAXED);
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+    __atomic_store_n(&g_sm_count[dev], n, __ATOMIC_RELAXED);
   }
-  return g_sm_count;
+  return n;
 }
 
-int init_mlp_tc();  // mlp_tc.cu: opt into large dynamic smem
+int init_mlp_tc();   // mlp_tc.cu: constant tables + large dynamic smem opt-ins of the tcgen05 kernels
+int init_ngp_mlp();  // ngp_mlp.cu
 
 }  // namespace lnrf
 
@@ -55,8 +55,10 @@ int lnrf_init(int device) {
   LNRF_REQUIRE(prop.major == 10, LNRF_E_UNSUPPORTED,
                "lnrf_init: device %d is sm_%d%d; liblnrf is built for sm_100a only", device,
                prop.major, prop.minor);
-  lnrf::g_sm_count = prop.multiProcessorCount;
-  return lnrf::init_mlp_tc();
+  if (device >= 0 && device < 64) __atomic_store_n(&lnrf::g_sm_count[device], prop.multiProcessorCount, __ATOMIC_RELAXED);
+  int rc = lnrf::init_mlp_tc();
+  if (rc) return rc;
+  return lnrf::init_ngp_mlp();
 }
 
 }  // extern "C"

@@ -1,16 +1,15 @@
 // K6 on the tensor cores: backward of the NeRF MLP (what jax.grad derives from
 // model.py:42-62 at train.py:90) as two tcgen05/TMEM kernels over the forward's stash.
 //
-//  nerf_bwd_dx_kernel  "dX chain", tile-major and fused like the forward: per tile of 128
-//      samples it forms dL/d(colour pre-act) and dL/d(density pre-act) from d_rgb/d_dens,
-//      then runs g8 = dc @ W10[:256]^T + spre (x) w9 and g_{l-1} = (g_l @ W_l[:256]^T) * relu'
-//      for l = 8..1 on the tensor cores (A = g tile in smem, B = streamed W chunks, D in
-//      TMEM), streaming every g_l tile image to the stash.
+//  dX chain: mlp_tc_bwd2.cu (per tile: head gradients, then g_{l-1} = (g_l @ W_l^T) * relu' for
+//      l = 8..1 on the tensor cores, every g_l tile image streamed to the stash).
 //  nerf_bwd_dw_kernel  "dW": dW_l = act_{l-1}^T @ g_l summed over all samples.  Both operands
 //      are the stashed tile images read as MN-major UMMA operands (K = samples); each CTA
 //      owns one (layer, tile-range) job, accumulates the full 256x256 fp32 dW in TMEM (all
 //      512 columns) across its tiles and adds it to global memory once.  The otherwise idle
 //      warps form the bias gradients (column sums of g) and the two tiny head gradients.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace lnrf {
@@ -20,223 +19,6 @@ using namespace ptx;
 bool tc_ready();
 int nerf_bwd_dx_pair(const TcBwdArgs& a, cudaStream_t st);  // mlp_tc_bwd2.cu
 int64_t tc_workspace_bytes(int64_t m, bool save);
-
-// ================================================================ dX chain
-constexpr uint32_t kBwdABytes = 4 * kABlockBytes;
-struct BwdSmem {
-  static constexpr uint32_t a_off = 0;
-  static constexpr uint32_t w_off = kBwdABytes;
-  static constexpr uint32_t bar_off = w_off + kChunkBytes256;
-  static constexpr uint32_t total = bar_off + 128;
-};
-
-__global__ void __launch_bounds__(kTcThreads, 2)
-nerf_bwd_dx_kernel(TcBwdArgs args) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const uint32_t smem_base = smem_u32(smem_raw);
-  if (smem_base & 1023u) __trap();
-  const uint32_t sA = smem_base + BwdSmem::a_off;
-  const uint32_t sW = smem_base + BwdSmem::w_off;
-  const uint32_t bars = smem_base + BwdSmem::bar_off;
-  const uint32_t bar_full = bars, bar_empty = bars + 8;
-  const uint32_t bar_a_ready = bars + 16, bar_acc_ready = bars + 24;
-  const uint32_t tmem_slot = bars + 32;
-  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_base));
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t tiles = (args.m + 127) / 128;
-  const int64_t my_tiles = (tiles > blockIdx.x) ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-
-  if (tid == 0) {
-    mbar_init(bar_full, 1);
-    mbar_init(bar_empty, 1);
-    mbar_init(bar_a_ready, 128);
-    mbar_init(bar_acc_ready, 1);
-    fence_barrier_init();
-  }
-  if (warp == 4) {
-    tmem_alloc(tmem_slot, 256);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot_ptr;
-
-  if (warp == 4) {
-    if (lane == 0) {  // ===== weight producer (single ring slot; the co-resident CTA fills the gaps)
-      uint32_t phase = 0;
-      for (int64_t t = 0; t < my_tiles; ++t) {
-        for (int ci = 0; ci < kBwChunks; ++ci) {
-          mbar_wait(bar_empty, phase ^ 1);
-          mbar_arrive_expect_tx(bar_full, kChunkBytes256);
-          bulk_g2s(sW, args.packed + c_chunks.b[ci].offset, kChunkBytes256, bar_full);
-          phase ^= 1;
-        }
-      }
-    }
-  } else if (warp == 5) {
-    if (lane == 0) {  // ===== MMA issuer
-      uint32_t phase = 0, ev = 0;
-      const uint32_t idesc = umma_idesc_bf16(128, 256);
-      for (int64_t t = 0; t < my_tiles; ++t) {
-        int ci = 0;
-        for (int tl = 0; tl < kBwLayers; ++tl) {
-          mbar_wait(bar_a_ready, ev & 1);
-          tc_fence_after();
-          bool first = true;
-          while (ci < kBwChunks && c_chunks.b[ci].tlayer == tl) {
-            mbar_wait(bar_full, phase);
-            tc_fence_after();
-            const uint32_t a_base = sA + c_chunks.b[ci].ablock * kABlockBytes;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(tmem, umma_desc_sw128_kmajor(a_base + k * 32),
-                        umma_desc_sw128_kmajor(sW + k * 32), idesc, (first && k == 0) ? 0u : 1u);
-            first = false;
-            umma_commit(bar_empty);
-            phase ^= 1;
-            ++ci;
-          }
-          umma_commit(bar_acc_ready);
-          ++ev;
-        }
-      }
-    }
-  } else {
-    // ===== epilogue warps: thread r owns tile row r
-    const int r = tid;
-    const uint32_t tm_lane = tmem + (uint32_t(warp * 32) << 16);
-    const float* P = args.P;
-    const float* w11 = P + c_nerf.w[11];
-    const float* w9 = P + c_nerf.w[9];
-    float acc_db9 = 0.f, acc_db11[3] = {0.f, 0.f, 0.f};
-    uint32_t ev = 0;
-    for (int64_t t = 0; t < my_tiles; ++t) {
-      const int64_t tile = blockIdx.x + t * gridDim.x;
-      const int64_t s = tile * 128 + r;
-      const bool valid = s < args.m;
-      // row-major ReLU masks written by the forward: [tile][layer 9][row 128][8 words], column
-      // 32 w + j of a row is bit (31 - j) of word w
-      const uint4* mask_row = reinterpret_cast<const uint4*>(args.stash.MASK + ((tile * 9) * 128 + r) * 8);
-      // ---- head gradients (model.py:57,60): softplus' = sigmoid(pre) = 1 - exp(-density)
-      float spre = 0.f, dp[3] = {0.f, 0.f, 0.f};
-      if (valid) {
-        spre = __ldg(args.d_dens + s) * (-expm1f(-__ldg(args.dens + s)));
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          const float y = __ldg(args.rgb + s * 3 + j);
-          dp[j] = __ldg(args.d_rgb + s * 3 + j) * (1.0f - y * y);
-        }
-      }
-      args.stash.SPRE[tile * 128 + r] = spre;
-      reinterpret_cast<float4*>(args.stash.DPRE)[tile * 128 + r] = make_float4(dp[0], dp[1], dp[2], 0.f);
-      acc_db9 += spre;
-      acc_db11[0] += dp[0]; acc_db11[1] += dp[1]; acc_db11[2] += dp[2];
-      // ---- dc = (dpre @ W11^T) * (c > 0) -> A blocks 0,1 (and the DC stash image)
-      if (tid == 0) bulk_wait_read0();  // previous tile's last image has left smem
-      epi_bar();
-      const uint4 mc4 = __ldg(mask_row + 8 * 256);
-      const uint32_t mc[4] = {mc4.x, mc4.y, mc4.z, mc4.w};
-#pragma unroll
-      for (int c0 = 0; c0 < kHC; c0 += 32) {
-        uint32_t pk[16];
-        const uint32_t mwd = mc[c0 >> 5];
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const float* wa = w11 + (c0 + j) * 3;
-          float v0 = dp[0] * __ldg(wa + 0) + dp[1] * __ldg(wa + 1) + dp[2] * __ldg(wa + 2);
-          float v1 = dp[0] * __ldg(wa + 3) + dp[1] * __ldg(wa + 4) + dp[2] * __ldg(wa + 5);
-          v0 = (mwd & (0x80000000u >> j)) ? v0 : 0.0f;
-          v1 = (mwd & (0x80000000u >> (j + 1))) ? v1 : 0.0f;
-          pk[j / 2] = pack_bf16x2(v0, v1);
-        }
-        const uint32_t blk = sA + (c0 >> 6) * kABlockBytes;
-        const int cbase = (c0 & 63) >> 3;
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          store_row_chunk(blk, r, cbase + q, pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
-      }
-      fence_proxy_async_smem();
-      epi_bar();
-      if (tid == 0) {
-        bulk_s2g(args.stash.DC + tile * 2 * kABlockBytes, sA, 2 * kABlockBytes);
-        bulk_commit();
-      }
-      tc_fence_before();
-      mbar_arrive(bar_a_ready);
-      // ---- B0: g8 = acc + spre * w9 (no mask);  B1..B8: g_{l-1} = acc * (h_{l-1} > 0), l = 9 - tl
-      for (int tl = 0; tl < kBwLayers; ++tl) {
-        mbar_wait(bar_acc_ready, ev & 1);
-        ++ev;
-        tc_fence_after();
-        if (tid == 0) bulk_wait_read0();
-        epi_bar();
-        const int out_layer = 8 - tl;  // index of the g tile produced here (g8 .. g0)
-        uint32_t mw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-        if (tl > 0) {
-          const uint4 ma = __ldg(mask_row + out_layer * 256), mb = __ldg(mask_row + out_layer * 256 + 1);
-          mw[0] = ma.x; mw[1] = ma.y; mw[2] = ma.z; mw[3] = ma.w;
-          mw[4] = mb.x; mw[5] = mb.y; mw[6] = mb.z; mw[7] = mb.w;
-        }
-#pragma unroll
-        for (int c0 = 0; c0 < 256; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(tm_lane + c0, v);
-          tmem_wait_ld();
-          uint32_t pk[16];
-          if (tl == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 w = __ldg(reinterpret_cast<const float4*>(w9 + c0 + j));
-              pk[j / 2] = pack_bf16x2(fmaf(spre, w.x, __uint_as_float(v[j])),
-                                      fmaf(spre, w.y, __uint_as_float(v[j + 1])));
-              pk[j / 2 + 1] = pack_bf16x2(fmaf(spre, w.z, __uint_as_float(v[j + 2])),
-                                          fmaf(spre, w.w, __uint_as_float(v[j + 3])));
-            }
-          } else {
-            const uint32_t mwd = mw[c0 >> 5];
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float f0 = (mwd & (0x80000000u >> j)) ? __uint_as_float(v[j]) : 0.0f;
-              const float f1 = (mwd & (0x80000000u >> (j + 1))) ? __uint_as_float(v[j + 1]) : 0.0f;
-              const float f2 = (mwd & (0x80000000u >> (j + 2))) ? __uint_as_float(v[j + 2]) : 0.0f;
-              const float f3 = (mwd & (0x80000000u >> (j + 3))) ? __uint_as_float(v[j + 3]) : 0.0f;
-              pk[j / 2] = pack_bf16x2(f0, f1);
-              pk[j / 2 + 1] = pack_bf16x2(f2, f3);
-            }
-          }
-          const uint32_t blk = sA + (c0 >> 6) * kABlockBytes;
-          const int cbase = (c0 & 63) >> 3;
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            store_row_chunk(blk, r, cbase + q, pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
-        }
-        fence_proxy_async_smem();
-        epi_bar();
-        if (tid == 0) {
-          bulk_s2g(args.stash.G[out_layer] + tile * kTileBytes, sA, kTileBytes);
-          bulk_commit();
-        }
-        tc_fence_before();
-        if (tl + 1 < kBwLayers) mbar_arrive(bar_a_ready);  // g0 feeds no further GEMM
-      }
-    }
-    if (tid == 0) bulk_wait0();
-    // bias gradients of the two heads: db9 = sum spre, db11 = sum dpre
-    acc_db9 = warp_sum(acc_db9);
-#pragma unroll
-    for (int j = 0; j < 3; ++j) acc_db11[j] = warp_sum(acc_db11[j]);
-    if (lane == 0) {
-      atomicAdd(args.G + c_nerf.b[9], acc_db9);
-#pragma unroll
-      for (int j = 0; j < 3; ++j) atomicAdd(args.G + c_nerf.b[11] + j, acc_db11[j]);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, 256);
-}
 
 // ================================================================ dW
 constexpr int kDwMaxJobs = 16;
@@ -471,32 +253,21 @@ nerf_bwd_dw_kernel(DwArgs args) {
 }
 
 // ================================================================ host side
+// CTAs per SM over the kernel's lifetime.  With one wave a job gets 12 or 13 of the 148 CTAs (6 %
+// imbalance, the slowest CTA sets the kernel time); three waves let the hardware scheduler balance
+// 444 smaller units: 5.48 -> 5.22 ms/step (2 waves 5.29, 4: 5.22, 6: 5.26).
+constexpr int kDwWaves = 3;
+// relative cost of the two jobs that also form a head gradient on the CUDA cores (tuned, round 1)
+constexpr double kDwHeadJobWeight = 8.0;
+// Ablation switches for profiling (bit flags 1 / 2 / 4 = dW kernel without loads / MMAs / worker
+// math: results are WRONG): read ONCE from the environment (LNRF_DEBUG_FLAGS) in lnrf_init, never
+// changed afterwards -- there is no run-time switch in the ABI.
 static int g_dw_debug = 0;
-static double g_dw_w1 = 8.0, g_dw_w2 = 8.0;
-// CTAs per SM over the kernel's lifetime (tuning: flags = 2000 + waves).  With one wave a job gets
-// 12 or 13 of the 148 CTAs (6 % imbalance, the slowest CTA sets the kernel time); three waves let
-// the hardware scheduler balance 444 smaller units: 5.48 -> 5.22 ms/step (2 waves 5.29, 4: 5.22, 6: 5.26).
-static int g_dw_waves = 3;
-void set_dw_debug(int flags) {
-  if (flags >= 2000) {
-    g_dw_waves = flags - 2000 < 1 ? 1 : flags - 2000;
-    return;
-  }
-  if (flags >= 1000) {  // tuning: flags = 1000 + 100 * w1 + w2
-    g_dw_w1 = double((flags - 1000) / 100);
-    g_dw_w2 = double((flags - 1000) % 100);
-    return;
-  }
-  g_dw_debug = flags;
-}
 
 int init_mlp_tc_bwd() {
+  if (const char* e = getenv("LNRF_DEBUG_FLAGS")) g_dw_debug = atoi(e) & 7;
   int rc = upload_tc_tables();
   if (rc) return rc;
-  LNRF_CUDA(cudaFuncSetAttribute(nerf_bwd_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)BwdSmem::total));
-  LNRF_CUDA(cudaFuncSetAttribute(nerf_bwd_dx_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                 cudaSharedmemCarveoutMaxShared));
   LNRF_CUDA(cudaFuncSetAttribute(nerf_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)(kDwSmemBytes)));
   LNRF_CUDA(cudaFuncSetAttribute(nerf_bwd_dw_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -516,12 +287,7 @@ int nerf_bwd_tc(const float* P, const void* packed, int64_t m, void* ws, int64_t
   const int64_t tiles = ceil_div(m, 128);
 
   TcBwdArgs a{reinterpret_cast<const uint8_t*>(packed), P, dens, rgb, d_dens, d_rgb, m, s, G};
-  if (g_dw_debug & 512) {  // A/B switch: the single-tile dX kernel (two CTAs per SM)
-    int64_t grid = int64_t(sm_count()) * 2;
-    if (grid > tiles) grid = tiles;
-    nerf_bwd_dx_kernel<<<(unsigned)grid, kTcThreads, BwdSmem::total, st>>>(a);
-    LNRF_LAUNCH_CHECK("nerf_bwd_dx_kernel");
-  } else {
+  {
     const int rc = nerf_bwd_dx_pair(a, st);
     if (rc) return rc;
   }
@@ -545,15 +311,14 @@ int nerf_bwd_tc(const float* P, const void* packed, int64_t m, void* ws, int64_t
   add(s.DE, 1, s.DC, 2, 1, kDE, kHC, G + kNerf.w[10] + int64_t(kH) * kHC, nullptr, 0, nullptr);  // dW10[256:]
   add(s.C, 2, nullptr, 0, 0, 0, 3, nullptr, nullptr, 2, G + kNerf.w[11]);                        // dW11
   d.n_jobs = nj;
-  const int total_ctas = sm_count() * g_dw_waves;
+  const int total_ctas = sm_count() * kDwWaves;
   double wsum = 0.0;
   double wj[kDwMaxJobs];
   for (int j = 0; j < nj; ++j) {
     wj[j] = d.jobs[j].a_blocks + d.jobs[j].b_blocks;
     // the two jobs that also form a head gradient on the CUDA cores are bounded by that row
-    // loop, not by the bytes they stream (g_dw_w1 / g_dw_w2: tuning knobs, see lnrf_set_debug_flags)
-    if (d.jobs[j].extra == 1) wj[j] = g_dw_w1;
-    if (d.jobs[j].extra == 2) wj[j] = g_dw_w2;
+    // loop, not by the bytes they stream
+    if (d.jobs[j].extra != 0) wj[j] = kDwHeadJobWeight;
     wsum += wj[j];
   }
   // largest-remainder apportionment so that every SM gets a CTA

@@ -9,6 +9,8 @@
 // output column 128 of the colour-layer GEMM; the 128 -> 3 rgb head runs in fp32 FMAs.
 // With SAVE the activation tile images and row-major 1-bit ReLU masks are streamed to the
 // stash with bulk stores for the backward kernels.
+#include <stdlib.h>
+
 #include "mlp_tc_pair.cuh"
 
 namespace lnrf {
@@ -371,10 +373,11 @@ nerf_fwd_pair_kernel(const __grid_constant__ TcFwdArgs2 args) {
   if (warp == 8) tmem_dealloc(tmem, 512);
 }
 
+// profiling ablations (see TcFwdArgs2::debug): read once from LNRF_DEBUG_FLAGS in lnrf_init
 static int g_fwd_debug = 0;
-void set_fwd_debug(int flags) { g_fwd_debug = flags; }
 
 int init_mlp_tc_fwd2() {
+  if (const char* e = getenv("LNRF_DEBUG_FLAGS")) g_fwd_debug = atoi(e) & (8 | 16 | 64);
   int rc = upload_tc_tables();
   if (rc) return rc;
   if ((rc = upload_pair_meta())) return rc;

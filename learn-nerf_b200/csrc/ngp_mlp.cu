@@ -495,6 +495,16 @@ static size_t ngp_fwd_smem(const NgpLayout& nl) { return size_t(align_up(nl.tota
 
 }  // namespace lnrf
 
+namespace lnrf {
+// per-device setup, called from lnrf_init (no lazily-set process state)
+int init_ngp_mlp() {
+  LNRF_CUDA(cudaFuncSetAttribute(ngp_mlp_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+  LNRF_CUDA(cudaFuncSetAttribute(ngp_mlp_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+  LNRF_CUDA(cudaFuncSetAttribute(ngp_mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+  return LNRF_OK;
+}
+}  // namespace lnrf
+
 extern "C" {
 
 int64_t lnrf_ngp_mlp_param_count(int32_t L) { return lnrf::ngp_layout(L).total; }
@@ -538,13 +548,6 @@ int lnrf_ngp_mlp_fwd(const float* params, int32_t L, const float* enc, const flo
   const NgpLayout nl = ngp_layout(L);
   NgpFwdArgs a{params, nl, 2 * L, enc, d, rays, T, m, w, dens, rgb};
   const size_t smem = ngp_fwd_smem(nl);
-  static bool configured = false;
-  if (!configured) {
-    LNRF_CUDA(cudaFuncSetAttribute(ngp_mlp_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-    LNRF_CUDA(cudaFuncSetAttribute(ngp_mlp_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-    LNRF_CUDA(cudaFuncSetAttribute(ngp_mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-    configured = true;
-  }
   if (save) ngp_mlp_fwd_kernel<true><<<ngp_grid(m), kNgpFwdThreads, smem, as_stream(stream)>>>(a);
   else ngp_mlp_fwd_kernel<false><<<ngp_grid(m), kNgpFwdThreads, smem, as_stream(stream)>>>(a);
   LNRF_LAUNCH_CHECK("ngp_mlp_fwd_kernel");

@@ -52,6 +52,29 @@ rgb_to_u8_kernel(const float* __restrict__ colors, int64_t count, uint8_t* __res
   }
 }
 
+// z-depth image of render_new_dataset.py:96-133: the expected hit point (coords / alpha) projected on
+// the camera direction, max_depth where the ray is mostly transparent (alpha <= 0.9), clipped to
+// [0, max_depth] and normalised; depth_u32 = (z * 0xFFFF).astype(uint32).  Individually rounded ops in
+// the reference's order ((c - o) @ dir as a left-to-right dot product).
+struct DepthCam { float origin[3], dir[3]; };
+__global__ void __launch_bounds__(256)
+z_depth_kernel(const float* __restrict__ coords, const float* __restrict__ alphas, DepthCam cam, float max_depth,
+               int64_t n, float* __restrict__ z_out, uint32_t* __restrict__ u32_out) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const float a = __ldg(alphas + i);
+    float dot = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float t = __fmul_rn(__fsub_rn(__ldg(coords + i * 3 + k), cam.origin[k]), cam.dir[k]);
+      dot = (k == 0) ? t : __fadd_rn(dot, t);
+    }
+    float z = (a > 0.9f) ? __fdiv_rn(dot, __fadd_rn(a, 1e-8f)) : max_depth;
+    z = __fdiv_rn(fminf(fmaxf(z, 0.0f), max_depth), max_depth);
+    if (z_out) z_out[i] = z;
+    if (u32_out) u32_out[i] = uint32_t(__fmul_rn(z, 65535.0f));
+  }
+}
+
 static inline unsigned rg_blocks(int64_t items) {
   int64_t b = ceil_div(items, 256);
   const int64_t cap = int64_t(sm_count()) * 16;
@@ -91,6 +114,24 @@ int lnrf_rgb_to_u8(const float* colors, int64_t count, uint8_t* out, lnrf_stream
   LNRF_REQUIRE(colors && out, LNRF_E_INVALID, "lnrf_rgb_to_u8: null pointer");
   lnrf::rgb_to_u8_kernel<<<lnrf::rg_blocks(count), 256, 0, lnrf::as_stream(stream)>>>(colors, count, out);
   LNRF_LAUNCH_CHECK("rgb_to_u8_kernel");
+  return LNRF_OK;
+}
+
+int lnrf_z_depth(const float* coords, const float* alphas, const float* camera_origin_host,
+                 const float* camera_direction_host, float max_depth, int64_t n, float* z_out, uint32_t* depth_u32_out,
+                 lnrf_stream_t stream) {
+  LNRF_REQUIRE(n >= 0 && max_depth > 0.0f, LNRF_E_INVALID, "lnrf_z_depth: n=%lld max_depth=%g", (long long)n, max_depth);
+  if (n == 0) return LNRF_OK;
+  LNRF_REQUIRE(coords && alphas && camera_origin_host && camera_direction_host && (z_out || depth_u32_out),
+               LNRF_E_INVALID, "lnrf_z_depth: null pointer");
+  lnrf::DepthCam cam;
+  for (int a = 0; a < 3; ++a) {
+    cam.origin[a] = camera_origin_host[a];
+    cam.dir[a] = camera_direction_host[a];
+  }
+  lnrf::z_depth_kernel<<<lnrf::rg_blocks(n), 256, 0, lnrf::as_stream(stream)>>>(coords, alphas, cam, max_depth, n, z_out,
+                                                                               depth_u32_out);
+  LNRF_LAUNCH_CHECK("z_depth_kernel");
   return LNRF_OK;
 }
 

@@ -404,9 +404,106 @@ sample_fine64_kernel(const float* __restrict__ ts_c, const float* __restrict__ d
   }
 }
 
+
+// ------------------------------------------------------------------ RaySamples helpers
+// starts / ends / deltas (render.py:259-268) and termination_probs (render.py:270-287) as
+// stand-alone calls for the RaySamples method surface; the same individually rounded arithmetic
+// as the fine-sampling kernels above (strictly sequential cumsum, lnrf_expf): bit-exact with
+// oracle.render_np.  One warp per ray, T <= 1024.
+__global__ void __launch_bounds__(256)
+ray_intervals_kernel(const float* __restrict__ ts, const float* __restrict__ t_min_in,
+                     const float* __restrict__ t_max_in, int64_t n, int T, float* __restrict__ starts,
+                     float* __restrict__ ends, float* __restrict__ deltas) {
+  const int64_t total = n * T;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = i / T;
+    const int k = int(i - r * T);
+    const float t = __ldg(ts + i);
+    const float start = (k == 0) ? __ldg(t_min_in + r) : __fdiv_rn(__fadd_rn(t, __ldg(ts + i - 1)), 2.0f);
+    const float end = (k == T - 1) ? __ldg(t_max_in + r) : __fdiv_rn(__fadd_rn(__ldg(ts + i + 1), t), 2.0f);
+    if (starts) starts[i] = start;
+    if (ends) ends[i] = end;
+    if (deltas) deltas[i] = __fsub_rn(end, start);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+termination_probs_kernel(const float* __restrict__ ts, const float* __restrict__ t_min_in,
+                         const float* __restrict__ t_max_in, const float* __restrict__ dens, int64_t n, int T,
+                         float* __restrict__ probs) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float* s_ts = smem + size_t(wib) * (3 * T + 1);
+  float* s_ddt = s_ts + T;
+  float* s_acc = s_ddt + T;  // T + 1 entries: acc_prev incl. the total
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t r = warp; r < n; r += nwarps) {
+    const float t_min = __ldg(t_min_in + r), t_max = __ldg(t_max_in + r);
+    for (int i = lane; i < T; i += 32) s_ts[i] = __ldg(ts + r * T + i);
+    __syncwarp();
+    for (int i = lane; i < T; i += 32) {
+      const float t = s_ts[i];
+      const float start = (i == 0) ? t_min : __fdiv_rn(__fadd_rn(t, s_ts[i - 1]), 2.0f);
+      const float end = (i == T - 1) ? t_max : __fdiv_rn(__fadd_rn(s_ts[i + 1], t), 2.0f);
+      s_ddt[i] = __fmul_rn(__ldg(dens + r * T + i), __fsub_rn(end, start));  // :271
+    }
+    __syncwarp();
+    if (lane == 0) {  // jnp.cumsum, strictly left to right (:275)
+      float acc = 0.0f;
+      for (int i = 0; i < T; ++i) {
+        s_acc[i] = acc;
+        acc = __fadd_rn(acc, s_ddt[i]);
+      }
+      s_acc[T] = acc;
+    }
+    __syncwarp();
+    for (int i = lane; i <= T; i += 32) {  // prob_survive * prob_terminate (:279-287)
+      const float surv = lnrf_expf(-s_acc[i]);
+      const float term = (i == T) ? 1.0f : __fsub_rn(1.0f, lnrf_expf(-s_ddt[i]));
+      probs[r * (T + 1) + i] = __fmul_rn(surv, term);
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace lnrf
 
 extern "C" {
+
+int lnrf_ray_intervals(const float* ts, const float* t_min, const float* t_max, int64_t n, int32_t T,
+                       float* starts, float* ends, float* deltas, lnrf_stream_t stream) {
+  LNRF_REQUIRE(n >= 0 && T > 0, LNRF_E_INVALID, "lnrf_ray_intervals: n=%lld T=%d", (long long)n, T);
+  if (n == 0) return LNRF_OK;
+  LNRF_REQUIRE(ts && t_min && t_max, LNRF_E_INVALID, "lnrf_ray_intervals: null pointer");
+  int64_t blocks = lnrf::ceil_div(n * T, 256);
+  const int64_t cap = int64_t(lnrf::sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  lnrf::ray_intervals_kernel<<<(unsigned)blocks, 256, 0, lnrf::as_stream(stream)>>>(ts, t_min, t_max, n, T, starts,
+                                                                                    ends, deltas);
+  LNRF_LAUNCH_CHECK("ray_intervals_kernel");
+  return LNRF_OK;
+}
+
+int lnrf_termination_probs(const float* ts, const float* t_min, const float* t_max, const float* dens, int64_t n,
+                           int32_t T, float* probs, lnrf_stream_t stream) {
+  LNRF_REQUIRE(n >= 0 && T > 0, LNRF_E_INVALID, "lnrf_termination_probs: n=%lld T=%d", (long long)n, T);
+  LNRF_REQUIRE(T <= 1024, LNRF_E_UNSUPPORTED, "lnrf_termination_probs: T=%d exceeds 1024", T);
+  if (n == 0) return LNRF_OK;
+  LNRF_REQUIRE(ts && t_min && t_max && dens && probs, LNRF_E_INVALID, "lnrf_termination_probs: null pointer");
+  const int warps = 8;
+  const size_t smem = size_t(warps) * (3 * T + 1) * sizeof(float);  // <= 98 KB at T = 1024
+  if (smem > 48 * 1024)
+    LNRF_CUDA(cudaFuncSetAttribute(lnrf::termination_probs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   96 * 1024 + 1024));
+  int64_t blocks = lnrf::ceil_div(n, warps);
+  const int64_t cap = int64_t(lnrf::sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  lnrf::termination_probs_kernel<<<(unsigned)blocks, warps * 32, smem, lnrf::as_stream(stream)>>>(ts, t_min, t_max,
+                                                                                               dens, n, T, probs);
+  LNRF_LAUNCH_CHECK("termination_probs_kernel");
+  return LNRF_OK;
+}
 
 int lnrf_sample_coarse(const float* rays, int64_t n, const float* bbox_min_host,
                        const float* bbox_max_host, float min_t_range, float epsilon,
@@ -474,12 +571,9 @@ int lnrf_sample_fine(const float* ts_c, const float* dens_c, const float* t_min,
   while (P < Tc + Tf) P <<= 1;
   const int warps = 8, threads = warps * 32;
   size_t smem = size_t(warps) * lnrf::fine_smem_floats(Tc, P) * sizeof(float);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem > 48 * 1024)  // per call: the attribute is per device, and setting it is cheap and idempotent
     LNRF_CUDA(cudaFuncSetAttribute(lnrf::sample_fine_kernel,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
   int64_t blocks = lnrf::ceil_div(n, warps);
   int64_t cap = int64_t(lnrf::sm_count()) * 8;
   if (blocks > cap) blocks = cap;

@@ -36,6 +36,12 @@ _SIGS = {
     "lnrf_stratified": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
     "lnrf_sample_fine": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                    c_int32, c_int32, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lnrf_ray_intervals": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p,
+                                     c_void_p]),
+    "lnrf_termination_probs": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p,
+                                         c_void_p]),
+    "lnrf_z_depth": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int64, c_void_p, c_void_p,
+                               c_void_p]),
     "lnrf_composite_fwd": (c_int32, [c_void_p] * 8 + [c_int64, c_int32] + [c_void_p] * 4),
     "lnrf_composite_bwd": (c_int32, [c_void_p] * 8 + [c_int64, c_int32] + [c_void_p] * 4),
     "lnrf_mse_loss": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p, c_void_p,
@@ -60,7 +66,6 @@ _SIGS = {
                                        c_void_p, c_void_p, c_void_p]),
     "lnrf_debug_umma_gemm": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "lnrf_debug_umma_gemm_tn": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
-    "lnrf_set_tc_stages": (c_int32, [c_int32]),
     "lnrf_bare_rays": (c_int32, [c_void_p] * 4 + [c_float, c_float, c_int32, c_int32, c_int32, c_int32, c_void_p,
                                                    c_void_p]),
     "lnrf_rgb_to_u8": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p]),
@@ -72,7 +77,6 @@ _SIGS = {
     "lnrf_refnerf_fwd": (c_int32, [c_void_p] * 5 + [c_int64, c_int32, c_int32, c_void_p, c_int64] +
                          [c_void_p] * 5),
     "lnrf_refnerf_bwd": (c_int32, [c_void_p] * 5 + [c_int64, c_int32, c_void_p, c_int64] + [c_void_p] * 6),
-    "lnrf_set_debug_flags": (c_int32, [c_int32]),
     "lnrf_ngpref_mlp_param_floats": (c_int64, [c_int32]),
     "lnrf_ngpref_param_offsets": (c_int32, [c_int32, c_void_p]),
     "lnrf_ngpref_workspace_bytes": (c_int32, [c_int64, c_int32, c_int32, c_void_p]),
@@ -524,5 +528,64 @@ def refnerf_bwd(flat, x, d, rays, ts, n, T, workspace, d_dens, d_rgb, d_aux_mse,
            "lnrf_refnerf_bwd")
 
 
-def set_tc_stages(stages: int):
-    _check(load().lnrf_set_tc_stages(stages), "lnrf_set_tc_stages")
+def ray_intervals(ts, t_min, t_max, want=("starts", "ends", "deltas")):
+    """RaySamples.starts / ends / deltas (render.py:259-268) -> dict of [n,T] tensors."""
+    ts = _f32c(ts, "ts")
+    ensure_init(ts.device)
+    n, T = ts.shape
+    out = {k: torch.empty(n, T, device=ts.device) for k in want}
+    _check(load().lnrf_ray_intervals(_p(ts), _p(_f32c(t_min, "t_min")), _p(_f32c(t_max, "t_max")), n, T,
+                                     _p(out.get("starts")), _p(out.get("ends")), _p(out.get("deltas")), _stream()),
+           "lnrf_ray_intervals")
+    return out
+
+
+def termination_probs(ts, t_min, t_max, dens):
+    """RaySamples.termination_probs (render.py:270-287) -> [n,T+1]."""
+    ts, dens = _f32c(ts, "ts"), _f32c(dens, "densities")
+    ensure_init(ts.device)
+    n, T = ts.shape
+    probs = torch.empty(n, T + 1, device=ts.device)
+    _check(load().lnrf_termination_probs(_p(ts), _p(_f32c(t_min, "t_min")), _p(_f32c(t_max, "t_max")), _p(dens), n, T,
+                                         _p(probs), _stream()), "lnrf_termination_probs")
+    return probs
+
+
+def z_depth(coords, alphas, camera_origin, camera_direction, max_depth: float):
+    """render_new_dataset.py:96-133 -> (z[n] in [0,1] fp32, depth[n] int32 holding the uint32 values)."""
+    coords = _f32c(coords, "coords")
+    alphas = _f32c(alphas.reshape(-1), "alphas")
+    ensure_init(coords.device)
+    n = coords.shape[0]
+    z = torch.empty(n, device=coords.device)
+    d32 = torch.empty(n, dtype=torch.int32, device=coords.device)
+    _check(load().lnrf_z_depth(_p(coords), _p(alphas), _host3(camera_origin), _host3(camera_direction), float(max_depth),
+                               n, _p(z), _p(d32), _stream()), "lnrf_z_depth")
+    return z, d32
+
+
+# --------------------------------------------------------------------------- device scoping
+# The kernels launch on the CUDA runtime's CURRENT device and stream.  Every wrapper above runs inside
+# the device of its first CUDA tensor argument, so TrainLoop(device="cuda:1") / render_view(device=...)
+# work whatever the caller's current device is (and the stream is that device's current stream).
+def _device_scoped(fn):
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        for a in args:
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                if a.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(a.device):
+                        return fn(*args, **kwargs)
+                break
+        return fn(*args, **kwargs)
+    return wrapper
+
+
+for _name in ("sample_coarse", "stratified", "sample_fine", "composite_fwd", "composite_bwd", "mse_loss",
+              "nerf_pack_weights", "nerf_mlp_fwd", "nerf_mlp_bwd", "adam_step", "adam_step_dk", "threefry_uniform_dk",
+              "adam_step_peers", "debug_umma_gemm", "debug_umma_gemm_tn", "hashgrid_fwd", "hashgrid_bwd", "ngpref_fwd",
+              "ngpref_bwd", "ngp_mlp_fwd", "ngp_mlp_bwd", "rgb_to_u8", "refnerf_fwd", "refnerf_bwd", "ray_intervals",
+              "termination_probs", "z_depth"):
+    globals()[_name] = _device_scoped(globals()[_name])

@@ -129,12 +129,35 @@ class ShuffledDataset:
         self.num_shards = num_shards
         self.shard_key, self.shuffle_key = prng.split(key)
         self._paths = [os.path.join(dir_path, str(i)) for i in range(num_shards)]
-        os.makedirs(dir_path, exist_ok=True)
         marker = os.path.join(dir_path, "done")
-        if not os.path.exists(marker):
+        # Multi-process runs (one rank per GPU sharing the directory): rank 0 alone writes the shards,
+        # into a scratch directory that is renamed into place once complete, and every rank waits at a
+        # barrier before it reads -- no rank can ever see a truncated or half-written shard.
+        from . import parallel
+        rank, world = parallel.world()
+        if rank == 0 and not os.path.exists(marker):
+            tmp_dir = dir_path.rstrip("/") + f".tmp.{os.getpid()}"
+            os.makedirs(tmp_dir, exist_ok=True)
+            final_paths, self._paths = self._paths, [os.path.join(tmp_dir, str(i)) for i in range(num_shards)]
             self._write_shards(dataset, ray_device)
-            with open(marker, "wb") as f:
+            self._paths = final_paths
+            with open(os.path.join(tmp_dir, "done"), "wb") as f:
                 f.write(b"done\n")
+            if os.path.isdir(dir_path):  # an unfinished directory of an earlier run: replace its files
+                for name in os.listdir(tmp_dir):
+                    if name != "done":
+                        os.replace(os.path.join(tmp_dir, name), os.path.join(dir_path, name))
+                os.replace(os.path.join(tmp_dir, "done"), marker)  # the marker appears last
+                os.rmdir(tmp_dir)
+            else:
+                os.makedirs(os.path.dirname(os.path.abspath(dir_path)), exist_ok=True)
+                os.rename(tmp_dir, dir_path)
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        if not os.path.exists(marker):
+            raise FileNotFoundError(f"{marker}: the shuffled shards were not written (is {dir_path} shared "
+                                    "between the ranks?)")
 
     # ---- stage one
     def _write_shards(self, dataset: NeRFDataset, ray_device):

@@ -14,7 +14,7 @@ from typing import Any, Dict, List, Optional
 import torch
 
 from . import _native
-from .model import ModelBase, ParamTree, _rng_seed, _trunc_normal_
+from .model import ModelBase, ParamTree, _rng_key, init_flat_
 
 
 def hash_table_lookup(table: torch.Tensor, coords: torch.Tensor) -> torch.Tensor:
@@ -108,12 +108,11 @@ class InstantNGPModel(ModelBase):
         else:
             flat.zero_()
         tree = self.bind(flat)
-        gen = torch.Generator(device=device)
-        gen.manual_seed(_rng_seed(rngs))
-        for i, (a, _) in enumerate(self.layer_dims()):
-            _trunc_normal_(tree[f"Dense_{i}"]["kernel"], math.sqrt(1.0 / a), gen)
-        for leaf in tree["MultiresHashTableEncoding_0"].values():  # 1e-4 * U(-1, 1), :181-186
-            leaf["table"].uniform_(-1e-4, 1e-4, generator=gen)
+        spec = self.spec()
+        offs = (_native.ngpref_param_offsets if isinstance(self, InstantNGPRefNERFModel)
+                else _native.ngp_mlp_param_offsets)(self.L)
+        init_flat_(flat, [(offs[2 * i], a, a * b) for i, (a, b) in enumerate(self.layer_dims())],
+                   [(o, r * 2) for o, r in zip(spec.offsets, spec.rows)], _rng_key(rngs))  # tables: :181-186
         return {"params": tree}
 
     # ------------------------------------------------------------------ native calls

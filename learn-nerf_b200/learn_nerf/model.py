@@ -56,20 +56,44 @@ def sinusoidal_emb(coords: torch.Tensor, freqs: int) -> torch.Tensor:
     return combined.reshape(combined.shape[:-2] + (-1,))
 
 
-def _trunc_normal_(t: torch.Tensor, std: float, gen: torch.Generator):
-    # lecun_normal-like (flax nn.Dense default is un-pinned in the reference): N(0, std) cut at 2 std
-    t.normal_(0.0, 1.0, generator=gen)
-    bad = t.abs() > 2.0
-    while bool(bad.any()):
-        t[bad] = torch.empty(int(bad.sum()), device=t.device).normal_(0.0, 1.0, generator=gen)
-        bad = t.abs() > 2.0
-    t.mul_(std)
+# flax nn.Dense default kernel_init = lecun_normal() = variance_scaling(1.0, "fan_in", "truncated_normal"):
+# stddev = sqrt(1 / fan_in) / 0.87962566103423978 (the std of a unit normal truncated at +-2), applied to
+# jax.random.truncated_normal(key, -2, 2) = sqrt(2) * erfinv(U(erf(-sqrt 2), erf(sqrt 2))).
+_TRUNC_STD = 0.87962566103423978
+_ERF_SQRT2 = math.erf(math.sqrt(2.0))
 
 
-def _rng_seed(rngs) -> int:
+def init_flat_(flat: torch.Tensor, dense_kernels, tables, key):
+    """Random-init a flat parameter buffer in a handful of launches (one Threefry uniform stream over
+    the whole buffer, then elementwise ops): Dense kernels get lecun_normal as Flax does (see above),
+    hash tables 1e-4 * (2 U - 1) (instant_ngp.py:181-186), biases and padding stay zero.
+    ``dense_kernels``: [(offset, fan_in, count)], ``tables``: [(offset, count)].
+    The per-parameter key derivation of flax (path-hashed fold_in) is not reproduced: the stream is
+    ``uniform(key, [len(flat)])`` indexed by buffer position."""
+    import numpy as np
+    from . import prng
+    n = flat.numel()
+    std = np.zeros(n, np.float32)
+    tab = np.zeros(n, np.float32)
+    for off, fan_in, count in dense_kernels:
+        std[off: off + count] = math.sqrt(1.0 / fan_in) / _TRUNC_STD
+    for off, count in tables:
+        tab[off: off + count] = 1e-4
+    dev = flat.device
+    u = prng.uniform(key, (n,), dev)
+    # truncated normal by inversion; clamped inside the open interval (-2, 2) as jax.random does
+    z = torch.erfinv(u * (2.0 * _ERF_SQRT2) - _ERF_SQRT2).mul_(math.sqrt(2.0)).clamp_(-1.9999999, 1.9999999)
+    flat.copy_(z * torch.from_numpy(std).to(dev))
+    if tables:
+        flat.add_((u * 2.0 - 1.0) * torch.from_numpy(tab).to(dev))
+    return flat
+
+
+def _rng_key(rngs):
+    """``model.init(dict(params=rng), ...)`` / ``model.init(rng, ...)`` -> the PRNG key."""
     if isinstance(rngs, dict):
         rngs = rngs["params"]
-    return _as_key(rngs).seed
+    return _as_key(rngs)
 
 
 @dataclass
@@ -139,10 +163,9 @@ class NeRFModel(ModelBase):
         else:
             flat.zero_()
         tree = self.bind(flat)
-        gen = torch.Generator(device=device)
-        gen.manual_seed(_rng_seed(rngs))
-        for i, (a, _) in enumerate(self.layer_dims()):
-            _trunc_normal_(tree[f"Dense_{i}"]["kernel"], math.sqrt(1.0 / a), gen)
+        offs = _native.nerf_param_offsets()
+        init_flat_(flat, [(offs[2 * i], a, a * b) for i, (a, b) in enumerate(self.layer_dims())], [],
+                   _rng_key(rngs))
         return {"params": tree}
 
     # ------------------------------------------------------------------ native calls

@@ -14,7 +14,7 @@ from typing import Any, Dict, Optional
 import torch
 
 from . import _native
-from .model import ModelBase, ParamTree, _rng_seed, _trunc_normal_
+from .model import ModelBase, ParamTree, _rng_key, init_flat_
 
 HARMONIC_COUNTS = [1, 3, 5, 7, 9, 11, 13, 15]  # ref_nerf.py:15
 
@@ -86,10 +86,9 @@ class RefNERFModel(ModelBase):
         else:
             flat.zero_()
         tree = self.bind(flat)
-        gen = torch.Generator(device=device)
-        gen.manual_seed(_rng_seed(rngs))
-        for i, (a, _) in enumerate(self.layer_dims()):
-            _trunc_normal_(tree[f"Dense_{i}"]["kernel"], math.sqrt(1.0 / a), gen)
+        offs = _native.refnerf_param_offsets()
+        init_flat_(flat, [(offs[2 * i], a, a * b) for i, (a, b) in enumerate(self.layer_dims())], [],
+                   _rng_key(rngs))
         return {"params": tree}
 
     # ------------------------------------------------------------------ native calls

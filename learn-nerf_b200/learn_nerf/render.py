@@ -102,6 +102,27 @@ class RaySamples:
         """render.py:145-153 (host helper; the kernels form points in-line)."""
         return rays[:, :1] + (rays[:, 1:] * self.ts[:, :, None])
 
+    def starts(self) -> torch.Tensor:
+        """render.py:259-261 -> [N,T]."""
+        return _native.ray_intervals(self.ts, self.t_min.contiguous(), self.t_max.contiguous(), ("starts",))["starts"]
+
+    def ends(self) -> torch.Tensor:
+        """render.py:263-265 -> [N,T]."""
+        return _native.ray_intervals(self.ts, self.t_min.contiguous(), self.t_max.contiguous(), ("ends",))["ends"]
+
+    def deltas(self) -> torch.Tensor:
+        """render.py:267-268 -> [N,T]."""
+        return _native.ray_intervals(self.ts, self.t_min.contiguous(), self.t_max.contiguous(), ("deltas",))["deltas"]
+
+    def termination_probs(self, densities: torch.Tensor) -> torch.Tensor:
+        """render.py:270-287 -> [N,T+1]; the last column is the probability of reaching the background."""
+        return _native.termination_probs(self.ts, self.t_min.contiguous(), self.t_max.contiguous(),
+                                         densities.contiguous())
+
+    def average_aux_losses(self, densities: torch.Tensor, aux: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """render.py:192-209 -> {name: scalar}."""
+        return average_aux_losses(self, densities.contiguous(), aux)
+
     def render_rays(self, densities, rgbs, background, _rays=None) -> torch.Tensor:
         """render.py:155-176 -> [N,3]."""
         rays = _rays if _rays is not None else _dummy_rays(self.ts)
@@ -157,7 +178,7 @@ def render_rays(model: ModelBase, params: Any, background: torch.Tensor, batch: 
                                                     densities, rgbs, background.contiguous())
     aux_mean = {}
     if aux:
-        aux_mean = average_aux_losses(ts, densities, aux)
+        aux_mean = ts.average_aux_losses(densities, aux)
     out = dict(outputs=outputs, rgbs=rgbs, densities=densities, alphas=alphas, coords=coords)
     if _save is not None:
         out["_ctx"] = ctx

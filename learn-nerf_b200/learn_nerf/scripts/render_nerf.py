@@ -35,6 +35,12 @@ class _ChunkGraph:
                 renderer.render_rays(keys, self.rays)
         torch.cuda.current_stream(device).wait_stream(side)
         torch.cuda.synchronize(device)
+        # The weight re-pack (bf16 path) must be PART of the graph: replays then always read the
+        # current fp32 parameters, also after in-place updates (Adam steps, TrainLoop.load) that no
+        # eager forward has seen.  Costs one 5 us launch per chunk.
+        for tree in (renderer.coarse_params, renderer.fine_params):
+            if hasattr(tree, "mark_updated"):
+                tree.mark_updated()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.out = renderer.render_rays(keys, self.rays)["fine"]["outputs"]
@@ -52,8 +58,9 @@ def render_view(renderer: NeRFRenderer, view: CameraView, width: int, height: in
                 key=0, device="cuda", gather: bool = False, shard: bool = True, cuda_graph: bool = False
                 ) -> torch.Tensor:
     """-> uint8 [rows, width, 3] (this rank's rows; the whole [height, width, 3] if ``gather``).
-    ``cuda_graph``: replay one captured ``render_rays`` per full chunk (cached on the renderer; the
-    renderer's parameters must not be swapped for other tensors while the cache is alive)."""
+    ``cuda_graph``: replay one captured ``render_rays`` per full chunk (cached on the renderer).  The
+    graph re-packs the bf16 weights from the fp32 parameter buffers on every replay, so in-place
+    parameter updates are picked up; only swapping the buffers for OTHER tensors invalidates it."""
     rank, world = parallel.world() if shard else (0, 1)
     row0, row1 = parallel.shard_bounds(height, rank, world)
     rays = view.bare_rays(width, height, device=device, row0=row0, rows=row1 - row0)

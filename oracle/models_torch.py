@@ -19,9 +19,8 @@ Params = Dict[str, Dict[str, torch.Tensor]]
 
 # --------------------------------------------------------------------------- init
 def _trunc_normal(gen: torch.Generator, shape, std: float) -> torch.Tensor:
-    """Truncated normal on [-2 std, 2 std] (lecun_normal-like; the reference's
-    Flax default init is un-pinned, the benchmark only needs "that architecture,
-    random init")."""
+    """Unit normal truncated to [-2, 2], times ``std`` (the draw of flax's lecun_normal; the
+    PRNG stream is torch's, not JAX's: the benchmark only needs "that architecture, random init")."""
     out = torch.empty(shape, dtype=torch.float64)
     flat = out.view(-1)
     filled = 0
@@ -34,7 +33,9 @@ def _trunc_normal(gen: torch.Generator, shape, std: float) -> torch.Tensor:
 
 
 def dense_init(gen: torch.Generator, fan_in: int, fan_out: int) -> Dict[str, torch.Tensor]:
-    return dict(kernel=_trunc_normal(gen, (fan_in, fan_out), math.sqrt(1.0 / fan_in)),
+    """flax nn.Dense defaults: kernel lecun_normal = variance_scaling(1, "fan_in", "truncated_normal"),
+    i.e. stddev sqrt(1 / fan_in) / 0.87962566103423978 on a +-2 truncated unit normal; zero bias."""
+    return dict(kernel=_trunc_normal(gen, (fan_in, fan_out), math.sqrt(1.0 / fan_in) / 0.87962566103423978),
                 bias=torch.zeros(fan_out))
 
 

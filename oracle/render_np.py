@@ -250,3 +250,18 @@ def rgb_to_u8(colors):
     """render_nerf.py:93-96: ((colors + 1) * 127.5).astype(uint8), colours clamped to [-1, 1]."""
     c = np.clip(np.asarray(colors, np.float32), -1.0, 1.0)
     return ((c + np.float32(1.0)) * np.float32(127.5)).astype(np.uint8)
+
+
+def z_depth(coords, alphas, camera_origin, camera_direction, max_depth):
+    """scripts/render_new_dataset.py:100-117 -> (z[N] fp32 in [0,1], (z * 0xFFFF).astype(uint32)).
+    ``(coords - origin) @ direction`` is a left-to-right fp32 dot product."""
+    f = np.float32
+    c = (np.asarray(coords, f) - np.asarray(camera_origin, f)).astype(f)
+    d = np.asarray(camera_direction, f)
+    prod = (c * d).astype(f)
+    dot = ((prod[:, 0] + prod[:, 1]).astype(f) + prod[:, 2]).astype(f)
+    a = np.asarray(alphas, f).reshape(-1)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        z = np.where(a > f(0.9), (dot / (a + f(1e-8)).astype(f)).astype(f), f(max_depth)).astype(f)
+    z = (np.clip(z, f(0.0), f(max_depth)) / f(max_depth)).astype(f)
+    return z, (z * f(0xFFFF)).astype(np.uint32)

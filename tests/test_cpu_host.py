@@ -188,3 +188,11 @@ def test_nerf_dataset_iterate_batches(tmp_path):
         it = sd.iterate_batches(64, repeat=True)
         got = [next(it) for _ in range(5)]  # 320 rays > one epoch of 200
     assert all(b.shape == (64, 3, 3) for b in got)
+
+
+def test_public_header_has_no_process_wide_switches():
+    """re-entrant boundary, no mutable globals after lnrf_init: the tuning / debug setters
+    of round 1 are gone from the ABI."""
+    import re
+    hdr = open(os.path.join(ROOT, "include", "lnrf.h")).read()
+    assert not re.search(r"lnrf_set_\w+", hdr)

@@ -398,3 +398,102 @@ def test_train_script_mirror_end_to_end(tmp_path):
         fine = [float(l.split(" fine=")[1].split()[0]) for l in logs if l.startswith("step")]
         assert len(fine) == 12 and fine[-1] < fine[0], fine
         assert os.path.exists(ck) and loop.state.step == 12
+
+
+# ------------------------------------------------------------------ RaySamples method surface
+@pytest.mark.parametrize("T", [64, 192, 7, 1])
+def test_ray_samples_methods_bit_exact(nat, T):
+    """RaySamples.starts / ends / deltas / termination_probs / average_aux_losses (render.py:192-209,
+    259-287) through the host mirror against oracle.render_np: bit-exact (aux means: 1e-6)."""
+    from learn_nerf.render import RaySamples
+    rays, s, dens, rgb, bg = _composite_case(130, T, 300 + T)
+    dens[0] = 0.0
+    dens[1] = 1e6
+    rs_ = RaySamples(t_min=dev(s.t_min), t_max=dev(s.t_max), mask=dev(s.mask), ts=dev(s.ts))
+    for name in ("starts", "ends", "deltas"):
+        got = getattr(rs_, name)().cpu().numpy()
+        np.testing.assert_array_equal(got.view(np.uint32), getattr(s, name)().view(np.uint32), err_msg=name)
+    probs = rs_.termination_probs(dev(dens)).cpu().numpy()
+    want = s.termination_probs(dens)
+    assert probs.shape == (130, T + 1)
+    np.testing.assert_array_equal(probs.view(np.uint32), want.view(np.uint32))
+    np.testing.assert_allclose(probs.sum(1), 1.0, atol=3e-6)
+    aux = {"a": np.abs(rgb[..., 0]), "b": rgb[..., 1] ** 2}
+    got = rs_.average_aux_losses(dev(dens), {k: dev(v) for k, v in aux.items()})
+    ref = s.average_aux_losses(dens, aux)
+    for k in aux:
+        np.testing.assert_allclose(float(got[k]), float(ref[k]), atol=1e-6, rtol=1e-5)
+
+
+def test_z_depth_bit_exact(nat):
+    """lnrf_z_depth (render_new_dataset.py:100-117) against the oracle restatement."""
+    from oracle import render_np
+    rs = np.random.RandomState(5)
+    n = 1000
+    coords = rs.uniform(-2, 2, (n, 3)).astype(F)
+    alphas = rs.uniform(0, 1, (n, 1)).astype(F)
+    alphas[:5, 0] = [0.9, 0.90000004, 1.0, 0.0, 0.95]
+    origin, direction = (0.5, -3.0, 1.0), (0.0, 0.8, -0.6)
+    z, d32 = nat.z_depth(dev(coords), dev(alphas), origin, direction, 4.0)
+    o_z, o_d = render_np.z_depth(coords, alphas, origin, direction, 4.0)
+    np.testing.assert_array_equal(z.cpu().numpy().view(np.uint32), o_z.view(np.uint32))
+    np.testing.assert_array_equal(d32.cpu().numpy().view(np.uint32), o_d)
+
+
+# ------------------------------------------------------------------ property tests (hypothesis, SURVEY 8c)
+try:
+    from hypothesis import given, settings, strategies as st
+    HAVE_HYPOTHESIS = True
+except Exception:  # noqa: BLE001
+    HAVE_HYPOTHESIS = False
+
+if HAVE_HYPOTHESIS:
+    _coord = st.floats(-6.0, 6.0, width=32, allow_nan=False)
+    _dirc = st.sampled_from([0.0, 1.0, -1.0, 1e-8, -1e-8, 0.25, -0.7, 3e-5, 0.5, -2.0])
+    _ray = st.tuples(st.tuples(_coord, _coord, _coord), st.tuples(_dirc, _dirc, _dirc))
+
+    @settings(max_examples=40, deadline=None)
+    @given(rays=st.lists(_ray, min_size=1, max_size=40), seed=st.integers(0, 2 ** 31 - 1), T=st.sampled_from([64, 37, 4]))
+    def test_k1_bit_exact_property(rays, seed, T):
+        """K1 on arbitrary origins and degenerate directions (zero components, +-1e-8 that cancel the
+        epsilon, rays inside / grazing / missing the box): masks, bounds and positions bit-exact."""
+        from learn_nerf import _native
+        from oracle import render_np
+        r = np.array(rays, F)
+        n = len(r)
+        u = (np.random.RandomState(seed).randint(0, 2 ** 23, (n, T)) * 2.0 ** -23).astype(F)
+        t_min, t_max, mask, ts = _native.sample_coarse(dev(r), BBOX_MIN, BBOX_MAX, dev(u))
+        o_min, o_max, o_mask = render_np.ray_t_range(BBOX_MIN, BBOX_MAX, r)
+        o = render_np.RaySamples.stratified_sampling(o_min, o_max, o_mask, T, u)
+        np.testing.assert_array_equal(mask.cpu().numpy().astype(bool), o_mask)
+        np.testing.assert_array_equal(t_min.cpu().numpy().view(np.uint32), o_min.view(np.uint32))
+        np.testing.assert_array_equal(t_max.cpu().numpy().view(np.uint32), o_max.view(np.uint32))
+        np.testing.assert_array_equal(ts.cpu().numpy().view(np.uint32), o.ts.view(np.uint32))
+
+    @settings(max_examples=40, deadline=None)
+    @given(seed=st.integers(0, 2 ** 31 - 1), kind=st.sampled_from(["gamma", "zero", "spike", "tiny", "huge", "sparse"]),
+           shape=st.sampled_from([(64, 128), (16, 48), (33, 17)]), top=st.booleans())
+    def test_k4_bit_exact_property(seed, kind, shape, top):
+        """K4 over random densities incl. the jnp.interp edge cases (SURVEY 7 hard-part 3): flat CDF bins
+        (zero / spike / sparse densities), the largest representable uniform, masked rays; bin indices
+        and sorted positions bit-exact against the oracle."""
+        from learn_nerf import _native
+        from oracle import render_np
+        Tc, Tf = shape
+        rs = np.random.RandomState(seed)
+        n = 24
+        rays = make_rays(n, seed=seed % 997, miss_frac=0.25, with_targets=False)
+        t_min, t_max, mask = render_np.ray_t_range(BBOX_MIN, BBOX_MAX, rays)
+        u_c = (rs.randint(0, 2 ** 23, (n, Tc)) * 2.0 ** -23).astype(F)
+        cs = render_np.RaySamples.stratified_sampling(t_min, t_max, mask, Tc, u_c)
+        dens = {"gamma": lambda: rs.gamma(0.5, 4.0, (n, Tc)), "zero": lambda: np.zeros((n, Tc)),
+                "spike": lambda: np.eye(Tc)[rs.randint(0, Tc, n)] * 1e6, "tiny": lambda: np.full((n, Tc), 1e-12),
+                "huge": lambda: np.full((n, Tc), 1e5),
+                "sparse": lambda: rs.gamma(0.3, 10.0, (n, Tc)) * (rs.uniform(size=(n, Tc)) < 0.2)}[kind]().astype(F)
+        u = (rs.randint(0, 2 ** 23, (n, Tf)) * 2.0 ** -23).astype(F)
+        if top:
+            u[:, -1] = np.float32(1.0 - 2.0 ** -23)
+        o, o_idx = cs.fine_sampling(Tf, u, dens, return_indices=True)
+        out, idx, _ = _native.sample_fine(dev(cs.ts), dev(dens), dev(t_min), dev(t_max), dev(u), debug=True)
+        np.testing.assert_array_equal(idx.cpu().numpy(), o_idx)
+        np.testing.assert_array_equal(out.cpu().numpy().view(np.uint32), o.ts.view(np.uint32))

@@ -315,3 +315,100 @@ def test_golden_ngpref_fixture():
                             density_points=(x, d))
     np.testing.assert_allclose(float(total), float(g["penalty_total"]), rtol=1e-5)
     np.testing.assert_allclose(float(ld["fine_density"]), float(g["penalty_fine"]), rtol=1e-5)
+
+
+# ------------------------------------------------------------------ property tests
+def test_interp_rows_matches_np_interp():
+    """render.py:251 calls jnp.interp, documented as NumPy's algorithm: cross-check the fp32
+    restatement (_interp_rows) against np.interp (float64 arithmetic) on monotone CDFs with flat
+    bins, queries on bin edges and at xp[0].  One documented difference is excluded: for x == xp[-1]
+    behind a flat last bin jnp.interp's formula (clip the index, dx == 0 -> fp[i-1]) returns fp[-2]
+    where NumPy returns fp[-1]; the restatement follows jnp (checked separately below)."""
+    rs = np.random.RandomState(0)
+    n, k, m = 64, 65, 128
+    w = rs.gamma(0.3, 1.0, (n, k - 1)) * (rs.uniform(size=(n, k - 1)) < 0.6)  # many empty (flat) bins
+    w[0] = 0.0
+    w[0, 7] = 1.0
+    xp = np.concatenate([np.zeros((n, 1)), np.cumsum(w + 1e-8, axis=1)], axis=1)
+    xp = (xp / xp[:, -1:]).astype(F)
+    fp = np.sort(rs.uniform(2.0, 6.0, (n, k)), axis=1).astype(F)
+    x = rs.uniform(0, 1, (n, m)).astype(F)
+    x[:, 0] = 0.0
+    x[:, 1] = 1.0
+    x[:, 2] = xp[:, 10]  # exactly on a bin edge: searchsorted side="right"
+    got, idx = render_np._interp_rows(x, xp, fp)
+    for r in range(n):
+        want = np.interp(x[r].astype(np.float64), xp[r].astype(np.float64), fp[r].astype(np.float64))
+        below_end = x[r] < xp[r, -1]
+        np.testing.assert_allclose(got[r][below_end], want[below_end], rtol=0, atol=4e-6 * 6.0, err_msg=f"row {r}")
+        i = idx[r]
+        at_end = ~below_end
+        flat_last = xp[r, -1] == xp[r, -2]
+        np.testing.assert_array_equal(got[r][at_end], np.full(at_end.sum(), fp[r, -2] if flat_last else fp[r, -1]))
+        assert ((1 <= i) & (i <= k - 1)).all()
+        # the bin the restatement picked brackets the query (left-closed, right-open, clamped at the ends)
+        inside = (x[r] > xp[r, 0]) & (x[r] < xp[r, -1])
+        assert (xp[r, i - 1][inside] <= x[r][inside]).all() and (x[r][inside] < xp[r, i][inside]).all()
+
+
+try:
+    from hypothesis import given, settings, strategies as st
+    HAVE_HYPOTHESIS = True
+except Exception:  # noqa: BLE001
+    HAVE_HYPOTHESIS = False
+
+if HAVE_HYPOTHESIS:
+    _coord = st.floats(-6.0, 6.0, width=32, allow_nan=False)
+    _dirc = st.sampled_from([0.0, 1.0, -1.0, 1e-8, -1e-8, 0.25, -0.7, 3e-5, 0.5])
+
+    @settings(max_examples=150, deadline=None)
+    @given(o=st.tuples(_coord, _coord, _coord), d=st.tuples(_dirc, _dirc, _dirc))
+    def test_ray_t_range_properties(o, d):
+        """render.py:346-389 on arbitrary origins / degenerate directions: t_max - t_min >= ~1e-3,
+        0 <= t_min, masked rays get exactly (0, 1e-3), and for hits both endpoints lie on or inside
+        the (slightly inflated) box."""
+        rays = np.array([[o, d]], F)
+        t_min, t_max, mask = render_np.ray_t_range(BBOX_MIN, BBOX_MAX, rays)
+        assert t_min[0] >= 0 and np.isfinite(t_min[0]) and np.isfinite(t_max[0])
+        assert t_max[0] - t_min[0] >= np.float32(1e-3) * np.float32(0.999)
+        if not mask[0]:
+            assert t_min[0] == 0 and t_max[0] == np.float32(1e-3)
+        elif np.linalg.norm(d) > 0.2:
+            p0 = np.asarray(o, np.float64) + np.asarray(d, np.float64) * float(t_min[0])
+            assert (np.abs(p0) <= 1.0 + 1e-3 * max(1.0, np.abs(o).max())).all() or t_min[0] == 0
+
+    @settings(max_examples=60, deadline=None)
+    @given(seed=st.integers(0, 2 ** 31 - 1), kind=st.sampled_from(["gamma", "zero", "spike", "tiny", "huge"]),
+           tc=st.sampled_from([8, 33, 64]), tf=st.sampled_from([5, 128]))
+    def test_fine_sampling_properties(seed, kind, tc, tf):
+        """render.py:211-257: the combined fine set is sorted, has Tc + Tf entries, contains every
+        coarse position, stays inside [t_min, t_max]; with zero density the CDF is linear in the bin
+        index, so the new samples are the piecewise-linear map of the stratified inputs through the bin
+        ends: monotone, and sample j lies in the bins that [j, j+1) / Tf covers."""
+        rs = np.random.RandomState(seed)
+        n = 6
+        rays = make_rays(n, seed=seed % 1000, miss_frac=0.3, with_targets=False)
+        t_min, t_max, mask = render_np.ray_t_range(BBOX_MIN, BBOX_MAX, rays)
+        u_c = (rs.randint(0, 2 ** 23, (n, tc)) * 2.0 ** -23).astype(F)
+        cs = render_np.RaySamples.stratified_sampling(t_min, t_max, mask, tc, u_c)
+        dens = {"gamma": lambda: rs.gamma(0.5, 4.0, (n, tc)), "zero": lambda: np.zeros((n, tc)),
+                "spike": lambda: np.eye(tc)[rs.randint(0, tc, n)] * 1e6, "tiny": lambda: np.full((n, tc), 1e-12),
+                "huge": lambda: np.full((n, tc), 1e5)}[kind]().astype(F)
+        u = (rs.randint(0, 2 ** 23, (n, tf)) * 2.0 ** -23).astype(F)
+        fs, idx = cs.fine_sampling(tf, u, dens, return_indices=True)
+        assert fs.ts.shape == (n, tc + tf)
+        assert (np.diff(fs.ts, axis=1) >= 0).all()
+        assert ((1 <= idx) & (idx <= tc)).all()
+        lo, hi = t_min[:, None], t_max[:, None]
+        slack = np.float32(1e-5) * np.maximum(np.float32(1.0), np.abs(hi))
+        assert (fs.ts >= lo - slack).all() and (fs.ts <= hi + slack).all()
+        for r in range(n):  # union: every coarse position survives the sort
+            assert np.isin(cs.ts[r], fs.ts[r]).all()
+        if kind == "zero":
+            new_only = cs.fine_sampling(tf, u, dens, combine=False).ts
+            assert (np.diff(new_only, axis=1) >= 0).all()
+            ys = np.concatenate([t_min[:, None], cs.ends()], axis=1)  # bin edges, [n, tc + 1]
+            j = np.arange(tf)
+            b_lo = np.floor(j * tc / tf).astype(int)
+            b_hi = np.minimum(np.ceil((j + 1) * tc / tf).astype(int), tc)
+            assert (new_only >= ys[:, b_lo] - slack).all() and (new_only <= ys[:, b_hi] + slack).all()
