@@ -6,8 +6,16 @@
 Workload at N=1: BASELINE.json configs[1] -- NeRF coarse+fine TRAINING STEP (fwd + bwd +
 Adam) on synthetic rays, 4096 rays/GPU, 64 coarse + 128 fine samples, random-init
 NeRFModel, bbox [-1,1]^3.  Rays shard over ranks (weak scaling: 4096 rays per GPU), one
-NCCL all-reduce of the flat gradient per step.  `--workload render` times config[4]-style
-rendering instead.  One JSON line is printed by rank 0.
+exchange of the flat gradient per step.  One JSON line is printed by rank 0.
+
+After the headline's timed regions the same run measures every other BASELINE.json config with
+the same method (own warm-up, CUDA-event step times with an L2 flush, e2e through the public API
+with host buffers, roofline of the dominant kernels, clocks) and attaches them as
+`extra_configs`: configs[1] fp32 leg, configs[0] (128x128 view in 1024-ray chunks, with its own
+CPU-port baseline), configs[2] (Instant-NGP, 32,768 rays/GPU = 2^18 global at N=8), configs[3]
+(Ref-NeRF) and configs[4] (800x800 render, rows sharded over the ranks); plus `hbm_stages`, the
+achieved GB/s of the HBM-bound kernels timed alone.  `--no_extra` skips them; `--workload`,
+`--model`, `--precision` select a single config as before.
 """
 import argparse
 import json
@@ -147,6 +155,35 @@ def cpu_train_sample(rays_per_step, steps, warmup, threads):
     return rays_per_step / sec, sec
 
 
+def cpu_render_sample(chunk_rays, chunks, threads):
+    """configs[0] on the CPU: the oracle's render_rays (numpy sampling / compositing + torch-CPU fp32
+    MLP) on `chunks` chunks of `chunk_rays` rays of a 128x128 view.  Returns (rays/s, s/chunk, rays)."""
+    import math
+    from oracle import models_torch as M
+    from oracle import render_np
+    from oracle import train_torch as T
+    torch.set_num_threads(threads)
+    nerf = M.NeRFModel()
+    params = T.init_params(nerf, nerf, 2)
+    rays = render_np.bare_rays((0.0, 0.0, -1.0), (0.0, 0.0, 4.0), (1.0, 0.0, 0.0), (0.0, -1.0, 0.0),
+                               math.radians(60.0), math.radians(60.0), 128, 128)
+    r = render_np.NeRFRenderer(M.as_numpy_model_fn(nerf, params["coarse"]), M.as_numpy_model_fn(nerf, params["fine"]),
+                               params["background"].numpy(), np.float32([-1, -1, -1]), np.float32([1, 1, 1]), 64, 128)
+    rs = np.random.RandomState(1)
+    times = []
+    for i in range(chunks + 1):
+        a = (6 + i) * chunk_rays  # chunks from the middle of the view (they hit the box)
+        sub = rays[a:a + chunk_rays]
+        uc = (rs.randint(0, 2 ** 23, (len(sub), 64)) * 2.0 ** -23).astype(np.float32)
+        uf = (rs.randint(0, 2 ** 23, (len(sub), 128)) * 2.0 ** -23).astype(np.float32)
+        t0 = time.perf_counter()
+        r.render_rays(uc, uf, sub)
+        if i > 0:  # first chunk = warm-up
+            times.append(time.perf_counter() - t0)
+    sec = float(np.mean(times))
+    return chunk_rays / sec, sec, chunk_rays * chunks
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -201,20 +238,13 @@ def ngp_grid_bytes_per_ray(train):
     return fwd + (bwd if train else 0)
 
 
-def run_ours(args):
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        torch.distributed.init_process_group("nccl", device_id=dev)
-
+def measure(args, rank, local_rank, world, dev, peaks):
+    """One config: warm-up, timed region 1 (device-resident inputs, CUDA events, L2 flush), timed
+    region 2 (e2e through the public API with host buffers).  Returns the JSON line (rank 0) or None."""
     from learn_nerf import _native
     from learn_nerf.render import NeRFRenderer
     from learn_nerf.train import TrainLoop
 
-    peaks = load_peaks()
     n = args.rays or (32768 if args.model in ("ngp", "ngpref") else 4096)
     prec = args.precision if args.model == "nerf" else "fp32"
     if args.model == "refnerf" and args.ray_chunk is None and n > 2048:
@@ -375,9 +405,15 @@ def run_ours(args):
                         # DRAM bytes of the three MLP kernels per 4096-ray step, from the ncu --set full
                         # capture profiles/r01d_nerf_train_kernels_ncu_full.txt (fine level 4.23 + 4.03 +
                         # 8.56 GB, coarse level = 1/3 of it); equals the algorithmic stash bytes
-                        "traffic": (NCU_TRAIN_DRAM_BYTES_PER_SAMPLE * SAMPLES_PER_RAY * n
+                        # every byte of the activation stash is written once (forward / dX) and read once
+                        # (dX / dW): 2 x the workspace sizes the library itself reports for the two levels
+                        "traffic": (2 * sum(_native.nerf_mlp_workspace_bytes(n * T, _native.PREC_BF16, True)
+                                            for T in (64, 192))
                                     if (train and prec == "bf16" and args.model == "nerf") else None),
-                        "traffic_unit": "bytes per step (dram__bytes_read.sum + dram__bytes_write.sum, ncu)",
+                        "traffic_unit": "bytes per step: 2 x lnrf_nerf_mlp_workspace_bytes (stash written once, "
+                                        "read once); ncu dram__bytes of the same kernels: profiles/",
+                        "traffic_ncu_r01d": (NCU_TRAIN_DRAM_BYTES_PER_SAMPLE * SAMPLES_PER_RAY * n
+                                             if (train and prec == "bf16" and args.model == "nerf") else None),
                         "peak_source": peaks["source"] + " (sustained bf16 cuBLAS)",
                         "kernel_ms_per_step": dom_ms, "kernel_share_of_step": dom_ms / ms,
                         "algorithmic_flop_per_sample": flop_per_sample}
@@ -423,15 +459,85 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": roofline,
         }
-        if args.cpu_baseline and world == 1 and args.model == "nerf" and train:
+        if args.cpu_baseline and world == 1 and args.model == "nerf" and train and prec == "bf16":
             threads = os.cpu_count() or 1
             cpu_steps = 16  # ~10 s of CPU work on the box's host cores
             v, sec = cpu_train_sample(args.cpu_rays, cpu_steps, 1, threads)
             line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": threads, "kind": "port",
-                                    "sample": f"oracle torch-CPU train step, {args.cpu_rays} rays/step x "
-                                              f"{cpu_steps} steps ({sec:.2f} s/step)"}
+                                    "sample": f"oracle torch-CPU train step (port of the reference, fp32, not JAX), "
+                                              f"{args.cpu_rays} rays/step x {cpu_steps} steps ({sec:.2f} s/step)"}
+        elif (args.cpu_baseline and world == 1 and args.workload == "image" and args.width * args.height <= 128 * 128
+              and args.model == "nerf"):
+            threads = os.cpu_count() or 1
+            v, sec, rays_done = cpu_render_sample(args.batch_size, 4, threads)
+            line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": threads, "kind": "port",
+                                    "sample": f"oracle numpy/torch-CPU render_rays (port of the reference, fp32, not "
+                                              f"JAX), {rays_done} of the view's {args.width * args.height} rays in "
+                                              f"{args.batch_size}-ray chunks ({sec:.2f} s/chunk)"}
         else:
             line["cpu_baseline"] = None
+        return line
+    return None
+
+
+# every other BASELINE.json config, measured after the headline in the same run
+EXTRA_CONFIGS = [
+    ("configs[1] fp32 leg", dict(workload="train", model="nerf", precision="fp32", steps=5, warmup=3)),
+    ("configs[0]", dict(workload="image", model="nerf", precision="bf16", width=128, height=128, batch_size=1024,
+                        steps=10, warmup=3)),
+    ("configs[2]", dict(workload="train", model="ngp", steps=5, warmup=3)),
+    ("configs[3]", dict(workload="train", model="refnerf", steps=3, warmup=3)),
+    ("configs[4]", dict(workload="image", model="nerf", precision="bf16", width=800, height=800, batch_size=65536,
+                        steps=5, warmup=3)),
+]
+
+
+def run_ours(args):
+    import copy
+    import gc
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+    line = measure(args, rank, local_rank, world, dev, peaks)
+    headline = (args.workload, args.model, args.precision, args.rays) == ("train", "nerf", "bf16", None)
+    if args.extra and headline:
+        extras = []
+        for name, over in EXTRA_CONFIGS:
+            a = copy.copy(args)
+            a.ray_chunk = None
+            for k, v in over.items():
+                setattr(a, k, v)
+            gc.collect()
+            torch.cuda.empty_cache()
+            try:
+                sub = measure(a, rank, local_rank, world, dev, peaks)
+            except Exception as e:  # noqa: BLE001  (one failing extra must not lose the headline)
+                sub = {"error": repr(e)[:300]}
+                torch.cuda.synchronize()
+            if rank == 0 and sub is not None:
+                sub["name"] = name
+                extras.append(sub)
+        stages = None
+        if rank == 0:
+            gc.collect()
+            torch.cuda.empty_cache()
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "profiles"))
+                from stage_bench import run_stages
+                stages = run_stages(262144, dev, peaks["hbm"])
+            except Exception as e:  # noqa: BLE001
+                stages = [{"error": repr(e)[:300]}]
+        if world > 1:
+            torch.distributed.barrier()
+        if rank == 0:
+            line["extra_configs"] = extras
+            line["hbm_stages"] = stages
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()
@@ -454,6 +560,8 @@ def main():
     ap.add_argument("--ray_chunk", type=int, default=None)
     ap.add_argument("--cpu_rays", type=int, default=512, help="rays per step of the CPU sample")
     ap.add_argument("--no_cpu_baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--no_extra", dest="extra", action="store_false",
+                    help="headline only: skip the extra_configs / hbm_stages blocks")
     ap.add_argument("--no_cuda_graph", dest="cuda_graph", action="store_false",
                     help="run the end-to-end region with the eager step instead of the CUDA-graph replay")
     args = ap.parse_args()

@@ -1,6 +1,9 @@
 // bf16 tcgen05 path of the NeRF MLP, host side: weight packing (B-operand images), the debug GEMMs
 // that pin the UMMA descriptor encodings, per-device init and the forward dispatch.  The kernels
 // live in mlp_tc_fwd2.cu (forward), mlp_tc_bwd2.cu (dX chain) and mlp_tc_bwd.cu (dW).
+#include <stdlib.h>
+#include <string.h>
+
 #include "tc_common.cuh"
 
 namespace lnrf {
@@ -186,6 +189,16 @@ static bool g_tc_ready = false;
 int init_mlp_tc_bwd();  // mlp_tc_bwd.cu
 int init_mlp_tc_fwd2();  // mlp_tc_fwd2.cu
 int init_mlp_tc_bwd2();  // mlp_tc_bwd2.cu
+int init_mlp_tc_cta2_fwd();  // mlp_tc_cta2_fwd.cu
+int init_mlp_tc_cta2_bwd();  // mlp_tc_cta2_bwd.cu
+int c2_fwd_on_pack(const void* packed, cudaStream_t st);
+int c2_bwd_on_pack(const void* packed, const float* P, cudaStream_t st);
+int nerf_fwd_cta2(const void* packed, const float* x, const float* d, const float* rays, const float* ts, int64_t m,
+                  int T, bool save, const TcStash& stash, float* dens, float* rgb, cudaStream_t st);
+// Which forward / dX kernels run: the CTA-pair (cta_group::2) kernels, or the single-CTA "pair" kernels
+// of round 1 (LNRF_TC_KERNELS=pair, read once in lnrf_init: an A/B switch for profiling, not an API).
+static bool g_use_cta2 = true;
+bool tc_use_cta2() { return g_use_cta2; }
 int nerf_fwd_pair(const void* packed, const float* x, const float* d, const float* rays, const float* ts,
                   int64_t m, int T, bool save, const TcStash& stash, float* dens, float* rgb, cudaStream_t st);
 
@@ -205,6 +218,9 @@ int init_mlp_tc() {
   if ((rc = init_mlp_tc_bwd())) return rc;
   if ((rc = init_mlp_tc_fwd2())) return rc;
   if ((rc = init_mlp_tc_bwd2())) return rc;
+  if ((rc = init_mlp_tc_cta2_fwd())) return rc;
+  if ((rc = init_mlp_tc_cta2_bwd())) return rc;
+  if (const char* e = getenv("LNRF_TC_KERNELS")) g_use_cta2 = strcmp(e, "pair") != 0;
   g_tc_ready = true;
   return LNRF_OK;
 }
@@ -227,6 +243,7 @@ int nerf_fwd_tc(const float* P, const void* packed, const float* x, const float*
                  "1024-byte aligned", (long long)ws_bytes, (long long)tc_workspace_bytes(m, true));
     stash = carve_stash(ws, m);
   }
+  if (g_use_cta2) return nerf_fwd_cta2(packed, x, d, rays, ts, m, T, save, stash, dens, rgb, st);
   return nerf_fwd_pair(packed, x, d, rays, ts, m, T, save, stash, dens, rgb, st);
 }
 
@@ -235,7 +252,10 @@ int nerf_pack_weights(const float* P, void* packed, cudaStream_t st) {
   dim3 grid(8, kAllChunks + 1);
   pack_weights_kernel<<<grid, 256, 0, st>>>(P, reinterpret_cast<uint8_t*>(packed));
   LNRF_LAUNCH_CHECK("pack_weights_kernel");
-  return LNRF_OK;
+  // refresh this buffer's constant-bank slots (biases / head weights) behind the pack kernel
+  int rc = c2_fwd_on_pack(packed, st);
+  if (rc) return rc;
+  return c2_bwd_on_pack(packed, P, st);
 }
 
 int64_t nerf_packed_bytes() { return kPackedBytes; }

@@ -18,6 +18,8 @@ using namespace ptx;
 
 bool tc_ready();
 int nerf_bwd_dx_pair(const TcBwdArgs& a, cudaStream_t st);  // mlp_tc_bwd2.cu
+int nerf_bwd_dx_cta2(const TcBwdArgs& a, cudaStream_t st);  // mlp_tc_cta2_bwd.cu
+bool tc_use_cta2();
 int64_t tc_workspace_bytes(int64_t m, bool save);
 
 // ================================================================ dW
@@ -288,7 +290,7 @@ int nerf_bwd_tc(const float* P, const void* packed, int64_t m, void* ws, int64_t
 
   TcBwdArgs a{reinterpret_cast<const uint8_t*>(packed), P, dens, rgb, d_dens, d_rgb, m, s, G};
   {
-    const int rc = nerf_bwd_dx_pair(a, st);
+    const int rc = tc_use_cta2() ? nerf_bwd_dx_cta2(a, st) : nerf_bwd_dx_pair(a, st);
     if (rc) return rc;
   }
 
