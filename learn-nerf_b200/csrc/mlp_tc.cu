@@ -191,8 +191,6 @@ int init_mlp_tc_fwd2();  // mlp_tc_fwd2.cu
 int init_mlp_tc_bwd2();  // mlp_tc_bwd2.cu
 int init_mlp_tc_cta2_fwd();  // mlp_tc_cta2_fwd.cu
 int init_mlp_tc_cta2_bwd();  // mlp_tc_cta2_bwd.cu
-int c2_fwd_on_pack(const void* packed, cudaStream_t st);
-int c2_bwd_on_pack(const void* packed, const float* P, cudaStream_t st);
 int nerf_fwd_cta2(const void* packed, const float* x, const float* d, const float* rays, const float* ts, int64_t m,
                   int T, bool save, const TcStash& stash, float* dens, float* rgb, cudaStream_t st);
 // Which forward / dX kernels run: the CTA-pair (cta_group::2) kernels, or the single-CTA "pair" kernels
@@ -252,10 +250,7 @@ int nerf_pack_weights(const float* P, void* packed, cudaStream_t st) {
   dim3 grid(8, kAllChunks + 1);
   pack_weights_kernel<<<grid, 256, 0, st>>>(P, reinterpret_cast<uint8_t*>(packed));
   LNRF_LAUNCH_CHECK("pack_weights_kernel");
-  // refresh this buffer's constant-bank slots (biases / head weights) behind the pack kernel
-  int rc = c2_fwd_on_pack(packed, st);
-  if (rc) return rc;
-  return c2_bwd_on_pack(packed, P, st);
+  return LNRF_OK;
 }
 
 int64_t nerf_packed_bytes() { return kPackedBytes; }

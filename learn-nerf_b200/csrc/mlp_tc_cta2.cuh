@@ -31,13 +31,13 @@ namespace lnrf {
 
 constexpr int kC2Threads = 576;
 constexpr int kC2Stages = 4;
-constexpr int kSmallSlots = 4;  // constant-bank slots for per-model small parameters (see c2_slot_*)
 
 struct C2Smem {
   static constexpr uint32_t a_off = 0;                               // group 0 tile, then group 1 tile (5 blocks each)
   static constexpr uint32_t w_off = 2 * kPairTileBytes;              // 163,840: ring of 4 x 16 KB chunk halves
   static constexpr uint32_t bar_off = w_off + kC2Stages * kChunkBytes128;  // 229,376
-  static constexpr uint32_t total = bar_off + 256;
+  static constexpr uint32_t total = bar_off + 128 + 2048;
+  static constexpr uint32_t bias = 128;     // 2 groups x 256 floats: the current layer's biases (forward) / w9 (dX)
   static constexpr uint32_t full = 0;       // [4]
   static constexpr uint32_t empty = 32;     // [4]
   static constexpr uint32_t a_ready = 64;   // [2]
@@ -325,35 +325,6 @@ __device__ __forceinline__ void c2_teardown(const C2Ctx& c) {
   tc_fence_before();
   cluster_sync_all();  // no CTA may exit (or free TMEM) while its peer can still signal it / read its smem
   if ((threadIdx.x >> 5) == 16) tmem_dealloc2(c.tmem, 512);
-}
-
-// ---------------------------------------------------------------- host: constant-bank slots
-// The epilogues read per-model small parameters (biases, head weights) as constant-bank operands.
-// Each packed weight buffer owns one of kSmallSlots slots of a __constant__ array (per device), filled
-// when the weights are packed (lnrf_nerf_pack_weights) and looked up by the buffer's address at
-// launch: kernels of different models never share a slot, so they may run on different streams
-// concurrently.  With more than kSmallSlots live packed buffers per device the least recently used
-// slot is re-filled on the launching stream (stream-ordered; racy only against a still-running
-// kernel of the evicted model on ANOTHER stream).
-struct SlotTable {
-  struct Entry { int dev; const void* key; unsigned long long stamp; };
-  Entry e[kSmallSlots];
-  unsigned long long clock;
-};
-// returns the slot; *hit = the slot already held `key`
-static inline int slot_claim(SlotTable& t, int dev, const void* key, bool* hit) {
-  int lru = 0;
-  for (int i = 0; i < kSmallSlots; ++i) {
-    if (t.e[i].key == key && t.e[i].dev == dev) {
-      t.e[i].stamp = ++t.clock;
-      *hit = true;
-      return i;
-    }
-    if (t.e[i].stamp < t.e[lru].stamp) lru = i;
-  }
-  t.e[lru] = SlotTable::Entry{dev, key, ++t.clock};
-  *hit = false;
-  return lru;
 }
 
 }  // namespace lnrf

@@ -8,7 +8,6 @@
 // of the exact shared-memory image, which the dW kernel reads back as an MN-major UMMA operand.
 #include <stdlib.h>
 
-#include <mutex>
 
 #include "mlp_tc_cta2.cuh"
 
@@ -16,38 +15,43 @@ namespace lnrf {
 
 using namespace ptx;
 
-// head weights of the model being differentiated, one slot per packed model (see mlp_tc_cta2.cuh)
-struct BwdSmall2 {
-  float w9[256];       // Dense_9 kernel [256,1]
-  float w11[128 * 3];  // Dense_11 kernel [128,3]
-};
-static __constant__ BwdSmall2 c_bsmall2[kSmallSlots];
-
 struct C2BwdArgs {
   TcBwdArgs a;
-  int slot;
   int off_b9, off_b11;  // float offsets of the two head biases inside the flat gradient
+  int off_w9, off_w11;  // float offsets of the two head kernels inside the flat parameters
   C2Sched sched;
 };
 
-// 32 accumulator columns [cb + C0, +32) -> four 16-byte row chunks of the g tile.
-// FIRST: g8 = acc + spre * w9 (no mask, model.py:57); else g = acc where the forward activation was
-// positive (mask bit 31-j of `mwd` <-> column C0+j of the team's half).
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+// 32 accumulator columns [C0, C0 + 32) of the team's half -> four 16-byte row chunks of the g tile.
+// FIRST: g8 = acc + spre * w9 (no mask, model.py:57), w9 staged in shared memory (`sw9`) by the team; else
+// g = acc where the forward activation was positive (mask bit 31-j of `mwd` <-> column C0+j of the half).
 template <int C0, bool FIRST>
 __device__ __forceinline__ void c2_bwd_store32(const uint32_t (&v)[32], uint32_t blk0, int r, uint32_t mwd, float spre,
-                                               int slot, int cb) {
+                                               uint32_t sw9) {
   uint32_t pk[16];
 #pragma unroll
-  for (int j = 0; j < 32; j += 2) {
-    float f0, f1;
+  for (int j = 0; j < 32; j += 4) {
+    float f0, f1, f2, f3;
     if (FIRST) {
-      f0 = fmaf(spre, c_bsmall2[slot].w9[cb + C0 + j], __uint_as_float(v[j]));
-      f1 = fmaf(spre, c_bsmall2[slot].w9[cb + C0 + j + 1], __uint_as_float(v[j + 1]));
+      const float4 w = lds_f4(sw9 + (C0 + j) * 4);
+      f0 = fmaf(spre, w.x, __uint_as_float(v[j]));
+      f1 = fmaf(spre, w.y, __uint_as_float(v[j + 1]));
+      f2 = fmaf(spre, w.z, __uint_as_float(v[j + 2]));
+      f3 = fmaf(spre, w.w, __uint_as_float(v[j + 3]));
     } else {
       f0 = (mwd & (0x80000000u >> j)) ? __uint_as_float(v[j]) : 0.0f;
       f1 = (mwd & (0x80000000u >> (j + 1))) ? __uint_as_float(v[j + 1]) : 0.0f;
+      f2 = (mwd & (0x80000000u >> (j + 2))) ? __uint_as_float(v[j + 2]) : 0.0f;
+      f3 = (mwd & (0x80000000u >> (j + 3))) ? __uint_as_float(v[j + 3]) : 0.0f;
     }
     pk[j / 2] = pack_bf16x2(f0, f1);
+    pk[j / 2 + 1] = pack_bf16x2(f2, f3);
   }
   const uint32_t blk = blk0 + (C0 >> 6) * kABlockBytes;
   constexpr int cbase = (C0 & 63) >> 3;
@@ -57,21 +61,21 @@ __device__ __forceinline__ void c2_bwd_store32(const uint32_t (&v)[32], uint32_t
 }
 
 template <bool FIRST>
-__device__ __forceinline__ void c2_bwd_epi_half(uint32_t tm, uint32_t blk0, int r, const uint4& m4, float spre, int slot,
-                                                int cb) {
+__device__ __forceinline__ void c2_bwd_epi_half(uint32_t tm, uint32_t blk0, int r, const uint4& m4, float spre,
+                                                uint32_t sw9) {
   uint32_t va[32], vb[32];
   tmem_ld32(tm, va);
   tmem_wait_ld_dep(va);
   tmem_ld32(tm + 32, vb);
-  c2_bwd_store32<0, FIRST>(va, blk0, r, m4.x, spre, slot, cb);
+  c2_bwd_store32<0, FIRST>(va, blk0, r, m4.x, spre, sw9);
   tmem_wait_ld_dep(vb);
   tmem_ld32(tm + 64, va);
-  c2_bwd_store32<32, FIRST>(vb, blk0, r, m4.y, spre, slot, cb);
+  c2_bwd_store32<32, FIRST>(vb, blk0, r, m4.y, spre, sw9);
   tmem_wait_ld_dep(va);
   tmem_ld32(tm + 96, vb);
-  c2_bwd_store32<64, FIRST>(va, blk0, r, m4.z, spre, slot, cb);
+  c2_bwd_store32<64, FIRST>(va, blk0, r, m4.z, spre, sw9);
   tmem_wait_ld_dep(vb);
-  c2_bwd_store32<96, FIRST>(vb, blk0, r, m4.w, spre, slot, cb);
+  c2_bwd_store32<96, FIRST>(vb, blk0, r, m4.w, spre, sw9);
 }
 
 // One epilogue team: group g, column half H (compile-time: see c2_fwd_team).
@@ -84,12 +88,14 @@ __device__ __forceinline__ void c2_bwd_team(const C2BwdArgs& cargs, const C2Ctx&
     // ===== epilogue team (g, h): thread r owns row r of group g's tile, columns 128 h .. 128 h + 127
     const int r = tid & 127;
     const bool leader = r == 0;
-    const int slot = cargs.slot;
     const uint32_t sA = cx.sA0 + g * kPairTileBytes;
     const uint32_t blk0 = sA + 2 * h * kABlockBytes;
     const uint32_t tm = cx.tmem + (uint32_t((warp & 3) * 32) << 16) + g * 256 + h * 128;
     const uint32_t bar_a = cx.bars + C2Smem::a_ready + 8 * g, bar_acc = cx.bars + C2Smem::acc_full + 8 * g;
     const int64_t cid = cluster_id_x(), ncl = nclusters_x();
+    const uint32_t sw9 = cx.bars + C2Smem::bias + uint32_t(g * 256 + H * 128) * 4u;
+    const float4* w11v = reinterpret_cast<const float4*>(args.P + cargs.off_w11);  // Dense_11 kernel [128,3]
+    const float w9_mine = __ldg(args.P + cargs.off_w9 + H * 128 + r);              // Dense_9 kernel [256,1]
     float acc_db9 = 0.f, acc_db11[3] = {0.f, 0.f, 0.f};
     uint32_t par = 0;  // nine layers per tile: the barrier phase parity keeps alternating
     for (int64_t t = 0; t < cx.my_iters; ++t) {
@@ -121,14 +127,19 @@ __device__ __forceinline__ void c2_bwd_team(const C2BwdArgs& cargs, const C2Ctx&
           uint32_t pk[16];
           const uint32_t mwd = mc[c0 >> 5];
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float v0 = dp[0] * c_bsmall2[slot].w11[(c0 + j) * 3 + 0] + dp[1] * c_bsmall2[slot].w11[(c0 + j) * 3 + 1] +
-                       dp[2] * c_bsmall2[slot].w11[(c0 + j) * 3 + 2];
-            float v1 = dp[0] * c_bsmall2[slot].w11[(c0 + j) * 3 + 3] + dp[1] * c_bsmall2[slot].w11[(c0 + j) * 3 + 4] +
-                       dp[2] * c_bsmall2[slot].w11[(c0 + j) * 3 + 5];
+          for (int j = 0; j < 32; j += 4) {  // 4 columns = 12 head weights = three 16-byte read-only loads (L1 broadcast)
+            const float4 wa = __ldg(w11v + (c0 + j) * 3 / 4), wb = __ldg(w11v + (c0 + j) * 3 / 4 + 1),
+                         wc = __ldg(w11v + (c0 + j) * 3 / 4 + 2);
+            float v0 = dp[0] * wa.x + dp[1] * wa.y + dp[2] * wa.z;
+            float v1 = dp[0] * wa.w + dp[1] * wb.x + dp[2] * wb.y;
+            float v2 = dp[0] * wb.z + dp[1] * wb.w + dp[2] * wc.x;
+            float v3 = dp[0] * wc.y + dp[1] * wc.z + dp[2] * wc.w;
             v0 = (mwd & (0x80000000u >> j)) ? v0 : 0.0f;
             v1 = (mwd & (0x80000000u >> (j + 1))) ? v1 : 0.0f;
+            v2 = (mwd & (0x80000000u >> (j + 2))) ? v2 : 0.0f;
+            v3 = (mwd & (0x80000000u >> (j + 3))) ? v3 : 0.0f;
             pk[j / 2] = pack_bf16x2(v0, v1);
+            pk[j / 2 + 1] = pack_bf16x2(v2, v3);
           }
           const uint32_t blk = sA + (c0 >> 6) * kABlockBytes;
           const int cbase = (c0 & 63) >> 3;
@@ -164,9 +175,10 @@ __device__ __forceinline__ void c2_bwd_team(const C2BwdArgs& cargs, const C2Ctx&
         par ^= 1;
         tc_fence_after();
         if (leader) bulk_wait_read0();  // this team's previous image (the same two blocks) has left smem
+        if (tl == 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(sw9 + r * 4), "f"(w9_mine) : "memory");
         team_bar(team);
-        if (tl == 0) c2_bwd_epi_half<true>(tm, blk0, r, m4, spre, slot, h * 128);
-        else c2_bwd_epi_half<false>(tm, blk0, r, m4, 0.0f, slot, h * 128);
+        if (tl == 0) c2_bwd_epi_half<true>(tm, blk0, r, m4, spre, sw9);
+        else c2_bwd_epi_half<false>(tm, blk0, r, m4, 0.0f, sw9);
         fence_proxy_async_smem();
         team_bar(team);
         if (leader) {
@@ -218,48 +230,15 @@ C2Sched c2_make_sched(const ChunkInfo* tab, int n, int layers);  // mlp_tc_cta2_
 int c2_max_clusters();
 
 static C2Sched g_bwd_sched;
-static SlotTable g_bwd_slots[16];
-static std::mutex g_bwd_mu;
-
-static int bwd_slot(const void* packed, const float* P, cudaStream_t st, bool force_upload, int* slot_out) {
-  int dev = 0;
-  LNRF_CUDA(cudaGetDevice(&dev));
-  LNRF_REQUIRE(dev >= 0 && dev < 16, LNRF_E_UNSUPPORTED, "device ordinal %d >= 16", dev);
-  bool hit = false;
-  int slot;
-  {
-    std::lock_guard<std::mutex> lock(g_bwd_mu);
-    slot = slot_claim(g_bwd_slots[dev], dev, packed, &hit);
-  }
-  if (!hit || force_upload) {
-    const size_t base = size_t(slot) * sizeof(BwdSmall2);
-    LNRF_CUDA(cudaMemcpyToSymbolAsync(c_bsmall2, P + kNerf.w[9], 256 * sizeof(float), base + offsetof(BwdSmall2, w9),
-                                      cudaMemcpyDeviceToDevice, st));
-    LNRF_CUDA(cudaMemcpyToSymbolAsync(c_bsmall2, P + kNerf.w[11], 384 * sizeof(float), base + offsetof(BwdSmall2, w11),
-                                      cudaMemcpyDeviceToDevice, st));
-  }
-  *slot_out = slot;
-  return LNRF_OK;
-}
-
-int c2_bwd_on_pack(const void* packed, const float* P, cudaStream_t st) {
-  int slot;
-  return bwd_slot(packed, P, st, true, &slot);
-}
-
 int init_mlp_tc_cta2_bwd() {
   const ChunkTable t = build_chunk_table();
   g_bwd_sched = c2_make_sched(t.b, kBwChunks, kBwLayers);
-  LNRF_CUDA(cudaFuncSetAttribute(nerf_bwd_dx_cta2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)C2Smem::total));
+  LNRF_CUDA(cudaFuncSetAttribute(nerf_bwd_dx_cta2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2Smem::total));
   return LNRF_OK;
 }
 
 int nerf_bwd_dx_cta2(const TcBwdArgs& a, cudaStream_t st) {
-  int slot;
-  int rc = bwd_slot(a.packed, a.P, st, false, &slot);
-  if (rc) return rc;
-  C2BwdArgs ca{a, slot, int(kNerf.b[9]), int(kNerf.b[11]), g_bwd_sched};
+  C2BwdArgs ca{a, int(kNerf.b[9]), int(kNerf.b[11]), int(kNerf.w[9]), int(kNerf.w[11]), g_bwd_sched};
   const int64_t quads = (ceil_div(a.m, 128) + 3) / 4;
   int64_t clusters = c2_max_clusters();
   if (clusters > quads) clusters = quads;

@@ -10,7 +10,6 @@
 // stash (same format as before: the dX / dW kernels are unchanged consumers).
 #include <stdlib.h>
 
-#include <mutex>
 #include <type_traits>
 
 #include "mlp_tc_cta2.cuh"
@@ -19,9 +18,6 @@ namespace lnrf {
 
 using namespace ptx;
 
-// biases and the rgb head, one slot per packed model (see mlp_tc_cta2.cuh)
-static __constant__ SmallParams c_small2[kSmallSlots];
-
 struct C2FwdArgs {
   const uint8_t* packed;
   const float* x;
@@ -29,7 +25,6 @@ struct C2FwdArgs {
   const float* rays;
   const float* ts;
   int T;
-  int slot;
   int64_t m;
   float* dens;
   float* rgb;
@@ -45,22 +40,47 @@ __device__ __forceinline__ void c2_fast_sincos(float a, float* s, float* c) {
   *c = __cosf(r);
 }
 
-// bias + (ReLU) + bf16 pack of 32 accumulator columns [cb + C0, cb + C0 + 32) -> four 16-byte row chunks of the
-// A tile.  cb (= 128 h), TL and slot are warp-uniform: every bias is a constant-bank operand behind a uniform
-// register.  SAVE: also collects the 32 "pre-activation > 0" bits in `mword` (column j -> bit 31-j).
+// packed fp32x2 add (FADD2 on sm_100): {a0, a1} += {b0, b1}
+__device__ __forceinline__ void fadd2(float& a0, float& a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 x, y;\n\t"
+      "mov.b64 x, {%0, %1};\n\t"
+      "mov.b64 y, {%2, %3};\n\t"
+      "add.rn.f32x2 x, x, y;\n\t"
+      "mov.b64 {%0, %1}, x;\n\t}"
+      : "+f"(a0), "+f"(a1)
+      : "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+// bias + (ReLU) + bf16 pack of 32 accumulator columns [C0, C0 + 32) of the team's half -> four 16-byte row
+// chunks of the A tile.  The layer's 128 biases of this half sit in shared memory (`sbias`, staged by the
+// team itself, see c2_fwd_team): broadcast 16-byte loads + packed fp32x2 adds -- no constant bank, so the
+// ten layers share ONE copy of this code without paying an indexed constant load per bias, and nothing
+// per-model lives in process-wide memory (re-entrant).  SAVE: also collects the 32 "pre-activation > 0"
+// bits in `mword` (column j -> bit 31-j).
 template <bool RELU, int C0, bool SAVE>
-__device__ __forceinline__ void c2_epi_store32(const uint32_t (&v)[32], uint32_t blk0, int r, uint32_t& mword, int slot,
-                                               int TL, int cb) {
+__device__ __forceinline__ void c2_epi_store32(const uint32_t (&v)[32], uint32_t blk0, int r, uint32_t& mword,
+                                               uint32_t sbias) {
   uint32_t pk[16];
   uint32_t signs = 0;
 #pragma unroll
-  for (int j = 0; j < 32; j += 2) {
-    const float f0 = __uint_as_float(v[j]) + c_small2[slot].b[TL][cb + C0 + j];
-    const float f1 = __uint_as_float(v[j + 1]) + c_small2[slot].b[TL][cb + C0 + j + 1];
+  for (int j = 0; j < 32; j += 4) {
+    const float4 bv = lds_f4(sbias + (C0 + j) * 4);
+    float f0 = __uint_as_float(v[j]), f1 = __uint_as_float(v[j + 1]);
+    float f2 = __uint_as_float(v[j + 2]), f3 = __uint_as_float(v[j + 3]);
+    fadd2(f0, f1, bv.x, bv.y);
+    fadd2(f2, f3, bv.z, bv.w);
     pk[j / 2] = RELU ? pack_bf16x2_relu(f0, f1) : pack_bf16x2(f0, f1);
+    pk[j / 2 + 1] = RELU ? pack_bf16x2_relu(f2, f3) : pack_bf16x2(f2, f3);
     if (SAVE && RELU) {
       signs = __funnelshift_l(__float_as_uint(f0), signs, 1);
       signs = __funnelshift_l(__float_as_uint(f1), signs, 1);
+      signs = __funnelshift_l(__float_as_uint(f2), signs, 1);
+      signs = __funnelshift_l(__float_as_uint(f3), signs, 1);
     }
   }
   mword = ~signs;
@@ -73,26 +93,27 @@ __device__ __forceinline__ void c2_epi_store32(const uint32_t (&v)[32], uint32_t
 
 // the team's 128 accumulator columns of a hidden layer -> its two A blocks
 template <bool RELU, bool SAVE>
-__device__ __forceinline__ void c2_epi_half(uint32_t tm, uint32_t blk0, int r, uint32_t (&mw)[4], int slot, int TL,
-                                            int cb) {
+__device__ __forceinline__ void c2_epi_half(uint32_t tm, uint32_t blk0, int r, uint32_t (&mw)[4], uint32_t sbias) {
   uint32_t va[32], vb[32];
   tmem_ld32(tm, va);
   tmem_wait_ld_dep(va);
   tmem_ld32(tm + 32, vb);
-  c2_epi_store32<RELU, 0, SAVE>(va, blk0, r, mw[0], slot, TL, cb);
+  c2_epi_store32<RELU, 0, SAVE>(va, blk0, r, mw[0], sbias);
   tmem_wait_ld_dep(vb);
   tmem_ld32(tm + 64, va);
-  c2_epi_store32<RELU, 32, SAVE>(vb, blk0, r, mw[1], slot, TL, cb);
+  c2_epi_store32<RELU, 32, SAVE>(vb, blk0, r, mw[1], sbias);
   tmem_wait_ld_dep(va);
   tmem_ld32(tm + 96, vb);
-  c2_epi_store32<RELU, 64, SAVE>(va, blk0, r, mw[2], slot, TL, cb);
+  c2_epi_store32<RELU, 64, SAVE>(va, blk0, r, mw[2], sbias);
   tmem_wait_ld_dep(vb);
-  c2_epi_store32<RELU, 96, SAVE>(vb, blk0, r, mw[3], slot, TL, cb);
+  c2_epi_store32<RELU, 96, SAVE>(vb, blk0, r, mw[3], sbias);
 }
 
-// One epilogue team: group g (0/1), column half H (compile-time so that every bias index is
-// "uniform register + immediate": with a thread-derived half the compiler falls back to one indexed LDC
-// per bias and the epilogue becomes MIO-bound, measured 3.7 k instead of ~2 k clk per layer).
+// One epilogue team: group g (0/1), column half H.  Per layer the team stages its 128 biases in shared
+// memory: every thread fetches ONE value from the packed buffer's SmallParams image before it waits for
+// the accumulator (latency hidden), stores it after the wait, and the team barrier publishes it.  No
+// barrier is needed before the next layer overwrites the buffer: that layer's accumulator only
+// completes after every thread of the team has arrived on a_ready, i.e. finished reading this layer's.
 template <bool SAVE, int H>
 __device__ __forceinline__ void c2_fwd_team(const C2FwdArgs& args, const C2Ctx& cx, int g, int64_t tiles) {
   constexpr int h = H;
@@ -101,12 +122,13 @@ __device__ __forceinline__ void c2_fwd_team(const C2FwdArgs& args, const C2Ctx& 
     // ===== epilogue team (g, h): thread r owns row r of group g's tile, columns 128 h .. 128 h + 127
     const int r = tid & 127;
     const bool leader = r == 0;
-    const int slot = args.slot;
     const uint32_t sA = cx.sA0 + g * kPairTileBytes;
     const uint32_t blk0 = sA + 2 * h * kABlockBytes;
     const uint32_t tm = cx.tmem + (uint32_t((warp & 3) * 32) << 16) + g * 256 + h * 128;
     const uint32_t bar_a = cx.bars + C2Smem::a_ready + 8 * g, bar_acc = cx.bars + C2Smem::acc_full + 8 * g;
     const int64_t cid = cluster_id_x(), ncl = nclusters_x();
+    const SmallParams* small = reinterpret_cast<const SmallParams*>(args.packed + kSmallOffset);
+    const uint32_t sbias = cx.bars + C2Smem::bias + uint32_t(g * 256 + H * 128) * 4u;
     uint32_t de[12];  // d_emb of the current tile (team 1 only)
 
     // inputs + sinusoidal_emb of tile `tile` -> A block 4 (x_emb) and `de` (d_emb); team h == 1 only
@@ -183,10 +205,10 @@ __device__ __forceinline__ void c2_fwd_team(const C2FwdArgs& args, const C2Ctx& 
       uint4* mask_row = (SAVE && tile_ok) ? reinterpret_cast<uint4*>(args.stash.MASK + ((tile * 9) * 128 + r) * 8) + h
                                           : nullptr;
       // ---- hidden layers T0..T8 (ten layers per tile: the barrier parity of layer TL is TL & 1).  T0..T7 share
-      // one copy of the code (runtime TL, a uniform register); T8 (no ReLU, d_emb) is its own instance.
-      auto layer = [&](auto tl_c, auto last_c) {
-        constexpr int TL = decltype(tl_c)::value;
+      // one copy of the code (runtime TL); T8 (no ReLU, d_emb) is its own instance.
+      auto layer = [&](int TL, auto last_c) {
         constexpr bool LAST = decltype(last_c)::value;
+        const float bval = __ldg(&small->b[TL][H * 128 + r]);  // in flight while we wait for the accumulator
 #ifdef LNRF_C2_TRACE
         const long long E0 = clock64();
 #endif
@@ -195,12 +217,17 @@ __device__ __forceinline__ void c2_fwd_team(const C2FwdArgs& args, const C2Ctx& 
 #ifdef LNRF_C2_TRACE
         const long long E1 = clock64();
 #endif
-        if (SAVE) {  // this team's previous image (same two blocks) must have left shared memory
-          if (leader) bulk_wait_read0();
-          team_bar(team);
-        }
+        if (SAVE && leader) bulk_wait_read0();  // this team's previous image (same two blocks) has left smem
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sbias + r * 4), "f"(bval) : "memory");
+        team_bar(team);
+#ifdef LNRF_C2_TRACE
+        const long long Ea = clock64();
+#endif
         uint32_t mw[4];
-        c2_epi_half<!LAST, SAVE>(tm, blk0, r, mw, slot, TL, h * 128);  // Dense_8 feeds the heads raw (model.py:53-58)
+        c2_epi_half<!LAST, SAVE>(tm, blk0, r, mw, sbias);  // Dense_8 feeds the heads raw (model.py:53-58)
+#ifdef LNRF_C2_TRACE
+        const long long Eb = clock64();
+#endif
         if (SAVE && !LAST && mask_row) mask_row[TL * 256] = make_uint4(mw[0], mw[1], mw[2], mw[3]);
         if (LAST && h == 1) {  // x_emb is dead after T5: block 4 now carries d_emb (24 cols) + zeros
           const uint32_t blk = sA + 4 * kABlockBytes;
@@ -221,31 +248,32 @@ __device__ __forceinline__ void c2_fwd_team(const C2FwdArgs& args, const C2Ctx& 
             bulk_commit();
           }
         }
+#ifdef LNRF_C2_TRACE
+        const long long Ed = clock64();
+#endif
         c2_arrive_a(bar_a, cx.rank);
 #ifdef LNRF_C2_TRACE
         if (leader && cid == 0 && cx.rank == 0 && t < 3) {
-          const int base = 1024 + int(((t * 10 + TL) * 4 + team) * 3);
-          C2_TRACE(base, E0); C2_TRACE(base + 1, E1); C2_TRACE(base + 2, clock64());
+          const int base = 1024 + int(((t * 10 + TL) * 4 + team) * 6);
+          C2_TRACE(base, E0); C2_TRACE(base + 1, E1); C2_TRACE(base + 2, Ea); C2_TRACE(base + 3, Eb);
+          C2_TRACE(base + 4, Ed); C2_TRACE(base + 5, clock64());
         }
 #endif
       };
-      layer(std::integral_constant<int, 0>{}, std::false_type{});
-      layer(std::integral_constant<int, 1>{}, std::false_type{});
-      layer(std::integral_constant<int, 2>{}, std::false_type{});
-      layer(std::integral_constant<int, 3>{}, std::false_type{});
-      layer(std::integral_constant<int, 4>{}, std::false_type{});
-      layer(std::integral_constant<int, 5>{}, std::false_type{});
-      layer(std::integral_constant<int, 6>{}, std::false_type{});
-      layer(std::integral_constant<int, 7>{}, std::false_type{});
-      layer(std::integral_constant<int, 8>{}, std::true_type{});
-      // ---- T9: colour layer (columns 0..127, team 0) + density column 128 (team 1) and the fp32 rgb head
+#pragma unroll 1
+      for (int TL = 0; TL < 8; ++TL) layer(TL, std::false_type{});
+      layer(8, std::true_type{});
+      // ---- T9: colour layer (columns 0..127, team 0) + density column 128 (team 1) and the fp32 rgb head.
+      // b10 is staged like a hidden layer's bias; the 128 x 3 rgb head weights are read with 16-byte
+      // read-only loads (every thread the same address: an L1 broadcast, once per tile).
+      const float bval9 = h == 0 ? __ldg(&small->b10[r]) : __ldg(&small->b9);
       mbar_wait(bar_acc, 1u);
       tc_fence_after();
       if (h == 0) {
-        if (SAVE) {  // blocks 0,1 get the colour-hidden image once the z8 image has left smem
-          if (leader) bulk_wait_read0();
-          team_bar(team);
-        }
+        if (SAVE && leader) bulk_wait_read0();  // blocks 0,1 get the colour-hidden image once the z8 image has left smem
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sbias + r * 4), "f"(bval9) : "memory");
+        team_bar(team);
+        const float4* w11v = reinterpret_cast<const float4*>(small->w11);
         float o0 = 0.f, o1 = 0.f, o2 = 0.f;
         uint32_t mwc[4];
 #pragma unroll
@@ -256,20 +284,24 @@ __device__ __forceinline__ void c2_fwd_team(const C2FwdArgs& args, const C2Ctx& 
           uint32_t pk[16];
           uint32_t signs = 0;
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const float p0 = __uint_as_float(v[j]) + c_small2[slot].b10[c0 + j];
-            const float p1 = __uint_as_float(v[j + 1]) + c_small2[slot].b10[c0 + j + 1];
-            const float h0 = fmaxf(p0, 0.0f), h1 = fmaxf(p1, 0.0f);  // model.py:59
-            o0 = fmaf(h0, c_small2[slot].w11[(c0 + j) * 3 + 0], o0);
-            o1 = fmaf(h0, c_small2[slot].w11[(c0 + j) * 3 + 1], o1);
-            o2 = fmaf(h0, c_small2[slot].w11[(c0 + j) * 3 + 2], o2);
-            o0 = fmaf(h1, c_small2[slot].w11[(c0 + j) * 3 + 3], o0);
-            o1 = fmaf(h1, c_small2[slot].w11[(c0 + j) * 3 + 4], o1);
-            o2 = fmaf(h1, c_small2[slot].w11[(c0 + j) * 3 + 5], o2);
+          for (int j = 0; j < 32; j += 4) {  // 4 columns: 4 biases (one 16-byte smem load), 12 head weights (three 16-byte loads)
+            const float4 bv = lds_f4(sbias + (c0 + j) * 4);
+            const float4 wa = __ldg(w11v + (c0 + j) * 3 / 4), wb = __ldg(w11v + (c0 + j) * 3 / 4 + 1),
+                         wc = __ldg(w11v + (c0 + j) * 3 / 4 + 2);
+            const float p0 = __uint_as_float(v[j]) + bv.x, p1 = __uint_as_float(v[j + 1]) + bv.y;
+            const float p2 = __uint_as_float(v[j + 2]) + bv.z, p3 = __uint_as_float(v[j + 3]) + bv.w;
+            const float h0 = fmaxf(p0, 0.0f), h1 = fmaxf(p1, 0.0f), h2 = fmaxf(p2, 0.0f), h3 = fmaxf(p3, 0.0f);  // model.py:59
+            o0 = fmaf(h0, wa.x, o0); o1 = fmaf(h0, wa.y, o1); o2 = fmaf(h0, wa.z, o2);
+            o0 = fmaf(h1, wa.w, o0); o1 = fmaf(h1, wb.x, o1); o2 = fmaf(h1, wb.y, o2);
+            o0 = fmaf(h2, wb.z, o0); o1 = fmaf(h2, wb.w, o1); o2 = fmaf(h2, wc.x, o2);
+            o0 = fmaf(h3, wc.y, o0); o1 = fmaf(h3, wc.z, o1); o2 = fmaf(h3, wc.w, o2);
             if (SAVE) {
               pk[j / 2] = pack_bf16x2(h0, h1);
+              pk[j / 2 + 1] = pack_bf16x2(h2, h3);
               signs = __funnelshift_l(__float_as_uint(p0), signs, 1);
               signs = __funnelshift_l(__float_as_uint(p1), signs, 1);
+              signs = __funnelshift_l(__float_as_uint(p2), signs, 1);
+              signs = __funnelshift_l(__float_as_uint(p3), signs, 1);
             }
           }
           if (SAVE) {
@@ -283,9 +315,9 @@ __device__ __forceinline__ void c2_fwd_team(const C2FwdArgs& args, const C2Ctx& 
         }
         if (SAVE && mask_row) mask_row[8 * 256] = make_uint4(mwc[0], mwc[1], mwc[2], mwc[3]);
         if (valid) {
-          args.rgb[s * 3 + 0] = tanhf(o0 + c_small2[slot].b11[0]);  // model.py:60
-          args.rgb[s * 3 + 1] = tanhf(o1 + c_small2[slot].b11[1]);
-          args.rgb[s * 3 + 2] = tanhf(o2 + c_small2[slot].b11[2]);
+          args.rgb[s * 3 + 0] = tanhf(o0 + __ldg(&small->b11[0]));  // model.py:60
+          args.rgb[s * 3 + 1] = tanhf(o1 + __ldg(&small->b11[1]));
+          args.rgb[s * 3 + 2] = tanhf(o2 + __ldg(&small->b11[2]));
         }
         if (SAVE) {
           fence_proxy_async_smem();
@@ -299,7 +331,7 @@ __device__ __forceinline__ void c2_fwd_team(const C2FwdArgs& args, const C2Ctx& 
         uint32_t v[32];
         tmem_ld32(tm, v);  // team 1's first column = accumulator column 128 = Dense_9 pre-activation
         tmem_wait_ld_dep(v);
-        if (valid) args.dens[s] = softplus_f(__uint_as_float(v[0]) + c_small2[slot].b9);  // model.py:57
+        if (valid) args.dens[s] = softplus_f(__uint_as_float(v[0]) + bval9);  // model.py:57
         if (t + 1 < cx.my_iters) prologue(tile_of(t + 1));  // T9's MMAs are complete: block 4 is free
       }
       if (t + 1 < cx.my_iters) {
@@ -333,33 +365,7 @@ nerf_fwd_cta2_kernel(const __grid_constant__ C2FwdArgs args) {
 
 // ---------------------------------------------------------------- host side
 static C2Sched g_fwd_sched;
-static SlotTable g_fwd_slots[16];
-static std::mutex g_fwd_mu;
 static int g_max_clusters = 0;
-
-static int fwd_slot(const void* packed, cudaStream_t st, bool force_upload, int* slot_out) {
-  int dev = 0;
-  LNRF_CUDA(cudaGetDevice(&dev));
-  LNRF_REQUIRE(dev >= 0 && dev < 16, LNRF_E_UNSUPPORTED, "device ordinal %d >= 16", dev);
-  bool hit = false;
-  int slot;
-  {
-    std::lock_guard<std::mutex> lock(g_fwd_mu);
-    slot = slot_claim(g_fwd_slots[dev], dev, packed, &hit);
-  }
-  if (!hit || force_upload)
-    LNRF_CUDA(cudaMemcpyToSymbolAsync(c_small2, reinterpret_cast<const uint8_t*>(packed) + kSmallOffset,
-                                      sizeof(SmallParams), size_t(slot) * sizeof(SmallParams),
-                                      cudaMemcpyDeviceToDevice, st));
-  *slot_out = slot;
-  return LNRF_OK;
-}
-
-// called by lnrf_nerf_pack_weights after the pack kernel (same stream): refresh this buffer's slot
-int c2_fwd_on_pack(const void* packed, cudaStream_t st) {
-  int slot;
-  return fwd_slot(packed, st, true, &slot);
-}
 
 C2Sched c2_make_sched(const ChunkInfo* tab, int n, int layers) {
   C2Sched s{};
@@ -372,18 +378,19 @@ C2Sched c2_make_sched(const ChunkInfo* tab, int n, int layers) {
     const int cnt = j - i;
     const bool shared = cnt <= kC2Stages;
     int slot_of[8];
-    for (int g = 0; g < 2; ++g)
+    for (int gi = 0; gi < 2; ++gi)
       for (int c = 0; c < cnt; ++c) {
+        const int g = gi;
         C2Step st{};
         st.offset = tab[i + c].offset;
         st.n = uint16_t(tab[i + c].n);
         st.ablock = uint8_t(tab[i + c].ablock);
         st.flags = uint8_t((g ? S_G1 : 0) | (c == 0 ? S_FIRST : 0) | (c == cnt - 1 ? S_LAST : 0));
-        if (!shared || g == 0) {
+        if (!shared || gi == 0) {
           st.flags |= S_LOAD;
           slot_of[c] = loads++ % kC2Stages;
         }
-        if (!shared || g == 1) st.flags |= S_RELEASE;
+        if (!shared || gi == 1) st.flags |= S_RELEASE;
         st.slot = uint8_t(slot_of[c]);
         s.step[s.steps++] = st;
       }
@@ -397,10 +404,8 @@ int c2_max_clusters() { return g_max_clusters; }
 int init_mlp_tc_cta2_fwd() {
   const ChunkTable t = build_chunk_table();
   g_fwd_sched = c2_make_sched(t.f, kTcChunks, kTcLayers);
-  LNRF_CUDA(cudaFuncSetAttribute(nerf_fwd_cta2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)C2Smem::total));
-  LNRF_CUDA(cudaFuncSetAttribute(nerf_fwd_cta2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)C2Smem::total));
+  LNRF_CUDA(cudaFuncSetAttribute(nerf_fwd_cta2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2Smem::total));
+  LNRF_CUDA(cudaFuncSetAttribute(nerf_fwd_cta2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2Smem::total));
   // how many CTA pairs the device can hold at once (one per TPC with this much shared memory)
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(unsigned(sm_count()), 1, 1);
@@ -421,15 +426,13 @@ int init_mlp_tc_cta2_fwd() {
 
 int nerf_fwd_cta2(const void* packed, const float* x, const float* d, const float* rays, const float* ts, int64_t m,
                   int T, bool save, const TcStash& stash, float* dens, float* rgb, cudaStream_t st) {
-  int slot;
-  int rc = fwd_slot(packed, st, false, &slot);
-  if (rc) return rc;
-  C2FwdArgs a{reinterpret_cast<const uint8_t*>(packed), x, d, rays, ts, T, slot, m, dens, rgb, stash, g_fwd_sched};
+  C2FwdArgs a{reinterpret_cast<const uint8_t*>(packed), x, d, rays, ts, T, m, dens, rgb, stash, g_fwd_sched};
   const int64_t quads = (ceil_div(m, 128) + 3) / 4;
   int64_t clusters = g_max_clusters;
   if (clusters > quads) clusters = quads;
-  if (save) nerf_fwd_cta2_kernel<true><<<unsigned(clusters * 2), kC2Threads, C2Smem::total, st>>>(a);
-  else nerf_fwd_cta2_kernel<false><<<unsigned(clusters * 2), kC2Threads, C2Smem::total, st>>>(a);
+  const unsigned grid = unsigned(clusters * 2);
+  if (save) nerf_fwd_cta2_kernel<true><<<grid, kC2Threads, C2Smem::total, st>>>(a);
+  else nerf_fwd_cta2_kernel<false><<<grid, kC2Threads, C2Smem::total, st>>>(a);
   LNRF_LAUNCH_CHECK("nerf_fwd_cta2_kernel");
   return LNRF_OK;
 }

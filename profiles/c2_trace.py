@@ -33,10 +33,10 @@ for t in range(2):
             b = ((t * 10 + L) * 2 + g) * 4
             T0, T1, T2, fw = a[b:b + 4]
             print(f"  t{t} L{L} g{g}: a_wait {T1 - T0:6d}  issue {T2 - T1:6d}  full_wait {fw:6d}   @ {T0 - t00:8d}")
-print("epilogue teams: (t,TL,team) acc-wait  epilogue  start(rel)")
+print("epilogue teams: (t,TL,team) acc-wait | stash-read wait+bar | tmem->smem | bar+bulk issue | arrive | start(rel)")
 for t in range(2):
     for TL in range(9):
         for team in range(4):
-            b = 1024 + ((t * 10 + TL) * 4 + team) * 3
-            E0, E1, E2 = a[b:b + 3]
-            print(f"  t{t} TL{TL} team{team}: acc_wait {E1 - E0:6d}  epi {E2 - E1:6d}   @ {E0 - t00:8d}")
+            b = 1024 + ((t * 10 + TL) * 4 + team) * 6
+            E0, E1, Ea, Eb, Ed, E2 = a[b:b + 6]
+            print(f"  t{t} TL{TL} team{team}: acc_wait {E1 - E0:6d} | {Ea - E1:5d} | {Eb - Ea:5d} | {Ed - Eb:5d} | {E2 - Ed:4d} |  @ {E0 - t00:8d}")
