@@ -1,6 +1,6 @@
 // bf16 tcgen05 path of the NeRF MLP, host side: weight packing (B-operand images), the debug GEMMs
 // that pin the UMMA descriptor encodings, per-device init and the forward dispatch.  The kernels
-// live in mlp_tc_fwd2.cu (forward), mlp_tc_bwd2.cu (dX chain) and mlp_tc_bwd.cu (dW).
+// live in mlp_tc_cta2_fwd.cu (forward), mlp_tc_cta2_bwd.cu (dX chain) and mlp_tc_bwd.cu (dW).
 #include <stdlib.h>
 #include <string.h>
 
@@ -29,10 +29,7 @@ pack_weights_kernel(const float* __restrict__ P, uint8_t* __restrict__ packed) {
     }
     return;
   }
-  const ChunkInfo c = ci < kTcChunks ? c_chunks.f[ci]
-                      : ci < kTcChunks + kBwChunks ? c_chunks.b[ci - kTcChunks]
-                      : ci < kTcChunks + kBwChunks + kF2Chunks ? c_chunks.f2[ci - kTcChunks - kBwChunks]
-                                                                : c_chunks.b2[ci - kTcChunks - kBwChunks - kF2Chunks];
+  const ChunkInfo c = ci < kTcChunks ? c_chunks.f[ci] : c_chunks.b[ci - kTcChunks];
   const int items = c.n * 8;
   const int out_dim = c_nerf.out[c.layer];
   const float* W = P + c_nerf.w[c.layer];
@@ -187,19 +184,10 @@ debug_umma_gemm_tn_kernel(const float* __restrict__ At, const float* __restrict_
 static bool g_tc_ready = false;
 
 int init_mlp_tc_bwd();  // mlp_tc_bwd.cu
-int init_mlp_tc_fwd2();  // mlp_tc_fwd2.cu
-int init_mlp_tc_bwd2();  // mlp_tc_bwd2.cu
 int init_mlp_tc_cta2_fwd();  // mlp_tc_cta2_fwd.cu
 int init_mlp_tc_cta2_bwd();  // mlp_tc_cta2_bwd.cu
 int nerf_fwd_cta2(const void* packed, const float* x, const float* d, const float* rays, const float* ts, int64_t m,
                   int T, bool save, const TcStash& stash, float* dens, float* rgb, cudaStream_t st);
-// Which forward / dX kernels run: the CTA-pair (cta_group::2) kernels, or the single-CTA "pair" kernels
-// of round 1 (LNRF_TC_KERNELS=pair, read once in lnrf_init: an A/B switch for profiling, not an API).
-static bool g_use_cta2 = true;
-bool tc_use_cta2() { return g_use_cta2; }
-int nerf_fwd_pair(const void* packed, const float* x, const float* d, const float* rays, const float* ts,
-                  int64_t m, int T, bool save, const TcStash& stash, float* dens, float* rgb, cudaStream_t st);
-
 template <typename K>
 static int set_smem(K kernel, int bytes) {
   LNRF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -214,11 +202,8 @@ int init_mlp_tc() {
   if ((rc = set_smem(debug_umma_gemm_kernel, 200 * 1024))) return rc;
   if ((rc = set_smem(debug_umma_gemm_tn_kernel, 200 * 1024))) return rc;
   if ((rc = init_mlp_tc_bwd())) return rc;
-  if ((rc = init_mlp_tc_fwd2())) return rc;
-  if ((rc = init_mlp_tc_bwd2())) return rc;
   if ((rc = init_mlp_tc_cta2_fwd())) return rc;
   if ((rc = init_mlp_tc_cta2_bwd())) return rc;
-  if (const char* e = getenv("LNRF_TC_KERNELS")) g_use_cta2 = strcmp(e, "pair") != 0;
   g_tc_ready = true;
   return LNRF_OK;
 }
@@ -241,8 +226,7 @@ int nerf_fwd_tc(const float* P, const void* packed, const float* x, const float*
                  "1024-byte aligned", (long long)ws_bytes, (long long)tc_workspace_bytes(m, true));
     stash = carve_stash(ws, m);
   }
-  if (g_use_cta2) return nerf_fwd_cta2(packed, x, d, rays, ts, m, T, save, stash, dens, rgb, st);
-  return nerf_fwd_pair(packed, x, d, rays, ts, m, T, save, stash, dens, rgb, st);
+  return nerf_fwd_cta2(packed, x, d, rays, ts, m, T, save, stash, dens, rgb, st);
 }
 
 int nerf_pack_weights(const float* P, void* packed, cudaStream_t st) {

@@ -1,7 +1,7 @@
 // K6 on the tensor cores: backward of the NeRF MLP (what jax.grad derives from
 // model.py:42-62 at train.py:90) as two tcgen05/TMEM kernels over the forward's stash.
 //
-//  dX chain: mlp_tc_bwd2.cu (per tile: head gradients, then g_{l-1} = (g_l @ W_l^T) * relu' for
+//  dX chain: mlp_tc_cta2_bwd.cu (per tile: head gradients, then g_{l-1} = (g_l @ W_l^T) * relu' for
 //      l = 8..1 on the tensor cores, every g_l tile image streamed to the stash).
 //  nerf_bwd_dw_kernel  "dW": dW_l = act_{l-1}^T @ g_l summed over all samples.  Both operands
 //      are the stashed tile images read as MN-major UMMA operands (K = samples); each CTA
@@ -17,9 +17,7 @@ namespace lnrf {
 using namespace ptx;
 
 bool tc_ready();
-int nerf_bwd_dx_pair(const TcBwdArgs& a, cudaStream_t st);  // mlp_tc_bwd2.cu
 int nerf_bwd_dx_cta2(const TcBwdArgs& a, cudaStream_t st);  // mlp_tc_cta2_bwd.cu
-bool tc_use_cta2();
 int64_t tc_workspace_bytes(int64_t m, bool save);
 
 // ================================================================ dW
@@ -290,7 +288,7 @@ int nerf_bwd_tc(const float* P, const void* packed, int64_t m, void* ws, int64_t
 
   TcBwdArgs a{reinterpret_cast<const uint8_t*>(packed), P, dens, rgb, d_dens, d_rgb, m, s, G};
   {
-    const int rc = tc_use_cta2() ? nerf_bwd_dx_cta2(a, st) : nerf_bwd_dx_pair(a, st);
+    const int rc = nerf_bwd_dx_cta2(a, st);
     if (rc) return rc;
   }
 

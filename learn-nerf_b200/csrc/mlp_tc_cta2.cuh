@@ -25,9 +25,34 @@
 // The MMA issuer, both producers and the relay walk the SAME static order (tile quad, layer, group,
 // chunk), so no barrier can be waited on out of order.
 #pragma once
-#include "mlp_tc_pair.cuh"
+#include "tc_common.cuh"
 
 namespace lnrf {
+
+constexpr uint32_t kPairTileBytes = 5 * kABlockBytes;  // one group's A tile: 4 activation blocks + embedding block
+
+// tcgen05.wait::ld that also carries a register dependency on the loaded values, so the
+// compiler cannot schedule their consumers above the wait.
+__device__ __forceinline__ void tmem_wait_ld_dep(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]),
+                 "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]),
+                 "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]),
+                 "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]),
+                 "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 
 constexpr int kC2Threads = 576;
 constexpr int kC2Stages = 4;

@@ -461,3 +461,37 @@ def test_cuda_graph_step_matches_eager(precision):
     uc, uf = dev(make_uniforms(256, 64, 1)), dev(make_uniforms(256, 128, 2))
     logs = sa((uc, uf), batch)
     assert np.isfinite(float(logs["fine"])) and a.state.step == 12
+
+
+def test_two_models_on_two_streams_match_serial():
+    """Re-entrancy of the boundary ("no mutable globals after lnrf_init"): the coarse and the
+    fine model -- different weights -- run their bf16 tcgen05 forward concurrently on two CUDA streams,
+    eight times in a row, and every result equals the serial run bit for bit.  (Round 1 staged each
+    model's biases in one __constant__ symbol before every launch: two streams raced.)"""
+    from learn_nerf.model import NeRFModel
+    _, _, nerf, params = oracle_setup()
+    n, T = 2048, 48  # 98,304 samples: 768 tiles, enough for both kernels to be resident together
+    rs = np.random.RandomState(3)
+    rays = dev(make_rays(n, seed=77, with_targets=False))
+    ts = torch.sort(torch.rand(n, T, device="cuda") * 2 + 3, dim=1).values.contiguous()
+    models = [NeRFModel(precision="bf16"), NeRFModel(precision="bf16")]
+    trees = [to_native(models[0], params["coarse"]), to_native(models[1], params["fine"])]
+    serial = []
+    for m, t in zip(models, trees):
+        d, c, _, _ = m.apply_rays(t, rays, ts)
+        serial.append((d.clone(), c.clone()))
+    torch.cuda.synchronize()
+    assert not torch.equal(serial[0][0], serial[1][0])  # the two models really differ
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for rep in range(8):
+        outs = [None, None]
+        for i in (0, 1):
+            streams[i].wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(streams[i]):
+                d, c, _, _ = models[i].apply_rays(trees[i], rays, ts)
+                outs[i] = (d, c)
+        for st in streams:
+            torch.cuda.current_stream().wait_stream(st)
+        torch.cuda.synchronize()
+        for i in (0, 1):
+            assert torch.equal(outs[i][0], serial[i][0]) and torch.equal(outs[i][1], serial[i][1]), (rep, i)
