@@ -215,7 +215,7 @@ def build_models(args, dev):
         from learn_nerf.instant_ngp import InstantNGPModel
         mk = lambda L: InstantNGPModel(table_sizes=[2 ** 18] * L,
                                        grid_sizes=[2 ** (4 + i // 2) for i in range(L)],
-                                       bbox_min=[-1.0] * 3, bbox_max=[1.0] * 3)
+                                       bbox_min=[-1.0] * 3, bbox_max=[1.0] * 3, precision=args.precision)
         return mk(6), mk(16), dict(adam_eps=1e-15, adam_b1=0.9, adam_b2=0.99)
     if args.model == "refnerf":
         from learn_nerf.ref_nerf import RefNERFModel
@@ -246,7 +246,7 @@ def measure(args, rank, local_rank, world, dev, peaks):
     from learn_nerf.train import TrainLoop
 
     n = args.rays or (32768 if args.model in ("ngp", "ngpref") else 4096)
-    prec = args.precision if args.model == "nerf" else "fp32"
+    prec = args.precision if args.model in ("nerf", "ngp") else "fp32"
     if args.model == "refnerf" and args.ray_chunk is None and n > 2048:
         args.ray_chunk = 2048  # 24 KB of saved activations per sample: keep the workspace near 10 GB
     coarse, fine, train_kwargs = build_models(args, dev)
@@ -383,7 +383,8 @@ def measure(args, rank, local_rank, world, dev, peaks):
         value = total_rays / (ms * 1e-3)
         e2e_value = total_rays / (e2e_ms * 1e-3)
         train = args.workload == "train"
-        what = {"nerf": "NeRF coarse+fine", "ngp": "Instant-NGP coarse (L=6) + fine (L=16)",
+        what = {"nerf": "NeRF coarse+fine",
+                "ngp": "Instant-NGP coarse (L=6) + fine (L=16), " + ("bf16 tcgen05 heads" if prec == "bf16" else "fp32 FFMA heads"),
                 "ngpref": "Instant-NGP Ref-NeRF (smooth hash grid, sh_degree 4) coarse (L=6) + fine (L=16)",
                 "refnerf": "Ref-NeRF (sh_degree 4) coarse+fine"}[args.model]
         cfg_name = {("nerf", True): "configs[1]: ", ("ngp", True): "configs[2]: ", ("refnerf", True): "configs[3]: ",
@@ -494,7 +495,8 @@ EXTRA_CONFIGS = [
     ("configs[1] fp32 leg", dict(workload="train", model="nerf", precision="fp32", steps=5, warmup=3)),
     ("configs[0]", dict(workload="image", model="nerf", precision="bf16", width=128, height=128, batch_size=1024,
                         steps=10, warmup=3)),
-    ("configs[2]", dict(workload="train", model="ngp", steps=5, warmup=3)),
+    ("configs[2]", dict(workload="train", model="ngp", precision="bf16", steps=5, warmup=3)),
+    ("configs[2] fp32 heads", dict(workload="train", model="ngp", precision="fp32", steps=5, warmup=3)),
     ("configs[3]", dict(workload="train", model="refnerf", steps=3, warmup=3)),
     ("configs[4]", dict(workload="image", model="nerf", precision="bf16", width=800, height=800, batch_size=65536,
                         steps=5, warmup=3)),

@@ -210,6 +210,23 @@ int lnrf_ngp_mlp_bwd(const float* params, int32_t L, const float* enc, int64_t m
                      const float* d_dens, const float* d_rgb, float* d_params, float* d_enc,
                      lnrf_stream_t stream);
 
+/* bf16 tensor-core variant of the same heads (tcgen05 / TMEM; 2e-2 abs on density / rgb like the bf16 NeRF
+ * path, gradients rel-L2 5e-2).  `packed`: bf16 operand images + biases built from the flat head
+ * parameters by lnrf_ngp_pack_weights (lnrf_ngp_packed_bytes() bytes, 1024-byte aligned; rebuild after
+ * every update).  With save_for_backward the forward leaves the five layer inputs of every 128-sample
+ * tile in `workspace` (lnrf_ngp_mlp_tc_workspace_bytes, 1024-byte aligned: 640 B/sample); the backward
+ * reads them, ACCUMULATES the head gradients into d_params (layout of lnrf_ngp_mlp_param_offsets) and
+ * overwrites d_enc[m,2L].                                                                          */
+int64_t lnrf_ngp_packed_bytes(void);
+int lnrf_ngp_pack_weights(const float* params, int32_t L, void* packed, lnrf_stream_t stream);
+int lnrf_ngp_mlp_tc_workspace_bytes(int64_t m, int64_t* bytes_out_host);
+int lnrf_ngp_mlp_fwd_tc(const void* packed, int32_t L, const float* enc, const float* d, const float* rays,
+                        int64_t n, int32_t T, int32_t save_for_backward, void* workspace,
+                        int64_t workspace_bytes, float* dens, float* rgb, lnrf_stream_t stream);
+int lnrf_ngp_mlp_bwd_tc(const void* packed, int32_t L, int64_t m, const void* workspace,
+                        int64_t workspace_bytes, const float* dens, const float* rgb, const float* d_dens,
+                        const float* d_rgb, float* d_params, float* d_enc, lnrf_stream_t stream);
+
 /* ---------------------------------------------------------------- K9 Ref-NeRF
  * RefNERFModel(sh_degree=4) (ref_nerf.py:34-107): spatial MLP (as NeRF's trunk), real_normal
  * from the input gradient of -spatial_out[:,0] (:38-43), activations, reflection direction,

@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "liblnrf.so")
 OBJ = os.path.join(HERE, "build")
 SOURCES = ["core.cu", "sample.cu", "composite.cu", "mlp_fp32.cu", "mlp_tc.cu", "mlp_tc_bwd.cu", "mlp_tc_cta2_fwd.cu", "mlp_tc_cta2_bwd.cu", "nerf_api.cu",
-           "adam.cu", "hashgrid.cu", "ngp_mlp.cu", "refnerf.cu", "raygen.cu", "prng.cu"]
+           "adam.cu", "hashgrid.cu", "ngp_mlp.cu", "ngp_tc.cu", "refnerf.cu", "raygen.cu", "prng.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 NVCC_FLAGS += os.environ.get("LNRF_EXTRA_NVCC_FLAGS", "").split()  # profiling builds, e.g. -DLNRF_C2_TRACE

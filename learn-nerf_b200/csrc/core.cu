@@ -37,6 +37,7 @@ int sm_count() {  // SMs of the CURRENT device
 
 int init_mlp_tc();   // mlp_tc.cu: constant tables + large dynamic smem opt-ins of the tcgen05 kernels
 int init_ngp_mlp();  // ngp_mlp.cu
+int init_ngp_tc();   // ngp_tc.cu
 
 }  // namespace lnrf
 
@@ -58,7 +59,8 @@ int lnrf_init(int device) {
   if (device >= 0 && device < 64) __atomic_store_n(&lnrf::g_sm_count[device], prop.multiProcessorCount, __ATOMIC_RELAXED);
   int rc = lnrf::init_mlp_tc();
   if (rc) return rc;
-  return lnrf::init_ngp_mlp();
+  if ((rc = lnrf::init_ngp_mlp())) return rc;
+  return lnrf::init_ngp_tc();
 }
 
 }  // extern "C"

@@ -91,6 +91,12 @@ _SIGS = {
     "lnrf_hashgrid_bwd": (c_int32, [c_void_p] * 3 + [c_int32, c_void_p, c_void_p, c_int32,
                                                      c_void_p, c_void_p, c_void_p, c_int64, c_int32,
                                                      c_void_p, c_void_p, c_void_p]),
+    "lnrf_ngp_packed_bytes": (c_int64, []),
+    "lnrf_ngp_pack_weights": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p]),
+    "lnrf_ngp_mlp_tc_workspace_bytes": (c_int32, [c_int64, c_void_p]),
+    "lnrf_ngp_mlp_fwd_tc": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32,
+                                      c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "lnrf_ngp_mlp_bwd_tc": (c_int32, [c_void_p, c_int32, c_int64, c_void_p, c_int64] + [c_void_p] * 7),
     "lnrf_ngp_mlp_param_count": (c_int64, [c_int32]),
     "lnrf_ngp_mlp_workspace_bytes": (c_int32, [c_int64, c_int32, c_void_p]),
     "lnrf_ngp_mlp_fwd": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32,
@@ -461,6 +467,35 @@ def ngp_mlp_bwd(flat, L, enc, m, workspace, dens, rgb, d_dens, d_rgb, d_flat, d_
                                    _p(d_flat), _p(d_enc), _stream()), "lnrf_ngp_mlp_bwd")
 
 
+def ngp_packed_bytes() -> int:
+    return int(load().lnrf_ngp_packed_bytes())
+
+
+def ngp_pack_weights(flat, L, packed):
+    ensure_init(flat.device)
+    _check(load().lnrf_ngp_pack_weights(_p(_f32c(flat, "params")), L, _p(packed), _stream()), "lnrf_ngp_pack_weights")
+
+
+def ngp_mlp_tc_workspace_bytes(m: int) -> int:
+    out = c_int64(0)
+    _check(load().lnrf_ngp_mlp_tc_workspace_bytes(m, ctypes.byref(out)), "lnrf_ngp_mlp_tc_workspace_bytes")
+    return int(out.value)
+
+
+def ngp_mlp_fwd_tc(packed, L, enc, d, rays, n, T, save, workspace, dens, rgb):
+    ensure_init(enc.device)
+    _check(load().lnrf_ngp_mlp_fwd_tc(_p(packed), L, _p(enc), _p(d), _p(rays), n, T, int(save), _p(workspace),
+                                      0 if workspace is None else workspace.numel(), _p(dens), _p(rgb), _stream()),
+           "lnrf_ngp_mlp_fwd_tc")
+
+
+def ngp_mlp_bwd_tc(packed, L, m, workspace, dens, rgb, d_dens, d_rgb, d_flat, d_enc):
+    ensure_init(d_enc.device)
+    _check(load().lnrf_ngp_mlp_bwd_tc(_p(packed), L, m, _p(workspace), workspace.numel(), _p(dens), _p(rgb),
+                                      _p(_f32c(d_dens, "d_dens")), _p(_f32c(d_rgb, "d_rgb")), _p(d_flat), _p(d_enc),
+                                      _stream()), "lnrf_ngp_mlp_bwd_tc")
+
+
 # --------------------------------------------------------------------------- rays / images
 def bare_rays(origin, x_axis, y_axis, z, tan_half_x_fov, tan_half_y_fov, width, height, row0, rows, device):
     device = torch.device(device)
@@ -586,6 +621,6 @@ def _device_scoped(fn):
 for _name in ("sample_coarse", "stratified", "sample_fine", "composite_fwd", "composite_bwd", "mse_loss",
               "nerf_pack_weights", "nerf_mlp_fwd", "nerf_mlp_bwd", "adam_step", "adam_step_dk", "threefry_uniform_dk",
               "adam_step_peers", "debug_umma_gemm", "debug_umma_gemm_tn", "hashgrid_fwd", "hashgrid_bwd", "ngpref_fwd",
-              "ngpref_bwd", "ngp_mlp_fwd", "ngp_mlp_bwd", "rgb_to_u8", "refnerf_fwd", "refnerf_bwd", "ray_intervals",
+              "ngpref_bwd", "ngp_mlp_fwd", "ngp_mlp_bwd", "ngp_pack_weights", "ngp_mlp_fwd_tc", "ngp_mlp_bwd_tc", "rgb_to_u8", "refnerf_fwd", "refnerf_bwd", "ray_intervals",
               "termination_probs", "z_depth"):
     globals()[_name] = _device_scoped(globals()[_name])

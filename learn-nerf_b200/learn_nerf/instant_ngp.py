@@ -26,7 +26,8 @@ def hash_table_lookup(table: torch.Tensor, coords: torch.Tensor) -> torch.Tensor
 
 @dataclass
 class InstantNGPModel(ModelBase):
-    """instant_ngp.py:16-54."""
+    """instant_ngp.py:16-54.  ``precision``: "fp32" (FFMA heads, 1e-5) or "bf16" (heads on the tcgen05
+    tensor cores, 2e-2 abs on density / rgb); the hash grid itself is fp32 on both paths."""
 
     table_sizes: List[int]
     grid_sizes: List[int]
@@ -49,6 +50,8 @@ class InstantNGPModel(ModelBase):
                                     "(F=2, hidden 64, density_dim 16, 1 density + 2 colour layers)")
         if len(self.grid_sizes) != len(self.table_sizes) or not 1 <= len(self.grid_sizes) <= 16:
             raise _native.LnrfError("1..16 levels supported")
+        if self.precision not in _native.PRECISIONS:
+            raise ValueError(f"precision must be one of {list(_native.PRECISIONS)}")
 
     @property
     def L(self) -> int:
@@ -116,13 +119,32 @@ class InstantNGPModel(ModelBase):
         return {"params": tree}
 
     # ------------------------------------------------------------------ native calls
+    def _packed(self, tree: ParamTree) -> Optional[torch.Tensor]:
+        """bf16 operand images of the head weights (bf16 path), rebuilt when the parameters changed."""
+        if self.precision != "bf16":
+            return None
+        key = tree.version_key()
+        if tree._packed is None or tree._packed_key != key:
+            if tree._packed is None:
+                nbytes = _native.ngp_packed_bytes()
+                raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=tree.flat.device)
+                shift = (-raw.data_ptr()) % 1024
+                tree._packed = raw[shift: shift + nbytes]
+            _native.ngp_pack_weights(tree.flat, self.L, tree._packed)
+            tree._packed_key = key
+        return tree._packed
+
     def _workspace(self, m: int, device, slot, save):
         cache = self.__dict__.setdefault("_ws_cache", {})
-        nbytes = _native.ngp_mlp_workspace_bytes(m, self.L) if save else 0
+        bf16 = self.precision == "bf16"
+        nbytes = 0
+        if save:
+            nbytes = _native.ngp_mlp_tc_workspace_bytes(m) if bf16 else _native.ngp_mlp_workspace_bytes(m, self.L)
         ws = cache.get((str(device), slot, save))
         if ws is None or ws[0].numel() < nbytes or ws[1].shape[0] < m:
-            ws = (torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device),
-                  torch.empty(m, 2 * self.L, device=device))
+            raw = torch.empty(max(nbytes, 256) + 1024, dtype=torch.uint8, device=device)
+            shift = (-raw.data_ptr()) % 1024  # the bf16 stash holds 1024-byte aligned tile images
+            ws = (raw[shift: shift + max(nbytes, 256)], torch.empty(m, 2 * self.L, device=device))
             cache[(str(device), slot, save)] = ws
         return ws
 
@@ -135,7 +157,10 @@ class InstantNGPModel(ModelBase):
         _native.hashgrid_fwd(tree.flat, spec, x, rays, ts, n, T, enc)
         dens = torch.empty(m, device=dev)
         rgb = torch.empty(m, 3, device=dev)
-        _native.ngp_mlp_fwd(tree.flat, self.L, enc, d, rays, n, T, save, ws if save else None, dens, rgb)
+        if self.precision == "bf16":
+            _native.ngp_mlp_fwd_tc(self._packed(tree), self.L, enc, d, rays, n, T, save, ws if save else None, dens, rgb)
+        else:
+            _native.ngp_mlp_fwd(tree.flat, self.L, enc, d, rays, n, T, save, ws if save else None, dens, rgb)
         return dens, rgb, ws, enc
 
     def encode(self, params, x: torch.Tensor) -> torch.Tensor:
@@ -165,8 +190,12 @@ class InstantNGPModel(ModelBase):
         tree = ctx["tree"]
         m = ctx["n"] * ctx["T"]
         d_enc = torch.empty_like(ctx["enc"])
-        _native.ngp_mlp_bwd(tree.flat, self.L, ctx["enc"], m, ctx["ws"], ctx["dens"], ctx["rgb"],
-                            d_dens.reshape(-1), d_rgb.reshape(-1, 3), d_flat, d_enc)
+        if self.precision == "bf16":
+            _native.ngp_mlp_bwd_tc(self._packed(tree), self.L, m, ctx["ws"], ctx["dens"], ctx["rgb"],
+                                   d_dens.reshape(-1), d_rgb.reshape(-1, 3), d_flat, d_enc)
+        else:
+            _native.ngp_mlp_bwd(tree.flat, self.L, ctx["enc"], m, ctx["ws"], ctx["dens"], ctx["rgb"],
+                                d_dens.reshape(-1), d_rgb.reshape(-1, 3), d_flat, d_enc)
         _native.hashgrid_bwd(self.spec(), None, ctx["rays"], ctx["ts"], ctx["n"], ctx["T"], d_enc, d_flat)
 
 

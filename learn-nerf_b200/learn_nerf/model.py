@@ -64,8 +64,8 @@ _ERF_SQRT2 = math.erf(math.sqrt(2.0))
 
 
 def init_flat_(flat: torch.Tensor, dense_kernels, tables, key):
-    """Random-init a flat parameter buffer in a handful of launches (one Threefry uniform stream over
-    the whole buffer, then elementwise ops): Dense kernels get lecun_normal as Flax does (see above),
+    """Random-init a flat parameter buffer (one Threefry uniform stream over the whole buffer, evaluated on
+    the host, one upload): Dense kernels get lecun_normal as Flax does (see above),
     hash tables 1e-4 * (2 U - 1) (instant_ngp.py:181-186), biases and padding stay zero.
     ``dense_kernels``: [(offset, fan_in, count)], ``tables``: [(offset, count)].
     The per-parameter key derivation of flax (path-hashed fold_in) is not reproduced: the stream is
@@ -79,13 +79,20 @@ def init_flat_(flat: torch.Tensor, dense_kernels, tables, key):
         std[off: off + count] = math.sqrt(1.0 / fan_in) / _TRUNC_STD
     for off, count in tables:
         tab[off: off + count] = 1e-4
-    dev = flat.device
-    u = prng.uniform(key, (n,), dev)
+    # Runs on the HOST (numpy Threefry stream + scipy erfinv), then one H2D copy: initialisation is not the
+    # hot path, and torch's CUDA erfinv is a run-time-compiled (NVRTC "jiterator") kernel.
+    from scipy.special import erfinv
+    k = prng._as_key(key)
+    bits = prng.random_bits_host(k, n)
+    u = ((bits >> np.uint32(9)) | np.uint32(0x3F800000)).view(np.float32) - np.float32(1.0)  # jax.random.uniform
     # truncated normal by inversion; clamped inside the open interval (-2, 2) as jax.random does
-    z = torch.erfinv(u * (2.0 * _ERF_SQRT2) - _ERF_SQRT2).mul_(math.sqrt(2.0)).clamp_(-1.9999999, 1.9999999)
-    flat.copy_(z * torch.from_numpy(std).to(dev))
+    dense = std > 0
+    host = np.zeros(n, np.float32)
+    z = np.clip(math.sqrt(2.0) * erfinv(u[dense].astype(np.float64) * (2.0 * _ERF_SQRT2) - _ERF_SQRT2), -1.9999999, 1.9999999)
+    host[dense] = (z * std[dense]).astype(np.float32)
     if tables:
-        flat.add_((u * 2.0 - 1.0) * torch.from_numpy(tab).to(dev))
+        host += ((u * np.float32(2.0) - np.float32(1.0)) * tab).astype(np.float32)
+    flat.copy_(torch.from_numpy(host))
     return flat
 
 

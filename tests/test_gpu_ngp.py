@@ -202,3 +202,129 @@ def test_golden_models_fixture_gpu():
     np.testing.assert_array_equal(CameraView(**cam).bare_rays(7, 5).cpu().numpy(), g["rays_7x5"])
     key = prng.PRNGKey(int(g["key"][0]), int(g["key"][1]))
     np.testing.assert_array_equal(prng.uniform(key, (5, 7), "cuda").cpu().numpy(), g["uniforms_5x7"])
+
+
+# ------------------------------------------------------------------ bf16 tensor-core heads (ngp_tc.cu)
+def _bf16_model(levels):
+    from learn_nerf.instant_ngp import InstantNGPModel
+    grids = [2 ** (4 + i // 2) for i in range(levels)]
+    return InstantNGPModel(table_sizes=[2 ** 18] * levels, grid_sizes=grids, bbox_min=BBOX_MIN, bbox_max=BBOX_MAX,
+                           precision="bf16")
+
+
+@pytest.mark.parametrize("levels,m", [(6, 1), (16, 127), (16, 4097), (6, 128 * 300 + 5)])
+def test_ngp_bf16_heads_forward(levels, m):
+    """InstantNGPModel(precision="bf16").apply: heads on tcgen05 (bf16 operands, fp32 accumulation)
+    against the fp32 oracle: rgb 2e-2 abs, density 2e-2 relative (density = exp(.), instant_ngp.py:49)."""
+    o, _ = models(levels)
+    n = _bf16_model(levels)
+    p = oracle_params(o, 5)
+    rs = np.random.RandomState(levels + m)
+    x = rs.uniform(-1, 1, (m, 3)).astype(F)
+    d = rs.randn(m, 3).astype(F)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    with torch.no_grad():
+        o_d, o_rgb, _ = o.apply(p, torch.from_numpy(x), torch.from_numpy(d))
+    dens, rgb, aux = n.apply(dict(params=to_native(n, p)), dev(x), dev(d))
+    assert dens.shape == (m, 1) and rgb.shape == (m, 3) and aux == {}
+    np.testing.assert_allclose(dens.cpu().numpy(), o_d.numpy(), rtol=2e-2, atol=2e-3)
+    np.testing.assert_allclose(rgb.cpu().numpy(), o_rgb.numpy(), atol=2e-2)
+
+
+@pytest.mark.parametrize("levels,n_rays,T", [(16, 40, 64), (6, 33, 192), (16, 3, 5)])
+def test_ngp_bf16_heads_backward_vs_fp64(levels, n_rays, T):
+    """lnrf_ngp_mlp_bwd_tc (dX chain + dW in TMEM + bias sums through the ones column) and the table
+    scatter behind it, against fp64 autograd of the oracle.  WHITE-NOISE upstream gradients are the worst
+    case (per-sample terms cancel in the batch sum, so bf16 rounding of the g tiles shows at full size):
+    rel-L2 per tensor 1.5e-1, as for the bf16 NeRF kernels (test_mlp_backward_vs_fp64_autograd 2.5e-1;
+    measured here 8.6e-2).  The realistic bound (gradients of the rendering loss, 5e-2) is checked in
+    test_ngp_bf16_train_step_matches_fp32_path."""
+    from oracle import models_torch as M
+    o, _ = models(levels)
+    n = _bf16_model(levels)
+    p = oracle_params(o, 9)
+    for i in range(5):
+        p[f"Dense_{i}"]["bias"] = torch.from_numpy((0.1 * np.random.RandomState(70 + i).randn(*p[f"Dense_{i}"]["bias"].shape)).astype(F))
+    rays = make_rays(n_rays, seed=levels + T, with_targets=False)
+    rs = np.random.RandomState(T)
+    ts = np.sort(rs.uniform(3.0, 5.0, (n_rays, T)).astype(F), axis=1)
+    d_dens = (rs.randn(n_rays, T) * 1e-2).astype(F)
+    d_rgb = (rs.randn(n_rays, T, 3) * 1e-2).astype(F)
+    pd = M.tree_map(lambda t: t.double().requires_grad_(True), p)
+    pts = torch.from_numpy(rays[:, :1].astype(np.float64)) + torch.from_numpy(rays[:, 1:2].astype(np.float64)) * \
+        torch.from_numpy(ts.astype(np.float64))[:, :, None]
+    dirs = torch.from_numpy(rays[:, 1:2].astype(np.float64)).expand(n_rays, T, 3)
+    # the points the kernels see are the fp32-rounded o + d t (render.py:153)
+    pts32 = (rays[:, :1] + (rays[:, 1:2] * ts[:, :, None]).astype(F)).astype(F)
+    de, rgb, _ = o.apply(pd, torch.from_numpy(pts32.astype(np.float64)).reshape(-1, 3), dirs.reshape(-1, 3))
+    loss = (de.reshape(n_rays, T) * torch.from_numpy(d_dens).double()).sum() + \
+        (rgb.reshape(n_rays, T, 3) * torch.from_numpy(d_rgb).double()).sum()
+    loss.backward()
+    tree = to_native(n, p)
+    dens, col, _, ctx = n.apply_rays(tree, dev(rays), dev(ts), save=True, slot="t")
+    np.testing.assert_allclose(col.cpu().numpy().reshape(-1, 3), rgb.detach().numpy(), atol=2e-2)
+    g = torch.zeros_like(tree.flat)
+    n.backward_rays(ctx, dev(d_dens), dev(d_rgb), g)
+    torch.cuda.synchronize()
+    gt = n.bind(g)
+    worst = []
+    for path, leaf in M.tree_leaves(pd):
+        node = gt
+        for part in path.split("/"):
+            node = node[part]
+        ref = leaf.grad.numpy()
+        if np.abs(ref).max() > 0:
+            worst.append((rel_l2(node.cpu().numpy(), ref), path))
+    worst.sort(reverse=True)
+    print("worst bf16 NGP grad rel-L2 vs fp64:", worst[:5])
+    assert worst[0][0] < (1.5e-1 if n_rays * T > 100 else 3e-1), worst[:5]
+
+
+def test_ngp_bf16_train_step_matches_fp32_path():
+    """One TrainLoop step (2048 rays) with bf16 heads on both levels against the fp32-head step of the same
+    parameters (itself checked against fp64 autograd in test_ngp_train_step_vs_oracle): losses within
+    2e-2; head kernels and biases rel-L2 5e-2; hash tables 2e-1 -- an entry of a fine hashed level sums
+    the gradients of a few UNRELATED points (collisions), so its net gradient is a small difference of
+    larger terms and the bf16 rounding of the four g tiles of the chain shows amplified (measured 1.2e-1
+    on level 14 with tables scaled to O(1), 2048 rays)."""
+    from learn_nerf.train import TrainLoop
+    n = 2048
+    batch = dev(make_rays(n, seed=31))
+    uc, uf = dev(make_uniforms(n, 64, 32)), dev(make_uniforms(n, 128, 33))
+    logs, grads, loops = {}, {}, {}
+    for prec in ("fp32", "bf16"):
+        mk = lambda L: __import__("learn_nerf.instant_ngp", fromlist=["x"]).InstantNGPModel(
+            table_sizes=[2 ** 18] * L, grid_sizes=[2 ** (4 + i // 2) for i in range(L)], bbox_min=BBOX_MIN,
+            bbox_max=BBOX_MAX, precision=prec)
+        loop = TrainLoop(mk(6), mk(16), init_rng=3, lr=1e-3, coarse_ts=64, fine_ts=128, adam_eps=1e-15, adam_b1=0.9,
+                         adam_b2=0.99)
+        for k in ("coarse", "fine"):  # O(1) tables so that the grid matters
+            for leaf in loop.state.params[k]["MultiresHashTableEncoding_0"].values():
+                leaf["table"].mul_(3e3)
+            loop.state.params[k].mark_updated()
+        out = loop.step_fn(BBOX_MIN, BBOX_MAX)((uc, uf), batch)
+        logs[prec] = {k: float(v) for k, v in out.items()}
+        grads[prec], loops[prec] = loop._grads.clone(), loop
+        assert all(np.isfinite(v) for v in logs[prec].values()), logs[prec]
+    for k in ("coarse", "fine"):
+        assert abs(logs["bf16"][k] - logs["fp32"][k]) < 2e-2, (k, logs)
+    assert abs(logs["bf16"]["grad_norm"] - logs["fp32"]["grad_norm"]) < 5e-2 * logs["fp32"]["grad_norm"], logs
+    from oracle import models_torch as M
+    worst = []
+    lp = loops["fp32"]
+    for name, model in (("coarse", lp.coarse), ("fine", lp.fine)):
+        a, b = lp._slices[name]
+        t32, t16 = model.bind(grads["fp32"][a:b]), model.bind(grads["bf16"][a:b])
+        for path, leaf in M.tree_leaves(dict(t32)):
+            node = t16
+            for part in path.split("/"):
+                node = node[part]
+            if float(leaf.abs().max()) > 0:
+                worst.append((rel_l2(node.cpu().numpy(), leaf.cpu().numpy()), name, path))
+    worst.sort(reverse=True)
+    print("worst bf16-vs-fp32 NGP gradient rel-L2:", worst[:5])
+    heads = [w for w in worst if "Dense_" in w[2]]
+    tables = [w for w in worst if "table" in w[2]]
+    print("worst head tensors:", heads[:3])
+    assert heads[0][0] < 5e-2, heads[:5]
+    assert tables[0][0] < 2e-1, tables[:5]
