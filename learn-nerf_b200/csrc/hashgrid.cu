@@ -126,6 +126,142 @@ hashgrid_bwd_kernel(GridLevels g, const float* __restrict__ x, const float* __re
   }
 }
 
+// ---------------------------------------------------------------- one thread per POINT
+// Consecutive threads are consecutive samples of a ray, so at the coarse levels (16^3 .. 128^3 cells)
+// most lanes of a warp sit in the same or a neighbouring cell and their gathers / scatters fall on
+// the same 32-byte L2 sectors (the (point, level)-per-thread kernels above spread a warp over all the
+// levels of two points: every lane a different table).  Each thread walks all LT levels and moves
+// its whole [2 LT] row with 16-byte accesses.
+template <int LT>
+__global__ void __launch_bounds__(256)
+hashgrid_fwd_pt_kernel(const float* __restrict__ tables, const __grid_constant__ GridLevels g,
+                       const float* __restrict__ x, const float* __restrict__ rays, const float* __restrict__ ts, int T,
+                       int64_t m, float* __restrict__ enc) {
+  for (int64_t s = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; s < m; s += int64_t(gridDim.x) * blockDim.x) {
+    float p[3];
+    load_point(x, rays, ts, T, s, p);
+    float2 out[LT];
+#pragma unroll
+    for (int l = 0; l < LT; ++l) {
+      const Corners c = level_corners(g, l, p);
+      const float2* tab = reinterpret_cast<const float2*>(tables + g.offset[l]);
+      float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {  // sum over the 8 corners in the reference's order (:206-208)
+        const float2 v = __ldg(tab + c.idx[k]);
+        acc.x += c.w[k] * v.x;
+        acc.y += c.w[k] * v.y;
+      }
+      out[l] = acc;
+    }
+    float4* dst = reinterpret_cast<float4*>(enc + s * 2 * LT);
+#pragma unroll
+    for (int q = 0; q < LT / 2; ++q) dst[q] = make_float4(out[2 * q].x, out[2 * q].y, out[2 * q + 1].x, out[2 * q + 1].y);
+  }
+}
+
+// Scatter-add.  On the DENSE levels (G^3 <= table size: 16^3 .. 64^3 cells) consecutive samples of a ray
+// mostly share a cell, i.e. the same eight table rows: the warp first sums the contributions of every run
+// of consecutive lanes with the same cell (segmented shuffle reduction, 16 values) and only the first lane
+// of a run issues the eight atomics -- otherwise thousands of same-address float2 atomics per table row
+// serialise in the L2.  Hashed levels scatter directly (their rows are unrelated).
+template <int LT>
+__global__ void __launch_bounds__(256)
+hashgrid_bwd_pt_kernel(const __grid_constant__ GridLevels g, const float* __restrict__ x, const float* __restrict__ rays,
+                       const float* __restrict__ ts, int T, int64_t m, const float* __restrict__ d_enc,
+                       float* __restrict__ d_tables) {
+  const int lane = threadIdx.x & 31;
+  const int64_t m_pad = (m + 31) / 32 * 32;  // whole warps stay in the loop (the reduction needs all 32 lanes)
+  for (int64_t s = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; s < m_pad; s += int64_t(gridDim.x) * blockDim.x) {
+    const bool in_range = s < m;
+    float2 d[LT];
+    bool any = false;
+    if (in_range) {
+      const float4* src = reinterpret_cast<const float4*>(d_enc + s * 2 * LT);
+#pragma unroll
+      for (int q = 0; q < LT / 2; ++q) {
+        const float4 v = __ldg(src + q);
+        d[2 * q] = make_float2(v.x, v.y);
+        d[2 * q + 1] = make_float2(v.z, v.w);
+        any |= (v.x != 0.0f) | (v.y != 0.0f) | (v.z != 0.0f) | (v.w != 0.0f);
+      }
+    } else {
+#pragma unroll
+      for (int l = 0; l < LT; ++l) d[l] = make_float2(0.f, 0.f);
+    }
+    if (!__any_sync(0xffffffffu, any)) continue;  // masked rays / dead units contribute nothing
+    float p[3] = {0.f, 0.f, 0.f};
+    if (in_range) load_point(x, rays, ts, T, s, p);
+#pragma unroll
+    for (int l = 0; l < LT; ++l) {
+      const bool live = in_range && (d[l].x != 0.0f || d[l].y != 0.0f);
+      const Corners c = level_corners(g, l, p);
+      float2* tab = reinterpret_cast<float2*>(d_tables + g.offset[l]);
+      if (g.hashed[l]) {
+        if (live) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) atomicAdd(tab + c.idx[k], make_float2(c.w[k] * d[l].x, c.w[k] * d[l].y));
+        }
+        continue;
+      }
+      // dense level: runs of consecutive lanes in the same cell (idx[0] is the cell's (0,0,0) corner)
+      const uint32_t cell = live ? c.idx[0] : 0xffffffffu - uint32_t(lane);  // dead lanes: singleton runs
+      const uint32_t prev = __shfl_up_sync(0xffffffffu, cell, 1);
+      const bool head = lane == 0 || prev != cell;
+      const unsigned heads = __ballot_sync(0xffffffffu, head);
+      const int run = __popc(heads & (0xffffffffu >> (31 - lane)));  // run id: monotone over the lanes
+      float v[16];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        v[2 * k] = live ? c.w[k] * d[l].x : 0.0f;
+        v[2 * k + 1] = live ? c.w[k] * d[l].y : 0.0f;
+      }
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int run2 = __shfl_down_sync(0xffffffffu, run, off);
+        const bool take = (lane + off < 32) && run2 == run;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float t = __shfl_down_sync(0xffffffffu, v[j], off);
+          if (take) v[j] += t;
+        }
+      }
+      if (head && live) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) atomicAdd(tab + c.idx[k], make_float2(v[2 * k], v[2 * k + 1]));
+      }
+    }
+  }
+}
+
+static int launch_hash_fwd(const float* tables, const GridLevels& g, const float* x, const float* rays, const float* ts,
+                           int T, int64_t m, float* enc, cudaStream_t st) {
+  const bool aligned = (uintptr_t)enc % 16 == 0;
+  if (g.L == 16 && aligned) {
+    hashgrid_fwd_pt_kernel<16><<<ew_blocks(m, 256), 256, 0, st>>>(tables, g, x, rays, ts, T, m, enc);
+  } else if (g.L == 6 && aligned) {
+    hashgrid_fwd_pt_kernel<6><<<ew_blocks(m, 256), 256, 0, st>>>(tables, g, x, rays, ts, T, m, enc);
+  } else {
+    hashgrid_fwd_kernel<<<ew_blocks(m * g.L, 256), 256, 0, st>>>(tables, g, x, rays, ts, T, m, enc);
+  }
+  LNRF_LAUNCH_CHECK("hashgrid_fwd_kernel");
+  return LNRF_OK;
+}
+
+static int launch_hash_bwd(const GridLevels& g, const float* x, const float* rays, const float* ts, int T, int64_t m,
+                           const float* d_enc, float* d_tables, cudaStream_t st) {
+  const bool aligned = (uintptr_t)d_enc % 16 == 0;
+  if (g.L == 16 && aligned) {
+    hashgrid_bwd_pt_kernel<16><<<ew_blocks(m, 256), 256, 0, st>>>(g, x, rays, ts, T, m, d_enc, d_tables);
+  } else if (g.L == 6 && aligned) {
+    hashgrid_bwd_pt_kernel<6><<<ew_blocks(m, 256), 256, 0, st>>>(g, x, rays, ts, T, m, d_enc, d_tables);
+  } else {
+    hashgrid_bwd_kernel<<<ew_blocks(m * g.L, 256), 256, 0, st>>>(g, x, rays, ts, T, m, d_enc, d_tables);
+  }
+  LNRF_LAUNCH_CHECK("hashgrid_bwd_kernel");
+  return LNRF_OK;
+}
+
 // ---------------------------------------------------------------- input Jacobian (InstantNGPRefNERFModel)
 // RefNERFBase differentiates the spatial block w.r.t. x (ref_nerf.py:38-43); with a hash-grid
 // spatial block (instant_ngp.py:69-82) that needs d enc / d x.  Per axis a and corner c:
@@ -275,13 +411,9 @@ int hashgrid_launch(int which, const float* tables, const int64_t* level_offsets
   if (m == 0) return LNRF_OK;
   switch (which) {
     case 0:  // enc = encode(x)
-      hashgrid_fwd_kernel<<<ew_blocks(m * L, 256), 256, 0, st>>>(tables, g, x, rays, ts, T, m, out0);
-      LNRF_LAUNCH_CHECK("hashgrid_fwd_kernel");
-      break;
+      return launch_hash_fwd(tables, g, x, rays, ts, T, m, out0, st);
     case 1:  // d_tables += scatter(d_enc = in0)
-      hashgrid_bwd_kernel<<<ew_blocks(m * L, 256), 256, 0, st>>>(g, x, rays, ts, T, m, in0, out0);
-      LNRF_LAUNCH_CHECK("hashgrid_bwd_kernel");
-      break;
+      return launch_hash_bwd(g, x, rays, ts, T, m, in0, out0, st);
     case 2:  // out0[m,4] = J^T in0
       hashgrid_jtv_kernel<<<ew_blocks(m, 256), 256, 0, st>>>(tables, g, x, rays, ts, T, m, in0, out0);
       LNRF_LAUNCH_CHECK("hashgrid_jtv_kernel");
@@ -315,10 +447,7 @@ int lnrf_hashgrid_fwd(const float* tables, const int64_t* level_offsets_host,
   if (m == 0) return LNRF_OK;
   LNRF_REQUIRE(tables && enc && ((x && !rays) || (!x && rays && ts)), LNRF_E_INVALID,
                "lnrf_hashgrid_fwd: null pointer / pass either x or (rays, ts)");
-  lnrf::hashgrid_fwd_kernel<<<lnrf::ew_blocks(m * L, 256), 256, 0, lnrf::as_stream(stream)>>>(
-      tables, g, x, rays, ts, T, m, enc);
-  LNRF_LAUNCH_CHECK("hashgrid_fwd_kernel");
-  return LNRF_OK;
+  return lnrf::launch_hash_fwd(tables, g, x, rays, ts, T, m, enc, lnrf::as_stream(stream));
 }
 
 int lnrf_hashgrid_bwd(const int64_t* level_offsets_host, const int32_t* grid_sizes_host,
@@ -336,10 +465,7 @@ int lnrf_hashgrid_bwd(const int64_t* level_offsets_host, const int32_t* grid_siz
   LNRF_REQUIRE(d_enc && d_tables && ((x && !rays) || (!x && rays && ts)), LNRF_E_INVALID,
                "lnrf_hashgrid_bwd: null pointer / pass either x or (rays, ts)");
   LNRF_REQUIRE((uintptr_t)d_tables % 8 == 0, LNRF_E_INVALID, "lnrf_hashgrid_bwd: d_tables not 8-byte aligned");
-  lnrf::hashgrid_bwd_kernel<<<lnrf::ew_blocks(m * L, 256), 256, 0, lnrf::as_stream(stream)>>>(
-      g, x, rays, ts, T, m, d_enc, d_tables);
-  LNRF_LAUNCH_CHECK("hashgrid_bwd_kernel");
-  return LNRF_OK;
+  return lnrf::launch_hash_bwd(g, x, rays, ts, T, m, d_enc, d_tables, lnrf::as_stream(stream));
 }
 
 }  // extern "C"

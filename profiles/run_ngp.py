@@ -8,7 +8,7 @@ from learn_nerf.instant_ngp import InstantNGPModel
 torch.cuda.set_device(0)
 L = int(os.environ.get("L", "16"))
 m = InstantNGPModel(table_sizes=[2 ** 18] * L, grid_sizes=[2 ** (4 + i // 2) for i in range(L)],
-                    bbox_min=[-1.0] * 3, bbox_max=[1.0] * 3)
+                    bbox_min=[-1.0] * 3, bbox_max=[1.0] * 3, precision=os.environ.get("PREC", "bf16"))
 tree = m.init(0, device="cuda")["params"]
 n, T = int(os.environ.get("N", "8192")), int(os.environ.get("T", "192"))
 o = torch.randn(n, 3, device="cuda"); o = 4 * o / o.norm(dim=1, keepdim=True)
