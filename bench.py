@@ -190,18 +190,20 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     rays = args.cpu_rays
-    value, sec = cpu_train_sample(rays, args.steps, min(args.warmup, 1), threads)
+    value, sec = cpu_train_sample(rays, args.steps, args.warmup, threads)
     line = {
         "impl": "reference", "metric": "rays/sec (NeRF train step fwd+bwd+Adam)", "value": value,
-        "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+        "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "fp32", "data": "synthetic",
         "config": {"workload": "configs[1]: NeRF coarse+fine train step, 64+128 samples/ray, "
                                "random-init 8x256 MLP", "rays_per_step": rays,
-                   "note": "reference-restatement CPU baseline (oracle torch-CPU port; JAX is "
-                           "not installable here), bounded sample of the 4096-ray step"},
+                   "note": "PORT, SAMPLED: the oracle's torch-CPU fp32 restatement of the reference's train step "
+                           "(JAX / Flax / optax are not installable here), on a bounded sample of the workload: "
+                           f"{rays} of the 4096 rays of a step, every step"},
         "cpu_baseline": {"value": value, "unit": "rays/s", "cores": threads, "kind": "port",
-                         "sample": f"{rays} rays/step x {args.steps} steps"},
+                         "sample": f"{rays}-ray sample of the 4096-ray step x {args.steps} steps ({sec:.2f} s/step), "
+                                   f"{args.warmup} warm-up steps"},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -274,6 +276,8 @@ def measure(args, rank, local_rank, world, dev, peaks):
             return r
         return wrapper
 
+    if world > 1 and args.workload == "train":
+        dom_names = dom_names + ["adam_step_peers"]  # the fused NVLink gradient exchange + Adam
     originals = {nm: getattr(_native, nm) for nm in dom_names}
 
     if args.workload == "image":  # configs[4] / configs[0]: one W x H view, rows sharded over ranks
@@ -337,6 +341,9 @@ def measure(args, rank, local_rank, world, dev, peaks):
     for nm in dom_names:
         setattr(_native, nm, originals[nm])
     step_ms = [a.elapsed_time(b) for a, b in evs]
+    exch_ms = sum(a.elapsed_time(b) for a, b, k in dom_events if k == "adam_step_peers") / max(args.steps, 1)
+    dom_events = [e for e in dom_events if e[2] != "adam_step_peers"]
+    dom_names = [nm for nm in dom_names if nm != "adam_step_peers"]
     dom_ms = sum(a.elapsed_time(b) for a, b, _ in dom_events) / max(args.steps, 1)
     part_ms = {nm: sum(a.elapsed_time(b) for a, b, k in dom_events if k == nm) / max(args.steps, 1) for nm in dom_names}
     ms = float(np.mean(step_ms))
@@ -373,10 +380,10 @@ def measure(args, rank, local_rank, world, dev, peaks):
         # roofline of an image is taken over the WHOLE render (sampling + MLP + compositing + uint8 conversion)
         dom_ms = ms
         image_note = "whole render step (chunk graphs hide the individual C-ABI calls): the MLP kernel's share is not separated"
-    t = torch.tensor([ms, e2e_ms, dom_ms], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms, e2e_ms, dom_ms, exch_ms], device=dev, dtype=torch.float64)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    ms, e2e_ms, dom_ms = [float(x) for x in t.tolist()]
+    ms, e2e_ms, dom_ms, exch_ms = [float(x) for x in t.tolist()]
 
     if rank == 0:
         total_rays = n * world if args.workload != "image" else args.width * args.height
@@ -469,6 +476,15 @@ def measure(args, rank, local_rank, world, dev, peaks):
             "gpu_launches": int(launches),
             "roofline": roofline,
         }
+        if world > 1 and train and exch_ms > 0:
+            nbytes = int(loop._n_params + 4) * 4
+            line["gradient_exchange"] = {
+                "kernel": "adam_peers_kernel (fused all-reduce over NVLink peer mappings + Adam + norms)",
+                "ms_per_step": exch_ms, "share_of_step": exch_ms / ms, "buffer_bytes": nbytes,
+                "nvlink_bytes_read_per_rank": nbytes * (world - 1),
+                "nvlink_gbs_per_rank": nbytes * (world - 1) / (exch_ms * 1e-3) / 1e9,
+                "note": "CUDA-event time of the kernel alone (max over ranks); the two cross-rank barriers around it "
+                        "are in the step time, not in this number"}
         if args.cpu_baseline and world == 1 and args.model == "nerf" and train and prec == "bf16":
             threads = os.cpu_count() or 1
             cpu_steps = 16  # ~10 s of CPU work on the box's host cores
