@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "liblnrf.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["core.cu", "sample.cu", "composite.cu", "mlp_fp32.cu", "mlp_tc.cu", "mlp_tc_bwd.cu", "mlp_tc_cta2_fwd.cu", "mlp_tc_cta2_bwd.cu", "nerf_api.cu",
+SOURCES = ["core.cu", "sample.cu", "composite.cu", "mlp_fp32.cu", "gemm_tc.cu", "mlp_tc.cu", "mlp_tc_bwd.cu", "mlp_tc_cta2_fwd.cu", "mlp_tc_cta2_bwd.cu", "nerf_api.cu",
            "adam.cu", "hashgrid.cu", "ngp_mlp.cu", "ngp_tc.cu", "refnerf.cu", "raygen.cu", "prng.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]

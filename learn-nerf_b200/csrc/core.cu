@@ -38,6 +38,8 @@ int sm_count() {  // SMs of the CURRENT device
 int init_mlp_tc();   // mlp_tc.cu: constant tables + large dynamic smem opt-ins of the tcgen05 kernels
 int init_ngp_mlp();  // ngp_mlp.cu
 int init_ngp_tc();   // ngp_tc.cu
+void init_mlp_fp32();  // mlp_fp32.cu: LNRF_FP32_FFMA
+int init_gemm_tc();  // gemm_tc.cu: split-fp16 tcgen05 GEMMs of the fp32-accurate paths
 
 }  // namespace lnrf
 
@@ -60,7 +62,9 @@ int lnrf_init(int device) {
   int rc = lnrf::init_mlp_tc();
   if (rc) return rc;
   if ((rc = lnrf::init_ngp_mlp())) return rc;
-  return lnrf::init_ngp_tc();
+  if ((rc = lnrf::init_ngp_tc())) return rc;
+  lnrf::init_mlp_fp32();
+  return lnrf::init_gemm_tc();
 }
 
 }  // extern "C"

@@ -1,0 +1,723 @@
+// fp32-accurate GEMMs on tcgen05 (see gemm_tc.cuh).
+//
+// Split-fp16 arithmetic: x * s = hi + lo with hi = fp16(x s), lo = fp16(x s - hi): 22 significant bits as
+// long as x s sits well inside the fp16 range, which the power-of-two scale s guarantees (max |x s| in
+// [64, 128): lo keeps full precision down to 2^-14, i.e. 2^-21 of the operand's maximum, and degrades
+// gracefully through the fp16 subnormals below that).  A product needs three MMAs:
+//     main += A_hi B_hi          corr += A_hi B_lo + A_lo B_hi          (A_lo B_lo ~ 2^-22: dropped)
+// `main` and `corr` are separate fp32 accumulators in TMEM, added once in the epilogue, so the small
+// correction terms are not absorbed one by one into the large sum.
+//
+//  tcg_rows_kernel  C[m, n] = epi(A[m, :] W): one CTA owns a 128-column half of W, converted ONCE into
+//      shared memory as resident UMMA B operands (hi + lo, K-major SW128, <= 160 KB), and walks over
+//      128-row tiles of A: eight producer warps load fp32 rows (coalesced), split them and write the
+//      swizzled A operand chunks into a small ring, one thread issues the MMAs, four epilogue warps read
+//      the double-buffered accumulators (tcgen05.ld) and store fp32 rows.  HBM-bound by design: every
+//      element of A and C crosses HBM once (the sibling CTA of the other column half re-reads A from L2).
+//  tcg_tn_kernel    C += A^T B over K = samples: both operands are converted into MN-major SW128 blocks
+//      (the byte image of a K-major block read transposed, as in mlp_tc_bwd.cu), the 128 x N result stays
+//      in TMEM over the CTA's whole sample range and is added to global memory once; the producers also
+//      form the column sums of B (bias gradients) on the way.
+#include <cuda_fp16.h>
+
+#include "gemm_tc.cuh"
+#include "sm100_ptx.cuh"
+
+namespace lnrf {
+
+using namespace ptx;
+
+namespace {
+
+// instruction descriptor, kind::f16 with fp16 A / B (format 0), fp32 D; K-major operands
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
+  return (1u << 4) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t idesc_f16_mn(int M, int N) { return idesc_f16(M, N) | (1u << 15) | (1u << 16); }
+
+// power of two s with amax * s in [64, 128); 1 for amax = 0 / inf / nan
+__device__ __forceinline__ float pow2_scale(float amax) {
+  if (!(amax > 0.0f) || !(amax < 3.0e38f)) return 1.0f;
+  int e = int((__float_as_uint(amax) >> 23) & 0xffu) - 127;
+  int se = 6 - e;
+  se = se < -60 ? -60 : (se > 60 ? 60 : se);
+  return __uint_as_float(uint32_t(se + 127) << 23);
+}
+
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// eight scaled floats -> 16 bytes of hi and 16 bytes of lo
+__device__ __forceinline__ void split8_store(const float4& a, const float4& b, float s, uint32_t hi_addr, uint32_t lo_addr) {
+  uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+  split2(a.x * s, a.y * s, h0, l0);
+  split2(a.z * s, a.w * s, h1, l1);
+  split2(b.x * s, b.y * s, h2, l2);
+  split2(b.z * s, b.w * s, h3, l3);
+  st_shared_v4(hi_addr, h0, h1, h2, h3);
+  st_shared_v4(lo_addr, l0, l1, l2, l3);
+}
+
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// D[tmem] (+)= A B with the two shared-memory descriptors given as 32-bit halves: the high words are
+// constant per layout, the low words are start addresses that the issue loop only increments (building
+// 64-bit descriptors per MMA in the single issuing thread costs more than the MMAs themselves).
+__device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO 1024 B, version 1, SWIZZLE_128B
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ================================================================ row GEMM
+constexpr int kRgThreads = 416;            // warps 0-3 epilogue, 4-11 producers, 12 MMA issuer
+constexpr int kRgProducers = 256;
+constexpr int kRgMaxChunks = 5;            // K <= 320
+constexpr uint32_t kRgBlock = 128 * 128;   // one [128 x 64] fp16 K-major SW128 block
+constexpr uint32_t kRgChunk = 2 * kRgBlock;  // hi + lo
+constexpr uint32_t kRgData = 7 * kRgChunk;   // resident B chunks first, the A ring behind them
+constexpr uint32_t kRgSmem = kRgData + 256;
+// barrier block (byte offsets inside it)
+constexpr uint32_t kRgAFull = 0, kRgAEmpty = 32, kRgAccFull = 64, kRgAccEmpty = 80, kRgTmemSlot = 96, kRgBMax = 100;
+
+struct RgChunkDesc {
+  const float* A;  // first column of the chunk (row 0)
+  int lda;
+  int kv;          // valid K columns (multiple of 4, <= 64)
+  int bk0;         // first K index of W
+};
+struct RgArgs {
+  RgChunkDesc ch[kRgMaxChunks];
+  int nchunks, stages, has_a1;
+  const float* B;
+  int ldb, btrans;
+  float* C;
+  int ldc;
+  int64_t M;
+  int N, nhalves, nc;  // nc = accumulator columns per CTA (multiple of 16)
+  const float* bias;
+  const float* aux;
+  int ldaux;
+  const float* r1s;
+  const float* r1w;
+  const float* a_amax;
+  const float* a1_amax;
+  float* c_amax;
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(kRgThreads, 1) tcg_rows_kernel(const __grid_constant__ RgArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t sbase = smem_u32(smem_raw);
+  if (sbase & 1023u) __trap();
+  const uint32_t sB = sbase, sA = sbase + uint32_t(a.nchunks) * kRgChunk, bars = sbase + kRgData;
+  volatile uint32_t* bar_words = reinterpret_cast<volatile uint32_t*>(smem_raw + kRgData);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int half = int(blockIdx.x) % a.nhalves, n0 = half * 128;
+  const int64_t tiles = ceil_div(a.M, 128);
+  const int64_t tstride = int64_t(gridDim.x) / a.nhalves, tfirst = int64_t(blockIdx.x) / a.nhalves;
+  const int64_t my_tiles = tiles > tfirst ? (tiles - tfirst + tstride - 1) / tstride : 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(bars + kRgAFull + 8 * s, kRgProducers / 32);
+      mbar_init(bars + kRgAEmpty + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bars + kRgAccFull + 8 * b, 1);
+      mbar_init(bars + kRgAccEmpty + 8 * b, 4);
+    }
+    bar_words[kRgBMax / 4] = 0u;
+    fence_barrier_init();
+  }
+  if (warp == 12) {
+    tmem_alloc(bars + kRgTmemSlot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bar_words[kRgTmemSlot / 4];
+
+  // ---- resident W operand of this column half: max |w| first (its own power-of-two scale), then hi / lo
+  auto w_at = [&](int c, int n, int k) -> float {  // chunk c, row n of the half, column k of the chunk
+    const RgChunkDesc cd = a.ch[c];
+    if (k >= cd.kv || n0 + n >= a.N) return 0.0f;
+    const int64_t kk = cd.bk0 + k, nn = n0 + n;
+    return a.btrans ? __ldg(a.B + nn * a.ldb + kk) : __ldg(a.B + kk * a.ldb + nn);
+  };
+  {
+    float mx = 0.0f;
+    for (int item = tid; item < a.nchunks * 1024; item += kRgThreads) {
+      const int c = item >> 10, n = item & 127, g8 = (item >> 7) & 7;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mx = fmaxf(mx, fabsf(w_at(c, n, g8 * 8 + j)));
+    }
+    mx = warp_max(mx);
+    if (lane == 0) atomicMax(const_cast<uint32_t*>(bar_words + kRgBMax / 4), __float_as_uint(mx));
+  }
+  __syncthreads();
+  const float sb = pow2_scale(__uint_as_float(bar_words[kRgBMax / 4]));
+  for (int item = tid; item < a.nchunks * 1024; item += kRgThreads) {
+    const int c = item >> 10, n = item & 127, g8 = (item >> 7) & 7;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = w_at(c, n, g8 * 8 + j);
+    const uint32_t off = uint32_t(n) * 128u + (uint32_t((g8 ^ (n & 7)) & 7) << 4);
+    split8_store(make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]), sb,
+                 sB + c * kRgChunk + off, sB + c * kRgChunk + kRgBlock + off);
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+
+  // one scale for both K segments (they share the accumulator): from the larger of the two maxima; a segment
+  // without an amax counts as O(1) once the other one has one
+  float sa = 1.0f;
+  if (a.a_amax != nullptr || a.a1_amax != nullptr) {
+    const float m0 = a.a_amax ? __ldg(a.a_amax) : 1.0f;
+    const float m1 = a.nchunks > 0 && a.a1_amax ? __ldg(a.a1_amax) : (a.has_a1 ? 1.0f : 0.0f);
+    sa = pow2_scale(fmaxf(m0, m1));
+  }
+
+  if (warp >= 4 && warp < 12) {
+    // ===== producers: thread owns 16-byte operand pieces (row, 8 columns); four pieces per chunk
+    const int pt = tid - 128;
+    const int g8 = pt & 7, r0 = pt >> 3;  // rows r0, r0 + 32, r0 + 64, r0 + 96
+    const int64_t total = my_tiles * a.nchunks;
+    // Three chunks of loads are kept in flight per thread (register ring b0 / b1 / b2): at ~23 B/clk of HBM
+    // bandwidth per SM and > 1 us of loaded latency one chunk (32 KB per SM) would bound the kernel.
+    float4 b0[8], b1[8], b2[8];
+    int lc = 0;                          // chunk index of the next load
+    int64_t lrow = tfirst * 128 + r0;    // this thread's first row of the tile of the next load
+    int lleft = total > 0x7fffffff ? 0x7fffffff : int(total), eleft = lleft;  // loads / emits still to do
+    const int k = g8 * 8;
+    auto load = [&](float4(&v)[8]) {
+      if (lleft <= 0) return;
+      --lleft;
+      const RgChunkDesc cd = a.ch[lc];
+      const bool vec8 = ((cd.lda & 7) == 0) && ((reinterpret_cast<uintptr_t>(cd.A) & 31) == 0) && k + 8 <= cd.kv;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t row = lrow + 32 * j;
+        v[2 * j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        v[2 * j + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < a.M) {
+          const float* p = cd.A + row * cd.lda + k;
+          if (vec8) {  // one 32-byte sector per lane: half the load instructions and L1 wavefronts
+            asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=f"(v[2 * j].x), "=f"(v[2 * j].y), "=f"(v[2 * j].z), "=f"(v[2 * j].w), "=f"(v[2 * j + 1].x),
+                           "=f"(v[2 * j + 1].y), "=f"(v[2 * j + 1].z), "=f"(v[2 * j + 1].w)
+                         : "l"(p));
+          } else {
+            if (k < cd.kv) v[2 * j] = __ldg(reinterpret_cast<const float4*>(p));
+            if (k + 4 < cd.kv) v[2 * j + 1] = __ldg(reinterpret_cast<const float4*>(p + 4));
+          }
+        }
+      }
+      if (++lc == a.nchunks) {
+        lc = 0;
+        lrow += tstride * 128;
+      }
+    };
+    uint32_t stage = 0, phases = 0;  // bit s = parity of a_empty[s] the next fill of slot s waits for
+    auto emit = [&](const float4(&v)[8]) {
+      if (eleft <= 0) return;
+      --eleft;
+      mbar_wait(bars + kRgAEmpty + 8 * stage, ((phases >> stage) & 1u) ^ 1u);
+      phases ^= 1u << stage;
+      const uint32_t base = sA + stage * kRgChunk;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = r0 + 32 * j;
+        const uint32_t off = uint32_t(r) * 128u + (uint32_t((g8 ^ (r & 7)) & 7) << 4);
+        split8_store(v[2 * j], v[2 * j + 1], sa, base + off, base + kRgBlock + off);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + kRgAFull + 8 * stage);
+      if (++stage == uint32_t(a.stages)) stage = 0;
+    };
+    load(b0);
+    load(b1);
+    while (eleft > 0) {
+      load(b2);
+      emit(b0);
+      load(b0);
+      emit(b1);
+      load(b1);
+      emit(b2);
+    }
+  } else if (warp == 12) {
+    // ===== MMA issuer
+    const uint32_t idesc = idesc_f16(128, a.nc);
+    uint32_t stage = 0, phases = 0;
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const uint32_t buf = uint32_t(it & 1);
+      mbar_wait(bars + kRgAccEmpty + 8 * buf, (uint32_t(it >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_main = tmem + buf * 256u, d_corr = d_main + 128u;
+      for (int c = 0; c < a.nchunks; ++c) {
+        mbar_wait(bars + kRgAFull + 8 * stage, (phases >> stage) & 1u);
+        phases ^= 1u << stage;
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const int ksteps = (a.ch[c].kv + 15) >> 4;
+          const uint32_t ah = (((sA + stage * kRgChunk) & 0x3FFFFu) >> 4) | (1u << 16), al = ah + (kRgBlock >> 4);
+          const uint32_t bh = (((sB + uint32_t(c) * kRgChunk) & 0x3FFFFu) >> 4) | (1u << 16), bl = bh + (kRgBlock >> 4);
+          for (int k = 0; k < ksteps; ++k) {  // 32 bytes (16 fp16) of K per step
+            const uint32_t acc = (c | k) ? 1u : 0u;
+            umma_f16_lohi(d_main, ah + 2 * k, bh + 2 * k, kDescHiSw128, idesc, acc);
+            umma_f16_lohi(d_corr, ah + 2 * k, bl + 2 * k, kDescHiSw128, idesc, acc);
+            umma_f16_lohi(d_corr, al + 2 * k, bh + 2 * k, kDescHiSw128, idesc, 1u);
+          }
+          umma_commit(bars + kRgAEmpty + 8 * stage);
+          if (c == a.nchunks - 1) umma_commit(bars + kRgAccFull + 8 * buf);
+        }
+        __syncwarp();
+        if (++stage == uint32_t(a.stages)) stage = 0;
+      }
+    }
+  } else if (warp < 4) {
+    // ===== epilogue.  tcgen05.ld hands lane r the 32 columns of tile row r: storing that directly makes every
+    // warp store touch 32 different lines, and the LSU (not HBM) bounds the kernel (measured: 1.8 TB/s).  So
+    // each 8-lane group first transposes its 8 rows x 8 four-column granules through shuffles: lane (a, b) =
+    // (lane / 8, lane % 8) ends up with granule b of rows 8a .. 8a+7, and store instruction i writes rows
+    // {8a + i}: eight lanes cover 128 contiguous bytes of a row.  The mask rows are read the same way.
+    const float inv = 1.0f / (sa * sb);
+    float amax = 0.0f;
+    const int la = lane >> 3, lb = lane & 7;
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const uint32_t buf = uint32_t(it & 1);
+      const int64_t row0 = (tfirst + it * tstride) * 128 + warp * 32 + la * 8;  // rows row0 + i, i = 0..7
+      float r1[8];
+      if (EPI == TCG_RANK1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r1[i] = row0 + i < a.M ? __ldg(a.r1s + row0 + i) : 0.0f;
+      }
+      mbar_wait(bars + kRgAccFull + 8 * buf, uint32_t(it >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t t_main = tmem + (uint32_t(warp * 32) << 16) + buf * 256u;
+      for (int c0 = 0; c0 < a.nc; c0 += 32) {
+        uint32_t vm[32], vc[32];
+        tmem_ld32(t_main + c0, vm);
+        tmem_ld32(t_main + 128 + c0, vc);
+        const int n = n0 + c0 + 4 * lb;               // this lane's four output columns
+        const bool col_ok = c0 + 4 * lb < a.nc && n < a.N;
+        float4 mk[8];  // EPI_MASK: the mask values of this lane's eight outputs, all loads in flight at once
+        float4 bw = make_float4(0.f, 0.f, 0.f, 0.f);  // bias (or the rank-1 row vector) of the four columns
+        if (EPI == TCG_MASK) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            mk[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (col_ok && row0 + i < a.M) mk[i] = __ldg(reinterpret_cast<const float4*>(a.aux + (row0 + i) * a.ldaux + n));
+          }
+        } else if (EPI == TCG_BIAS_RELU || EPI == TCG_BIAS) {
+          if (col_ok) bw = __ldg(reinterpret_cast<const float4*>(a.bias + n));
+        } else if (EPI == TCG_RANK1) {
+          if (col_ok) bw = __ldg(reinterpret_cast<const float4*>(a.r1w + n));
+        }
+        tmem_wait_ld();
+        float x[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = (__uint_as_float(vm[j]) + __uint_as_float(vc[j])) * inv;
+        // 8 x 8 transpose of granules (x[4g .. 4g+3] = granule g of this lane's row) inside each 8-lane group
+#pragma unroll
+        for (int s2 = 1; s2 < 8; s2 <<= 1) {
+          const bool up = (lb & s2) != 0;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            if (g & s2) continue;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float lo_v = x[4 * g + e], hi_v = x[4 * (g + s2) + e];
+              const float recv = __shfl_xor_sync(0xffffffffu, up ? lo_v : hi_v, s2);
+              x[4 * g + e] = up ? recv : lo_v;
+              x[4 * (g + s2) + e] = up ? hi_v : recv;
+            }
+          }
+        }
+        // x[4i .. 4i+3] = granule lb (columns n .. n+3) of row row0 + i
+        if (col_ok) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (row0 + i >= a.M) continue;
+            float v[4] = {x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]};
+            if (EPI == TCG_BIAS_RELU || EPI == TCG_BIAS) {
+              v[0] += bw.x; v[1] += bw.y; v[2] += bw.z; v[3] += bw.w;
+              if (EPI == TCG_BIAS_RELU) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.0f);
+              }
+            } else if (EPI == TCG_MASK) {
+              v[0] = mk[i].x > 0.f ? v[0] : 0.f; v[1] = mk[i].y > 0.f ? v[1] : 0.f;
+              v[2] = mk[i].z > 0.f ? v[2] : 0.f; v[3] = mk[i].w > 0.f ? v[3] : 0.f;
+            } else if (EPI == TCG_RANK1) {
+              v[0] = fmaf(r1[i], bw.x, v[0]); v[1] = fmaf(r1[i], bw.y, v[1]);
+              v[2] = fmaf(r1[i], bw.z, v[2]); v[3] = fmaf(r1[i], bw.w, v[3]);
+            }
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3]))));
+            *reinterpret_cast<float4*>(a.C + (row0 + i) * a.ldc + n) = make_float4(v[0], v[1], v[2], v[3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + kRgAccEmpty + 8 * buf);
+    }
+    if (a.c_amax) {
+      amax = warp_max(amax);
+      if (lane == 0 && amax > 0.0f && amax < 3.0e38f) atomicMax(reinterpret_cast<uint32_t*>(a.c_amax), __float_as_uint(amax));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) tmem_dealloc(tmem, 512);
+}
+
+// ================================================================ TN GEMM (K = samples)
+constexpr int kTnThreads = 288;             // warps 0-7 producers (0-3 also drain the accumulator), warp 8 MMA issuer
+constexpr uint32_t kTnHalf = 64 * 128;      // one [64 samples x 64 features] fp16 block
+constexpr uint32_t kTnAPart = 2 * kTnHalf;  // A hi (or lo): features 0..127 of the CTA's M block
+constexpr uint32_t kTnBPart = 4 * kTnHalf;  // B hi (or lo): up to 256 columns
+constexpr uint32_t kTnStage = 2 * kTnAPart + 2 * kTnBPart;  // 96 KB
+constexpr int kTnStages = 2;
+constexpr uint32_t kTnSmem = kTnStages * kTnStage + 256;
+constexpr uint32_t kTnFull = 0, kTnEmpty = 16, kTnDone = 32, kTnTmemSlot = 40;
+
+struct TnArgs {
+  const float* At;
+  int lda, M;
+  const float* B;
+  int ldb, N;
+  int64_t K;
+  float* C;
+  int ldc;
+  float* db;
+  const float* a_amax;
+  const float* b_amax;
+  int mblocks, nb;  // nb = 64-column blocks of B (N padded)
+  int64_t chunks_per_cta, chunks;
+};
+
+__global__ void __launch_bounds__(kTnThreads, 1) tcg_tn_kernel(const __grid_constant__ TnArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t sbase = smem_u32(smem_raw);
+  if (sbase & 1023u) __trap();
+  const uint32_t bars = sbase + kTnStages * kTnStage;
+  volatile uint32_t* bar_words = reinterpret_cast<volatile uint32_t*>(smem_raw + kTnStages * kTnStage);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int mb = int(blockIdx.x) % a.mblocks;
+  const int64_t ks = int64_t(blockIdx.x) / a.mblocks;
+  const int64_t q0 = ks * a.chunks_per_cta;
+  const int64_t q1 = q0 + a.chunks_per_cta < a.chunks ? q0 + a.chunks_per_cta : a.chunks;
+  const int64_t nq = q1 > q0 ? q1 - q0 : 0;
+  const int Npad = a.nb * 64;
+
+  if (tid == 0) {
+    for (int s = 0; s < kTnStages; ++s) {
+      mbar_init(bars + kTnFull + 8 * s, 8);
+      mbar_init(bars + kTnEmpty + 8 * s, 1);
+    }
+    mbar_init(bars + kTnDone, 1);
+    fence_barrier_init();
+  }
+  if (warp == 8) {
+    tmem_alloc(bars + kTnTmemSlot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bar_words[kTnTmemSlot / 4];
+  const float sa = a.a_amax ? pow2_scale(__ldg(a.a_amax)) : 1.0f;
+  const float sb = a.b_amax ? pow2_scale(__ldg(a.b_amax)) : 1.0f;
+
+  if (warp < 8) {
+    // ===== producers
+    const int ag8 = tid & 15, ar0 = tid >> 4;  // A pieces: rows ar0 + 16 j, features mb 128 + 8 ag8 ..
+    const int bg8 = tid & 31, br0 = tid >> 5;  // B pieces: rows br0 + 8 j, columns 8 bg8 ..  (fixed columns per thread)
+    const int af = mb * 128 + ag8 * 8, bc = bg8 * 8;
+    const bool b_active = bg8 < a.nb * 8;
+    float cs[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cs[j] = 0.0f;
+    const bool do_db = a.db != nullptr && mb == 0;
+    uint32_t stage = 0, phases = 0;
+    // One chunk = 8 + 16 sixteen-byte loads per thread, all issued before the first use (96 KB in flight per
+    // SM); nine warps cap the kernel at 168 registers, which rules out a second chunk of register prefetch
+    // (measured: a three-deep ring of half chunks spills and runs 3x slower).
+    for (int64_t q = 0; q < nq; ++q) {
+      const int64_t k0 = (q0 + q) * 64;
+      float4 va[8], vb[16];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t row = k0 + ar0 + 16 * j;
+        va[2 * j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        va[2 * j + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < a.K) {
+          const float* p = a.At + row * a.lda + af;
+          if (af < a.M) va[2 * j] = __ldg(reinterpret_cast<const float4*>(p));
+          if (af + 4 < a.M) va[2 * j + 1] = __ldg(reinterpret_cast<const float4*>(p + 4));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int64_t row = k0 + br0 + 8 * j;
+        vb[2 * j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        vb[2 * j + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b_active && row < a.K) {
+          const float* p = a.B + row * a.ldb + bc;
+          if (bc < a.N) vb[2 * j] = __ldg(reinterpret_cast<const float4*>(p));
+          if (bc + 4 < a.N) vb[2 * j + 1] = __ldg(reinterpret_cast<const float4*>(p + 4));
+        }
+      }
+      mbar_wait(bars + kTnEmpty + 8 * stage, ((phases >> stage) & 1u) ^ 1u);
+      phases ^= 1u << stage;
+      const uint32_t s_ah = sbase + stage * kTnStage, s_al = s_ah + kTnAPart;
+      const uint32_t s_bh = s_al + kTnAPart, s_bl = s_bh + kTnBPart;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = ar0 + 16 * j;
+        const uint32_t off = uint32_t(ag8 >> 3) * kTnHalf + uint32_t(r) * 128u + (uint32_t(((ag8 & 7) ^ (r & 7)) & 7) << 4);
+        split8_store(va[2 * j], va[2 * j + 1], sa, s_ah + off, s_al + off);
+      }
+      if (b_active) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = br0 + 8 * j;
+          const uint32_t off = uint32_t(bg8 >> 3) * kTnHalf + uint32_t(r) * 128u + (uint32_t(((bg8 & 7) ^ (r & 7)) & 7) << 4);
+          split8_store(vb[2 * j], vb[2 * j + 1], sb, s_bh + off, s_bl + off);
+          if (do_db) {
+            cs[0] += vb[2 * j].x; cs[1] += vb[2 * j].y; cs[2] += vb[2 * j].z; cs[3] += vb[2 * j].w;
+            cs[4] += vb[2 * j + 1].x; cs[5] += vb[2 * j + 1].y; cs[6] += vb[2 * j + 1].z; cs[7] += vb[2 * j + 1].w;
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + kTnFull + 8 * stage);
+      if (++stage == kTnStages) stage = 0;
+    }
+    // wait for the last MMAs: shared memory and the accumulator are then free / complete
+    mbar_wait(bars + kTnDone, 0);
+    tc_fence_after();
+    if (do_db) {  // fold the eight row groups of a column through shared memory, one atomic per column
+      float* s_cs = reinterpret_cast<float*>(smem_raw);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (b_active) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s_cs[br0 * 256 + bc + j] = cs[j];
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (tid < a.N) {
+        float t = 0.0f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) t += s_cs[g * 256 + tid];
+        atomicAdd(a.db + tid, t);
+      }
+    }
+    if (warp < 4 && nq > 0) {
+      const float inv = 1.0f / (sa * sb);
+      const int row = mb * 128 + tid;
+      const uint32_t t0 = tmem + (uint32_t(warp * 32) << 16);
+      for (int c0 = 0; c0 < Npad; c0 += 32) {
+        uint32_t vm[32], vc[32];
+        tmem_ld32(t0 + c0, vm);
+        tmem_ld32(t0 + 256 + c0, vc);
+        tmem_wait_ld();
+        if (row < a.M) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (c0 + j < a.N)
+              red_add_v4(a.C + int64_t(row) * a.ldc + c0 + j,
+                         (__uint_as_float(vm[j]) + __uint_as_float(vc[j])) * inv,
+                         (__uint_as_float(vm[j + 1]) + __uint_as_float(vc[j + 1])) * inv,
+                         (__uint_as_float(vm[j + 2]) + __uint_as_float(vc[j + 2])) * inv,
+                         (__uint_as_float(vm[j + 3]) + __uint_as_float(vc[j + 3])) * inv);
+          }
+        }
+      }
+    }
+  } else {
+    // ===== MMA issuer: main += Ah^T Bh, corr += Ah^T Bl + Al^T Bh; operands MN-major, K = 16 samples per MMA
+    const uint32_t idesc = idesc_f16_mn(128, Npad);
+    uint32_t stage = 0, phases = 0;
+    for (int64_t q = 0; q < nq; ++q) {
+      mbar_wait(bars + kTnFull + 8 * stage, (phases >> stage) & 1u);
+      phases ^= 1u << stage;
+      tc_fence_after();
+      if (elect_one_sync()) {
+        // MN-major SW128: 64-feature blocks kTnHalf bytes apart (LBO), 16 samples = 2048 bytes per K step
+        const uint32_t lbo = (kTnHalf >> 4) << 16;
+        const uint32_t ah = (((sbase + stage * kTnStage) & 0x3FFFFu) >> 4) | lbo, al = ah + (kTnAPart >> 4);
+        const uint32_t bh = al + (kTnAPart >> 4), bl = bh + (kTnBPart >> 4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t acc = (q | k) ? 1u : 0u;
+          umma_f16_lohi(tmem, ah + 128 * k, bh + 128 * k, kDescHiSw128, idesc, acc);
+          umma_f16_lohi(tmem + 256, ah + 128 * k, bl + 128 * k, kDescHiSw128, idesc, acc);
+          umma_f16_lohi(tmem + 256, al + 128 * k, bh + 128 * k, kDescHiSw128, idesc, 1u);
+        }
+        umma_commit(bars + kTnEmpty + 8 * stage);
+        if (q == nq - 1) umma_commit(bars + kTnDone);
+      }
+      __syncwarp();
+      if (++stage == kTnStages) stage = 0;
+    }
+    if (nq == 0 && elect_one_sync()) mbar_arrive(bars + kTnDone);
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, 512);
+}
+
+__global__ void __launch_bounds__(256) tcg_amax_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ amax) {
+  float m = 0.0f;
+  const int64_t n4 = n >> 2;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += int64_t(gridDim.x) * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) m = fmaxf(m, fabsf(__ldg(x + (n4 << 2) + threadIdx.x)));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.0f && m < 3.0e38f) atomicMax(reinterpret_cast<uint32_t*>(amax), __float_as_uint(m));
+}
+
+template <int EPI>
+int launch_rows(const RgArgs& a, unsigned grid, cudaStream_t st) {
+  tcg_rows_kernel<EPI><<<grid, kRgThreads, kRgSmem, st>>>(a);
+  LNRF_LAUNCH_CHECK("tcg_rows_kernel");
+  return LNRF_OK;
+}
+
+}  // namespace
+
+bool tcg_supported(int N, int K0, int K1) {
+  if (N <= 0 || N > 256 || N % 4) return false;
+  if (K0 <= 0 || K0 % 4 || K1 < 0 || K1 % 4) return false;
+  return ceil_div(K0, 64) + ceil_div(K1, 64) <= kRgMaxChunks;
+}
+
+int tcg_rows(cudaStream_t st, int epi, bool btrans, int64_t M, int N, const float* A0, int lda0, int K0,
+             const float* A1, int lda1, int K1, const float* B, int ldb, float* C, int ldc, const float* bias,
+             const float* aux, int ldaux, const float* r1s, const float* r1w, const float* a_amax, const float* a1_amax, float* c_amax) {
+  LNRF_REQUIRE(tcg_supported(N, K0, K1), LNRF_E_UNSUPPORTED, "tcg_rows: N=%d K0=%d K1=%d", N, K0, K1);
+  LNRF_REQUIRE(lda0 % 4 == 0 && lda1 % 4 == 0 && ldc % 4 == 0 && ldaux % 4 == 0, LNRF_E_UNSUPPORTED,
+               "tcg_rows: leading dimensions must be multiples of 4");
+  if (M <= 0) return LNRF_OK;
+  RgArgs a{};
+  int nch = 0;
+  for (int k = 0; k < K0; k += 64) a.ch[nch++] = RgChunkDesc{A0 + k, lda0, K0 - k < 64 ? K0 - k : 64, k};
+  for (int k = 0; k < K1; k += 64) a.ch[nch++] = RgChunkDesc{A1 + k, lda1, K1 - k < 64 ? K1 - k : 64, K0 + k};
+  a.nchunks = nch;
+  a.stages = 7 - nch > 4 ? 4 : 7 - nch;
+  a.B = B; a.ldb = ldb; a.btrans = btrans ? 1 : 0;
+  a.C = C; a.ldc = ldc; a.M = M; a.N = N;
+  a.nhalves = N > 128 ? 2 : 1;
+  const int ncols = a.nhalves == 2 ? 128 : N;
+  a.nc = int(align_up(ncols, 16));
+  a.bias = bias; a.aux = aux; a.ldaux = ldaux; a.r1s = r1s; a.r1w = r1w;
+  a.a_amax = a_amax; a.a1_amax = K1 > 0 ? a1_amax : nullptr; a.c_amax = c_amax; a.has_a1 = K1 > 0 ? 1 : 0;
+  const int64_t tiles = ceil_div(M, 128);
+  int64_t grid = sm_count() / a.nhalves;
+  if (grid > tiles) grid = tiles;
+  grid *= a.nhalves;
+  switch (epi) {
+    case TCG_BIAS_RELU: return launch_rows<TCG_BIAS_RELU>(a, unsigned(grid), st);
+    case TCG_BIAS: return launch_rows<TCG_BIAS>(a, unsigned(grid), st);
+    case TCG_MASK: return launch_rows<TCG_MASK>(a, unsigned(grid), st);
+    case TCG_RANK1: return launch_rows<TCG_RANK1>(a, unsigned(grid), st);
+    case TCG_STORE: return launch_rows<TCG_STORE>(a, unsigned(grid), st);
+  }
+  LNRF_REQUIRE(false, LNRF_E_INVALID, "tcg_rows: unknown epilogue %d", epi);
+}
+
+int tcg_tn_acc(cudaStream_t st, int M, int N, const float* At, int lda, const float* B, int ldb, int64_t K, float* C,
+               int ldc, float* db, const float* a_amax, const float* b_amax) {
+  LNRF_REQUIRE(M > 0 && M <= 256 && M % 4 == 0 && N > 0 && N <= 256 && N % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 &&
+                   ldc % 4 == 0,
+               LNRF_E_UNSUPPORTED, "tcg_tn_acc: M=%d N=%d lda=%d ldb=%d ldc=%d", M, N, lda, ldb, ldc);
+  if (K <= 0) return LNRF_OK;
+  TnArgs a{};
+  a.At = At; a.lda = lda; a.M = M; a.B = B; a.ldb = ldb; a.N = N; a.K = K; a.C = C; a.ldc = ldc; a.db = db;
+  a.a_amax = a_amax; a.b_amax = b_amax;
+  a.mblocks = int(ceil_div(M, 128));
+  a.nb = int(ceil_div(N, 64));
+  a.chunks = ceil_div(K, 64);
+  int64_t splits = sm_count() / a.mblocks;
+  if (splits < 1) splits = 1;
+  a.chunks_per_cta = ceil_div(a.chunks, splits);
+  if (a.chunks_per_cta < 4) a.chunks_per_cta = 4;
+  splits = ceil_div(a.chunks, a.chunks_per_cta);
+  tcg_tn_kernel<<<unsigned(splits * a.mblocks), kTnThreads, kTnSmem, st>>>(a);
+  LNRF_LAUNCH_CHECK("tcg_tn_kernel");
+  return LNRF_OK;
+}
+
+int tcg_amax(cudaStream_t st, const float* x, int64_t n, float* amax) {
+  if (n <= 0) return LNRF_OK;
+  int64_t blocks = ceil_div(n, 256 * 16);
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  tcg_amax_kernel<<<unsigned(blocks), 256, 0, st>>>(x, n, amax);
+  LNRF_LAUNCH_CHECK("tcg_amax_kernel");
+  return LNRF_OK;
+}
+
+int init_gemm_tc() {
+  LNRF_CUDA(cudaFuncSetAttribute(tcg_rows_kernel<TCG_BIAS_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRgSmem));
+  LNRF_CUDA(cudaFuncSetAttribute(tcg_rows_kernel<TCG_BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRgSmem));
+  LNRF_CUDA(cudaFuncSetAttribute(tcg_rows_kernel<TCG_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRgSmem));
+  LNRF_CUDA(cudaFuncSetAttribute(tcg_rows_kernel<TCG_RANK1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRgSmem));
+  LNRF_CUDA(cudaFuncSetAttribute(tcg_rows_kernel<TCG_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRgSmem));
+  LNRF_CUDA(cudaFuncSetAttribute(tcg_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTnSmem));
+  return LNRF_OK;
+}
+
+}  // namespace lnrf
+
+// Diagnostic entry (tests): the GEMM engine on its own.  mode 0: rows NN, 1: rows NT, 2: TN accumulate
+// (C[K0, N] += A0[M, K0]^T B[M, N]: M = samples), 3: c_amax = max |A0[0..M)|.
+extern "C" int lnrf_tcgemm(int mode, int epi, int64_t M, int N, const float* A0, int lda0, int K0, const float* A1,
+                           int lda1, int K1, const float* B, int ldb, float* C, int ldc, const float* bias,
+                           const float* aux, int ldaux, const float* r1s, const float* r1w, float* db,
+                           const float* a_amax, const float* b_amax, float* c_amax, lnrf_stream_t stream) {
+  using namespace lnrf;
+  cudaStream_t st = as_stream(stream);
+  if (mode == 0 || mode == 1)
+    return tcg_rows(st, epi, mode == 1, M, N, A0, lda0, K0, A1, lda1, K1, B, ldb, C, ldc, bias, aux, ldaux, r1s, r1w,
+                    a_amax, nullptr, c_amax);
+  if (mode == 2) return tcg_tn_acc(st, K0, N, A0, lda0, B, ldb, M, C, ldc, db, a_amax, b_amax);
+  if (mode == 3) return tcg_amax(st, A0, M, c_amax);
+  set_error("lnrf_tcgemm: unknown mode %d", mode);
+  return LNRF_E_INVALID;
+}

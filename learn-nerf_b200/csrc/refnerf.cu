@@ -17,10 +17,47 @@
 #include "embed.cuh"
 #include "lnrf_common.cuh"
 #include "lnrf_math.cuh"
+#include "gemm_tc.cuh"
 #include "nerf_layout.cuh"
 #include "sgemm.cuh"
 
 namespace lnrf {
+
+// ---- the contractions: split-fp16 tcgen05 GEMMs (gemm_tc.cu), or the FFMA GEMMs of sgemm.cuh when
+// LNRF_FP32_FFMA=1 was set at lnrf_init (A/B measurements).  `*_amax` are device floats holding max |operand|
+// (see gemm_tc.cuh); nullptr = the operand is O(1).
+bool fp32_ffma();  // mlp_fp32.cu
+template <int EPI>
+static int rg_nn(cudaStream_t st, int64_t m, int N, const float* A0, int lda0, int K0, const float* A1, int lda1, int K1,
+                 const float* W, float* C, const float* bias, const float* aux, const float* a_amax,
+                 const float* a1_amax, float* c_amax) {
+  if (fp32_ffma() || !tcg_supported(N, K0, K1)) return gemm_nn<EPI>(st, m, N, A0, lda0, K0, A1, lda1, K1, W, N, C, N, bias, aux, N);
+  return tcg_rows(st, EPI, false, m, N, A0, lda0, K0, A1, lda1, K1, W, N, C, N, bias, aux, N, nullptr, nullptr, a_amax,
+                  a1_amax, c_amax);
+}
+// C[m,N] = epi(Gr[m,K] @ W[N rows, K cols]^T)
+template <int EPI>
+static int rg_nt(cudaStream_t st, int64_t m, int N, const float* Gr, int K, const float* W, float* C, const float* aux,
+                 const float* a_amax, float* c_amax) {
+  if (fp32_ffma() || !tcg_supported(N, K, 0)) return gemm_nt<EPI>(st, m, N, Gr, K, K, W, K, C, N, aux, N);
+  return tcg_rows(st, EPI, true, m, N, Gr, K, K, nullptr, 0, 0, W, K, C, N, nullptr, aux, N, nullptr, nullptr, a_amax,
+                  nullptr, c_amax);
+}
+// dW[M,N] += H[m,M]^T Gr[m,N]; db[N] += column sums of Gr (nullable)
+static int rg_tn(cudaStream_t st, int M, int N, const float* H, const float* Gr, int64_t m, float* dW, float* db,
+                 const float* h_amax, const float* g_amax) {
+  if (fp32_ffma()) {
+    const int rc = gemm_tn_acc(st, M, N, H, M, Gr, N, m, dW, N);
+    if (rc || db == nullptr) return rc;
+    colsum_kernel<><<<ew_blocks(m, 512), 256, 0, st>>>(Gr, m, N, db);
+    LNRF_LAUNCH_CHECK("colsum_kernel");
+    return LNRF_OK;
+  }
+  return tcg_tn_acc(st, M, N, H, M, Gr, N, m, dW, N, db, h_amax, g_amax);
+}
+// amax slots of the Ref-NeRF workspace (floats at RefWs::amax): forward 0..18, backward 19..
+constexpr int kRaH = 0, kRaGn = 9, kRaC = 17, kRaW8 = 18, kRaFwdEnd = 19;
+constexpr int kRaGc = 19, kRaG8pre = 20, kRaG = 21 /* g8 .. g0: 9 */, kRaTemb = 30, kRaT = 31 /* T0 .. T7 */, kRaEnd = 40;
 
 constexpr int kRefLayers = 11;
 constexpr int kRefEnc = 16;            // sum(HARMONIC_COUNTS[:4])
@@ -464,6 +501,7 @@ struct RefWs {
   float* o;       // [m,4]
   // backward only
   float *gA, *gB, *tA, *tB, *temb, *d_o, *gc, *dE, *u;
+  float* amax;    // [64] max |operand| slots of the tensor-core GEMMs (kRa*)
   int64_t bytes;
 };
 static RefWs carve_ref(void* base, int64_t m, bool save) {
@@ -490,6 +528,7 @@ static RefWs carve_ref(void* base, int64_t m, bool save) {
   w.E = take(m * kRefE);
   w.c = take(m * kHC);
   w.o = take(m * 4);
+  w.amax = take(64);
   if (save) {
     w.gA = take(m * kH);
     w.gB = take(m * kH);
@@ -630,40 +669,44 @@ int lnrf_refnerf_fwd(const float* params, const float* x, const float* d, const 
   cudaStream_t st = as_stream(stream);
   const float* P = params;
   int rc;
+  float* am = w.amax;
+  LNRF_CUDA(cudaMemsetAsync(am, 0, kRaFwdEnd * sizeof(float), st));
   // ---- spatial_block (ref_nerf.py:92-103)
   embed_kernel<kXFreqs><<<ew_blocks(m * 3 * kXFreqs, 256), 256, 0, st>>>(x, rays, ts, T, 0, m, w.xe);
   LNRF_LAUNCH_CHECK("embed_kernel<x>");
-  if ((rc = gemm_nn<EPI_BIAS_RELU>(st, m, kH, w.xe, kXE, kXE, nullptr, 0, 0, P + kRef.w[0], kH, w.h[0], kH,
-                                   P + kRef.b[0]))) return rc;
+  if ((rc = rg_nn<EPI_BIAS_RELU>(st, m, kH, w.xe, kXE, kXE, nullptr, 0, 0, P + kRef.w[0], w.h[0], P + kRef.b[0], nullptr,
+                                 nullptr, nullptr, am + kRaH + 0))) return rc;
   for (int l = 1; l <= 4; ++l)
-    if ((rc = gemm_nn<EPI_BIAS_RELU>(st, m, kH, w.h[l - 1], kH, kH, nullptr, 0, 0, P + kRef.w[l], kH, w.h[l], kH,
-                                     P + kRef.b[l]))) return rc;
-  if ((rc = gemm_nn<EPI_BIAS_RELU>(st, m, kH, w.h[4], kH, kH, w.xe, kXE, kXE, P + kRef.w[5], kH, w.h[5], kH,
-                                   P + kRef.b[5]))) return rc;
+    if ((rc = rg_nn<EPI_BIAS_RELU>(st, m, kH, w.h[l - 1], kH, kH, nullptr, 0, 0, P + kRef.w[l], w.h[l], P + kRef.b[l],
+                                   nullptr, am + kRaH + l - 1, nullptr, am + kRaH + l))) return rc;
+  if ((rc = rg_nn<EPI_BIAS_RELU>(st, m, kH, w.h[4], kH, kH, w.xe, kXE, kXE, P + kRef.w[5], w.h[5], P + kRef.b[5], nullptr,
+                                 am + kRaH + 4, nullptr, am + kRaH + 5))) return rc;
   for (int l = 6; l <= 7; ++l)
-    if ((rc = gemm_nn<EPI_BIAS_RELU>(st, m, kH, w.h[l - 1], kH, kH, nullptr, 0, 0, P + kRef.w[l], kH, w.h[l], kH,
-                                     P + kRef.b[l]))) return rc;
-  if ((rc = gemm_nn<EPI_BIAS>(st, m, kH, w.h[7], kH, kH, nullptr, 0, 0, P + kRef.w[8], kH, w.h[8], kH,
-                              P + kRef.b[8]))) return rc;
+    if ((rc = rg_nn<EPI_BIAS_RELU>(st, m, kH, w.h[l - 1], kH, kH, nullptr, 0, 0, P + kRef.w[l], w.h[l], P + kRef.b[l],
+                                   nullptr, am + kRaH + l - 1, nullptr, am + kRaH + l))) return rc;
+  if ((rc = rg_nn<EPI_BIAS>(st, m, kH, w.h[7], kH, kH, nullptr, 0, 0, P + kRef.w[8], w.h[8], P + kRef.b[8], nullptr,
+                            am + kRaH + 7, nullptr, am + kRaH + 8))) return rc;
   // ---- real_normal: VJP of -z8[:, 0] w.r.t. x (ref_nerf.py:38-43)
   ref_seed_kernel<<<ew_blocks(m * kH, 256), 256, 0, st>>>(w.h[7], P + kRef.w[8], m, w.gn[7]);
   LNRF_LAUNCH_CHECK("ref_seed_kernel");
+  // |Gn_7| <= max |W_8|: a bound is all the scale needs
+  if ((rc = tcg_amax(st, P + kRef.w[8], int64_t(kH) * kH, am + kRaGn + 7))) return rc;
   for (int l = 7; l >= 1; --l) {
     if (l == 5)  // the skip input [z | x_emb]: rows 256.. of Dense_5 feed x_emb directly
-      if ((rc = gemm_nt<EPI_STORE>(st, m, kXE, w.gn[5], kH, kH, P + kRef.w[5] + int64_t(kH) * kH, kH, w.dxe5,
-                                   kXE))) return rc;
-    if ((rc = gemm_nt<EPI_MASK>(st, m, kH, w.gn[l], kH, kH, P + kRef.w[l], kH, w.gn[l - 1], kH, w.h[l - 1],
-                                kH))) return rc;
+      if ((rc = rg_nt<EPI_STORE>(st, m, kXE, w.gn[5], kH, P + kRef.w[5] + int64_t(kH) * kH, w.dxe5, nullptr,
+                                 am + kRaGn + 5, nullptr))) return rc;
+    if ((rc = rg_nt<EPI_MASK>(st, m, kH, w.gn[l], kH, P + kRef.w[l], w.gn[l - 1], w.h[l - 1], am + kRaGn + l,
+                              am + kRaGn + l - 1))) return rc;
   }
-  if ((rc = gemm_nt<EPI_STORE>(st, m, kXE, w.gn[0], kH, kH, P + kRef.w[0], kH, w.dxe0, kXE))) return rc;
+  if ((rc = rg_nt<EPI_STORE>(st, m, kXE, w.gn[0], kH, P + kRef.w[0], w.dxe0, nullptr, am + kRaGn + 0, nullptr))) return rc;
   ref_nraw_kernel<<<ew_blocks(m * 3, 256), 256, 0, st>>>(x, rays, ts, T, m, w.dxe0, w.dxe5, w.nraw);
   LNRF_LAUNCH_CHECK("ref_nraw_kernel");
   // ---- heads (ref_nerf.py:45-75)
   ref_head_fwd1_kernel<<<ew_blocks(m, 256), 256, 0, st>>>(w.h[8], d, rays, T, w.nraw, m, dens, w.E,
                                                           aux_normal_mse, aux_neg_normal);
   LNRF_LAUNCH_CHECK("ref_head_fwd1_kernel");
-  if ((rc = gemm_nn<EPI_BIAS_RELU>(st, m, kHC, w.h[8], kH, kH, w.E, kRefE, kRefE, P + kRef.w[9], kHC, w.c, kHC,
-                                   P + kRef.b[9]))) return rc;  // directional_block :105-106
+  if ((rc = rg_nn<EPI_BIAS_RELU>(st, m, kHC, w.h[8], kH, kH, w.E, kRefE, kRefE, P + kRef.w[9], w.c, P + kRef.b[9], nullptr,
+                                 am + kRaH + 8, nullptr, am + kRaC))) return rc;  // directional_block :105-106
   ref_out_fwd_kernel<4><<<ew_blocks(m, 8), 256, 0, st>>>(w.c, P + kRef.w[10], P + kRef.b[10], m, w.o);  // :107
   LNRF_LAUNCH_CHECK("ref_out_fwd_kernel");
   ref_head_fwd2_kernel<<<ew_blocks(m, 256), 256, 0, st>>>(w.h[8], w.o, m, rgb);
@@ -695,49 +738,51 @@ int lnrf_refnerf_bwd(const float* params, const float* x, const float* d, const 
   ref_out_bwd_kernel<4><<<ew_blocks(m, 8 * 16), 256, 0, st>>>(w.h[8], w.o, w.c, d_rgb, P + kRef.w[10], m, w.d_o,
                                                                w.gc, G + kRef.w[10], G + kRef.b[10], kH);
   LNRF_LAUNCH_CHECK("ref_out_bwd_kernel");
-  if ((rc = gemm_tn_acc(st, kH, kHC, w.h[8], kH, w.gc, kHC, m, G + kRef.w[9], kHC))) return rc;
-  if ((rc = gemm_tn_acc(st, kRefE, kHC, w.E, kRefE, w.gc, kHC, m, G + kRef.w[9] + int64_t(kH) * kHC, kHC))) return rc;
-  colsum_kernel<><<<cb, 256, 0, st>>>(w.gc, m, kHC, G + kRef.b[9]);
-  LNRF_LAUNCH_CHECK("colsum_kernel");
+  float* am = w.amax;
+  LNRF_CUDA(cudaMemsetAsync(am + kRaFwdEnd, 0, (64 - kRaFwdEnd) * sizeof(float), st));
+  if ((rc = tcg_amax(st, w.gc, m * kHC, am + kRaGc))) return rc;
+  if ((rc = rg_tn(st, kH, kHC, w.h[8], w.gc, m, G + kRef.w[9], G + kRef.b[9], am + kRaH + 8, am + kRaGc))) return rc;
+  if ((rc = rg_tn(st, kRefE, kHC, w.E, w.gc, m, G + kRef.w[9] + int64_t(kH) * kHC, nullptr, nullptr, am + kRaGc))) return rc;
   float* g = w.gA;
   float* gnext = w.gB;
-  if ((rc = gemm_nt<EPI_STORE>(st, m, kH, w.gc, kHC, kHC, P + kRef.w[9], kHC, g, kH))) return rc;
-  if ((rc = gemm_nt<EPI_STORE>(st, m, kRefE, w.gc, kHC, kHC, P + kRef.w[9] + int64_t(kH) * kHC, kHC, w.dE,
-                               kRefE))) return rc;
+  if ((rc = rg_nt<EPI_STORE>(st, m, kH, w.gc, kHC, P + kRef.w[9], g, nullptr, am + kRaGc, nullptr))) return rc;
+  if ((rc = rg_nt<EPI_STORE>(st, m, kRefE, w.gc, kHC, P + kRef.w[9] + int64_t(kH) * kHC, w.dE, nullptr, am + kRaGc,
+                             nullptr))) return rc;
   // ---- heads: adds dL/dz8[:, :9] into g, produces u = dL/dn_raw
   ref_head_bwd_kernel<<<ew_blocks(m, 256), 256, 0, st>>>(w.h[8], d, rays, T, w.nraw, w.o, d_dens, d_rgb,
                                                          d_aux_normal_mse, d_aux_neg_normal, w.dE, m, g, w.u);
   LNRF_LAUNCH_CHECK("ref_head_bwd_kernel");
+  if ((rc = tcg_amax(st, g, m * kH, am + kRaG))) return rc;  // G_8 as the chain sees it (the heads changed nine columns)
   // ---- first-order chain through the spatial block (as NeRF's, from G_8 = g)
   for (int l = 8; l >= 1; --l) {
-    if ((rc = gemm_tn_acc(st, kH, kH, w.h[l - 1], kH, g, kH, m, G + kRef.w[l], kH))) return rc;
+    const float* ga = am + kRaG + (8 - l);
+    if ((rc = rg_tn(st, kH, kH, w.h[l - 1], g, m, G + kRef.w[l], G + kRef.b[l], am + kRaH + l - 1, ga))) return rc;
     if (l == 5)
-      if ((rc = gemm_tn_acc(st, kXE, kH, w.xe, kXE, g, kH, m, G + kRef.w[5] + int64_t(kH) * kH, kH))) return rc;
-    colsum_kernel<><<<cb, 256, 0, st>>>(g, m, kH, G + kRef.b[l]);
-    LNRF_LAUNCH_CHECK("colsum_kernel");
-    if ((rc = gemm_nt<EPI_MASK>(st, m, kH, g, kH, kH, P + kRef.w[l], kH, gnext, kH, w.h[l - 1], kH))) return rc;
+      if ((rc = rg_tn(st, kXE, kH, w.xe, g, m, G + kRef.w[5] + int64_t(kH) * kH, nullptr, nullptr, ga))) return rc;
+    if ((rc = rg_nt<EPI_MASK>(st, m, kH, g, kH, P + kRef.w[l], gnext, w.h[l - 1], ga, am + kRaG + (9 - l)))) return rc;
     float* t = g; g = gnext; gnext = t;
   }
-  if ((rc = gemm_tn_acc(st, kXE, kH, w.xe, kXE, g, kH, m, G + kRef.w[0], kH))) return rc;
-  colsum_kernel<><<<cb, 256, 0, st>>>(g, m, kH, G + kRef.b[0]);
-  LNRF_LAUNCH_CHECK("colsum_kernel");
+  if ((rc = rg_tn(st, kXE, kH, w.xe, g, m, G + kRef.w[0], G + kRef.b[0], nullptr, am + kRaG + 8))) return rc;
   // ---- second-order term through real_normal: tangent pass along u
   ref_temb_kernel<<<ew_blocks(m * 3 * kXFreqs, 256), 256, 0, st>>>(x, rays, ts, T, m, w.u, w.temb);
   LNRF_LAUNCH_CHECK("ref_temb_kernel");
-  if ((rc = gemm_tn_acc(st, kXE, kH, w.temb, kXE, w.gn[0], kH, m, G + kRef.w[0], kH))) return rc;  // dW_0 += T_emb^T Gn_0
+  if ((rc = tcg_amax(st, w.temb, m * kXE, am + kRaTemb))) return rc;
+  if ((rc = rg_tn(st, kXE, kH, w.temb, w.gn[0], m, G + kRef.w[0], nullptr, am + kRaTemb, am + kRaGn + 0))) return rc;  // dW_0 += T_emb^T Gn_0
   float* tc = w.tA;
   float* tn = w.tB;
-  if ((rc = gemm_nn<EPI_MASK>(st, m, kH, w.temb, kXE, kXE, nullptr, 0, 0, P + kRef.w[0], kH, tc, kH, nullptr,
-                              w.h[0], kH))) return rc;  // T_0
+  if ((rc = rg_nn<EPI_MASK>(st, m, kH, w.temb, kXE, kXE, nullptr, 0, 0, P + kRef.w[0], tc, nullptr, w.h[0], am + kRaTemb,
+                            nullptr, am + kRaT + 0))) return rc;  // T_0
   for (int l = 1; l <= 7; ++l) {
-    if ((rc = gemm_tn_acc(st, kH, kH, tc, kH, w.gn[l], kH, m, G + kRef.w[l], kH))) return rc;  // dW_l += T_{l-1}^T Gn_l
+    const float* ta = am + kRaT + l - 1;
+    if ((rc = rg_tn(st, kH, kH, tc, w.gn[l], m, G + kRef.w[l], nullptr, ta, am + kRaGn + l))) return rc;  // dW_l += T_{l-1}^T Gn_l
     if (l == 5) {
-      if ((rc = gemm_tn_acc(st, kXE, kH, w.temb, kXE, w.gn[5], kH, m, G + kRef.w[5] + int64_t(kH) * kH, kH))) return rc;
-      if ((rc = gemm_nn<EPI_MASK>(st, m, kH, tc, kH, kH, w.temb, kXE, kXE, P + kRef.w[5], kH, tn, kH, nullptr,
-                                  w.h[5], kH))) return rc;
+      if ((rc = rg_tn(st, kXE, kH, w.temb, w.gn[5], m, G + kRef.w[5] + int64_t(kH) * kH, nullptr, am + kRaTemb,
+                      am + kRaGn + 5))) return rc;
+      if ((rc = rg_nn<EPI_MASK>(st, m, kH, tc, kH, kH, w.temb, kXE, kXE, P + kRef.w[5], tn, nullptr, w.h[5], ta,
+                                am + kRaTemb, am + kRaT + 5))) return rc;
     } else {
-      if ((rc = gemm_nn<EPI_MASK>(st, m, kH, tc, kH, kH, nullptr, 0, 0, P + kRef.w[l], kH, tn, kH, nullptr,
-                                  w.h[l], kH))) return rc;
+      if ((rc = rg_nn<EPI_MASK>(st, m, kH, tc, kH, kH, nullptr, 0, 0, P + kRef.w[l], tn, nullptr, w.h[l], ta, nullptr,
+                                am + kRaT + l))) return rc;
     }
     float* t = tc; tc = tn; tn = t;
   }
