@@ -288,14 +288,16 @@ int lnrf_debug_umma_gemm_tn(const float* at, const float* bt, int32_t M, int32_t
  *   mode 0: C[M,N] = epi((A0[M,K0] | A1[M,K1]) @ B[K0+K1,N])     mode 1: the same with B given as Bt[N,K]
  *   mode 2: C[K0,N] += A0[M,K0]^T @ B[M,N] (M = samples), db[N] += column sums of B (nullable)
  *   mode 3: *c_amax = max(*c_amax, max |A0[0..M)|)
- * epi: 0 bias+ReLU, 1 bias, 2 mask by aux[m,n] > 0, 3 + r1s[m] r1w[n], 5 plain store.  a_amax / b_amax:
+ * epi: 0 bias+ReLU (also writes the bit mask [C > 0] to mask_out if given: M/32 * N/32 * 32 words, rounded up),
+ * 1 bias, 2 mask by aux[m,n] > 0, 3 + r1s[m] r1w[n], 5 plain store, 6 mask by the bits of mask_in.  a_amax / b_amax:
  * device addresses of max|operand| for operands far from O(1) (gradients), nullable; c_amax: receives
  * max |C| by atomic max (the caller zeroes it), nullable.  N <= 256, K0 + K1 <= 320 (64-column chunks),
  * every dimension / leading dimension a multiple of 4, 16-byte aligned bases.                           */
 int lnrf_tcgemm(int32_t mode, int32_t epi, int64_t M, int32_t N, const float* A0, int32_t lda0, int32_t K0,
                 const float* A1, int32_t lda1, int32_t K1, const float* B, int32_t ldb, float* C, int32_t ldc,
                 const float* bias, const float* aux, int32_t ldaux, const float* r1s, const float* r1w, float* db,
-                const float* a_amax, const float* b_amax, float* c_amax, lnrf_stream_t stream);
+                const float* a_amax, const float* b_amax, float* c_amax, const uint32_t* mask_in, uint32_t* mask_out,
+                lnrf_stream_t stream);
 /* ---- InstantNGPRefNERFModel (instant_ngp.py:57-89 on RefNERFBase, ref_nerf.py:34-77): Ref-NeRF
  * heads on a SMOOTH multiresolution hash grid.  Flat parameter layout: Dense_0 [2L,64], Dense_1
  * [64,16], Dense_2 [36 rows (33 used),64], Dense_3 [64,64], Dense_4 [64,3] at

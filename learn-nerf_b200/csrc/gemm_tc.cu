@@ -132,6 +132,8 @@ struct RgArgs {
   const float* a_amax;
   const float* a1_amax;
   float* c_amax;
+  const uint32_t* mask_in;  // TCG_MASKBITS: ReLU bit masks written by an earlier TCG_BIAS_RELU call (same M, N)
+  uint32_t* mask_out;       // TCG_BIAS_RELU: receives the bits [C > 0] (nullable)
 };
 
 template <int EPI>
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(kRgThreads, 1) tcg_rows_kernel(const __grid_co
   float sa = 1.0f;
   if (a.a_amax != nullptr || a.a1_amax != nullptr) {
     const float m0 = a.a_amax ? __ldg(a.a_amax) : 1.0f;
-    const float m1 = a.nchunks > 0 && a.a1_amax ? __ldg(a.a1_amax) : (a.has_a1 ? 1.0f : 0.0f);
+    const float m1 = a.a1_amax ? __ldg(a.a1_amax) : (a.has_a1 ? 1.0f : 0.0f);
     sa = pow2_scale(fmaxf(m0, m1));
   }
 
@@ -334,6 +336,10 @@ __global__ void __launch_bounds__(kRgThreads, 1) tcg_rows_kernel(const __grid_co
         const bool col_ok = c0 + 4 * lb < a.nc && n < a.N;
         float4 mk[8];  // EPI_MASK: the mask values of this lane's eight outputs, all loads in flight at once
         float4 bw = make_float4(0.f, 0.f, 0.f, 0.f);  // bias (or the rank-1 row vector) of the four columns
+        // bit masks: one word per lane and 32 x 32 block = [rows row0 .. row0+7] x [columns n .. n+3], bit 4 i + e
+        const int64_t mword = ((row0 >> 5) * ((a.N + 31) >> 5) + ((n0 + c0) >> 5)) * 32 + lane;
+        uint32_t mbits = 0;
+        if (EPI == TCG_MASKBITS) mbits = __ldg(a.mask_in + mword);
         if (EPI == TCG_MASK) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -375,8 +381,14 @@ __global__ void __launch_bounds__(kRgThreads, 1) tcg_rows_kernel(const __grid_co
               v[0] += bw.x; v[1] += bw.y; v[2] += bw.z; v[3] += bw.w;
               if (EPI == TCG_BIAS_RELU) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.0f);
+                for (int e = 0; e < 4; ++e) {
+                  v[e] = fmaxf(v[e], 0.0f);
+                  mbits |= (v[e] > 0.0f ? 1u : 0u) << (4 * i + e);
+                }
               }
+            } else if (EPI == TCG_MASKBITS) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[e] = (mbits >> (4 * i + e)) & 1u ? v[e] : 0.0f;
             } else if (EPI == TCG_MASK) {
               v[0] = mk[i].x > 0.f ? v[0] : 0.f; v[1] = mk[i].y > 0.f ? v[1] : 0.f;
               v[2] = mk[i].z > 0.f ? v[2] : 0.f; v[3] = mk[i].w > 0.f ? v[3] : 0.f;
@@ -388,6 +400,7 @@ __global__ void __launch_bounds__(kRgThreads, 1) tcg_rows_kernel(const __grid_co
             *reinterpret_cast<float4*>(a.C + (row0 + i) * a.ldc + n) = make_float4(v[0], v[1], v[2], v[3]);
           }
         }
+        if (EPI == TCG_BIAS_RELU && a.mask_out != nullptr) a.mask_out[mword] = mbits;
       }
       tc_fence_before();
       __syncwarp();
@@ -630,7 +643,8 @@ bool tcg_supported(int N, int K0, int K1) {
 
 int tcg_rows(cudaStream_t st, int epi, bool btrans, int64_t M, int N, const float* A0, int lda0, int K0,
              const float* A1, int lda1, int K1, const float* B, int ldb, float* C, int ldc, const float* bias,
-             const float* aux, int ldaux, const float* r1s, const float* r1w, const float* a_amax, const float* a1_amax, float* c_amax) {
+             const float* aux, int ldaux, const float* r1s, const float* r1w, const float* a_amax, const float* a1_amax, float* c_amax,
+             const uint32_t* mask_in, uint32_t* mask_out) {
   LNRF_REQUIRE(tcg_supported(N, K0, K1), LNRF_E_UNSUPPORTED, "tcg_rows: N=%d K0=%d K1=%d", N, K0, K1);
   LNRF_REQUIRE(lda0 % 4 == 0 && lda1 % 4 == 0 && ldc % 4 == 0 && ldaux % 4 == 0, LNRF_E_UNSUPPORTED,
                "tcg_rows: leading dimensions must be multiples of 4");
@@ -648,6 +662,8 @@ int tcg_rows(cudaStream_t st, int epi, bool btrans, int64_t M, int N, const floa
   a.nc = int(align_up(ncols, 16));
   a.bias = bias; a.aux = aux; a.ldaux = ldaux; a.r1s = r1s; a.r1w = r1w;
   a.a_amax = a_amax; a.a1_amax = K1 > 0 ? a1_amax : nullptr; a.c_amax = c_amax; a.has_a1 = K1 > 0 ? 1 : 0;
+  a.mask_in = mask_in; a.mask_out = mask_out;
+  LNRF_REQUIRE(epi != TCG_MASKBITS || mask_in != nullptr, LNRF_E_INVALID, "tcg_rows: TCG_MASKBITS without mask_in");
   const int64_t tiles = ceil_div(M, 128);
   int64_t grid = sm_count() / a.nhalves;
   if (grid > tiles) grid = tiles;
@@ -658,6 +674,7 @@ int tcg_rows(cudaStream_t st, int epi, bool btrans, int64_t M, int N, const floa
     case TCG_MASK: return launch_rows<TCG_MASK>(a, unsigned(grid), st);
     case TCG_RANK1: return launch_rows<TCG_RANK1>(a, unsigned(grid), st);
     case TCG_STORE: return launch_rows<TCG_STORE>(a, unsigned(grid), st);
+    case TCG_MASKBITS: return launch_rows<TCG_MASKBITS>(a, unsigned(grid), st);
   }
   LNRF_REQUIRE(false, LNRF_E_INVALID, "tcg_rows: unknown epilogue %d", epi);
 }
@@ -699,6 +716,7 @@ int init_gemm_tc() {
   LNRF_CUDA(cudaFuncSetAttribute(tcg_rows_kernel<TCG_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRgSmem));
   LNRF_CUDA(cudaFuncSetAttribute(tcg_rows_kernel<TCG_RANK1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRgSmem));
   LNRF_CUDA(cudaFuncSetAttribute(tcg_rows_kernel<TCG_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRgSmem));
+  LNRF_CUDA(cudaFuncSetAttribute(tcg_rows_kernel<TCG_MASKBITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRgSmem));
   LNRF_CUDA(cudaFuncSetAttribute(tcg_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTnSmem));
   return LNRF_OK;
 }
@@ -710,12 +728,13 @@ int init_gemm_tc() {
 extern "C" int lnrf_tcgemm(int mode, int epi, int64_t M, int N, const float* A0, int lda0, int K0, const float* A1,
                            int lda1, int K1, const float* B, int ldb, float* C, int ldc, const float* bias,
                            const float* aux, int ldaux, const float* r1s, const float* r1w, float* db,
-                           const float* a_amax, const float* b_amax, float* c_amax, lnrf_stream_t stream) {
+                           const float* a_amax, const float* b_amax, float* c_amax, const uint32_t* mask_in,
+                           uint32_t* mask_out, lnrf_stream_t stream) {
   using namespace lnrf;
   cudaStream_t st = as_stream(stream);
   if (mode == 0 || mode == 1)
     return tcg_rows(st, epi, mode == 1, M, N, A0, lda0, K0, A1, lda1, K1, B, ldb, C, ldc, bias, aux, ldaux, r1s, r1w,
-                    a_amax, nullptr, c_amax);
+                    a_amax, nullptr, c_amax, mask_in, mask_out);
   if (mode == 2) return tcg_tn_acc(st, K0, N, A0, lda0, B, ldb, M, C, ldc, db, a_amax, b_amax);
   if (mode == 3) return tcg_amax(st, A0, M, c_amax);
   set_error("lnrf_tcgemm: unknown mode %d", mode);

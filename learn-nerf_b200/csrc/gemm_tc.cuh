@@ -13,6 +13,7 @@ constexpr int TCG_BIAS = 1;       // C = acc + bias[n]
 constexpr int TCG_MASK = 2;       // C = acc * (aux[m,n] > 0)
 constexpr int TCG_RANK1 = 3;      // C = acc + r1s[m] * r1w[n]
 constexpr int TCG_STORE = 5;      // C = acc
+constexpr int TCG_MASKBITS = 6;   // C = acc * bit, bits written by an earlier TCG_BIAS_RELU call with mask_out (same M, N)
 
 // Operand range: an operand whose magnitude is far from 1 (gradients) must come with the device
 // address of max|operand| (`*_amax`, a float written by the producer of that operand: every tcg_rows
@@ -25,7 +26,9 @@ constexpr int TCG_STORE = 5;      // C = acc
 int tcg_rows(cudaStream_t st, int epi, bool btrans, int64_t M, int N, const float* A0, int lda0, int K0,
              const float* A1, int lda1, int K1, const float* B, int ldb, float* C, int ldc, const float* bias,
              const float* aux, int ldaux, const float* r1s, const float* r1w, const float* a_amax, const float* a1_amax,
-             float* c_amax);
+             float* c_amax, const uint32_t* mask_in = nullptr, uint32_t* mask_out = nullptr);
+// 32-bit words a [M, N] bit mask occupies (layout private to gemm_tc.cu)
+inline int64_t tcg_mask_words(int64_t M, int N) { return ceil_div(M, 32) * ceil_div(N, 32) * 32; }
 
 // C[M,N] += At[K,M]^T @ B[K,N] (K = samples, split over the grid, atomic accumulation) and, if db is not
 // null, db[N] += column sums of B.

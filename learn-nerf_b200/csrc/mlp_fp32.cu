@@ -178,6 +178,7 @@ struct Fp32Ws {
   float* gA;     // [m,256] backward ping-pong
   float* gB;
   float* dc;     // [m,128]
+  uint32_t* mask[8];  // ReLU bit masks of h0..h7 (tcg_mask_words each; training only)
   float* amax;   // [32] max |.| of the GEMM operands: 0..8 h0..h7, z8; 9 c; 10 dc; 11..19 g8..g0 (see gemm_tc.cuh)
   int64_t bytes;
 };
@@ -210,6 +211,7 @@ static Fp32Ws carve_fp32(void* base, int64_t m, bool save) {
   w.c = take(m * kHC);
   w.amax = take(32);
   if (save) {
+    for (int i = 0; i < 8; ++i) w.mask[i] = reinterpret_cast<uint32_t*>(take(tcg_mask_words(m, kH)));
     w.spre = take(m);
     w.gA = take(m * kH);
     w.gB = take(m * kH);
@@ -224,17 +226,21 @@ int64_t fp32_workspace_bytes(int64_t m, bool save) { return carve_fp32(nullptr, 
 // ---- the three contractions, on the tensor cores (gemm_tc.cu) or, for A/B runs, on FFMA (sgemm.cuh)
 template <int EPI>
 static int dense_fwd(cudaStream_t st, int64_t m, int N, const float* A0, int lda0, int K0, const float* A1, int lda1,
-                     int K1, const float* W, float* C, const float* bias, const float* a_amax, float* c_amax) {
+                     int K1, const float* W, float* C, const float* bias, const float* a_amax, float* c_amax,
+                     uint32_t* mask_out = nullptr) {
   if (g_fp32_ffma) return gemm_nn<EPI>(st, m, N, A0, lda0, K0, A1, lda1, K1, W, N, C, N, bias);
   return tcg_rows(st, EPI, false, m, N, A0, lda0, K0, A1, lda1, K1, W, N, C, N, bias, nullptr, 0, nullptr, nullptr,
-                  a_amax, nullptr, c_amax);
+                  a_amax, nullptr, c_amax, nullptr, mask_out);
 }
 // C[m,N] = epi(G[m,K] @ W[N rows, K cols]^T)
 template <int EPI>
 static int dense_dx(cudaStream_t st, int64_t m, int N, const float* G, int K, const float* W, float* C,
-                    const float* aux, const float* r1s, const float* r1w, const float* a_amax, float* c_amax) {
+                    const float* aux, const float* r1s, const float* r1w, const float* a_amax, float* c_amax,
+                    const uint32_t* mask_in = nullptr) {
   if (g_fp32_ffma) return gemm_nt<EPI>(st, m, N, G, K, K, W, K, C, N, aux, N, r1s, r1w);
-  return tcg_rows(st, EPI, true, m, N, G, K, K, nullptr, 0, 0, W, K, C, N, nullptr, aux, N, r1s, r1w, a_amax, nullptr, c_amax);
+  // ReLU masks travel as bits (32 B instead of 1 KB per sample and layer)
+  return tcg_rows(st, EPI == EPI_MASK ? TCG_MASKBITS : EPI, true, m, N, G, K, K, nullptr, 0, 0, W, K, C, N, nullptr, aux, N,
+                  r1s, r1w, a_amax, nullptr, c_amax, mask_in, nullptr);
 }
 // dW[M,N] += H[m,M]^T G[m,N]; db[N] += column sums of G (nullable)
 static int dense_dw(cudaStream_t st, int M, int N, const float* H, const float* G, int64_t m, float* dW, float* db,
@@ -265,19 +271,19 @@ int nerf_fwd_fp32(const float* P, const float* x, const float* d, const float* r
   float* am = w.amax;  // am[l] = max |h_l| (encodings are O(1): no scale)
   // input stack, model.py:50-51
   if ((rc = dense_fwd<EPI_BIAS_RELU>(st, m, kH, w.xe, kXE, kXE, nullptr, 0, 0, P + kNerf.w[0], w.h[0], P + kNerf.b[0],
-                                     nullptr, am + 0)))
+                                     nullptr, am + 0, save ? w.mask[0] : nullptr)))
     return rc;
   for (int l = 1; l <= 4; ++l)
     if ((rc = dense_fwd<EPI_BIAS_RELU>(st, m, kH, w.h[l - 1], kH, kH, nullptr, 0, 0, P + kNerf.w[l], w.h[l],
-                                       P + kNerf.b[l], am + l - 1, am + l)))
+                                       P + kNerf.b[l], am + l - 1, am + l, save ? w.mask[l] : nullptr)))
       return rc;
   // skip concat [z | x_emb], model.py:52; Dense_5..7 outputs are consumed through ReLU (:53-56)
   if ((rc = dense_fwd<EPI_BIAS_RELU>(st, m, kH, w.h[4], kH, kH, w.xe, kXE, kXE, P + kNerf.w[5], w.h[5], P + kNerf.b[5],
-                                     nullptr, am + 5)))
+                                     nullptr, am + 5, save ? w.mask[5] : nullptr)))
     return rc;
   for (int l = 6; l <= 7; ++l)
     if ((rc = dense_fwd<EPI_BIAS_RELU>(st, m, kH, w.h[l - 1], kH, kH, nullptr, 0, 0, P + kNerf.w[l], w.h[l],
-                                       P + kNerf.b[l], am + l - 1, am + l)))
+                                       P + kNerf.b[l], am + l - 1, am + l, save ? w.mask[l] : nullptr)))
       return rc;
   // Dense_8 output z is used raw by both heads (:57-58)
   if ((rc = dense_fwd<EPI_BIAS>(st, m, kH, w.h[7], kH, kH, nullptr, 0, 0, P + kNerf.w[8], w.h[8], P + kNerf.b[8],
@@ -328,7 +334,7 @@ int nerf_bwd_fp32(const float* P, int64_t m, void* ws_base, int64_t ws_bytes, co
     if (l == 5 && (rc = dense_dw(st, kXE, kH, w.xe, g, m, G + kNerf.w[5] + int64_t(kH) * kH, nullptr, nullptr, ga)))
       return rc;
     if ((rc = dense_dx<EPI_MASK>(st, m, kH, g, kH, P + kNerf.w[l], gn, w.h[l - 1], nullptr, nullptr, ga,
-                                 am + kAmaxG + (9 - l))))
+                                 am + kAmaxG + (9 - l), w.mask[l - 1])))
       return rc;
     float* t = g; g = gn; gn = t;
   }

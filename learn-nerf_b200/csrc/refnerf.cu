@@ -30,18 +30,19 @@ bool fp32_ffma();  // mlp_fp32.cu
 template <int EPI>
 static int rg_nn(cudaStream_t st, int64_t m, int N, const float* A0, int lda0, int K0, const float* A1, int lda1, int K1,
                  const float* W, float* C, const float* bias, const float* aux, const float* a_amax,
-                 const float* a1_amax, float* c_amax) {
+                 const float* a1_amax, float* c_amax, const uint32_t* mask_in = nullptr, uint32_t* mask_out = nullptr) {
   if (fp32_ffma() || !tcg_supported(N, K0, K1)) return gemm_nn<EPI>(st, m, N, A0, lda0, K0, A1, lda1, K1, W, N, C, N, bias, aux, N);
-  return tcg_rows(st, EPI, false, m, N, A0, lda0, K0, A1, lda1, K1, W, N, C, N, bias, aux, N, nullptr, nullptr, a_amax,
-                  a1_amax, c_amax);
+  // ReLU masks travel as bits when the caller has them (32 B instead of 1 KB per sample and layer)
+  return tcg_rows(st, EPI == EPI_MASK && mask_in ? TCG_MASKBITS : EPI, false, m, N, A0, lda0, K0, A1, lda1, K1, W, N, C, N,
+                  bias, aux, N, nullptr, nullptr, a_amax, a1_amax, c_amax, mask_in, mask_out);
 }
 // C[m,N] = epi(Gr[m,K] @ W[N rows, K cols]^T)
 template <int EPI>
 static int rg_nt(cudaStream_t st, int64_t m, int N, const float* Gr, int K, const float* W, float* C, const float* aux,
-                 const float* a_amax, float* c_amax) {
+                 const float* a_amax, float* c_amax, const uint32_t* mask_in = nullptr) {
   if (fp32_ffma() || !tcg_supported(N, K, 0)) return gemm_nt<EPI>(st, m, N, Gr, K, K, W, K, C, N, aux, N);
-  return tcg_rows(st, EPI, true, m, N, Gr, K, K, nullptr, 0, 0, W, K, C, N, nullptr, aux, N, nullptr, nullptr, a_amax,
-                  nullptr, c_amax);
+  return tcg_rows(st, EPI == EPI_MASK && mask_in ? TCG_MASKBITS : EPI, true, m, N, Gr, K, K, nullptr, 0, 0, W, K, C, N,
+                  nullptr, aux, N, nullptr, nullptr, a_amax, nullptr, c_amax, mask_in, nullptr);
 }
 // dW[M,N] += H[m,M]^T Gr[m,N]; db[N] += column sums of Gr (nullable)
 static int rg_tn(cudaStream_t st, int M, int N, const float* H, const float* Gr, int64_t m, float* dW, float* db,
@@ -502,6 +503,7 @@ struct RefWs {
   // backward only
   float *gA, *gB, *tA, *tB, *temb, *d_o, *gc, *dE, *u;
   float* amax;    // [64] max |operand| slots of the tensor-core GEMMs (kRa*)
+  uint32_t* mask[8];  // ReLU bit masks of h0..h7 (written by the forward GEMM epilogues)
   int64_t bytes;
 };
 static RefWs carve_ref(void* base, int64_t m, bool save) {
@@ -529,6 +531,7 @@ static RefWs carve_ref(void* base, int64_t m, bool save) {
   w.c = take(m * kHC);
   w.o = take(m * 4);
   w.amax = take(64);
+  for (int i = 0; i < 8; ++i) w.mask[i] = reinterpret_cast<uint32_t*>(take(tcg_mask_words(m, kH)));
   if (save) {
     w.gA = take(m * kH);
     w.gB = take(m * kH);
@@ -675,15 +678,15 @@ int lnrf_refnerf_fwd(const float* params, const float* x, const float* d, const 
   embed_kernel<kXFreqs><<<ew_blocks(m * 3 * kXFreqs, 256), 256, 0, st>>>(x, rays, ts, T, 0, m, w.xe);
   LNRF_LAUNCH_CHECK("embed_kernel<x>");
   if ((rc = rg_nn<EPI_BIAS_RELU>(st, m, kH, w.xe, kXE, kXE, nullptr, 0, 0, P + kRef.w[0], w.h[0], P + kRef.b[0], nullptr,
-                                 nullptr, nullptr, am + kRaH + 0))) return rc;
+                                 nullptr, nullptr, am + kRaH + 0, nullptr, w.mask[0]))) return rc;
   for (int l = 1; l <= 4; ++l)
     if ((rc = rg_nn<EPI_BIAS_RELU>(st, m, kH, w.h[l - 1], kH, kH, nullptr, 0, 0, P + kRef.w[l], w.h[l], P + kRef.b[l],
-                                   nullptr, am + kRaH + l - 1, nullptr, am + kRaH + l))) return rc;
+                                   nullptr, am + kRaH + l - 1, nullptr, am + kRaH + l, nullptr, w.mask[l]))) return rc;
   if ((rc = rg_nn<EPI_BIAS_RELU>(st, m, kH, w.h[4], kH, kH, w.xe, kXE, kXE, P + kRef.w[5], w.h[5], P + kRef.b[5], nullptr,
-                                 am + kRaH + 4, nullptr, am + kRaH + 5))) return rc;
+                                 am + kRaH + 4, nullptr, am + kRaH + 5, nullptr, w.mask[5]))) return rc;
   for (int l = 6; l <= 7; ++l)
     if ((rc = rg_nn<EPI_BIAS_RELU>(st, m, kH, w.h[l - 1], kH, kH, nullptr, 0, 0, P + kRef.w[l], w.h[l], P + kRef.b[l],
-                                   nullptr, am + kRaH + l - 1, nullptr, am + kRaH + l))) return rc;
+                                   nullptr, am + kRaH + l - 1, nullptr, am + kRaH + l, nullptr, w.mask[l]))) return rc;
   if ((rc = rg_nn<EPI_BIAS>(st, m, kH, w.h[7], kH, kH, nullptr, 0, 0, P + kRef.w[8], w.h[8], P + kRef.b[8], nullptr,
                             am + kRaH + 7, nullptr, am + kRaH + 8))) return rc;
   // ---- real_normal: VJP of -z8[:, 0] w.r.t. x (ref_nerf.py:38-43)
@@ -696,7 +699,7 @@ int lnrf_refnerf_fwd(const float* params, const float* x, const float* d, const 
       if ((rc = rg_nt<EPI_STORE>(st, m, kXE, w.gn[5], kH, P + kRef.w[5] + int64_t(kH) * kH, w.dxe5, nullptr,
                                  am + kRaGn + 5, nullptr))) return rc;
     if ((rc = rg_nt<EPI_MASK>(st, m, kH, w.gn[l], kH, P + kRef.w[l], w.gn[l - 1], w.h[l - 1], am + kRaGn + l,
-                              am + kRaGn + l - 1))) return rc;
+                              am + kRaGn + l - 1, w.mask[l - 1]))) return rc;
   }
   if ((rc = rg_nt<EPI_STORE>(st, m, kXE, w.gn[0], kH, P + kRef.w[0], w.dxe0, nullptr, am + kRaGn + 0, nullptr))) return rc;
   ref_nraw_kernel<<<ew_blocks(m * 3, 256), 256, 0, st>>>(x, rays, ts, T, m, w.dxe0, w.dxe5, w.nraw);
@@ -759,7 +762,7 @@ int lnrf_refnerf_bwd(const float* params, const float* x, const float* d, const 
     if ((rc = rg_tn(st, kH, kH, w.h[l - 1], g, m, G + kRef.w[l], G + kRef.b[l], am + kRaH + l - 1, ga))) return rc;
     if (l == 5)
       if ((rc = rg_tn(st, kXE, kH, w.xe, g, m, G + kRef.w[5] + int64_t(kH) * kH, nullptr, nullptr, ga))) return rc;
-    if ((rc = rg_nt<EPI_MASK>(st, m, kH, g, kH, P + kRef.w[l], gnext, w.h[l - 1], ga, am + kRaG + (9 - l)))) return rc;
+    if ((rc = rg_nt<EPI_MASK>(st, m, kH, g, kH, P + kRef.w[l], gnext, w.h[l - 1], ga, am + kRaG + (9 - l), w.mask[l - 1]))) return rc;
     float* t = g; g = gnext; gnext = t;
   }
   if ((rc = rg_tn(st, kXE, kH, w.xe, g, m, G + kRef.w[0], G + kRef.b[0], nullptr, am + kRaG + 8))) return rc;
@@ -771,7 +774,7 @@ int lnrf_refnerf_bwd(const float* params, const float* x, const float* d, const 
   float* tc = w.tA;
   float* tn = w.tB;
   if ((rc = rg_nn<EPI_MASK>(st, m, kH, w.temb, kXE, kXE, nullptr, 0, 0, P + kRef.w[0], tc, nullptr, w.h[0], am + kRaTemb,
-                            nullptr, am + kRaT + 0))) return rc;  // T_0
+                            nullptr, am + kRaT + 0, w.mask[0]))) return rc;  // T_0
   for (int l = 1; l <= 7; ++l) {
     const float* ta = am + kRaT + l - 1;
     if ((rc = rg_tn(st, kH, kH, tc, w.gn[l], m, G + kRef.w[l], nullptr, ta, am + kRaGn + l))) return rc;  // dW_l += T_{l-1}^T Gn_l
@@ -779,10 +782,10 @@ int lnrf_refnerf_bwd(const float* params, const float* x, const float* d, const 
       if ((rc = rg_tn(st, kXE, kH, w.temb, w.gn[5], m, G + kRef.w[5] + int64_t(kH) * kH, nullptr, am + kRaTemb,
                       am + kRaGn + 5))) return rc;
       if ((rc = rg_nn<EPI_MASK>(st, m, kH, tc, kH, kH, w.temb, kXE, kXE, P + kRef.w[5], tn, nullptr, w.h[5], ta,
-                                am + kRaTemb, am + kRaT + 5))) return rc;
+                                am + kRaTemb, am + kRaT + 5, w.mask[5]))) return rc;
     } else {
       if ((rc = rg_nn<EPI_MASK>(st, m, kH, tc, kH, kH, nullptr, 0, 0, P + kRef.w[l], tn, nullptr, w.h[l], ta, nullptr,
-                                am + kRaT + l))) return rc;
+                                am + kRaT + l, w.mask[l]))) return rc;
     }
     float* t = tc; tc = tn; tn = t;
   }

@@ -67,7 +67,7 @@ _SIGS = {
     "lnrf_debug_umma_gemm": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "lnrf_debug_umma_gemm_tn": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "lnrf_tcgemm": (c_int32, [c_int32, c_int32, c_int64, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_int32, c_int32,
-                              c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_int32] + [c_void_p] * 7),
+                              c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_int32] + [c_void_p] * 9),
     "lnrf_bare_rays": (c_int32, [c_void_p] * 4 + [c_float, c_float, c_int32, c_int32, c_int32, c_int32, c_void_p,
                                                    c_void_p]),
     "lnrf_rgb_to_u8": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p]),

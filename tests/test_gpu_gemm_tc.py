@@ -13,12 +13,12 @@ pytestmark = pytest.mark.gpu
 
 
 def _call(mode, epi, M, N, A0, lda0, K0, A1, lda1, K1, B, ldb, C, ldc, bias=None, aux=None, ldaux=0, r1s=None,
-          r1w=None, db=None, a_amax=None, b_amax=None, c_amax=None):
+          r1w=None, db=None, a_amax=None, b_amax=None, c_amax=None, mask_in=None, mask_out=None):
     _native.ensure_init(C.device)
     p = _native._p
     rc = _native.load().lnrf_tcgemm(mode, epi, M, N, p(A0), lda0, K0, p(A1), lda1, K1, p(B), ldb, p(C), ldc, p(bias),
                                     p(aux), ldaux, p(r1s), p(r1w), p(db), p(a_amax), p(b_amax), p(c_amax),
-                                    _native._stream())
+                                    p(mask_in), p(mask_out), _native._stream())
     _native._check(rc, "lnrf_tcgemm")
 
 
@@ -113,3 +113,25 @@ def test_tn_vs_fp64(Ksamp, M, N):
     print(f"dW rel-L2 {r:.3e} (torch fp32 CPU: {f32:.3e}); db {_rel(db.cpu().double().numpy(), refdb):.3e}")
     assert r < 2e-6
     assert _rel(db.cpu().double().numpy(), refdb) < 1e-5
+
+
+@pytest.mark.parametrize("M,N", [(1000, 256), (4099, 128), (77, 64)])
+def test_relu_bit_masks_roundtrip(M, N):
+    """epi 0 writes the bits [relu output > 0]; epi 6 applies them: same result as masking by the fp32 activations."""
+    g = torch.Generator().manual_seed(M)
+    K = 256
+    A = torch.randn(M, K, generator=g).cuda()
+    W = (torch.randn(K, N, generator=g) / 16).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    Hh = torch.empty(M, N, device="cuda")
+    words = ((M + 31) // 32) * ((N + 31) // 32) * 32
+    bits = torch.full((words,), -1, dtype=torch.int32, device="cuda")
+    _call(0, 0, M, N, A, K, K, None, 0, 0, W, N, Hh, N, bias, mask_out=bits)
+    G = torch.randn(M, N, generator=g).cuda()
+    Wt = (torch.randn(N, N, generator=g) / 16).cuda()   # [N rows (outputs), K = N cols]
+    C_bits = torch.empty(M, N, device="cuda")
+    C_aux = torch.empty(M, N, device="cuda")
+    _call(1, 6, M, N, G, N, N, None, 0, 0, Wt, N, C_bits, N, mask_in=bits)
+    _call(1, 2, M, N, G, N, N, None, 0, 0, Wt, N, C_aux, N, aux=Hh, ldaux=N)
+    assert torch.equal(C_bits, C_aux)
+    assert (C_aux == 0).float().mean() > 0.3
