@@ -40,6 +40,14 @@ FLOP_TRAIN_PER_SAMPLE = 3_481_344        # fwd + dW + dX, no padding / recompute
 REF_FLOP_FWD_PER_SAMPLE = 2 * (590_336 + 489_472)
 REF_FLOP_TRAIN_PER_SAMPLE = 2 * 3_709_088
 SAMPLES_PER_RAY = 64 + 192
+# fp32-accurate paths: an UNFUSED chain of split-fp16 tcgen05 GEMMs whose fp32 activations cross HBM once per
+# producer and once per consumer, i.e. HBM-bound.  Algorithmic fp32 values moved per sample,
+# every GEMM counted as (K inputs read + N outputs written), dW GEMMs as (M + N read), bit masks as 8 words:
+#   NeRF  forward 5,264 (ten Dense layers + the two head kernels), backward 10,320 (heads, 13 dW, 9 dX)
+#   Ref-NeRF forward 9,750 (trunk + 7-layer normal chain + d x_emb + heads), backward 19,464 (directional block,
+#   8 dX + 10 dW of the first-order chain, tangent pass: 8 T GEMMs + 9 dW, three amax passes)
+FP32_BYTES_PER_SAMPLE = {("nerf", False): 4 * 5264, ("nerf", True): 4 * (5264 + 10320),
+                         ("refnerf", False): 4 * 9750, ("refnerf", True): 4 * (9750 + 19464)}
 # ncu (profiles/r01d_nerf_train_kernels_ncu_full.txt): fwd 4.230 + dX 4.035 + dW 8.539 GB of DRAM
 # traffic for the 786,432 samples of the fine level
 NCU_TRAIN_DRAM_BYTES_PER_SAMPLE = (4.230e9 + 4.035e9 + 8.539e9) / 786432
@@ -410,7 +418,21 @@ def measure(args, rank, local_rank, world, dev, peaks):
                 flop_per_sample = REF_FLOP_TRAIN_PER_SAMPLE if train else REF_FLOP_FWD_PER_SAMPLE
             flops = flop_per_sample * SAMPLES_PER_RAY * n  # per rank, per step
             achieved = flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
-            roofline = {"bound": "tensor",
+            if prec == "fp32":  # unfused chain of fp32-in / fp32-out tensor-core GEMMs: bounded by HBM
+                nbytes = FP32_BYTES_PER_SAMPLE[(args.model, train)] * SAMPLES_PER_RAY * n
+                gbs = nbytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+                roofline = {"bound": "hbm",
+                            "kernel": "tcg_rows_kernel + tcg_tn_kernel chain (split-fp16 tcgen05 GEMMs, three MMAs per "
+                                      "fp32 product; fp32 activations cross HBM between layers)",
+                            "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
+                            "traffic": None, "peak_source": peaks["source"] + " (HBM copy)",
+                            "kernel_ms_per_step": dom_ms, "kernel_share_of_step": dom_ms / ms,
+                            "algorithmic_bytes_per_sample": FP32_BYTES_PER_SAMPLE[(args.model, train)],
+                            "algorithmic_flop_per_sample": flop_per_sample,
+                            "algorithmic_tflops": achieved, "frac_of_bf16_tensor_peak": achieved / peaks["tf"],
+                            "note": "1e-5 path; the tensor pipe executes 3x the algorithmic FLOPs (hi/lo split)"}
+            else:
+              roofline = {"bound": "tensor",
                         "kernel": "nerf_fwd_cta2_kernel" + (" + nerf_bwd_dx_cta2_kernel + nerf_bwd_dw_kernel"
                                                             if train else "") if prec == "bf16"
                                   else "sgemm_kernel chain (fp32 FFMA)",
@@ -439,7 +461,7 @@ def measure(args, rank, local_rank, world, dev, peaks):
                 names = {"nerf_mlp_fwd": "nerf_fwd_cta2_kernel",
                          "nerf_mlp_bwd": "nerf_bwd_dx_cta2_kernel + nerf_bwd_dw_kernel"}
                 roofline["parts"] = [
-                    {"kernel": names[nm] if prec == "bf16" else nm + " (fp32 FFMA chain)", "ms_per_step": part_ms[nm],
+                    {"kernel": names[nm] if prec == "bf16" else nm + " (split-fp16 tcgen05 GEMM chain)", "ms_per_step": part_ms[nm],
                      "achieved": fl[nm] * SAMPLES_PER_RAY * n / (part_ms[nm] * 1e-3) / 1e12,
                      "frac": fl[nm] * SAMPLES_PER_RAY * n / (part_ms[nm] * 1e-3) / 1e12 / peaks["tf"]}
                     for nm in dom_names if part_ms.get(nm, 0) > 0]
@@ -582,7 +604,7 @@ def main():
     ap.add_argument("--batch_size", type=int, default=65536, help="rays per render_rays call (image workload)")
     ap.add_argument("--model", default="nerf", choices=["nerf", "ngp", "refnerf", "ngpref"])
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
-                    help="NeRF MLP path: bf16 tcgen05 (2e-2) or fp32 FFMA (1e-5)")
+                    help="MLP path: bf16 tcgen05 (2e-2) or fp32-accurate (1e-5: split-fp16 tcgen05 GEMMs)")
     ap.add_argument("--rays", type=int, default=None, help="rays per GPU per step (4096 NeRF, 32768 NGP)")
     ap.add_argument("--ray_chunk", type=int, default=None)
     ap.add_argument("--cpu_rays", type=int, default=512, help="rays per step of the CPU sample")

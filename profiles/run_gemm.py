@@ -23,15 +23,18 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 p, lib, st = _native._p, _native.load(), _native._stream
 
 
+bits = torch.zeros(((M + 31) // 32) * (N // 32) * 32, dtype=torch.int32, device=dev)
+
+
 def rows(epi, mode):
     rc = lib.lnrf_tcgemm(mode, epi, M, N, p(A), K, K, None, 0, 0, p(W), N, p(C), N, p(bias), p(H), N, None, None, None,
-                         p(amax), None, None, st())
+                         p(amax), None, None, p(bits), p(bits) if epi == 0 else None, st())
     assert rc == 0, lib.lnrf_last_error()
 
 
 def tn():
     rc = lib.lnrf_tcgemm(2, 0, M, N, p(H), K, K, None, 0, 0, p(A), N, p(dW), N, None, None, 0, None, None, p(db), None,
-                         p(amax), None, st())
+                         p(amax), None, None, None, st())
     assert rc == 0, lib.lnrf_last_error()
 
 
@@ -49,6 +52,7 @@ def timed(fn, name, nbytes):
 
 
 timed(lambda: rows(0, 0), "rows NN bias+relu", 2 * M * N * 4)
-timed(lambda: rows(2, 1), "rows NT mask     ", 3 * M * N * 4)
+timed(lambda: rows(2, 1), "rows NT fp32 mask", 3 * M * N * 4)
+timed(lambda: rows(6, 1), "rows NT bit mask ", 2 * M * N * 4)
 timed(tn, "TN 256x256 + db  ", 2 * M * N * 4)
 print("ok")
