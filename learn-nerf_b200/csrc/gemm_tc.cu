@@ -177,20 +177,31 @@ __global__ void __launch_bounds__(kRgThreads, 1) tcg_rows_kernel(const __grid_co
     const int64_t kk = cd.bk0 + k, nn = n0 + n;
     return a.btrans ? __ldg(a.B + nn * a.ldb + kk) : __ldg(a.B + kk * a.ldb + nn);
   };
+  // item -> (chunk c, row n, 8-column group g8); consecutive threads walk along the contiguous axis of W
+  // (n for W[k][n], k for Wt[n][k]) so that the loads of a warp coalesce
+  const int bt = a.btrans;
   {
+    // max |w| over this CTA's part of W with coalesced 16-byte loads: [Ktot rows] x [ncols contiguous floats] for
+    // W[k][n], [ncols rows] x [Ktot contiguous floats] for Wt[n][k]
     float mx = 0.0f;
-    for (int item = tid; item < a.nchunks * 1024; item += kRgThreads) {
-      const int c = item >> 10, n = item & 127, g8 = (item >> 7) & 7;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) mx = fmaxf(mx, fabsf(w_at(c, n, g8 * 8 + j)));
+    const int ktot = a.ch[a.nchunks - 1].bk0 + a.ch[a.nchunks - 1].kv;
+    const int ncols = a.N - n0 < 128 ? a.N - n0 : 128;
+    const int rows = bt ? ncols : ktot, q4 = (bt ? ktot : ncols) >> 2;
+    const float* base = bt ? a.B + int64_t(n0) * a.ldb : a.B + n0;
+#pragma unroll 4
+    for (int i = tid; i < rows * q4; i += kRgThreads) {
+      const int r = i / q4, q = i - r * q4;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(base + int64_t(r) * a.ldb) + q);
+      mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
     }
     mx = warp_max(mx);
     if (lane == 0) atomicMax(const_cast<uint32_t*>(bar_words + kRgBMax / 4), __float_as_uint(mx));
   }
   __syncthreads();
   const float sb = pow2_scale(__uint_as_float(bar_words[kRgBMax / 4]));
+#pragma unroll 2
   for (int item = tid; item < a.nchunks * 1024; item += kRgThreads) {
-    const int c = item >> 10, n = item & 127, g8 = (item >> 7) & 7;
+    const int c = item >> 10, n = bt ? (item >> 3) & 127 : item & 127, g8 = bt ? item & 7 : (item >> 7) & 7;
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = w_at(c, n, g8 * 8 + j);

@@ -10,13 +10,14 @@ torch.cuda.set_device(0)
 dev = torch.device("cuda:0")
 _native.ensure_init(dev)
 M = int(os.environ.get("M", str(4096 * 192)))
-N = K = 256
+N = 256
+K = int(os.environ.get("K", "256"))
 A = torch.randn(M, K, device=dev)
-H = torch.relu(torch.randn(M, K, device=dev))
-W = torch.randn(K, N, device=dev) / 16
+H = torch.relu(torch.randn(M, N, device=dev))
+W = torch.randn(max(K, N), N, device=dev) / 16
 bias = torch.zeros(N, device=dev)
 C = torch.empty(M, N, device=dev)
-dW = torch.zeros(K, N, device=dev)
+dW = torch.zeros(N, N, device=dev)
 db = torch.zeros(N, device=dev)
 amax = torch.ones(1, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -33,7 +34,7 @@ def rows(epi, mode):
 
 
 def tn():
-    rc = lib.lnrf_tcgemm(2, 0, M, N, p(H), K, K, None, 0, 0, p(A), N, p(dW), N, None, None, 0, None, None, p(db), None,
+    rc = lib.lnrf_tcgemm(2, 0, M, N, p(H), N, N, None, 0, 0, p(C), N, p(dW), N, None, None, 0, None, None, p(db), None,
                          p(amax), None, None, None, st())
     assert rc == 0, lib.lnrf_last_error()
 
@@ -51,8 +52,12 @@ def timed(fn, name, nbytes):
     print(f"{name}: {ms:.3f} ms  {nbytes / ms / 1e6:.0f} GB/s algorithmic ({nbytes / 1e9:.2f} GB)")
 
 
-timed(lambda: rows(0, 0), "rows NN bias+relu", 2 * M * N * 4)
+timed(lambda: rows(0, 0), "rows NN bias+relu", (K + N) * M * 4)
 timed(lambda: rows(2, 1), "rows NT fp32 mask", 3 * M * N * 4)
 timed(lambda: rows(6, 1), "rows NT bit mask ", 2 * M * N * 4)
 timed(tn, "TN 256x256 + db  ", 2 * M * N * 4)
+M_full = M
+M = 4096   # one tile per CTA pair: the launch + weight-conversion prologue
+timed(lambda: rows(0, 0), "rows NN, M = 4096 (fixed cost)", 2 * M * N * 4)
+timed(lambda: rows(6, 1), "rows NT, M = 4096 (fixed cost)", 2 * M * N * 4)
 print("ok")
