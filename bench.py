@@ -405,7 +405,8 @@ def measure(args, rank, local_rank, world, dev, peaks):
         cfg_name = {("nerf", True): "configs[1]: ", ("ngp", True): "configs[2]: ", ("refnerf", True): "configs[3]: ",
                     ("nerf", False): "configs[4]-style: "}.get((args.model, train), "")
         if args.workload == "image":
-            cfg_name = f"configs[4]: {args.width}x{args.height} view in chunks of {args.batch_size} rays, device-side ray generation and uint8 conversion, "
+            which = "configs[0]" if (args.width, args.height, args.batch_size) == (128, 128, 1024) else "configs[4]"
+            cfg_name = f"{which}: {args.width}x{args.height} view in chunks of {args.batch_size} rays, device-side ray generation and uint8 conversion, "
         if args.model == "ngpref":
             roofline = {"bound": "hbm", "kernel": "lnrf_ngpref_fwd" + (" + lnrf_ngpref_bwd" if train else ""),
                         "achieved": None, "peak": peaks["hbm"], "unit": "GB/s", "frac": None, "traffic": None,

@@ -583,8 +583,12 @@ static NgpRefLayout ngpref_layout(int L) {
 struct NgpRefWs {
   float *enc, *h0, *z, *gn0, *vec, *nraw, *E, *c1, *c2, *o;       // forward
   float *d_o, *gc2, *gc1, *g, *dE, *u, *g0, *d_enc, *tenc, *t0;   // backward only
+  float* amax;                // [32] max |operand| slots of the tensor-core GEMMs (kNa*)
+  uint32_t *mask_h0, *mask_c1;  // ReLU bit masks written by the forward GEMM epilogues
   int64_t bytes;
 };
+// amax slots: forward 0..7, backward 8..
+constexpr int kNaGn0 = 0, kNaFwdEnd = 8, kNaGc2 = 8, kNaGc1 = 9, kNaG = 10, kNaG0 = 11, kNaTenc = 12;
 static NgpRefWs carve_ngpref(void* base, int64_t m, int E, bool save) {
   NgpRefWs w{};
   char* p = reinterpret_cast<char*>(base);
@@ -604,6 +608,9 @@ static NgpRefWs carve_ngpref(void* base, int64_t m, int E, bool save) {
   w.c1 = take(m * kNrHidden);
   w.c2 = take(m * kNrHidden);
   w.o = take(m * 4);
+  w.amax = take(32);
+  w.mask_h0 = reinterpret_cast<uint32_t*>(take(tcg_mask_words(m, kNrHidden)));
+  w.mask_c1 = reinterpret_cast<uint32_t*>(take(tcg_mask_words(m, kNrHidden)));
   if (save) {
     w.d_o = take(m * 4);
     w.gc2 = take(m * kNrHidden);
@@ -841,24 +848,27 @@ int lnrf_ngpref_fwd(const float* params, const int64_t* level_offsets_host, cons
                   1, x, rays, ts, T, m, in0, in1, out0, out1, st)
   // ---- spatial_block (instant_ngp.py:69-82): smooth hash grid -> Dense_0 ReLU -> Dense_1
   if ((rc = LNRF_GRID(0, nullptr, nullptr, w.enc, nullptr))) return rc;
-  if ((rc = gemm_nn<EPI_BIAS_RELU>(st, m, kNrHidden, w.enc, E, E, nullptr, 0, 0, P + nl.w[0], kNrHidden, w.h0,
-                                   kNrHidden, P + nl.b[0]))) return rc;
-  if ((rc = gemm_nn<EPI_BIAS>(st, m, kNrOut, w.h0, kNrHidden, kNrHidden, nullptr, 0, 0, P + nl.w[1], kNrOut, w.z,
-                              kNrOut, P + nl.b[1]))) return rc;
+  float* am = w.amax;
+  LNRF_CUDA(cudaMemsetAsync(am, 0, kNaFwdEnd * sizeof(float), st));
+  if ((rc = rg_nn<EPI_BIAS_RELU>(st, m, kNrHidden, w.enc, E, E, nullptr, 0, 0, P + nl.w[0], w.h0, P + nl.b[0], nullptr,
+                                 nullptr, nullptr, nullptr, nullptr, w.mask_h0))) return rc;
+  if ((rc = rg_nn<EPI_BIAS>(st, m, kNrOut, w.h0, kNrHidden, kNrHidden, nullptr, 0, 0, P + nl.w[1], w.z, P + nl.b[1],
+                            nullptr, nullptr, nullptr, nullptr))) return rc;
   // ---- real_normal (ref_nerf.py:38-43): Gn_0 = -W_1[:,0] [h_0 > 0]; vec = Gn_0 W_0^T; n_raw = J^T vec
   ref_seed_kernel<<<ew_blocks(m * kNrHidden, 256), 256, 0, st>>>(w.h0, P + nl.w[1], m, w.gn0, kNrHidden, kNrOut);
   LNRF_LAUNCH_CHECK("ref_seed_kernel");
-  if ((rc = gemm_nt<EPI_STORE>(st, m, E, w.gn0, kNrHidden, kNrHidden, P + nl.w[0], kNrHidden, w.vec, E))) return rc;
+  if ((rc = tcg_amax(st, P + nl.w[1], int64_t(kNrHidden) * kNrOut, am + kNaGn0))) return rc;  // |Gn_0| <= max |W_1|
+  if ((rc = rg_nt<EPI_STORE>(st, m, E, w.gn0, kNrHidden, P + nl.w[0], w.vec, nullptr, am + kNaGn0, nullptr))) return rc;
   if ((rc = LNRF_GRID(2, w.vec, nullptr, w.nraw, nullptr))) return rc;
   // ---- heads (ref_nerf.py:45-75)
   ref_head_fwd1_kernel<<<ew_blocks(m, 256), 256, 0, st>>>(w.z, d, rays, T, w.nraw, m, dens, w.E, aux_normal_mse,
                                                           aux_neg_normal, kNrOut);
   LNRF_LAUNCH_CHECK("ref_head_fwd1_kernel");
   // ---- directional_block (instant_ngp.py:84-89): [spatial_out | IDE | n.(-d)] -> 64 -> 64 -> 3
-  if ((rc = gemm_nn<EPI_BIAS_RELU>(st, m, kNrHidden, w.z, kNrOut, kNrOut, w.E, kRefE, kRefE, P + nl.w[2], kNrHidden,
-                                   w.c1, kNrHidden, P + nl.b[2]))) return rc;
-  if ((rc = gemm_nn<EPI_BIAS_RELU>(st, m, kNrHidden, w.c1, kNrHidden, kNrHidden, nullptr, 0, 0, P + nl.w[3],
-                                   kNrHidden, w.c2, kNrHidden, P + nl.b[3]))) return rc;
+  if ((rc = rg_nn<EPI_BIAS_RELU>(st, m, kNrHidden, w.z, kNrOut, kNrOut, w.E, kRefE, kRefE, P + nl.w[2], w.c1, P + nl.b[2],
+                                 nullptr, nullptr, nullptr, nullptr, nullptr, w.mask_c1))) return rc;
+  if ((rc = rg_nn<EPI_BIAS_RELU>(st, m, kNrHidden, w.c1, kNrHidden, kNrHidden, nullptr, 0, 0, P + nl.w[3], w.c2,
+                                 P + nl.b[3], nullptr, nullptr, nullptr, nullptr))) return rc;
   ref_out_fwd_kernel<2><<<ew_blocks(m, 8), 256, 0, st>>>(w.c2, P + nl.w[4], P + nl.b[4], m, w.o);
   LNRF_LAUNCH_CHECK("ref_out_fwd_kernel");
   ref_head_fwd2_kernel<<<ew_blocks(m, 256), 256, 0, st>>>(w.z, w.o, m, rgb, kNrOut);
@@ -894,36 +904,39 @@ int lnrf_ngpref_bwd(const float* params, const int64_t* level_offsets_host, cons
   ref_out_bwd_kernel<2><<<ew_blocks(m, 8 * 16), 256, 0, st>>>(w.z, w.o, w.c2, d_rgb, P + nl.w[4], m, w.d_o, w.gc2,
                                                                G + nl.w[4], G + nl.b[4], kNrOut);
   LNRF_LAUNCH_CHECK("ref_out_bwd_kernel");
-  if ((rc = gemm_tn_small(st, kNrHidden, kNrHidden, w.c1, kNrHidden, w.gc2, kNrHidden, m, G + nl.w[3], kNrHidden,
-                          G + nl.b[3]))) return rc;
-  if ((rc = gemm_nt<EPI_MASK>(st, m, kNrHidden, w.gc2, kNrHidden, kNrHidden, P + nl.w[3], kNrHidden, w.gc1, kNrHidden,
-                              w.c1, kNrHidden))) return rc;
-  if ((rc = gemm_tn_small(st, kNrOut, kNrHidden, w.z, kNrOut, w.gc1, kNrHidden, m, G + nl.w[2], kNrHidden,
-                          G + nl.b[2]))) return rc;
-  if ((rc = gemm_tn_small(st, kRefE, kNrHidden, w.E, kRefE, w.gc1, kNrHidden, m,
-                          G + nl.w[2] + int64_t(kNrOut) * kNrHidden, kNrHidden, nullptr))) return rc;
-  if ((rc = gemm_nt<EPI_STORE>(st, m, kNrOut, w.gc1, kNrHidden, kNrHidden, P + nl.w[2], kNrHidden, w.g, kNrOut))) return rc;
-  if ((rc = gemm_nt<EPI_STORE>(st, m, kRefE, w.gc1, kNrHidden, kNrHidden, P + nl.w[2] + int64_t(kNrOut) * kNrHidden,
-                               kNrHidden, w.dE, kRefE))) return rc;
+  float* am = w.amax;
+  LNRF_CUDA(cudaMemsetAsync(am + kNaFwdEnd, 0, (32 - kNaFwdEnd) * sizeof(float), st));
+  if ((rc = tcg_amax(st, w.gc2, m * kNrHidden, am + kNaGc2))) return rc;
+  if ((rc = rg_tn(st, kNrHidden, kNrHidden, w.c1, w.gc2, m, G + nl.w[3], G + nl.b[3], nullptr, am + kNaGc2))) return rc;
+  if ((rc = rg_nt<EPI_MASK>(st, m, kNrHidden, w.gc2, kNrHidden, P + nl.w[3], w.gc1, w.c1, am + kNaGc2, am + kNaGc1,
+                            w.mask_c1))) return rc;
+  if ((rc = rg_tn(st, kNrOut, kNrHidden, w.z, w.gc1, m, G + nl.w[2], G + nl.b[2], nullptr, am + kNaGc1))) return rc;
+  if ((rc = rg_tn(st, kRefE, kNrHidden, w.E, w.gc1, m, G + nl.w[2] + int64_t(kNrOut) * kNrHidden, nullptr, nullptr,
+                  am + kNaGc1))) return rc;
+  if ((rc = rg_nt<EPI_STORE>(st, m, kNrOut, w.gc1, kNrHidden, P + nl.w[2], w.g, nullptr, am + kNaGc1, nullptr))) return rc;
+  if ((rc = rg_nt<EPI_STORE>(st, m, kRefE, w.gc1, kNrHidden, P + nl.w[2] + int64_t(kNrOut) * kNrHidden, w.dE, nullptr,
+                             am + kNaGc1, nullptr))) return rc;
   // ---- heads: adds dL/dspatial_out[:, :9] into g, produces u = dL/dn_raw
   ref_head_bwd_kernel<<<ew_blocks(m, 256), 256, 0, st>>>(w.z, d, rays, T, w.nraw, w.o, d_dens, d_rgb, d_aux_normal_mse,
                                                          d_aux_neg_normal, w.dE, m, w.g, w.u, kNrOut);
   LNRF_LAUNCH_CHECK("ref_head_bwd_kernel");
   // ---- first-order chain through the spatial block and the hash grid
-  if ((rc = gemm_tn_small(st, kNrHidden, kNrOut, w.h0, kNrHidden, w.g, kNrOut, m, G + nl.w[1], kNrOut, G + nl.b[1]))) return rc;
-  if ((rc = gemm_nt<EPI_MASK>(st, m, kNrHidden, w.g, kNrOut, kNrOut, P + nl.w[1], kNrOut, w.g0, kNrHidden, w.h0,
-                              kNrHidden))) return rc;
-  if ((rc = gemm_tn_small(st, E, kNrHidden, w.enc, E, w.g0, kNrHidden, m, G + nl.w[0], kNrHidden, G + nl.b[0]))) return rc;
-  if ((rc = gemm_nt<EPI_STORE>(st, m, E, w.g0, kNrHidden, kNrHidden, P + nl.w[0], kNrHidden, w.d_enc, E))) return rc;
+  if ((rc = tcg_amax(st, w.g, m * kNrOut, am + kNaG))) return rc;  // after the heads changed nine columns
+  if ((rc = rg_tn(st, kNrHidden, kNrOut, w.h0, w.g, m, G + nl.w[1], G + nl.b[1], nullptr, am + kNaG))) return rc;
+  if ((rc = rg_nt<EPI_MASK>(st, m, kNrHidden, w.g, kNrOut, P + nl.w[1], w.g0, w.h0, am + kNaG, am + kNaG0,
+                            w.mask_h0))) return rc;
+  if ((rc = rg_tn(st, E, kNrHidden, w.enc, w.g0, m, G + nl.w[0], G + nl.b[0], nullptr, am + kNaG0))) return rc;
+  if ((rc = rg_nt<EPI_STORE>(st, m, E, w.g0, kNrHidden, P + nl.w[0], w.d_enc, nullptr, am + kNaG0, nullptr))) return rc;
 #define LNRF_GRID_B(which, in0, in1, out0, out1)                                                                \
   hashgrid_launch(which, P, level_offsets_host, grid_sizes_host, table_sizes_host, L, bbox_min_host, bbox_max_host, \
                   1, x, rays, ts, T, m, in0, in1, out0, out1, st)
   if ((rc = LNRF_GRID_B(1, w.d_enc, nullptr, G, nullptr))) return rc;
   // ---- second-order term through real_normal: tangent pass along u
   if ((rc = LNRF_GRID_B(3, w.vec, w.u, w.tenc, G))) return rc;                                   // T_enc = J u; tables
-  if ((rc = gemm_tn_small(st, E, kNrHidden, w.tenc, E, w.gn0, kNrHidden, m, G + nl.w[0], kNrHidden, nullptr))) return rc;
-  if ((rc = gemm_nn<EPI_MASK>(st, m, kNrHidden, w.tenc, E, E, nullptr, 0, 0, P + nl.w[0], kNrHidden, w.t0, kNrHidden,
-                              nullptr, w.h0, kNrHidden))) return rc;                               // T_0
+  if ((rc = tcg_amax(st, w.tenc, m * E, am + kNaTenc))) return rc;
+  if ((rc = rg_tn(st, E, kNrHidden, w.tenc, w.gn0, m, G + nl.w[0], nullptr, am + kNaTenc, am + kNaGn0))) return rc;
+  if ((rc = rg_nn<EPI_MASK>(st, m, kNrHidden, w.tenc, E, E, nullptr, 0, 0, P + nl.w[0], w.t0, nullptr, w.h0,
+                            am + kNaTenc, nullptr, nullptr, w.mask_h0))) return rc;                // T_0
   ref_w8col_kernel<<<ew_blocks(m, 512), kNrHidden, 0, st>>>(w.t0, m, G + nl.w[1], kNrOut);         // dW_1[:,0] -= sum T_0
   LNRF_LAUNCH_CHECK("ref_w8col_kernel");
   return LNRF_OK;
