@@ -387,7 +387,7 @@ struct NgpBwdSmem {
   static constexpr uint32_t g = 6 * kBlk;              // D4, G3, G2, DZ1, G0
   static constexpr uint32_t w = 11 * kBlk;             // 180,224: five transposed weight images
   static constexpr uint32_t bar = w + kNgpBwdBytes;    // 221,184: [0] weights, [8] stash tile, [16] chain MMA, [24] dW MMAs, [32] tmem
-  static constexpr uint32_t total = bar + 64;
+  static constexpr uint32_t total = bar + 128;         // [64..103] one barrier per stash block (progressive refill)
 };
 // TMEM columns: chain accumulator, then the five dW accumulators
 constexpr uint32_t kTmChain = 0;
@@ -403,7 +403,7 @@ ngp_bwd_tc_kernel(const __grid_constant__ NgpTcBwdArgs args) {
   const uint32_t D4 = sb + NgpBwdSmem::g, G3 = D4 + kBlk, G2 = D4 + 2 * kBlk, DZ1 = D4 + 3 * kBlk, G0 = D4 + 4 * kBlk;
   const uint32_t sW = sb + NgpBwdSmem::w;
   const uint32_t bar_w = sb + NgpBwdSmem::bar, bar_ld = bar_w + 8, bar_mma = bar_w + 16, bar_dw = bar_w + 24,
-                 tmem_slot = bar_w + 32;
+                 tmem_slot = bar_w + 32, bar_blk = bar_w + 64;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int r = tid & 127, ch = warp >> 2;
   const int E = args.E;
@@ -418,10 +418,13 @@ ngp_bwd_tc_kernel(const __grid_constant__ NgpTcBwdArgs args) {
     fence_barrier_init();
     mbar_arrive_expect_tx(bar_w, kNgpBwdBytes);
     bulk_g2s(sW, args.packed + kNgpFwdBytes, kNgpBwdBytes, bar_w);
-    if (my_tiles > 0) {
-      mbar_arrive_expect_tx(bar_ld, uint32_t(kNgpStashTileBytes));
-      bulk_g2s(sb, args.stash + int64_t(blockIdx.x) * kNgpStashTileBytes, uint32_t(kNgpStashTileBytes), bar_ld);
-    }
+    for (int b = 0; b < 5; ++b) mbar_init(bar_blk + 8 * b, 1);
+    fence_barrier_init();
+    if (my_tiles > 0)
+      for (int b = 0; b < 5; ++b) {
+        mbar_arrive_expect_tx(bar_blk + 8 * b, kBlk);
+        bulk_g2s(sb + b * kBlk, args.stash + int64_t(blockIdx.x) * kNgpStashTileBytes + b * kBlk, kBlk, bar_blk + 8 * b);
+      }
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, 512);
@@ -442,6 +445,14 @@ ngp_bwd_tc_kernel(const __grid_constant__ NgpTcBwdArgs args) {
   const uint32_t tlane = tmem + (uint32_t((warp & 3) * 32) << 16);
   mbar_wait(bar_w, 0);
   uint32_t ph_mma = 0, ph_ld = 0, ph_dw = 0;
+  // The five stash blocks of the NEXT tile are fetched one by one as soon as the last reader of the block
+  // (the dW MMA of its step, retired once the following step's chain MMA has committed) is done, so the loads
+  // run under the remaining steps of the current tile instead of in front of the next one.
+  auto block_landed = [&](int b) { mbar_wait(bar_blk + 8 * b, ph_ld); };
+  auto refill = [&](int b, int64_t next_tile) {  // thread 0 only
+    mbar_arrive_expect_tx(bar_blk + 8 * b, kBlk);
+    bulk_g2s(sb + b * kBlk, args.stash + next_tile * kNgpStashTileBytes + b * kBlk, kBlk, bar_blk + 8 * b);
+  };
   auto chain_done = [&]() {
     mbar_wait(bar_mma, ph_mma);
     ph_mma ^= 1;
@@ -489,8 +500,9 @@ ngp_bwd_tc_kernel(const __grid_constant__ NgpTcBwdArgs args) {
       }
       store_row_chunk(D4, r, 0, pack_bf16x2(d4[0], d4[1]), pack_bf16x2(d4[2], 0.0f), 0u, 0u);
     }
-    mbar_wait(bar_ld, ph_ld);  // the tile's stash blocks have landed
-    ph_ld ^= 1;
+    const bool more = t + 1 < my_tiles;
+    const int64_t next_tile = tile + gridDim.x;
+    block_landed(4);  // H3
     publish();
     // ---- g3 = (d4 @ W4^T) * (h3 > 0);  dW4 += [H3 | 1]^T d4
     if (tid == 0) {
@@ -501,6 +513,7 @@ ngp_bwd_tc_kernel(const __grid_constant__ NgpTcBwdArgs args) {
     }
     chain_done();
     epi_mask32(H3, G3);
+    block_landed(3);  // H2
     publish();
     // ---- g2 = (g3 @ W3^T) * (h2 > 0);  dW3 += [H2 | 1]^T g3
     if (tid == 0) {
@@ -509,8 +522,10 @@ ngp_bwd_tc_kernel(const __grid_constant__ NgpTcBwdArgs args) {
       umma_commit(bar_mma);
       ngp_mma_tn(tmem + tm_dw(3), H2, ONES, G3, 64, t > 0);
     }
-    chain_done();
+    chain_done();  // dW4's MMAs retired with it: H3 is free
+    if (tid == 0 && more) refill(4, next_tile);
     epi_mask32(H2, G2);
+    block_landed(2);  // IN2
     publish();
     // ---- d_in2 = g2 @ W2^T: columns 24..39 are d_out1 (+ the density term on column 24);  dW2 += [IN2 | 1]^T g2
     if (tid == 0) {
@@ -520,6 +535,7 @@ ngp_bwd_tc_kernel(const __grid_constant__ NgpTcBwdArgs args) {
       ngp_mma_tn(tmem + tm_dw(2), IN2, ONES, G2, 64, t > 0);
     }
     chain_done();
+    if (tid == 0 && more) refill(3, next_tile);  // H2
     {
       uint32_t v[16];
       tmem_ld16(tlane + kTmChain + (ch == 0 ? 16 : 32), v);  // ch 0: columns 16..31, ch 1: columns 32..47
@@ -531,6 +547,7 @@ ngp_bwd_tc_kernel(const __grid_constant__ NgpTcBwdArgs args) {
       store_row_chunk(DZ1, r, ch, pack_bf16x2(z[0], z[1]), pack_bf16x2(z[2], z[3]), pack_bf16x2(z[4], z[5]),
                       pack_bf16x2(z[6], z[7]));
     }
+    block_landed(1);  // H0
     publish();
     // ---- g0 = (dz1 @ W1^T) * (h0 > 0);  dW1 += [H0 | 1]^T dz1
     if (tid == 0) {
@@ -540,7 +557,9 @@ ngp_bwd_tc_kernel(const __grid_constant__ NgpTcBwdArgs args) {
       ngp_mma_tn(tmem + tm_dw(1), H0, ONES, DZ1, 16, t > 0);
     }
     chain_done();
+    if (tid == 0 && more) refill(2, next_tile);  // IN2
     epi_mask32(H0, G0);
+    block_landed(0);  // ENC
     publish();
     // ---- d_enc = g0 @ W0^T;  dW0 += [ENC | 1]^T g0
     if (tid == 0) {
@@ -551,6 +570,7 @@ ngp_bwd_tc_kernel(const __grid_constant__ NgpTcBwdArgs args) {
       umma_commit(bar_dw);  // every dW MMA of this tile has retired: its operand blocks may be overwritten
     }
     chain_done();
+    if (tid == 0 && more) refill(1, next_tile);  // H0
     if (ch * 32 < E) {
       uint32_t v[32];
       tmem_ld32(tlane + kTmChain + ch * 32, v);
@@ -568,10 +588,8 @@ ngp_bwd_tc_kernel(const __grid_constant__ NgpTcBwdArgs args) {
     mbar_wait(bar_dw, ph_dw);
     ph_dw ^= 1;
     __syncthreads();
-    if (tid == 0 && t + 1 < my_tiles) {  // next tile's stash blocks
-      mbar_arrive_expect_tx(bar_ld, uint32_t(kNgpStashTileBytes));
-      bulk_g2s(sb, args.stash + (tile + gridDim.x) * kNgpStashTileBytes, uint32_t(kNgpStashTileBytes), bar_ld);
-    }
+    if (tid == 0 && more) refill(0, next_tile);  // ENC
+    ph_ld ^= 1;
   }
   // ---- drain: dW_l[k][n] += D_l[row k][col n] for k < in_l; db_l[n] += D_l[row 64][col n]
   tc_fence_after();
