@@ -18,6 +18,7 @@
 //      (the byte image of a K-major block read transposed, as in mlp_tc_bwd.cu), the 128 x N result stays
 //      in TMEM over the CTA's whole sample range and is added to global memory once; the producers also
 //      form the column sums of B (bias gradients) on the way.
+#include <cuda.h>
 #include <cuda_fp16.h>
 
 #include "gemm_tc.cuh"
@@ -62,6 +63,20 @@ __device__ __forceinline__ void split8_store(const float4& a, const float4& b, f
   st_shared_v4(lo_addr, l0, l1, l2, l3);
 }
 
+// 2-D tiled TMA load (box = [128 rows x 64 fp32]) into shared memory, completion counted in bytes on `bar`;
+// rows / columns outside the tensor arrive as zeros (UTMALDG in SASS)
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* tm, int32_t col, int32_t row, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst_smem), "l"(tm), "r"(col), "r"(row), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
 __device__ __forceinline__ bool elect_one_sync() {
   uint32_t pred;
   asm volatile(
@@ -99,7 +114,7 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ================================================================ row GEMM
-constexpr int kRgThreads = 416;            // warps 0-3 epilogue, 4-11 producers, 12 MMA issuer
+constexpr int kRgThreads = 576;            // warps 0-7 epilogue, 8-15 converters, 16 MMA issuer, 17 TMA issuer
 constexpr int kRgProducers = 256;
 constexpr int kRgMaxChunks = 5;            // K <= 320
 constexpr uint32_t kRgBlock = 128 * 128;   // one [128 x 64] fp16 K-major SW128 block
@@ -107,15 +122,17 @@ constexpr uint32_t kRgChunk = 2 * kRgBlock;  // hi + lo
 constexpr uint32_t kRgData = 7 * kRgChunk;   // resident B chunks first, the A ring behind them
 constexpr uint32_t kRgSmem = kRgData + 256;
 // barrier block (byte offsets inside it)
-constexpr uint32_t kRgAFull = 0, kRgAEmpty = 32, kRgAccFull = 64, kRgAccEmpty = 80, kRgTmemSlot = 96, kRgBMax = 100;
+constexpr uint32_t kRgAFull = 0, kRgAEmpty = 32, kRgAccFull = 64, kRgAccEmpty = 80, kRgTmemSlot = 96, kRgBMax = 100,
+                   kRgTmaFull = 104;
 
 struct RgChunkDesc {
-  const float* A;  // first column of the chunk (row 0)
-  int lda;
+  int seg;         // which K segment (tensor map) of A
+  int k0;          // first column inside the segment
   int kv;          // valid K columns (multiple of 4, <= 64)
   int bk0;         // first K index of W
 };
 struct RgArgs {
+  alignas(64) CUtensorMap tm[2];  // the two K segments of A as [M rows x K_seg] fp32 tensors, box 128 x 64
   RgChunkDesc ch[kRgMaxChunks];
   int nchunks, stages, has_a1;
   const float* B;
@@ -153,15 +170,16 @@ __global__ void __launch_bounds__(kRgThreads, 1) tcg_rows_kernel(const __grid_co
     for (int s = 0; s < 4; ++s) {
       mbar_init(bars + kRgAFull + 8 * s, kRgProducers / 32);
       mbar_init(bars + kRgAEmpty + 8 * s, 1);
+      mbar_init(bars + kRgTmaFull + 8 * s, 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bars + kRgAccFull + 8 * b, 1);
-      mbar_init(bars + kRgAccEmpty + 8 * b, 4);
+      mbar_init(bars + kRgAccEmpty + 8 * b, 8);
     }
     bar_words[kRgBMax / 4] = 0u;
     fence_barrier_init();
   }
-  if (warp == 12) {
+  if (warp == 16) {
     tmem_alloc(bars + kRgTmemSlot, 512);
     tmem_relinquish();
   }
@@ -221,75 +239,52 @@ __global__ void __launch_bounds__(kRgThreads, 1) tcg_rows_kernel(const __grid_co
     sa = pow2_scale(fmaxf(m0, m1));
   }
 
-  if (warp >= 4 && warp < 12) {
-    // ===== producers: thread owns 16-byte operand pieces (row, 8 columns); four pieces per chunk
-    const int pt = tid - 128;
-    const int g8 = pt & 7, r0 = pt >> 3;  // rows r0, r0 + 32, r0 + 64, r0 + 96
-    const int64_t total = my_tiles * a.nchunks;
-    // Three chunks of loads are kept in flight per thread (register ring b0 / b1 / b2): at ~23 B/clk of HBM
-    // bandwidth per SM and > 1 us of loaded latency one chunk (32 KB per SM) would bound the kernel.
-    float4 b0[8], b1[8], b2[8];
-    int lc = 0;                          // chunk index of the next load
-    int64_t lrow = tfirst * 128 + r0;    // this thread's first row of the tile of the next load
-    int lleft = total > 0x7fffffff ? 0x7fffffff : int(total), eleft = lleft;  // loads / emits still to do
-    const int k = g8 * 8;
-    auto load = [&](float4(&v)[8]) {
-      if (lleft <= 0) return;
-      --lleft;
-      const RgChunkDesc cd = a.ch[lc];
-      const bool vec8 = ((cd.lda & 7) == 0) && ((reinterpret_cast<uintptr_t>(cd.A) & 31) == 0) && k + 8 <= cd.kv;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int64_t row = lrow + 32 * j;
-        v[2 * j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        v[2 * j + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < a.M) {
-          const float* p = cd.A + row * cd.lda + k;
-          if (vec8) {  // one 32-byte sector per lane: half the load instructions and L1 wavefronts
-            asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                         : "=f"(v[2 * j].x), "=f"(v[2 * j].y), "=f"(v[2 * j].z), "=f"(v[2 * j].w), "=f"(v[2 * j + 1].x),
-                           "=f"(v[2 * j + 1].y), "=f"(v[2 * j + 1].z), "=f"(v[2 * j + 1].w)
-                         : "l"(p));
-          } else {
-            if (k < cd.kv) v[2 * j] = __ldg(reinterpret_cast<const float4*>(p));
-            if (k + 4 < cd.kv) v[2 * j + 1] = __ldg(reinterpret_cast<const float4*>(p + 4));
-          }
+  if (warp == 17) {
+    // ===== TMA issuer: one 128 x 64 fp32 box of A per ring slot, as soon as the MMAs that read the slot retired.
+    // (Loading A through registers was bounded by the L1's outstanding-request capacity: issuing the next chunk's
+    // four 256-bit loads stalled ~2 k clk per chunk, i.e. ~3 TB/s, however deep the register ring.)
+    if (lane == 0) {
+      uint32_t stage = 0, phases = 0;
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        const int32_t row = int32_t((tfirst + it * tstride) * 128);
+        for (int c = 0; c < a.nchunks; ++c) {
+          mbar_wait(bars + kRgAEmpty + 8 * stage, ((phases >> stage) & 1u) ^ 1u);
+          phases ^= 1u << stage;
+          mbar_arrive_expect_tx(bars + kRgTmaFull + 8 * stage, kRgChunk);
+          tma_load_2d(sA + stage * kRgChunk, &a.tm[a.ch[c].seg], a.ch[c].k0, row, bars + kRgTmaFull + 8 * stage);
+          if (++stage == uint32_t(a.stages)) stage = 0;
         }
       }
-      if (++lc == a.nchunks) {
-        lc = 0;
-        lrow += tstride * 128;
-      }
-    };
-    uint32_t stage = 0, phases = 0;  // bit s = parity of a_empty[s] the next fill of slot s waits for
-    auto emit = [&](const float4(&v)[8]) {
-      if (eleft <= 0) return;
-      --eleft;
-      mbar_wait(bars + kRgAEmpty + 8 * stage, ((phases >> stage) & 1u) ^ 1u);
+    }
+  } else if (warp >= 8 && warp < 16) {
+    // ===== converters: the slot arrives as raw fp32 rows (256 B each); every thread reads its four 32-byte pieces
+    // (row, 8 columns), all 256 threads meet, then the hi / lo fp16 operand blocks are written IN PLACE.
+    const int pt = tid - 256;
+    const int g8 = pt & 7, r0 = pt >> 3;  // rows r0 + 32 j
+    const uint32_t raw0 = uint32_t(r0) * 256u + uint32_t(g8) * 32u;
+    const uint32_t off0 = uint32_t(r0) * 128u + (uint32_t((g8 ^ (r0 & 7)) & 7) << 4);  // rows r0 + 32 j share r & 7
+    const int64_t total = my_tiles * a.nchunks;
+    uint32_t stage = 0, phases = 0;
+    for (int64_t q = 0; q < total; ++q) {
+      mbar_wait(bars + kRgTmaFull + 8 * stage, (phases >> stage) & 1u);
       phases ^= 1u << stage;
       const uint32_t base = sA + stage * kRgChunk;
+      float4 v[8];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int r = r0 + 32 * j;
-        const uint32_t off = uint32_t(r) * 128u + (uint32_t((g8 ^ (r & 7)) & 7) << 4);
-        split8_store(v[2 * j], v[2 * j + 1], sa, base + off, base + kRgBlock + off);
+        v[2 * j] = lds_f4(base + raw0 + j * 8192u);
+        v[2 * j + 1] = lds_f4(base + raw0 + j * 8192u + 16u);
       }
+      asm volatile("bar.sync 2, 256;" ::: "memory");  // every raw piece is in registers before any is overwritten
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        split8_store(v[2 * j], v[2 * j + 1], sa, base + off0 + j * 4096u, base + kRgBlock + off0 + j * 4096u);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(bars + kRgAFull + 8 * stage);
       if (++stage == uint32_t(a.stages)) stage = 0;
-    };
-    load(b0);
-    load(b1);
-    while (eleft > 0) {
-      load(b2);
-      emit(b0);
-      load(b0);
-      emit(b1);
-      load(b1);
-      emit(b2);
     }
-  } else if (warp == 12) {
+  } else if (warp == 16) {
     // ===== MMA issuer
     const uint32_t idesc = idesc_f16(128, a.nc);
     uint32_t stage = 0, phases = 0;
@@ -319,8 +314,9 @@ __global__ void __launch_bounds__(kRgThreads, 1) tcg_rows_kernel(const __grid_co
         if (++stage == uint32_t(a.stages)) stage = 0;
       }
     }
-  } else if (warp < 4) {
-    // ===== epilogue.  tcgen05.ld hands lane r the 32 columns of tile row r: storing that directly makes every
+  } else if (warp < 8) {
+    // ===== epilogue (eight warps: TMEM lane quadrant warp & 3, accumulator column half warp >> 2: one warp per
+    // scheduler needs ~7 k clk per tile, a single dependent instruction chain, against 3.4 k clk of MMAs).  tcgen05.ld hands lane r the 32 columns of tile row r: storing that directly makes every
     // warp store touch 32 different lines, and the LSU (not HBM) bounds the kernel (measured: 1.8 TB/s).  So
     // each 8-lane group first transposes its 8 rows x 8 four-column granules through shuffles: lane (a, b) =
     // (lane / 8, lane % 8) ends up with granule b of rows 8a .. 8a+7, and store instruction i writes rows
@@ -330,7 +326,7 @@ __global__ void __launch_bounds__(kRgThreads, 1) tcg_rows_kernel(const __grid_co
     const int la = lane >> 3, lb = lane & 7;
     for (int64_t it = 0; it < my_tiles; ++it) {
       const uint32_t buf = uint32_t(it & 1);
-      const int64_t row0 = (tfirst + it * tstride) * 128 + warp * 32 + la * 8;  // rows row0 + i, i = 0..7
+      const int64_t row0 = (tfirst + it * tstride) * 128 + (warp & 3) * 32 + la * 8;  // rows row0 + i, i = 0..7
       float r1[8];
       if (EPI == TCG_RANK1) {
 #pragma unroll
@@ -338,8 +334,9 @@ __global__ void __launch_bounds__(kRgThreads, 1) tcg_rows_kernel(const __grid_co
       }
       mbar_wait(bars + kRgAccFull + 8 * buf, uint32_t(it >> 1) & 1u);
       tc_fence_after();
-      const uint32_t t_main = tmem + (uint32_t(warp * 32) << 16) + buf * 256u;
-      for (int c0 = 0; c0 < a.nc; c0 += 32) {
+      const uint32_t t_main = tmem + (uint32_t((warp & 3) * 32) << 16) + buf * 256u;
+      const int c_beg = (warp >> 2) * 64, c_end = a.nc < c_beg + 64 ? a.nc : c_beg + 64;
+      for (int c0 = c_beg; c0 < c_end; c0 += 32) {
         uint32_t vm[32], vc[32];
         tmem_ld32(t_main + c0, vm);
         tmem_ld32(t_main + 128 + c0, vc);
@@ -424,7 +421,7 @@ __global__ void __launch_bounds__(kRgThreads, 1) tcg_rows_kernel(const __grid_co
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 12) tmem_dealloc(tmem, 512);
+  if (warp == 16) tmem_dealloc(tmem, 512);
 }
 
 // ================================================================ TN GEMM (K = samples)
@@ -637,6 +634,26 @@ __global__ void __launch_bounds__(256) tcg_amax_kernel(const float* __restrict__
   if ((threadIdx.x & 31) == 0 && m > 0.0f && m < 3.0e38f) atomicMax(reinterpret_cast<uint32_t*>(amax), __float_as_uint(m));
 }
 
+// tensor map of a row-major fp32 [M x K] matrix with leading dimension lda, box = 128 rows x 64 columns
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode_tiled = nullptr;  // resolved once in init_gemm_tc (driver entry point: no libcuda link)
+int make_tmap(CUtensorMap* tm, const float* A, int64_t M, int K, int lda) {
+  LNRF_REQUIRE(g_encode_tiled != nullptr, LNRF_E_INVALID, "tcg_rows: call lnrf_init first");
+  LNRF_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0, LNRF_E_INVALID, "tcg_rows: operand not 16-byte aligned");
+  const cuuint64_t dims[2] = {cuuint64_t(K), cuuint64_t(M)};
+  const cuuint64_t strides[1] = {cuuint64_t(lda) * 4u};
+  const cuuint32_t box[2] = {64u, 128u};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult r = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(A), dims, strides, box, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LNRF_REQUIRE(r == CUDA_SUCCESS, LNRF_E_INVALID, "tcg_rows: cuTensorMapEncodeTiled failed (%d) M=%lld K=%d lda=%d", int(r),
+               (long long)M, K, lda);
+  return LNRF_OK;
+}
+
 template <int EPI>
 int launch_rows(const RgArgs& a, unsigned grid, cudaStream_t st) {
   tcg_rows_kernel<EPI><<<grid, kRgThreads, kRgSmem, st>>>(a);
@@ -662,8 +679,13 @@ int tcg_rows(cudaStream_t st, int epi, bool btrans, int64_t M, int N, const floa
   if (M <= 0) return LNRF_OK;
   RgArgs a{};
   int nch = 0;
-  for (int k = 0; k < K0; k += 64) a.ch[nch++] = RgChunkDesc{A0 + k, lda0, K0 - k < 64 ? K0 - k : 64, k};
-  for (int k = 0; k < K1; k += 64) a.ch[nch++] = RgChunkDesc{A1 + k, lda1, K1 - k < 64 ? K1 - k : 64, K0 + k};
+  for (int k = 0; k < K0; k += 64) a.ch[nch++] = RgChunkDesc{0, k, K0 - k < 64 ? K0 - k : 64, k};
+  for (int k = 0; k < K1; k += 64) a.ch[nch++] = RgChunkDesc{1, k, K1 - k < 64 ? K1 - k : 64, K0 + k};
+  {
+    int rc = make_tmap(&a.tm[0], A0, M, K0, lda0);
+    if (rc) return rc;
+    if (K1 > 0 && (rc = make_tmap(&a.tm[1], A1, M, K1, lda1))) return rc;
+  }
   a.nchunks = nch;
   a.stages = 7 - nch > 4 ? 4 : 7 - nch;
   a.B = B; a.ldb = ldb; a.btrans = btrans ? 1 : 0;
@@ -722,6 +744,14 @@ int tcg_amax(cudaStream_t st, const float* x, int64_t n, float* amax) {
 }
 
 int init_gemm_tc() {
+  if (g_encode_tiled == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    LNRF_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    LNRF_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, LNRF_E_UNSUPPORTED,
+                 "lnrf_init: the driver does not export cuTensorMapEncodeTiled");
+    g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+  }
   LNRF_CUDA(cudaFuncSetAttribute(tcg_rows_kernel<TCG_BIAS_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRgSmem));
   LNRF_CUDA(cudaFuncSetAttribute(tcg_rows_kernel<TCG_BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRgSmem));
   LNRF_CUDA(cudaFuncSetAttribute(tcg_rows_kernel<TCG_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRgSmem));
