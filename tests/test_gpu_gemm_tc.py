@@ -28,6 +28,11 @@ def _rel(a, b):
 
 @pytest.mark.parametrize("M,N,K0,K1,epi,btrans", [
     (1000, 256, 256, 0, 0, False),
+    (40000 + 77, 256, 256, 0, 0, False),  # several tiles per CTA: ring slots and accumulator buffers wrap
+    (30000, 256, 256, 60, 0, False),
+    (50000, 128, 256, 24, 1, False),
+    (25000 + 3, 256, 128, 0, 3, True),
+    (33000, 60, 256, 0, 5, True),
     (4099, 256, 256, 60, 0, False),   # skip layer: two K segments, ragged last tile
     (777, 256, 60, 0, 0, False),      # first layer: one partial chunk
     (2048, 128, 256, 24, 1, False),   # colour layer shape
@@ -68,7 +73,7 @@ def test_rows_vs_fp64(M, N, K0, K1, epi, btrans):
     fp32 = np.abs((torch.cat([A0] + ([A1] if K1 else []), 1).cpu() @ W.cpu()).double().numpy()
                   - A @ W.cpu().double().numpy()).max()
     print(f"max abs err {err:.3e} (torch fp32 CPU matmul: {fp32:.3e})")
-    assert err < 4e-6, err   # |C| ~ 1: a few fp32 ulps
+    assert err < max(4e-6, 1.5 * fp32), err   # |C| ~ 1: a few fp32 ulps, no worse than an fp32 matmul
     assert abs(float(c_amax) - np.abs(out).max()) <= 1e-6 * np.abs(out).max()
 
 
@@ -115,7 +120,7 @@ def test_tn_vs_fp64(Ksamp, M, N):
     assert _rel(db.cpu().double().numpy(), refdb) < 1e-5
 
 
-@pytest.mark.parametrize("M,N", [(1000, 256), (4099, 128), (77, 64)])
+@pytest.mark.parametrize("M,N", [(1000, 256), (4099, 128), (77, 64), (45000, 256)])
 def test_relu_bit_masks_roundtrip(M, N):
     """epi 0 writes the bits [relu output > 0]; epi 6 applies them: same result as masking by the fp32 activations."""
     g = torch.Generator().manual_seed(M)
