@@ -40,7 +40,7 @@ FLOP_TRAIN_PER_SAMPLE = 3_481_344        # fwd + dW + dX, no padding / recompute
 REF_FLOP_FWD_PER_SAMPLE = 2 * (590_336 + 489_472)
 REF_FLOP_TRAIN_PER_SAMPLE = 2 * 3_709_088
 SAMPLES_PER_RAY = 64 + 192
-# fp32-accurate paths: an UNFUSED chain of split-fp16 tcgen05 GEMMs whose fp32 activations cross HBM once per
+# fp32-accurate paths: an UNFUSED chain of split-fp16 tcgen05 GEMMs (A by TMA) whose fp32 activations cross HBM once per
 # producer and once per consumer, i.e. HBM-bound.  Algorithmic fp32 values moved per sample,
 # every GEMM counted as (K inputs read + N outputs written), dW GEMMs as (M + N read), bit masks as 8 words:
 #   NeRF  forward 5,264 (ten Dense layers + the two head kernels), backward 10,320 (heads, 13 dW, 9 dX)
