@@ -140,3 +140,27 @@ def test_relu_bit_masks_roundtrip(M, N):
     _call(1, 2, M, N, G, N, N, None, 0, 0, Wt, N, C_aux, N, aux=Hh, ldaux=N)
     assert torch.equal(C_bits, C_aux)
     assert (C_aux == 0).float().mean() > 0.3
+
+
+def test_rows_strided_operands():
+    """Leading dimensions larger than the logical widths (views into wider matrices) for A, W and C: the TMA
+    tensor map of A, the weight conversion and the epilogue all honour them."""
+    g = torch.Generator().manual_seed(11)
+    M, N, K0, K1 = 2500, 192, 128, 60
+    A0w = torch.randn(M, 384, generator=g).cuda()   # A0 = columns 64 .. 191 of a 384-wide matrix
+    A1w = torch.randn(M, 64, generator=g).cuda()    # A1 = columns 0 .. 59 of a 64-wide matrix
+    Ww = (torch.randn(K0 + K1, 256, generator=g) / 14).cuda()  # W = columns 0 .. 191 of a 256-wide matrix
+    Cw = torch.full((M, 200), 7.0, device="cuda")
+    bias = torch.randn(N, generator=g).cuda()
+    A0 = A0w[:, 64:192]
+    _native.ensure_init(Cw.device)
+    p = _native._p
+    a0_ptr = ctypes.c_void_p(A0w.data_ptr() + 64 * 4)
+    rc = _native.load().lnrf_tcgemm(0, 1, M, N, a0_ptr, 384, K0, p(A1w), 64, K1, p(Ww), 256, p(Cw), 200, p(bias), None, 0,
+                                    None, None, None, None, None, None, None, None, _native._stream())
+    _native._check(rc, "lnrf_tcgemm")
+    A = np.concatenate([A0.cpu().double().numpy(), A1w[:, :K1].cpu().double().numpy()], axis=1)
+    ref = A @ Ww[:, :N].cpu().double().numpy() + bias.cpu().double().numpy()
+    out = Cw.cpu().double().numpy()
+    assert np.abs(out[:, :N] - ref).max() < 4e-6
+    assert (out[:, N:] == 7.0).all()   # nothing written beyond the N columns
