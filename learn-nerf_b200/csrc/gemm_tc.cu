@@ -270,10 +270,16 @@ __global__ void __launch_bounds__(kRgThreads, 1) tcg_rows_kernel(const __grid_co
       phases ^= 1u << stage;
       const uint32_t base = sA + stage * kRgChunk;
       float4 v[8];
+      // The eight lanes of a row read 16-byte units {0,2,4,6,9,11,13,15} first and {1,3,5,7,8,10,12,14} second:
+      // each instruction covers all 32 banks once (reading both halves in piece order is a 2-way conflict, and
+      // shared-memory bandwidth is this kernel's limiter)
+      const uint32_t hi_half = g8 >= 4 ? 16u : 0u;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        v[2 * j] = lds_f4(base + raw0 + j * 8192u);
-        v[2 * j + 1] = lds_f4(base + raw0 + j * 8192u + 16u);
+        const float4 p0 = lds_f4(base + raw0 + j * 8192u + hi_half);
+        const float4 p1 = lds_f4(base + raw0 + j * 8192u + (16u - hi_half));
+        v[2 * j] = hi_half ? p1 : p0;
+        v[2 * j + 1] = hi_half ? p0 : p1;
       }
       asm volatile("bar.sync 2, 256;" ::: "memory");  // every raw piece is in registers before any is overwritten
 #pragma unroll
@@ -286,7 +292,7 @@ __global__ void __launch_bounds__(kRgThreads, 1) tcg_rows_kernel(const __grid_co
     }
   } else if (warp == 16) {
     // ===== MMA issuer
-    const uint32_t idesc = idesc_f16(128, a.nc);
+    const uint32_t idesc = idesc_f16(128, a.nc), idesc256 = idesc_f16(128, 256);
     uint32_t stage = 0, phases = 0;
     for (int64_t it = 0; it < my_tiles; ++it) {
       const uint32_t buf = uint32_t(it & 1);
@@ -300,11 +306,12 @@ __global__ void __launch_bounds__(kRgThreads, 1) tcg_rows_kernel(const __grid_co
         if (elect_one_sync()) {
           const int ksteps = (a.ch[c].kv + 15) >> 4;
           const uint32_t ah = (((sA + stage * kRgChunk) & 0x3FFFFu) >> 4) | (1u << 16), al = ah + (kRgBlock >> 4);
-          const uint32_t bh = (((sB + uint32_t(c) * kRgChunk) & 0x3FFFFu) >> 4) | (1u << 16), bl = bh + (kRgBlock >> 4);
+          const uint32_t bh = (((sB + uint32_t(c) * kRgChunk) & 0x3FFFFu) >> 4) | (1u << 16);  // hi block, lo block behind it
           for (int k = 0; k < ksteps; ++k) {  // 32 bytes (16 fp16) of K per step
             const uint32_t acc = (c | k) ? 1u : 0u;
-            umma_f16_lohi(d_main, ah + 2 * k, bh + 2 * k, kDescHiSw128, idesc, acc);
-            umma_f16_lohi(d_corr, ah + 2 * k, bl + 2 * k, kDescHiSw128, idesc, acc);
+            // [main | corr] (+)= A_hi [B_hi ; B_lo]^T as ONE N = 256 MMA (the lo block follows the hi block in
+            // shared memory, the corr columns follow the main columns in TMEM): A_hi is read once instead of twice
+            umma_f16_lohi(d_main, ah + 2 * k, bh + 2 * k, kDescHiSw128, idesc256, acc);
             umma_f16_lohi(d_corr, al + 2 * k, bh + 2 * k, kDescHiSw128, idesc, 1u);
           }
           umma_commit(bars + kRgAEmpty + 8 * stage);
