@@ -10,6 +10,12 @@
 
 namespace lnrf {
 
+// exp of the compositing kernels: the hardware ex2 (MUFU.EX2, ~2 ulp).  Compositing is compared by tolerance
+// (1e-5 abs on outputs / alphas / coords), so it does not need the bit-exact 25-instruction lnrf_expf of the
+// sampling kernels (whose weights decide sample POSITIONS and must match the oracle bit for bit): with two to
+// three exponentials per sample that polynomial made K3 / K5 issue-bound at 0.3 - 0.5 of the HBM roofline.
+__device__ __forceinline__ float comp_expf(float x) { return __expf(x); }
+
 constexpr int kCompWarps = 4;
 
 // exclusive prefix sum of one value per lane; `total` = sum over the warp
@@ -112,7 +118,7 @@ composite_fwd_kernel(const float* __restrict__ rays, const float* __restrict__ t
     }
     float c_rgb[3] = {0.f, 0.f, 0.f}, c_xyz[3] = {0.f, 0.f, 0.f};
     for (int i = c0; i < c1; ++i) {
-      float p = lnrf_expf(-s_acc[i]) * (1.0f - lnrf_expf(-s_a[i]));  // :279-287
+      float p = comp_expf(-s_acc[i]) * (1.0f - comp_expf(-s_a[i]));  // :279-287
       float t = s_ts[i];
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
@@ -125,7 +131,7 @@ composite_fwd_kernel(const float* __restrict__ rays, const float* __restrict__ t
       c_rgb[k] = warp_sum(c_rgb[k]);
       c_xyz[k] = warp_sum(c_xyz[k]);
     }
-    const float p_esc = lnrf_expf(-total);  // last column of termination_probs
+    const float p_esc = comp_expf(-total);  // last column of termination_probs
     if (lane == 0) {
       outputs[r * 3 + 0] = c_rgb[0] + p_esc * bg0;
       outputs[r * 3 + 1] = c_rgb[1] + p_esc * bg1;
@@ -236,7 +242,7 @@ composite_fwd_pf_kernel(const float* __restrict__ rays, const float* __restrict_
     __syncwarp();
     float c_rgb[3] = {0.f, 0.f, 0.f}, c_xyz[3] = {0.f, 0.f, 0.f};
     for (int i = c0; i < c1; ++i) {
-      float p = lnrf_expf(-s_acc[i]) * (1.0f - lnrf_expf(-s_a[i]));  // :279-287
+      float p = comp_expf(-s_acc[i]) * (1.0f - comp_expf(-s_a[i]));  // :279-287
       float t = s_ts[i];
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
@@ -249,7 +255,7 @@ composite_fwd_pf_kernel(const float* __restrict__ rays, const float* __restrict_
       c_rgb[k] = warp_sum(c_rgb[k]);
       c_xyz[k] = warp_sum(c_xyz[k]);
     }
-    const float p_esc = lnrf_expf(-total);  // last column of termination_probs
+    const float p_esc = comp_expf(-total);  // last column of termination_probs
     if (lane == 0) {
       outputs[r * 3 + 0] = c_rgb[0] + p_esc * bg0;
       outputs[r * 3 + 1] = c_rgb[1] + p_esc * bg1;
@@ -304,12 +310,12 @@ composite_bwd_kernel(const float* __restrict__ ts, const float* __restrict__ t_m
     float total = stage_ray(ts, dens, r, T, __ldg(t_min_in + r), __ldg(t_max_in + r), lane, c0, c1,
                             s_ts, s_delta, s_a, s_acc);
     __syncwarp();
-    const float p_esc = lnrf_expf(-total);
+    const float p_esc = comp_expf(-total);
     const float g_bg = bg0 * g0 + bg1 * g1 + bg2 * g2;
     // forward sweep over the chunk: p_k, p_k*g_k; stash p in s_ts (ts no longer needed)
     float local = 0.0f;
     for (int i = c0; i < c1; ++i) {
-      float p = lnrf_expf(-s_acc[i]) * (1.0f - lnrf_expf(-s_a[i]));
+      float p = comp_expf(-s_acc[i]) * (1.0f - comp_expf(-s_a[i]));
       float gk = s_rgb[i * 3] * g0 + s_rgb[i * 3 + 1] * g1 + s_rgb[i * 3 + 2] * g2;
       s_ts[i] = p;
       local += p * gk;
@@ -318,7 +324,7 @@ composite_bwd_kernel(const float* __restrict__ ts, const float* __restrict__ t_m
     for (int i = c1 - 1; i >= c0; --i) {
       float p = s_ts[i];
       float gk = s_rgb[i * 3] * g0 + s_rgb[i * 3 + 1] * g1 + s_rgb[i * 3 + 2] * g2;
-      float t_next = lnrf_expf(-(s_acc[i] + s_a[i]));  // T_{k+1}
+      float t_next = comp_expf(-(s_acc[i] + s_a[i]));  // T_{k+1}
       float dla = t_next * gk - suffix;
       suffix += p * gk;
       s_a[i] = dla * s_delta[i];  // d_dens
@@ -386,11 +392,11 @@ composite_bwd_pf_kernel(const float* __restrict__ ts, const float* __restrict__ 
     __syncwarp();
     float total = stage_ray_smem(T, t_min, t_max, lane, c0, c1, s_ts, s_delta, s_a, s_acc);
     __syncwarp();
-    const float p_esc = lnrf_expf(-total);
+    const float p_esc = comp_expf(-total);
     const float g_bg = bg0 * g0 + bg1 * g1 + bg2 * g2;
     float local = 0.0f;
     for (int i = c0; i < c1; ++i) {
-      float p = lnrf_expf(-s_acc[i]) * (1.0f - lnrf_expf(-s_a[i]));
+      float p = comp_expf(-s_acc[i]) * (1.0f - comp_expf(-s_a[i]));
       float gk = s_rgb[i * 3] * g0 + s_rgb[i * 3 + 1] * g1 + s_rgb[i * 3 + 2] * g2;
       s_ts[i] = p;
       local += p * gk;
@@ -399,7 +405,7 @@ composite_bwd_pf_kernel(const float* __restrict__ ts, const float* __restrict__ 
     for (int i = c1 - 1; i >= c0; --i) {
       float p = s_ts[i];
       float gk = s_rgb[i * 3] * g0 + s_rgb[i * 3 + 1] * g1 + s_rgb[i * 3 + 2] * g2;
-      float t_next = lnrf_expf(-(s_acc[i] + s_a[i]));  // T_{k+1}
+      float t_next = comp_expf(-(s_acc[i] + s_a[i]));  // T_{k+1}
       float dla = t_next * gk - suffix;
       suffix += p * gk;
       s_a[i] = dla * s_delta[i];  // d_dens
