@@ -139,6 +139,20 @@ int lnrf_nerf_mlp_fwd(const float* params, const void* packed, const float* x, c
                       const float* rays, const float* ts, int64_t n, int32_t T, int32_t precision,
                       int32_t save_for_backward, void* workspace, int64_t workspace_bytes,
                       float* dens, float* rgb, lnrf_stream_t stream);
+/* NeRFRenderer.render_rays (render.py:39-91) for two NeRFModels as ONE call: t_range + stratified coarse
+ * sampling, coarse model, compositing, inverse-CDF fine sampling (eps 1e-8, render.py:217) of Tf more points,
+ * fine model over the Tc + Tf sorted points, compositing.  rays[n,2,3]; u_coarse[n,Tc] / u_fine[n,Tf] are the
+ * uniforms of jax.random.uniform(coarse_key) / (fine_key) (render.py:55,142; lnrf_threefry_uniform produces
+ * them from a key); *_packed as for lnrf_nerf_mlp_fwd (bf16 only).  Outputs: coarse_outputs[n,3],
+ * fine_outputs[n,3], and optionally the fine level's alphas[n] and coords[n,3] (nullable).  Same kernels and
+ * bits as the six separate calls.  workspace: lnrf_nerf_render_workspace_bytes, 1024-byte aligned.        */
+int lnrf_nerf_render_workspace_bytes(int64_t n, int32_t Tc, int32_t Tf, int32_t precision, int64_t* bytes_out_host);
+int lnrf_nerf_render_rays(const float* rays, const float* bbox_min_host, const float* bbox_max_host, float min_t_range,
+                          const float* u_coarse, const float* u_fine, const float* coarse_params,
+                          const void* coarse_packed, const float* fine_params, const void* fine_packed,
+                          int32_t precision, const float* background, int64_t n, int32_t Tc, int32_t Tf,
+                          void* workspace, int64_t workspace_bytes, float* coarse_outputs, float* fine_outputs,
+                          float* fine_alphas, float* fine_coords, lnrf_stream_t stream);
 /* Gradient of the above w.r.t. params given d_dens[m], d_rgb[m,3]; uses the
  * workspace written by the matching forward call.  d_params
  * (lnrf_nerf_param_floats() floats) is ACCUMULATED.  Inputs x/d/rays/ts carry

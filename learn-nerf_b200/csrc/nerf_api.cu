@@ -103,4 +103,88 @@ int lnrf_nerf_mlp_bwd(const float* params, const void* packed, int64_t m, int32_
                            d_params, lnrf::as_stream(stream));
 }
 
+// ---------------------------------------------------------------- one call per NeRFRenderer.render_rays
+// render.py:39-91 for two NeRFModels: t_range + stratified coarse sampling (K1), coarse MLP (K2), compositing (K3),
+// inverse-CDF fine sampling (K4), fine MLP, compositing -- the same six launches the Python mirror issues, in
+// one C call for a binding that wants a single custom call per seam.  The workspace holds the per-ray / per-sample
+// intermediates and the MLP workspace of the larger level.
+namespace {
+struct RenderWs {
+  float *t_min, *t_max, *ts_c, *dens_c, *rgb_c, *ts_f, *dens_f, *rgb_f;
+  uint8_t* mask;
+  void* mlp;
+  int64_t mlp_bytes, bytes;
+};
+int carve_render(void* base, int64_t n, int Tc, int Tf, int precision, RenderWs* w) {
+  char* p = reinterpret_cast<char*>(base);
+  int64_t off = 0;
+  auto take = [&](int64_t bytes) {
+    char* r = p + off;
+    off += (bytes + 1023) / 1024 * 1024;
+    return r;
+  };
+  const int T2 = Tc + Tf;
+  w->t_min = reinterpret_cast<float*>(take(n * 4));
+  w->t_max = reinterpret_cast<float*>(take(n * 4));
+  w->mask = reinterpret_cast<uint8_t*>(take(n));
+  w->ts_c = reinterpret_cast<float*>(take(n * Tc * 4));
+  w->dens_c = reinterpret_cast<float*>(take(n * Tc * 4));
+  w->rgb_c = reinterpret_cast<float*>(take(n * Tc * 12));
+  w->ts_f = reinterpret_cast<float*>(take(n * T2 * 4));
+  w->dens_f = reinterpret_cast<float*>(take(n * T2 * 4));
+  w->rgb_f = reinterpret_cast<float*>(take(n * T2 * 12));
+  int64_t bc = 0, bf = 0;
+  int rc = lnrf_nerf_mlp_workspace_bytes(n * Tc, precision, 0, &bc);
+  if (rc) return rc;
+  if ((rc = lnrf_nerf_mlp_workspace_bytes(n * T2, precision, 0, &bf))) return rc;
+  w->mlp_bytes = bc > bf ? bc : bf;
+  w->mlp = take(w->mlp_bytes);
+  w->bytes = off;
+  return LNRF_OK;
+}
+}  // namespace
+
+int lnrf_nerf_render_workspace_bytes(int64_t n, int32_t Tc, int32_t Tf, int32_t precision, int64_t* bytes_out_host) {
+  LNRF_REQUIRE(n >= 0 && Tc >= 1 && Tf >= 1 && bytes_out_host, LNRF_E_INVALID, "lnrf_nerf_render_workspace_bytes: bad args");
+  RenderWs w{};
+  const int rc = carve_render(nullptr, n, Tc, Tf, precision, &w);
+  if (rc) return rc;
+  *bytes_out_host = w.bytes;
+  return LNRF_OK;
+}
+
+int lnrf_nerf_render_rays(const float* rays, const float* bbox_min_host, const float* bbox_max_host, float min_t_range,
+                          const float* u_coarse, const float* u_fine, const float* coarse_params,
+                          const void* coarse_packed, const float* fine_params, const void* fine_packed,
+                          int32_t precision, const float* background, int64_t n, int32_t Tc, int32_t Tf,
+                          void* workspace, int64_t workspace_bytes, float* coarse_outputs, float* fine_outputs,
+                          float* fine_alphas, float* fine_coords, lnrf_stream_t stream) {
+  LNRF_REQUIRE(n >= 0 && Tc >= 1 && Tf >= 1, LNRF_E_INVALID, "lnrf_nerf_render_rays: n=%lld Tc=%d Tf=%d", (long long)n, Tc, Tf);
+  if (n == 0) return LNRF_OK;
+  LNRF_REQUIRE(rays && bbox_min_host && bbox_max_host && u_coarse && u_fine && coarse_params && fine_params && background &&
+                   workspace && coarse_outputs && fine_outputs,
+               LNRF_E_INVALID, "lnrf_nerf_render_rays: null pointer");
+  LNRF_REQUIRE((uintptr_t)workspace % 1024 == 0, LNRF_E_WORKSPACE, "lnrf_nerf_render_rays: workspace not 1024-byte aligned");
+  RenderWs w{};
+  int rc = carve_render(workspace, n, Tc, Tf, precision, &w);
+  if (rc) return rc;
+  LNRF_REQUIRE(workspace_bytes >= w.bytes, LNRF_E_WORKSPACE, "lnrf_nerf_render_rays: workspace %lld < %lld bytes",
+               (long long)workspace_bytes, (long long)w.bytes);
+  const int T2 = Tc + Tf;
+  // coarse level (render.py:53-66)
+  if ((rc = lnrf_sample_coarse(rays, n, bbox_min_host, bbox_max_host, min_t_range, 1e-8f, u_coarse, Tc, w.t_min, w.t_max,
+                               w.mask, w.ts_c, stream))) return rc;
+  if ((rc = lnrf_nerf_mlp_fwd(coarse_params, coarse_packed, nullptr, nullptr, rays, w.ts_c, n, Tc, precision, 0, w.mlp,
+                              w.mlp_bytes, w.dens_c, w.rgb_c, stream))) return rc;
+  if ((rc = lnrf_composite_fwd(rays, w.ts_c, w.t_min, w.t_max, w.mask, w.dens_c, w.rgb_c, background, n, Tc,
+                               coarse_outputs, nullptr, nullptr, stream))) return rc;
+  // fine level (:68-84): inverse-CDF samples from the coarse densities (stop-gradient), merged with the coarse ones
+  if ((rc = lnrf_sample_fine(w.ts_c, w.dens_c, w.t_min, w.t_max, u_fine, n, Tc, Tf, 1e-8f, w.ts_f, nullptr, nullptr,
+                             stream))) return rc;
+  if ((rc = lnrf_nerf_mlp_fwd(fine_params, fine_packed, nullptr, nullptr, rays, w.ts_f, n, T2, precision, 0, w.mlp,
+                              w.mlp_bytes, w.dens_f, w.rgb_f, stream))) return rc;
+  return lnrf_composite_fwd(rays, w.ts_f, w.t_min, w.t_max, w.mask, w.dens_f, w.rgb_f, background, n, T2, fine_outputs,
+                            fine_alphas, fine_coords, stream);
+}
+
 }  // extern "C"

@@ -56,6 +56,9 @@ _SIGS = {
                                                      c_int64, c_void_p, c_void_p, c_void_p]),
     "lnrf_nerf_mlp_bwd": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int64] +
                           [c_void_p] * 6),
+    "lnrf_nerf_render_workspace_bytes": (c_int32, [c_int64, c_int32, c_int32, c_int32, c_void_p]),
+    "lnrf_nerf_render_rays": (c_int32, [c_void_p, c_void_p, c_void_p, c_float] + [c_void_p] * 6 + [c_int32, c_void_p, c_int64,
+                                        c_int32, c_int32, c_void_p, c_int64] + [c_void_p] * 5),
     "lnrf_adam_step": (c_int32, [c_void_p] * 4 + [c_int64, c_float, c_float, c_float, c_float,
                                                   c_int32, c_float, c_void_p, c_void_p]),
     "lnrf_adam_step_dk": (c_int32, [c_void_p] * 4 + [c_int64, c_float, c_float, c_float, c_float, c_void_p,
@@ -273,6 +276,34 @@ def nerf_mlp_workspace_bytes(m: int, precision: int, save: bool) -> int:
     _check(load().lnrf_nerf_mlp_workspace_bytes(m, precision, int(save), ctypes.byref(out)),
            "lnrf_nerf_mlp_workspace_bytes")
     return int(out.value)
+
+
+def nerf_render_rays(rays, bbox_min, bbox_max, u_coarse, u_fine, coarse_flat, coarse_packed, fine_flat, fine_packed,
+                     precision, background, min_t_range=1e-3, want_aux=True):
+    """One C call for NeRFRenderer.render_rays (reference render.py:39-91) with two NeRFModels: returns
+    (coarse_outputs[n,3], fine_outputs[n,3], fine_alphas[n,1] | None, fine_coords[n,3] | None)."""
+    rays, u_coarse, u_fine = _f32c(rays, "rays"), _f32c(u_coarse, "u_coarse"), _f32c(u_fine, "u_fine")
+    ensure_init(rays.device)
+    n, Tc = u_coarse.shape
+    Tf = u_fine.shape[1]
+    dev = rays.device
+    nbytes = c_int64(0)
+    _check(load().lnrf_nerf_render_workspace_bytes(n, Tc, Tf, precision, ctypes.byref(nbytes)),
+           "lnrf_nerf_render_workspace_bytes")
+    raw = torch.empty(int(nbytes.value) + 1024, dtype=torch.uint8, device=dev)
+    shift = (-raw.data_ptr()) % 1024
+    ws = raw[shift: shift + int(nbytes.value)]
+    coarse_out = torch.empty(n, 3, device=dev)
+    fine_out = torch.empty(n, 3, device=dev)
+    alphas = torch.empty(n, 1, device=dev) if want_aux else None
+    coords = torch.empty(n, 3, device=dev) if want_aux else None
+    lo, hi = _host3(bbox_min), _host3(bbox_max)
+    _check(load().lnrf_nerf_render_rays(_p(rays), lo, hi, min_t_range, _p(u_coarse), _p(u_fine), _p(coarse_flat),
+                                        _p(coarse_packed), _p(fine_flat), _p(fine_packed), precision,
+                                        _p(_f32c(background, "background")), n, Tc, Tf, _p(ws), int(nbytes.value),
+                                        _p(coarse_out), _p(fine_out), _p(alphas), _p(coords), _stream()),
+           "lnrf_nerf_render_rays")
+    return coarse_out, fine_out, alphas, coords
 
 
 def nerf_mlp_fwd(flat, packed, x, d, rays, ts, n, T, precision, save, workspace, dens, rgb):
@@ -621,7 +652,7 @@ def _device_scoped(fn):
 
 
 for _name in ("sample_coarse", "stratified", "sample_fine", "composite_fwd", "composite_bwd", "mse_loss",
-              "nerf_pack_weights", "nerf_mlp_fwd", "nerf_mlp_bwd", "adam_step", "adam_step_dk", "threefry_uniform_dk",
+              "nerf_pack_weights", "nerf_mlp_fwd", "nerf_mlp_bwd", "nerf_render_rays", "adam_step", "adam_step_dk", "threefry_uniform_dk",
               "adam_step_peers", "debug_umma_gemm", "debug_umma_gemm_tn", "hashgrid_fwd", "hashgrid_bwd", "ngpref_fwd",
               "ngpref_bwd", "ngp_mlp_fwd", "ngp_mlp_bwd", "ngp_pack_weights", "ngp_mlp_fwd_tc", "ngp_mlp_bwd_tc", "rgb_to_u8", "refnerf_fwd", "refnerf_bwd", "ray_intervals",
               "termination_probs", "z_depth"):

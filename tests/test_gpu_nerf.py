@@ -129,6 +129,29 @@ def test_render_rays_end_to_end(precision, tol):
         np.testing.assert_allclose(out["fine"]["rgbs"].cpu().numpy(), o_out["fine"]["rgbs"], atol=1e-4)
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_render_rays_single_c_call_matches_the_python_orchestration(precision):
+    """lnrf_nerf_render_rays = the six launches of NeRFRenderer.render_rays behind one C entry: same bits."""
+    from learn_nerf import _native
+    M, _, nerf, params = oracle_setup()
+    batch, uc, uf = _render_case(333, 40)
+    r = _native_renderer(precision, params)
+    out = r.render_rays((dev(uc), dev(uf)), dev(batch[:, :2]))
+    c_out, f_out, alphas, coords = _native.nerf_render_rays(
+        dev(batch[:, :2]), BBOX_MIN, BBOX_MAX, dev(uc), dev(uf), r.coarse_params.flat, r.coarse._packed(r.coarse_params),
+        r.fine_params.flat, r.fine._packed(r.fine_params), _native.PRECISIONS[precision], r.background)
+    torch.cuda.synchronize()
+    assert torch.equal(c_out, out["coarse"]["outputs"])
+    assert torch.equal(f_out, out["fine"]["outputs"])
+    assert torch.equal(alphas, out["fine"]["alphas"])
+    assert torch.equal(coords, out["fine"]["coords"])
+    # null aux outputs and an undersized workspace are handled
+    c2, f2, a2, x2 = _native.nerf_render_rays(
+        dev(batch[:, :2]), BBOX_MIN, BBOX_MAX, dev(uc), dev(uf), r.coarse_params.flat, r.coarse._packed(r.coarse_params),
+        r.fine_params.flat, r.fine._packed(r.fine_params), _native.PRECISIONS[precision], r.background, want_aux=False)
+    assert a2 is None and x2 is None and torch.equal(f2, f_out)
+
+
 def test_fine_positions_given_same_densities():
     """North star: positions and indices bit-exact given the same uniforms (and inputs)."""
     from learn_nerf.render import RaySamples
