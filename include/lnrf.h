@@ -153,6 +153,21 @@ int lnrf_nerf_render_rays(const float* rays, const float* bbox_min_host, const f
                           int32_t precision, const float* background, int64_t n, int32_t Tc, int32_t Tf,
                           void* workspace, int64_t workspace_bytes, float* coarse_outputs, float* fine_outputs,
                           float* fine_alphas, float* fine_coords, lnrf_stream_t stream);
+/* TrainLoop.step_fn (train.py:78-112 around the losses of train.py:114-151) for two NeRFModels on one device as
+ * ONE call: both levels rendered with the activation stash, the two MSE losses, compositing and MLP backward of both
+ * levels, tree norms + optax.adam + apply_gradients.  batch[n,3,3] = (origin, direction, target colour);
+ * params / adam_m / adam_v / grads are flat buffers [coarse model | fine model | background(3) + 1 pad] of
+ * 2 * lnrf_nerf_param_floats() + 4 floats (grads is overwritten); coarse_packed / fine_packed: scratch of
+ * lnrf_nerf_packed_bytes() each, 1024-byte aligned, re-packed inside the call (bf16 only, NULL for fp32);
+ * step is 1-based.  scalars_out (device[4]) receives {sum of squared errors coarse, fine (divide by 3 n),
+ * |grad|^2, |params before the update|^2}.  No density penalty / aux losses / gradient exchange: those stay with
+ * the per-op entries.  workspace: lnrf_nerf_train_workspace_bytes, 1024-byte aligned.                       */
+int lnrf_nerf_train_workspace_bytes(int64_t n, int32_t Tc, int32_t Tf, int32_t precision, int64_t* bytes_out_host);
+int lnrf_nerf_train_step(const float* batch, const float* bbox_min_host, const float* bbox_max_host, float min_t_range,
+                         const float* u_coarse, const float* u_fine, float* params, float* adam_m, float* adam_v,
+                         float* grads, void* coarse_packed, void* fine_packed, int32_t precision, int64_t n, int32_t Tc,
+                         int32_t Tf, float lr, float b1, float b2, float eps, int32_t step, void* workspace,
+                         int64_t workspace_bytes, float* scalars_out, lnrf_stream_t stream);
 /* Gradient of the above w.r.t. params given d_dens[m], d_rgb[m,3]; uses the
  * workspace written by the matching forward call.  d_params
  * (lnrf_nerf_param_floats() floats) is ACCUMULATED.  Inputs x/d/rays/ts carry

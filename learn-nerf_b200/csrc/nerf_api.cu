@@ -187,4 +187,122 @@ int lnrf_nerf_render_rays(const float* rays, const float* bbox_min_host, const f
                             fine_alphas, fine_coords, stream);
 }
 
+// ---------------------------------------------------------------- one call per TrainLoop.step_fn
+// train.py:78-112 (step_fn) around train.py:114-151 (losses) for two NeRFModels on one device: both levels rendered
+// with the activation stash, MSE losses, compositing and MLP backward of both levels, tree norms + Adam -- the 19
+// launches of the Python mirror's step in one C call.  Parameters / gradients / Adam moments are flat buffers
+// [coarse model | fine model | background(3) + 1 pad].
+namespace {
+struct TrainWs {
+  float *rays, *t_min, *t_max, *ts_c, *dens_c, *rgb_c, *ts_f, *dens_f, *rgb_f, *out_c, *out_f, *d_out, *d_dens, *d_rgb;
+  uint8_t* mask;
+  void *mlp_c, *mlp_f;
+  int64_t mlp_c_bytes, mlp_f_bytes, bytes;
+};
+int carve_train(void* base, int64_t n, int Tc, int Tf, int precision, TrainWs* w) {
+  char* p = reinterpret_cast<char*>(base);
+  int64_t off = 0;
+  auto take = [&](int64_t bytes) {
+    char* r = p + off;
+    off += (bytes + 1023) / 1024 * 1024;
+    return r;
+  };
+  const int T2 = Tc + Tf;
+  w->rays = reinterpret_cast<float*>(take(n * 24));
+  w->t_min = reinterpret_cast<float*>(take(n * 4));
+  w->t_max = reinterpret_cast<float*>(take(n * 4));
+  w->mask = reinterpret_cast<uint8_t*>(take(n));
+  w->ts_c = reinterpret_cast<float*>(take(n * Tc * 4));
+  w->dens_c = reinterpret_cast<float*>(take(n * Tc * 4));
+  w->rgb_c = reinterpret_cast<float*>(take(n * Tc * 12));
+  w->ts_f = reinterpret_cast<float*>(take(n * T2 * 4));
+  w->dens_f = reinterpret_cast<float*>(take(n * T2 * 4));
+  w->rgb_f = reinterpret_cast<float*>(take(n * T2 * 12));
+  w->out_c = reinterpret_cast<float*>(take(n * 12));
+  w->out_f = reinterpret_cast<float*>(take(n * 12));
+  w->d_out = reinterpret_cast<float*>(take(n * 12));
+  w->d_dens = reinterpret_cast<float*>(take(n * T2 * 4));
+  w->d_rgb = reinterpret_cast<float*>(take(n * T2 * 12));
+  int rc = lnrf_nerf_mlp_workspace_bytes(n * Tc, precision, 1, &w->mlp_c_bytes);
+  if (rc) return rc;
+  if ((rc = lnrf_nerf_mlp_workspace_bytes(n * T2, precision, 1, &w->mlp_f_bytes))) return rc;
+  w->mlp_c = take(w->mlp_c_bytes);
+  w->mlp_f = take(w->mlp_f_bytes);
+  w->bytes = off;
+  return LNRF_OK;
+}
+}  // namespace
+
+int lnrf_nerf_train_workspace_bytes(int64_t n, int32_t Tc, int32_t Tf, int32_t precision, int64_t* bytes_out_host) {
+  LNRF_REQUIRE(n >= 0 && Tc >= 1 && Tf >= 1 && bytes_out_host, LNRF_E_INVALID, "lnrf_nerf_train_workspace_bytes: bad args");
+  TrainWs w{};
+  const int rc = carve_train(nullptr, n, Tc, Tf, precision, &w);
+  if (rc) return rc;
+  *bytes_out_host = w.bytes;
+  return LNRF_OK;
+}
+
+int lnrf_nerf_train_step(const float* batch, const float* bbox_min_host, const float* bbox_max_host, float min_t_range,
+                         const float* u_coarse, const float* u_fine, float* params, float* adam_m, float* adam_v,
+                         float* grads, void* coarse_packed, void* fine_packed, int32_t precision, int64_t n, int32_t Tc,
+                         int32_t Tf, float lr, float b1, float b2, float eps, int32_t step, void* workspace,
+                         int64_t workspace_bytes, float* scalars_out, lnrf_stream_t stream) {
+  LNRF_REQUIRE(n >= 1 && Tc >= 1 && Tf >= 1 && step >= 1, LNRF_E_INVALID, "lnrf_nerf_train_step: n=%lld Tc=%d Tf=%d step=%d",
+               (long long)n, Tc, Tf, step);
+  LNRF_REQUIRE(batch && bbox_min_host && bbox_max_host && u_coarse && u_fine && params && adam_m && adam_v && grads &&
+                   workspace && scalars_out,
+               LNRF_E_INVALID, "lnrf_nerf_train_step: null pointer");
+  LNRF_REQUIRE(precision == LNRF_PREC_FP32 || (coarse_packed && fine_packed), LNRF_E_INVALID,
+               "lnrf_nerf_train_step(bf16): packed-weight buffers missing");
+  LNRF_REQUIRE((uintptr_t)workspace % 1024 == 0, LNRF_E_WORKSPACE, "lnrf_nerf_train_step: workspace not 1024-byte aligned");
+  TrainWs w{};
+  int rc = carve_train(workspace, n, Tc, Tf, precision, &w);
+  if (rc) return rc;
+  LNRF_REQUIRE(workspace_bytes >= w.bytes, LNRF_E_WORKSPACE, "lnrf_nerf_train_step: workspace %lld < %lld bytes",
+               (long long)workspace_bytes, (long long)w.bytes);
+  cudaStream_t st = lnrf::as_stream(stream);
+  const int64_t np = lnrf::kNerf.total, count = 2 * np + 4;
+  float* p_c = params;
+  float* p_f = params + np;
+  float* bg = params + 2 * np;
+  const int T2 = Tc + Tf;
+  LNRF_CUDA(cudaMemsetAsync(grads, 0, count * sizeof(float), st));
+  LNRF_CUDA(cudaMemsetAsync(scalars_out, 0, 4 * sizeof(float), st));
+  // rays = batch[:, :2] (train.py:134): rows of 6 floats out of rows of 9
+  LNRF_CUDA(cudaMemcpy2DAsync(w.rays, 24, batch, 36, 24, size_t(n), cudaMemcpyDeviceToDevice, st));
+  if (precision == LNRF_PREC_BF16) {
+    if ((rc = lnrf_nerf_pack_weights(p_c, coarse_packed, stream))) return rc;
+    if ((rc = lnrf_nerf_pack_weights(p_f, fine_packed, stream))) return rc;
+  }
+  // ---- forward with the stash (render.py:39-91)
+  if ((rc = lnrf_sample_coarse(w.rays, n, bbox_min_host, bbox_max_host, min_t_range, 1e-8f, u_coarse, Tc, w.t_min, w.t_max,
+                               w.mask, w.ts_c, stream))) return rc;
+  if ((rc = lnrf_nerf_mlp_fwd(p_c, coarse_packed, nullptr, nullptr, w.rays, w.ts_c, n, Tc, precision, 1, w.mlp_c,
+                              w.mlp_c_bytes, w.dens_c, w.rgb_c, stream))) return rc;
+  if ((rc = lnrf_composite_fwd(w.rays, w.ts_c, w.t_min, w.t_max, w.mask, w.dens_c, w.rgb_c, bg, n, Tc, w.out_c, nullptr,
+                               nullptr, stream))) return rc;
+  if ((rc = lnrf_sample_fine(w.ts_c, w.dens_c, w.t_min, w.t_max, u_fine, n, Tc, Tf, 1e-8f, w.ts_f, nullptr, nullptr,
+                             stream))) return rc;
+  if ((rc = lnrf_nerf_mlp_fwd(p_f, fine_packed, nullptr, nullptr, w.rays, w.ts_f, n, T2, precision, 1, w.mlp_f,
+                              w.mlp_f_bytes, w.dens_f, w.rgb_f, stream))) return rc;
+  if ((rc = lnrf_composite_fwd(w.rays, w.ts_f, w.t_min, w.t_max, w.mask, w.dens_f, w.rgb_f, bg, n, T2, w.out_f, nullptr,
+                               nullptr, stream))) return rc;
+  // ---- losses and backward, coarse level then fine level (train.py:140-151)
+  const float inv_count = 1.0f / (3.0f * float(n));
+  const float* targets = batch + 6;  // batch[:, 2], row stride 9
+  struct Level { const float *ts, *dens, *rgb, *out; int T; float* P; const void* packed; void* ws; int64_t ws_bytes; int64_t goff; };
+  const Level lv[2] = {{w.ts_c, w.dens_c, w.rgb_c, w.out_c, Tc, p_c, coarse_packed, w.mlp_c, w.mlp_c_bytes, 0},
+                       {w.ts_f, w.dens_f, w.rgb_f, w.out_f, T2, p_f, fine_packed, w.mlp_f, w.mlp_f_bytes, np}};
+  for (int li = 0; li < 2; ++li) {
+    const Level& L = lv[li];
+    if ((rc = lnrf_mse_loss(L.out, targets, 9, n, inv_count, scalars_out + li, w.d_out, stream))) return rc;
+    if ((rc = lnrf_composite_bwd(L.ts, w.t_min, w.t_max, w.mask, L.dens, L.rgb, bg, w.d_out, n, L.T, w.d_dens, w.d_rgb,
+                                 grads + 2 * np, stream))) return rc;
+    if ((rc = lnrf_nerf_mlp_bwd(L.P, L.packed, n * L.T, precision, L.ws, L.ws_bytes, L.dens, L.rgb, w.d_dens, w.d_rgb,
+                                grads + L.goff, stream))) return rc;
+  }
+  // ---- tree norms + optax.adam + apply_gradients (train.py:59, 92-106)
+  return lnrf_adam_step(params, grads, adam_m, adam_v, count, lr, b1, b2, eps, step, 1.0f, scalars_out + 2, stream);
+}
+
 }  // extern "C"

@@ -59,6 +59,10 @@ _SIGS = {
     "lnrf_nerf_render_workspace_bytes": (c_int32, [c_int64, c_int32, c_int32, c_int32, c_void_p]),
     "lnrf_nerf_render_rays": (c_int32, [c_void_p, c_void_p, c_void_p, c_float] + [c_void_p] * 6 + [c_int32, c_void_p, c_int64,
                                         c_int32, c_int32, c_void_p, c_int64] + [c_void_p] * 5),
+    "lnrf_nerf_train_workspace_bytes": (c_int32, [c_int64, c_int32, c_int32, c_int32, c_void_p]),
+    "lnrf_nerf_train_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_float] + [c_void_p] * 8 + [c_int32, c_int64, c_int32,
+                                       c_int32, c_float, c_float, c_float, c_float, c_int32, c_void_p, c_int64, c_void_p,
+                                       c_void_p]),
     "lnrf_adam_step": (c_int32, [c_void_p] * 4 + [c_int64, c_float, c_float, c_float, c_float,
                                                   c_int32, c_float, c_void_p, c_void_p]),
     "lnrf_adam_step_dk": (c_int32, [c_void_p] * 4 + [c_int64, c_float, c_float, c_float, c_float, c_void_p,
@@ -304,6 +308,37 @@ def nerf_render_rays(rays, bbox_min, bbox_max, u_coarse, u_fine, coarse_flat, co
                                         _p(coarse_out), _p(fine_out), _p(alphas), _p(coords), _stream()),
            "lnrf_nerf_render_rays")
     return coarse_out, fine_out, alphas, coords
+
+
+def _aligned_bytes(nbytes: int, device) -> torch.Tensor:
+    raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+    shift = (-raw.data_ptr()) % 1024
+    return raw[shift: shift + nbytes]
+
+
+def nerf_train_step(batch, bbox_min, bbox_max, u_coarse, u_fine, flat, m, v, grads, precision, lr, b1, b2, eps, step,
+                    min_t_range=1e-3):
+    """One C call for TrainLoop.step_fn (reference train.py:78-112) with two NeRFModels on one device.
+    flat / m / v / grads: [coarse | fine | background(3) + pad].  Returns the device scalars
+    [sse_coarse, sse_fine, |g|^2, |p|^2]."""
+    batch, u_coarse, u_fine = _f32c(batch, "batch"), _f32c(u_coarse, "u_coarse"), _f32c(u_fine, "u_fine")
+    ensure_init(batch.device)
+    n, Tc = u_coarse.shape
+    Tf = u_fine.shape[1]
+    dev = batch.device
+    nbytes = c_int64(0)
+    _check(load().lnrf_nerf_train_workspace_bytes(n, Tc, Tf, precision, ctypes.byref(nbytes)),
+           "lnrf_nerf_train_workspace_bytes")
+    ws = _aligned_bytes(int(nbytes.value), dev)
+    pc = pf = None
+    if precision == PREC_BF16:
+        pc, pf = _aligned_bytes(nerf_packed_bytes(), dev), _aligned_bytes(nerf_packed_bytes(), dev)
+    scalars = torch.empty(4, device=dev)
+    lo, hi = _host3(bbox_min), _host3(bbox_max)
+    _check(load().lnrf_nerf_train_step(_p(batch), lo, hi, min_t_range, _p(u_coarse), _p(u_fine), _p(flat), _p(m), _p(v),
+                                       _p(grads), _p(pc), _p(pf), precision, n, Tc, Tf, lr, b1, b2, eps, step, _p(ws),
+                                       int(nbytes.value), _p(scalars), _stream()), "lnrf_nerf_train_step")
+    return scalars
 
 
 def nerf_mlp_fwd(flat, packed, x, d, rays, ts, n, T, precision, save, workspace, dens, rgb):
@@ -652,7 +687,7 @@ def _device_scoped(fn):
 
 
 for _name in ("sample_coarse", "stratified", "sample_fine", "composite_fwd", "composite_bwd", "mse_loss",
-              "nerf_pack_weights", "nerf_mlp_fwd", "nerf_mlp_bwd", "nerf_render_rays", "adam_step", "adam_step_dk", "threefry_uniform_dk",
+              "nerf_pack_weights", "nerf_mlp_fwd", "nerf_mlp_bwd", "nerf_render_rays", "nerf_train_step", "adam_step", "adam_step_dk", "threefry_uniform_dk",
               "adam_step_peers", "debug_umma_gemm", "debug_umma_gemm_tn", "hashgrid_fwd", "hashgrid_bwd", "ngpref_fwd",
               "ngpref_bwd", "ngp_mlp_fwd", "ngp_mlp_bwd", "ngp_pack_weights", "ngp_mlp_fwd_tc", "ngp_mlp_bwd_tc", "rgb_to_u8", "refnerf_fwd", "refnerf_bwd", "ray_intervals",
               "termination_probs", "z_depth"):

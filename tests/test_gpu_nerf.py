@@ -152,6 +152,34 @@ def test_render_rays_single_c_call_matches_the_python_orchestration(precision):
     assert a2 is None and x2 is None and torch.equal(f2, f_out)
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_train_step_single_c_call_matches_the_python_step(precision):
+    """lnrf_nerf_train_step = the 19 launches of TrainLoop.step_fn (train.py:78-112) behind one C entry: the same
+    losses (the forward is deterministic) and, up to the order of the dW atomics, the same gradient norm and update."""
+    from learn_nerf import _native
+    from learn_nerf.model import NeRFModel
+    from learn_nerf.train import TrainLoop
+    loop = TrainLoop(NeRFModel(precision=precision), NeRFModel(precision=precision), init_rng=4, lr=1e-4, coarse_ts=64,
+                     fine_ts=128)
+    flat = loop.state.flat.clone()
+    n = 384
+    batch, uc, uf = dev(make_rays(n, seed=70)), dev(make_uniforms(n, 64, 71)), dev(make_uniforms(n, 128, 72))
+    logs = {k: float(v) for k, v in loop.step_fn(BBOX_MIN, BBOX_MAX)((uc, uf), batch).items()}
+    m, v, g = torch.zeros_like(flat), torch.zeros_like(flat), torch.empty_like(flat)
+    p0 = flat.clone()
+    s = _native.nerf_train_step(batch, BBOX_MIN, BBOX_MAX, uc, uf, flat, m, v, g, _native.PRECISIONS[precision], loop.lr,
+                                loop.b1, loop.b2, loop.eps, 1)
+    s = s.cpu().double().numpy()
+    np.testing.assert_allclose(s[0] / (3 * n), logs["coarse"], rtol=1e-6)
+    np.testing.assert_allclose(s[1] / (3 * n), logs["fine"], rtol=1e-6)
+    np.testing.assert_allclose(np.sqrt(s[2]), logs["grad_norm"], rtol=2e-4)
+    np.testing.assert_allclose(np.sqrt(s[3]), logs["param_norm"], rtol=1e-6)
+    assert float((flat - p0).abs().max()) > 0.5e-4           # Adam's first step moves every touched weight by ~lr
+    assert float((flat - loop.state.flat).abs().max()) <= 2.2e-4  # same update up to the sign of near-zero gradients
+    assert float((flat - loop.state.flat).abs().mean()) < 2e-6
+    assert torch.isfinite(g).all() and float(g.abs().max()) > 0
+
+
 def test_fine_positions_given_same_densities():
     """North star: positions and indices bit-exact given the same uniforms (and inputs)."""
     from learn_nerf.render import RaySamples
