@@ -440,6 +440,13 @@ constexpr uint32_t kTnStage = 2 * kTnAPart + 2 * kTnBPart;  // 96 KB
 constexpr int kTnStages = 2;
 constexpr uint32_t kTnSmem = kTnStages * kTnStage + 256;
 constexpr uint32_t kTnFull = 0, kTnEmpty = 16, kTnDone = 32, kTnTmemSlot = 40;
+// SMALL variant (M <= 64 and N <= 64: the 64-wide Instant-NGP heads): a chunk of 64 samples would be 32 KB, and
+// with one chunk of loads in flight per CTA the kernel sat at 2.3 TB/s.  There a chunk is 192 samples of ONE
+// 64-feature block per operand (4 x 24 KB = the same 96 KB stage, the same 24 loads per thread); the M = 128 MMA
+// reads the rows 64.. of the A part as "features 64..127": finite values into accumulator lanes nobody reads.
+constexpr int kTnSmallRows = 192;
+constexpr uint32_t kTnSmallPart = kTnSmallRows * 128;
+static_assert(4 * kTnSmallPart == kTnStage, "small-shape stage layout");
 
 struct TnArgs {
   const float* At;
@@ -456,6 +463,7 @@ struct TnArgs {
   int64_t chunks_per_cta, chunks;
 };
 
+template <bool SMALL>
 __global__ void __launch_bounds__(kTnThreads, 1) tcg_tn_kernel(const __grid_constant__ TnArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t sbase = smem_u32(smem_raw);
@@ -500,6 +508,46 @@ __global__ void __launch_bounds__(kTnThreads, 1) tcg_tn_kernel(const __grid_cons
     for (int j = 0; j < 8; ++j) cs[j] = 0.0f;
     const bool do_db = a.db != nullptr && mb == 0;
     uint32_t stage = 0, phases = 0;
+    if constexpr (SMALL) {
+      // pieces of 8 floats: p = tid + 256 j -> sample p / 8, features / columns 8 (tid & 7) .. (fixed per thread)
+      const int g8 = tid & 7, f0 = g8 * 8;
+      for (int64_t q = 0; q < nq; ++q) {
+        const int64_t k0 = (q0 + q) * kTnSmallRows;
+        float4 va[12], vb[12];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          const int64_t row = k0 + (tid >> 3) + 32 * j;
+          va[2 * j] = va[2 * j + 1] = vb[2 * j] = vb[2 * j + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row < a.K) {
+            const float* pa = a.At + row * a.lda + f0;
+            if (f0 < a.M) va[2 * j] = __ldg(reinterpret_cast<const float4*>(pa));
+            if (f0 + 4 < a.M) va[2 * j + 1] = __ldg(reinterpret_cast<const float4*>(pa + 4));
+            const float* pb = a.B + row * a.ldb + f0;
+            if (f0 < a.N) vb[2 * j] = __ldg(reinterpret_cast<const float4*>(pb));
+            if (f0 + 4 < a.N) vb[2 * j + 1] = __ldg(reinterpret_cast<const float4*>(pb + 4));
+          }
+        }
+        mbar_wait(bars + kTnEmpty + 8 * stage, ((phases >> stage) & 1u) ^ 1u);
+        phases ^= 1u << stage;
+        const uint32_t s_ah = sbase + stage * kTnStage, s_al = s_ah + kTnSmallPart;
+        const uint32_t s_bh = s_al + kTnSmallPart, s_bl = s_bh + kTnSmallPart;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          const int r = (tid >> 3) + 32 * j;
+          const uint32_t off = uint32_t(r) * 128u + (uint32_t((g8 ^ (r & 7)) & 7) << 4);
+          split8_store(va[2 * j], va[2 * j + 1], sa, s_ah + off, s_al + off);
+          split8_store(vb[2 * j], vb[2 * j + 1], sb, s_bh + off, s_bl + off);
+          if (do_db) {
+            cs[0] += vb[2 * j].x; cs[1] += vb[2 * j].y; cs[2] += vb[2 * j].z; cs[3] += vb[2 * j].w;
+            cs[4] += vb[2 * j + 1].x; cs[5] += vb[2 * j + 1].y; cs[6] += vb[2 * j + 1].z; cs[7] += vb[2 * j + 1].w;
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + kTnFull + 8 * stage);
+        if (++stage == kTnStages) stage = 0;
+      }
+    } else
     // One chunk = 8 + 16 sixteen-byte loads per thread, all issued before the first use (96 KB in flight per
     // SM); nine warps cap the kernel at 168 registers, which rules out a second chunk of register prefetch
     // (measured: a three-deep ring of half chunks spills and runs 3x slower).
@@ -561,15 +609,23 @@ __global__ void __launch_bounds__(kTnThreads, 1) tcg_tn_kernel(const __grid_cons
     if (do_db) {  // fold the eight row groups of a column through shared memory, one atomic per column
       float* s_cs = reinterpret_cast<float*>(smem_raw);
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (b_active) {
+      if constexpr (SMALL) {  // 32 row groups x 64 columns
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s_cs[(tid >> 3) * 64 + (tid & 7) * 8 + j] = cs[j];
+      } else if (b_active) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) s_cs[br0 * 256 + bc + j] = cs[j];
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (tid < a.N) {
         float t = 0.0f;
+        if constexpr (SMALL) {
+#pragma unroll 8
+          for (int g = 0; g < 32; ++g) t += s_cs[g * 64 + tid];
+        } else {
 #pragma unroll
-        for (int g = 0; g < 8; ++g) t += s_cs[g * 256 + tid];
+          for (int g = 0; g < 8; ++g) t += s_cs[g * 256 + tid];
+        }
         atomicAdd(a.db + tid, t);
       }
     }
@@ -606,10 +662,11 @@ __global__ void __launch_bounds__(kTnThreads, 1) tcg_tn_kernel(const __grid_cons
       if (elect_one_sync()) {
         // MN-major SW128: 64-feature blocks kTnHalf bytes apart (LBO), 16 samples = 2048 bytes per K step
         const uint32_t lbo = (kTnHalf >> 4) << 16;
-        const uint32_t ah = (((sbase + stage * kTnStage) & 0x3FFFFu) >> 4) | lbo, al = ah + (kTnAPart >> 4);
-        const uint32_t bh = al + (kTnAPart >> 4), bl = bh + (kTnBPart >> 4);
+        constexpr uint32_t kAP = SMALL ? kTnSmallPart : kTnAPart, kBP = SMALL ? kTnSmallPart : kTnBPart;
+        const uint32_t ah = (((sbase + stage * kTnStage) & 0x3FFFFu) >> 4) | lbo, al = ah + (kAP >> 4);
+        const uint32_t bh = al + (kAP >> 4), bl = bh + (kBP >> 4);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < (SMALL ? kTnSmallRows / 16 : 4); ++k) {
           const uint32_t acc = (q | k) ? 1u : 0u;
           umma_f16_lohi(tmem, ah + 128 * k, bh + 128 * k, kDescHiSw128, idesc, acc);
           umma_f16_lohi(tmem + 256, ah + 128 * k, bl + 128 * k, kDescHiSw128, idesc, acc);
@@ -730,13 +787,15 @@ int tcg_tn_acc(cudaStream_t st, int M, int N, const float* At, int lda, const fl
   a.a_amax = a_amax; a.b_amax = b_amax;
   a.mblocks = int(ceil_div(M, 128));
   a.nb = int(ceil_div(N, 64));
-  a.chunks = ceil_div(K, 64);
+  const bool small = M <= 64 && N <= 64;
+  a.chunks = ceil_div(K, small ? kTnSmallRows : 64);
   int64_t splits = sm_count() / a.mblocks;
   if (splits < 1) splits = 1;
   a.chunks_per_cta = ceil_div(a.chunks, splits);
   if (a.chunks_per_cta < 4) a.chunks_per_cta = 4;
   splits = ceil_div(a.chunks, a.chunks_per_cta);
-  tcg_tn_kernel<<<unsigned(splits * a.mblocks), kTnThreads, kTnSmem, st>>>(a);
+  if (small) tcg_tn_kernel<true><<<unsigned(splits * a.mblocks), kTnThreads, kTnSmem, st>>>(a);
+  else tcg_tn_kernel<false><<<unsigned(splits * a.mblocks), kTnThreads, kTnSmem, st>>>(a);
   LNRF_LAUNCH_CHECK("tcg_tn_kernel");
   return LNRF_OK;
 }
@@ -765,7 +824,8 @@ int init_gemm_tc() {
   LNRF_CUDA(cudaFuncSetAttribute(tcg_rows_kernel<TCG_RANK1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRgSmem));
   LNRF_CUDA(cudaFuncSetAttribute(tcg_rows_kernel<TCG_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRgSmem));
   LNRF_CUDA(cudaFuncSetAttribute(tcg_rows_kernel<TCG_MASKBITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRgSmem));
-  LNRF_CUDA(cudaFuncSetAttribute(tcg_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTnSmem));
+  LNRF_CUDA(cudaFuncSetAttribute(tcg_tn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTnSmem));
+  LNRF_CUDA(cudaFuncSetAttribute(tcg_tn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTnSmem));
   return LNRF_OK;
 }
 

@@ -7,13 +7,17 @@
 // and the current activations sit in shared memory, and every layer is an 8x8 register-tiled
 // FFMA GEMM over that tile (64 FFMA per four 128-bit shared loads).  Only what the weight
 // gradients need (layer inputs and per-layer dL/dpre-activation) goes to HBM; dW = act^T g runs
-// on the 64x64 split-K kernel of sgemm.cuh.
+// on the split-fp16 tcgen05 GEMM of gemm_tc.cu (the dX kernel publishes max|g| per tensor for its operand
+// scales); LNRF_FP32_FFMA=1 keeps the 64x64 split-K FFMA kernel of sgemm.cuh for A/B measurements.
 #include "embed.cuh"
+#include "gemm_tc.cuh"
 #include "lnrf_common.cuh"
 #include "lnrf_math.cuh"
 #include "sgemm.cuh"
 
 namespace lnrf {
+
+bool fp32_ffma();  // mlp_fp32.cu
 
 constexpr int kNgpMaxLevels = 16;
 constexpr int kNgpHidden = 64, kNgpDensity = 16, kNgpDE = 24;
@@ -49,6 +53,8 @@ static NgpLayout ngp_layout(int L) {
 struct NgpWs {
   float *h0, *in2, *h2, *h3;     // layer inputs kept for dW: [m,64], [m,40] = [d_emb | out], [m,64], [m,64]
   float *g0, *go1, *g2, *g3;     // dL/d pre-activation of Dense_0..3: [m,64], [m,16], [m,64], [m,64]
+  float* amax;                   // operand ranges for the dW GEMMs: [0..3] max|g0|, |go1|, |g2|, |g3| (backward),
+                                 // [4..7] max|enc|, |h0|, |in2|, |h2| (forward with save_for_backward)
   int64_t bytes;
 };
 static NgpWs carve_ngp(void* base, int64_t m) {
@@ -68,6 +74,7 @@ static NgpWs carve_ngp(void* base, int64_t m) {
   w.go1 = take(m * kNgpDensity);
   w.g2 = take(m * kNgpHidden);
   w.g3 = take(m * kNgpHidden);
+  w.amax = take(8);
   w.bytes = off;
   return w;
 }
@@ -163,6 +170,16 @@ __device__ __forceinline__ void tile_mask(const float* __restrict__ h, int64_t r
   }
 }
 
+// max |acc| over a thread's register tile (rows past m hold zeros)
+template <int kCW>
+__device__ __forceinline__ float tile_absmax(const float (&v)[8][kCW], float mx) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < kCW; ++j) mx = fmaxf(mx, fabsf(v[i][j]));
+  return mx;
+}
+
 struct NgpFwdArgs {
   const float* P;
   NgpLayout nl;
@@ -196,6 +213,7 @@ ngp_mlp_fwd_kernel(const __grid_constant__ NgpFwdArgs a) {
   const int t = threadIdx.x, tx = t % (64 / kCW), ty = t / (64 / kCW);
   const int64_t tiles = ceil_div(a.m, kTM);
   float acc[8][kCW];
+  float mxe = 0.0f, mxh0 = 0.0f, mxo = 0.0f, mxh2 = 0.0f;  // SAVE: max|enc|, |h0|, |Dense_1 out|, |h2| seen by this thread
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int64_t row0 = tile * kTM;
     const bool owner = t < kTM;   // the first 128 threads each own one sample in the per-sample phases
@@ -208,6 +226,7 @@ ngp_mlp_fwd_kernel(const __grid_constant__ NgpFwdArgs a) {
       for (int k4 = 0; k4 < a.E / 4; ++k4) {
         float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
         if (valid) x = __ldg(reinterpret_cast<const float4*>(a.enc + s * a.E) + k4);
+        if (SAVE) mxe = fmaxf(fmaxf(mxe, fmaxf(fabsf(x.x), fabsf(x.y))), fmaxf(fabsf(x.z), fabsf(x.w)));
         Xa[xoff(k4 * 4 + 0, rg) + rl] = x.x;
         Xa[xoff(k4 * 4 + 1, rg) + rl] = x.y;
         Xa[xoff(k4 * 4 + 2, rg) + rl] = x.z;
@@ -234,7 +253,10 @@ ngp_mlp_fwd_kernel(const __grid_constant__ NgpFwdArgs a) {
 #pragma unroll
       for (int j = 0; j < kCW; ++j) acc[i][j] = fmaxf(acc[i][j] + B0[tx * kCW + j], 0.0f);
     tile_store_smem(Xb, 0, acc, tx, ty);
-    if (SAVE) tile_store_global(a.ws.h0, kNgpHidden, 0, row0, a.m, acc, tx, ty, kNgpHidden);
+    if (SAVE) {
+      tile_store_global(a.ws.h0, kNgpHidden, 0, row0, a.m, acc, tx, ty, kNgpHidden);
+      mxh0 = tile_absmax(acc, mxh0);
+    }
     __syncthreads();
     // ---- Dense_1 (64 -> 16) -> Xa[24..39]; d_emb -> Xa[0..23]; density = exp(out[0])   :48-50
     tile_gemm<16>(Xb, kNgpHidden, W1, kNgpDensity, acc, tx, ty);
@@ -244,7 +266,10 @@ ngp_mlp_fwd_kernel(const __grid_constant__ NgpFwdArgs a) {
 #pragma unroll
         for (int j = 0; j < kCW; ++j) acc[i][j] += B1[tx * kCW + j];
       tile_store_smem(Xa, kNgpDE, acc, tx, ty);
-      if (SAVE) tile_store_global(a.ws.in2, kNgpIn2, kNgpDE, row0, a.m, acc, tx, ty, kNgpDensity);
+      if (SAVE) {
+        tile_store_global(a.ws.in2, kNgpIn2, kNgpDE, row0, a.m, acc, tx, ty, kNgpDensity);
+        mxo = tile_absmax(acc, mxo);
+      }
       if (tx == 0) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -271,7 +296,10 @@ ngp_mlp_fwd_kernel(const __grid_constant__ NgpFwdArgs a) {
 #pragma unroll
       for (int j = 0; j < kCW; ++j) acc[i][j] = fmaxf(acc[i][j] + B2[tx * kCW + j], 0.0f);
     tile_store_smem(Xb, 0, acc, tx, ty);  // readers of Xb (Dense_1) finished before the last barrier
-    if (SAVE) tile_store_global(a.ws.h2, kNgpHidden, 0, row0, a.m, acc, tx, ty, kNgpHidden);
+    if (SAVE) {
+      tile_store_global(a.ws.h2, kNgpHidden, 0, row0, a.m, acc, tx, ty, kNgpHidden);
+      mxh2 = tile_absmax(acc, mxh2);
+    }
     __syncthreads();
     // ---- Dense_3 (64 -> 64) + relu -> Xa
     tile_gemm<64>(Xb, kNgpHidden, W3, kNgpHidden, acc, tx, ty);
@@ -298,6 +326,14 @@ ngp_mlp_fwd_kernel(const __grid_constant__ NgpFwdArgs a) {
         a.rgb[s * 3 + 1] = tanhf(o1);
         a.rgb[s * 3 + 2] = tanhf(o2);
       }
+    }
+  }
+  if (SAVE) {  // operand ranges of the dW GEMMs (in2 = [d_emb | Dense_1 out]: |d_emb| <= 1)
+    const float mx[4] = {mxe, mxh0, fmaxf(mxo, 1.0f), mxh2};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t w = __reduce_max_sync(0xffffffffu, __float_as_uint(mx[i] < 3.0e38f ? mx[i] : 0.0f));
+      if ((t & 31) == 0 && w != 0u) atomicMax(reinterpret_cast<uint32_t*>(a.ws.amax) + 4 + i, w);
     }
   }
 }
@@ -369,6 +405,7 @@ ngp_mlp_bwd_kernel(const __grid_constant__ NgpBwdArgs a) {
   const int rg = t >> 3, rl = t & 7;
   const int64_t tiles = ceil_div(a.m, kTM);
   float acc[8][kCW];
+  float mx0 = 0.0f, mx1 = 0.0f, mx2 = 0.0f, mx3 = 0.0f;  // max|g0|, |g_out1|, |g2|, |g3| of this thread's stores
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int64_t row0 = tile * kTM;
     const bool owner = t < kTM;  // the first 128 threads each own one sample in the per-sample phase
@@ -394,12 +431,14 @@ ngp_mlp_bwd_kernel(const __grid_constant__ NgpBwdArgs a) {
     tile_mask(a.ws.h3, row0, a.m, acc, tx, ty);
     tile_store_smem(Xb, 0, acc, tx, ty);
     tile_store_global(a.ws.g3, kNgpHidden, 0, row0, a.m, acc, tx, ty, kNgpHidden);
+    mx3 = tile_absmax(acc, mx3);
     __syncthreads();
     // ---- g2 = (g3 @ W3^T) * [h2 > 0] -> Xa, global
     tile_gemm<64>(Xb, kNgpHidden, Wt3, kNgpHidden, acc, tx, ty);
     tile_mask(a.ws.h2, row0, a.m, acc, tx, ty);
     tile_store_smem(Xa, 0, acc, tx, ty);
     tile_store_global(a.ws.g2, kNgpHidden, 0, row0, a.m, acc, tx, ty, kNgpHidden);
+    mx2 = tile_absmax(acc, mx2);
     __syncthreads();
     // ---- g_out1 = g2 @ W2[24:40]^T, + d_dens * density on column 0 -> Xb[0..15], global
     tile_gemm<16>(Xa, kNgpHidden, Wt2o, kNgpDensity, acc, tx, ty);
@@ -413,6 +452,7 @@ ngp_mlp_bwd_kernel(const __grid_constant__ NgpBwdArgs a) {
       }
       tile_store_smem(Xb, 0, acc, tx, ty);
       tile_store_global(a.ws.go1, kNgpDensity, 0, row0, a.m, acc, tx, ty, kNgpDensity);
+      mx1 = tile_absmax(acc, mx1);
     }
     __syncthreads();
     // ---- g0 = (g_out1 @ W1^T) * [h0 > 0] -> Xa, global
@@ -420,6 +460,7 @@ ngp_mlp_bwd_kernel(const __grid_constant__ NgpBwdArgs a) {
     tile_mask(a.ws.h0, row0, a.m, acc, tx, ty);
     tile_store_smem(Xa, 0, acc, tx, ty);
     tile_store_global(a.ws.g0, kNgpHidden, 0, row0, a.m, acc, tx, ty, kNgpHidden);
+    mx0 = tile_absmax(acc, mx0);
     __syncthreads();
     // ---- d_enc = g0 @ W0^T -> global [m, E]
     if (tx * kCW < L.epad) {
@@ -442,6 +483,13 @@ ngp_mlp_bwd_kernel(const __grid_constant__ NgpBwdArgs a) {
       }
       tile_store_global(a.d_enc, a.E, 0, row0, a.m, acc, tx, ty, a.E);
     }
+  }
+  // operand ranges of the dW GEMMs (atomic max on the bit pattern: the values are non-negative)
+  const float mx[4] = {mx0, mx1, mx2, mx3};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t w = __reduce_max_sync(0xffffffffu, __float_as_uint(mx[i] < 3.0e38f ? mx[i] : 0.0f));
+    if ((t & 31) == 0 && w != 0u) atomicMax(reinterpret_cast<uint32_t*>(a.ws.amax) + i, w);
   }
 }
 
@@ -548,6 +596,7 @@ int lnrf_ngp_mlp_fwd(const float* params, int32_t L, const float* enc, const flo
   const NgpLayout nl = ngp_layout(L);
   NgpFwdArgs a{params, nl, 2 * L, enc, d, rays, T, m, w, dens, rgb};
   const size_t smem = ngp_fwd_smem(nl);
+  if (save) LNRF_CUDA(cudaMemsetAsync(w.amax + 4, 0, 4 * sizeof(float), as_stream(stream)));
   if (save) ngp_mlp_fwd_kernel<true><<<ngp_grid(m), kNgpFwdThreads, smem, as_stream(stream)>>>(a);
   else ngp_mlp_fwd_kernel<false><<<ngp_grid(m), kNgpFwdThreads, smem, as_stream(stream)>>>(a);
   LNRF_LAUNCH_CHECK("ngp_mlp_fwd_kernel");
@@ -570,12 +619,24 @@ int lnrf_ngp_mlp_bwd(const float* params, int32_t L, const float* enc, int64_t m
   cudaStream_t st = as_stream(stream);
   float* G = d_params;
   NgpBwdArgs a{params, nl, 2 * L, m, w, dens, rgb, d_dens, d_rgb, d_enc};
+  LNRF_CUDA(cudaMemsetAsync(w.amax, 0, 4 * sizeof(float), st));
   ngp_mlp_bwd_kernel<<<ngp_grid(m), kNgpBwdThreads, size_t(ngp_bwd_smem(2 * L).total) * sizeof(float), st>>>(a);
   LNRF_LAUNCH_CHECK("ngp_mlp_bwd_kernel");
   // weight / bias gradients: dW_l = input_l^T g_l (split-K FFMA GEMM), db_l = column sums
   int rc;
   ngp_dw4_kernel<<<ew_blocks(m, 8 * 16), 256, 0, st>>>(w.h3, rgb, d_rgb, m, G + nl.w[4], G + nl.b[4]);
   LNRF_LAUNCH_CHECK("ngp_dw4_kernel");
+  if (!fp32_ffma()) {
+    // operand ranges: layer inputs from the forward (slots 4..7), gradients from the dX kernel above (0..3)
+    if ((rc = tcg_tn_acc(st, kNgpHidden, kNgpHidden, w.h2, kNgpHidden, w.g3, kNgpHidden, m, G + nl.w[3], kNgpHidden,
+                         G + nl.b[3], w.amax + 7, w.amax + 3))) return rc;
+    if ((rc = tcg_tn_acc(st, kNgpIn2, kNgpHidden, w.in2, kNgpIn2, w.g2, kNgpHidden, m, G + nl.w[2], kNgpHidden,
+                         G + nl.b[2], w.amax + 6, w.amax + 2))) return rc;
+    if ((rc = tcg_tn_acc(st, kNgpHidden, kNgpDensity, w.h0, kNgpHidden, w.go1, kNgpDensity, m, G + nl.w[1],
+                         kNgpDensity, G + nl.b[1], w.amax + 5, w.amax + 1))) return rc;
+    return tcg_tn_acc(st, 2 * L, kNgpHidden, enc, 2 * L, w.g0, kNgpHidden, m, G + nl.w[0], kNgpHidden, G + nl.b[0],
+                      w.amax + 4, w.amax + 0);
+  }
   if ((rc = gemm_tn_small(st, kNgpHidden, kNgpHidden, w.h2, kNgpHidden, w.g3, kNgpHidden, m, G + nl.w[3], kNgpHidden,
                           G + nl.b[3]))) return rc;
   if ((rc = gemm_tn_small(st, kNgpIn2, kNgpHidden, w.in2, kNgpIn2, w.g2, kNgpHidden, m, G + nl.w[2], kNgpHidden,

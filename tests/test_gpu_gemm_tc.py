@@ -100,7 +100,10 @@ def test_rows_scaled_operand(scale):
 
 
 @pytest.mark.parametrize("Ksamp,M,N", [(5000, 256, 256), (4096 + 17, 60, 256), (3001, 256, 128), (777, 24, 128),
-                                       (200, 64, 64), (100000, 256, 256)])
+                                       (200, 64, 64), (100000, 256, 256),
+                                       # M, N <= 64: the 192-sample-chunk variant (the Instant-NGP head shapes)
+                                       (100001, 64, 64), (50000, 40, 64), (7777, 64, 16), (191, 32, 64),
+                                       (193, 12, 64), (768, 64, 4)])
 def test_tn_vs_fp64(Ksamp, M, N):
     g = torch.Generator().manual_seed(Ksamp)
     H = torch.relu(torch.randn(Ksamp, M, generator=g)).cuda()
