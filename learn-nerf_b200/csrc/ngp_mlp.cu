@@ -501,21 +501,32 @@ ngp_dw4_kernel(const float* __restrict__ h3, const float* __restrict__ rgb, cons
   const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
   float gw[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}}, gb[3] = {0.f, 0.f, 0.f};
-  for (int64_t s = warp; s < m; s += nwarps) {
-    float dp[3];
+  // 32 samples at a time: every lane forms dp of its own sample, the warp then streams the 32 rows of h3
+  for (int64_t base = warp * 32; base < m; base += nwarps * 32) {
+    const int64_t s = base + lane;
+    float dp[3] = {0.f, 0.f, 0.f};
+    if (s < m) {
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const float y = __ldg(rgb + s * 3 + j);
-      dp[j] = __ldg(d_rgb + s * 3 + j) * (1.0f - y * y);
-      gb[j] += dp[j];
+      for (int j = 0; j < 3; ++j) {
+        const float y = __ldg(rgb + s * 3 + j);
+        dp[j] = __ldg(d_rgb + s * 3 + j) * (1.0f - y * y);
+        gb[j] += dp[j];
+      }
     }
-    const float2 a = __ldg(reinterpret_cast<const float2*>(h3 + s * kNgpHidden) + lane);
+    const int cnt = m - base < 32 ? int(m - base) : 32;
+#pragma unroll 4
+    for (int t = 0; t < cnt; ++t) {
+      const float2 a = __ldg(reinterpret_cast<const float2*>(h3 + (base + t) * kNgpHidden) + lane);
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      gw[0][j] = fmaf(a.x, dp[j], gw[0][j]);
-      gw[1][j] = fmaf(a.y, dp[j], gw[1][j]);
+      for (int j = 0; j < 3; ++j) {
+        const float d = __shfl_sync(0xffffffffu, dp[j], t);
+        gw[0][j] = fmaf(a.x, d, gw[0][j]);
+        gw[1][j] = fmaf(a.y, d, gw[1][j]);
+      }
     }
   }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) gb[j] = warp_sum(gb[j]);
   __shared__ float s_gw[8][kNgpHidden * 3];
 #pragma unroll
   for (int k = 0; k < 2; ++k)
@@ -624,7 +635,7 @@ int lnrf_ngp_mlp_bwd(const float* params, int32_t L, const float* enc, int64_t m
   LNRF_LAUNCH_CHECK("ngp_mlp_bwd_kernel");
   // weight / bias gradients: dW_l = input_l^T g_l (split-K FFMA GEMM), db_l = column sums
   int rc;
-  ngp_dw4_kernel<<<ew_blocks(m, 8 * 16), 256, 0, st>>>(w.h3, rgb, d_rgb, m, G + nl.w[4], G + nl.b[4]);
+  ngp_dw4_kernel<<<ew_blocks(m, 8 * 128), 256, 0, st>>>(w.h3, rgb, d_rgb, m, G + nl.w[4], G + nl.b[4]);
   LNRF_LAUNCH_CHECK("ngp_dw4_kernel");
   if (!fp32_ffma()) {
     // operand ranges: layer inputs from the forward (slots 4..7), gradients from the dX kernel above (0..3)

@@ -323,6 +323,12 @@ __device__ __forceinline__ void load_per(const float* p, float (&v)[2]) {
   const float2 a = __ldg(reinterpret_cast<const float2*>(p));
   v[0] = a.x; v[1] = a.y;
 }
+__device__ __forceinline__ void store_per(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store_per(float* p, const float (&v)[2]) {
+  *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+}
 template <int PER>
 __global__ void __launch_bounds__(256)
 ref_out_fwd_kernel(const float* __restrict__ c, const float* __restrict__ w10, const float* __restrict__ b10,
@@ -370,33 +376,48 @@ ref_out_bwd_kernel(const float* __restrict__ z8, const float* __restrict__ o, co
       w[k][j] = __ldg(w10 + (lane * PER + k) * 3 + j);
       gw[k][j] = 0.0f;
     }
-  for (int64_t s = warp; s < m; s += nwarps) {
-    const float spec = sigmoid_f(__ldg(z8 + s * ldz + 4));
-    float dov[3];
+  // A warp takes 32 samples at a time: each lane first forms d_o of ITS sample (the sigmoids and the sRGB
+  // derivative once per sample, not once per lane), then the warp streams the 32 feature rows with d_o
+  // broadcast by shuffles.
+  for (int64_t base = warp * 32; base < m; base += nwarps * 32) {
+    const int64_t s = base + lane;
+    float dov[3] = {0.f, 0.f, 0.f};
+    if (s < m) {
+      const float spec = sigmoid_f(__ldg(z8 + s * ldz + 4));
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const float dif = sigmoid_f(__ldg(z8 + s * ldz + 1 + i) - 1.0986122886681098f);
-      const float sc = sigmoid_f(__ldg(o + s * 4 + i));
-      const float lin = sc * spec + dif;
-      const float cl = fminf(fmaxf(lin, 0.0f), 1.0f);
-      const float dlin = 2.0f * __ldg(d_rgb + s * 3 + i) * srgb_df(cl);  // straight-through clip
-      dov[i] = dlin * spec * sc * (1.0f - sc);
-      gb[i] += dov[i];
+      for (int i = 0; i < 3; ++i) {
+        const float dif = sigmoid_f(__ldg(z8 + s * ldz + 1 + i) - 1.0986122886681098f);
+        const float sc = sigmoid_f(__ldg(o + s * 4 + i));
+        const float lin = sc * spec + dif;
+        const float cl = fminf(fmaxf(lin, 0.0f), 1.0f);
+        const float dlin = 2.0f * __ldg(d_rgb + s * 3 + i) * srgb_df(cl);  // straight-through clip
+        dov[i] = dlin * spec * sc * (1.0f - sc);
+        gb[i] += dov[i];
+        d_o[s * 4 + i] = dov[i];
+      }
     }
-    if (lane < 3) d_o[s * 4 + lane] = lane == 0 ? dov[0] : (lane == 1 ? dov[1] : dov[2]);
-    float av[PER];
-    load_per(c + s * kW + lane * PER, av);
-    float g4[PER];
+    const int cnt = m - base < 32 ? int(m - base) : 32;
+#pragma unroll 4
+    for (int t = 0; t < cnt; ++t) {
+      const float d0 = __shfl_sync(0xffffffffu, dov[0], t), d1 = __shfl_sync(0xffffffffu, dov[1], t),
+                  d2 = __shfl_sync(0xffffffffu, dov[2], t);
+      const int64_t st = base + t;
+      float av[PER];
+      load_per(c + st * kW + lane * PER, av);
+      float g4[PER];
 #pragma unroll
-    for (int k = 0; k < PER; ++k) {
-      const float t = dov[0] * w[k][0] + dov[1] * w[k][1] + dov[2] * w[k][2];
-      g4[k] = av[k] > 0.0f ? t : 0.0f;
-#pragma unroll
-      for (int j = 0; j < 3; ++j) gw[k][j] = fmaf(av[k], dov[j], gw[k][j]);
+      for (int k = 0; k < PER; ++k) {
+        const float tt = d0 * w[k][0] + d1 * w[k][1] + d2 * w[k][2];
+        g4[k] = av[k] > 0.0f ? tt : 0.0f;
+        gw[k][0] = fmaf(av[k], d0, gw[k][0]);
+        gw[k][1] = fmaf(av[k], d1, gw[k][1]);
+        gw[k][2] = fmaf(av[k], d2, gw[k][2]);
+      }
+      store_per(gc + st * kW + lane * PER, g4);
     }
-#pragma unroll
-    for (int k = 0; k < PER; ++k) gc[s * kW + lane * PER + k] = g4[k];
   }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) gb[i] = warp_sum(gb[i]);
   __shared__ float s_gw[8][kW * 3];
 #pragma unroll
   for (int k = 0; k < PER; ++k)
@@ -745,7 +766,7 @@ int lnrf_refnerf_bwd(const float* params, const float* x, const float* d, const 
   const unsigned cb = ew_blocks(m, 512);  // >= 1k blocks at training sizes
   int rc;
   // ---- directional block
-  ref_out_bwd_kernel<4><<<ew_blocks(m, 8 * 16), 256, 0, st>>>(w.h[8], w.o, w.c, d_rgb, P + kRef.w[10], m, w.d_o,
+  ref_out_bwd_kernel<4><<<ew_blocks(m, 8 * 128), 256, 0, st>>>(w.h[8], w.o, w.c, d_rgb, P + kRef.w[10], m, w.d_o,
                                                                w.gc, G + kRef.w[10], G + kRef.b[10], kH);
   LNRF_LAUNCH_CHECK("ref_out_bwd_kernel");
   float* am = w.amax;
@@ -901,7 +922,7 @@ int lnrf_ngpref_bwd(const float* params, const int64_t* level_offsets_host, cons
   float* G = d_params;
   int rc;
   // ---- directional block: Dense_4, Dense_3, Dense_2
-  ref_out_bwd_kernel<2><<<ew_blocks(m, 8 * 16), 256, 0, st>>>(w.z, w.o, w.c2, d_rgb, P + nl.w[4], m, w.d_o, w.gc2,
+  ref_out_bwd_kernel<2><<<ew_blocks(m, 8 * 128), 256, 0, st>>>(w.z, w.o, w.c2, d_rgb, P + nl.w[4], m, w.d_o, w.gc2,
                                                                G + nl.w[4], G + nl.b[4], kNrOut);
   LNRF_LAUNCH_CHECK("ref_out_bwd_kernel");
   float* am = w.amax;
