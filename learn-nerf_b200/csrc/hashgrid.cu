@@ -374,6 +374,95 @@ hashgrid_jtv_bwd_kernel(const float* __restrict__ tables, GridLevels g, const fl
   }
 }
 
+// The same, one thread per POINT (see hashgrid_bwd_pt_kernel: consecutive lanes are consecutive samples of a
+// ray, the gathers share L2 sectors, and on the dense levels a run of lanes in one cell issues ONE set of eight
+// atomics after a segmented shuffle reduction).
+template <int LT>
+__global__ void __launch_bounds__(256)
+hashgrid_jtv_bwd_pt_kernel(const float* __restrict__ tables, const __grid_constant__ GridLevels g,
+                           const float* __restrict__ x, const float* __restrict__ rays, const float* __restrict__ ts,
+                           int T, int64_t m, const float* __restrict__ vec, const float* __restrict__ u,
+                           float* __restrict__ tvec, float* __restrict__ d_tables) {
+  const int lane = threadIdx.x & 31;
+  const int64_t m_pad = (m + 31) / 32 * 32;  // whole warps stay in the loop (the reduction needs all 32 lanes)
+  for (int64_t s = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; s < m_pad; s += int64_t(gridDim.x) * blockDim.x) {
+    const bool in_range = s < m;
+    float4 uu = make_float4(0.f, 0.f, 0.f, 0.f);
+    float2 v[LT], out[LT];
+    float p[3] = {0.f, 0.f, 0.f};
+    if (in_range) {
+      uu = __ldg(reinterpret_cast<const float4*>(u) + s);
+      const float4* src = reinterpret_cast<const float4*>(vec + s * 2 * LT);
+#pragma unroll
+      for (int q = 0; q < LT / 2; ++q) {
+        const float4 t = __ldg(src + q);
+        v[2 * q] = make_float2(t.x, t.y);
+        v[2 * q + 1] = make_float2(t.z, t.w);
+      }
+      load_point(x, rays, ts, T, s, p);
+    } else {
+#pragma unroll
+      for (int l = 0; l < LT; ++l) v[l] = make_float2(0.f, 0.f);
+    }
+    const bool live = in_range && (uu.x != 0.0f || uu.y != 0.0f || uu.z != 0.0f);
+#pragma unroll
+    for (int l = 0; l < LT; ++l) {
+      const CornersD c = level_corners_dx(g, l, p);
+      const float2* tab = reinterpret_cast<const float2*>(tables + g.offset[l]);
+      float2* dtab = reinterpret_cast<float2*>(d_tables + g.offset[l]);
+      float du[8];
+      float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        du[k] = c.dw[k][0] * uu.x + c.dw[k][1] * uu.y + c.dw[k][2] * uu.z;
+        const float2 t = __ldg(tab + c.idx[k]);
+        acc.x = fmaf(du[k], t.x, acc.x);
+        acc.y = fmaf(du[k], t.y, acc.y);
+      }
+      out[l] = acc;
+      if (g.hashed[l]) {
+        if (live) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (du[k] != 0.0f) atomicAdd(dtab + c.idx[k], make_float2(du[k] * v[l].x, du[k] * v[l].y));
+        }
+        continue;
+      }
+      if (!__any_sync(0xffffffffu, live)) continue;
+      const uint32_t cell = live ? c.idx[0] : 0xffffffffu - uint32_t(lane);  // dead lanes: singleton runs
+      const uint32_t prev = __shfl_up_sync(0xffffffffu, cell, 1);
+      const bool head = lane == 0 || prev != cell;
+      const unsigned heads = __ballot_sync(0xffffffffu, head);
+      const int run = __popc(heads & (0xffffffffu >> (31 - lane)));
+      float w[16];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        w[2 * k] = live ? du[k] * v[l].x : 0.0f;
+        w[2 * k + 1] = live ? du[k] * v[l].y : 0.0f;
+      }
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int run2 = __shfl_down_sync(0xffffffffu, run, off);
+        const bool take = (lane + off < 32) && run2 == run;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float t = __shfl_down_sync(0xffffffffu, w[j], off);
+          if (take) w[j] += t;
+        }
+      }
+      if (head && live) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) atomicAdd(dtab + c.idx[k], make_float2(w[2 * k], w[2 * k + 1]));
+      }
+    }
+    if (in_range) {
+      float4* dst = reinterpret_cast<float4*>(tvec + s * 2 * LT);
+#pragma unroll
+      for (int q = 0; q < LT / 2; ++q) dst[q] = make_float4(out[2 * q].x, out[2 * q].y, out[2 * q + 1].x, out[2 * q + 1].y);
+    }
+  }
+}
+
 static int make_levels(GridLevels& g, const int64_t* level_offsets, const int32_t* grid_sizes,
                        const int32_t* table_sizes, int L, const float* bmin, const float* bmax,
                        int smooth, const char* who) {
@@ -419,8 +508,13 @@ int hashgrid_launch(int which, const float* tables, const int64_t* level_offsets
       LNRF_LAUNCH_CHECK("hashgrid_jtv_kernel");
       break;
     case 3:  // out0 = J in1(u), d_tables(out1) += second-order scatter with vec = in0
-      hashgrid_jtv_bwd_kernel<<<ew_blocks(m * L, 256), 256, 0, st>>>(tables, g, x, rays, ts, T, m, in0, in1, out0,
-                                                                     out1);
+      if (L == 16 && (uintptr_t)in0 % 16 == 0 && (uintptr_t)out0 % 16 == 0)
+        hashgrid_jtv_bwd_pt_kernel<16><<<ew_blocks(m, 256), 256, 0, st>>>(tables, g, x, rays, ts, T, m, in0, in1, out0, out1);
+      else if (L == 6 && (uintptr_t)in0 % 16 == 0 && (uintptr_t)out0 % 16 == 0)
+        hashgrid_jtv_bwd_pt_kernel<6><<<ew_blocks(m, 256), 256, 0, st>>>(tables, g, x, rays, ts, T, m, in0, in1, out0, out1);
+      else
+        hashgrid_jtv_bwd_kernel<<<ew_blocks(m * L, 256), 256, 0, st>>>(tables, g, x, rays, ts, T, m, in0, in1, out0,
+                                                                       out1);
       LNRF_LAUNCH_CHECK("hashgrid_jtv_bwd_kernel");
       break;
     default:
