@@ -53,8 +53,9 @@ static NgpLayout ngp_layout(int L) {
 struct NgpWs {
   float *h0, *in2, *h2, *h3;     // layer inputs kept for dW: [m,64], [m,40] = [d_emb | out], [m,64], [m,64]
   float *g0, *go1, *g2, *g3;     // dL/d pre-activation of Dense_0..3: [m,64], [m,16], [m,64], [m,64]
-  float* amax;                   // operand ranges for the dW GEMMs: [0..3] max|g0|, |go1|, |g2|, |g3| (backward),
-                                 // [4..7] max|enc|, |h0|, |in2|, |h2| (forward with save_for_backward)
+  float* amax;                   // operand ranges of the tensor-core GEMMs: [0..3] max|g0|, |go1|, |g2|, |g3| (backward),
+                                 // [4..7] max|enc|, |h0|, |in2|, |h2|, [8] max|Dense_1 out| (forward with save_for_backward)
+  uint32_t *mask0, *mask2;       // ReLU bit masks of Dense_0 / Dense_2 (tcg_rows layout; engine path only)
   int64_t bytes;
 };
 static NgpWs carve_ngp(void* base, int64_t m) {
@@ -74,7 +75,9 @@ static NgpWs carve_ngp(void* base, int64_t m) {
   w.go1 = take(m * kNgpDensity);
   w.g2 = take(m * kNgpHidden);
   w.g3 = take(m * kNgpHidden);
-  w.amax = take(8);
+  w.amax = take(16);
+  w.mask0 = reinterpret_cast<uint32_t*>(take(tcg_mask_words(m, kNgpHidden)));
+  w.mask2 = reinterpret_cast<uint32_t*>(take(tcg_mask_words(m, kNgpHidden)));
   w.bytes = off;
   return w;
 }
@@ -545,6 +548,216 @@ ngp_dw4_kernel(const float* __restrict__ h3, const float* __restrict__ rgb, cons
   }
 }
 
+
+// ---------------------------------------------------------------- the train path on the tensor-core engine
+// With save_for_backward the five layers run as split-fp16 tcgen05 GEMMs (gemm_tc.cu: fp32-accurate, ReLU masks
+// as bits, operand ranges through the amax slots) with three small kernels around them; the fused FFMA kernels
+// above stay for the forward without a workspace (render) and for LNRF_FP32_FFMA=1.
+
+// after Dense_1: density = exp(out[0]), d_emb = sinusoidal_emb(d, 4) into in2[:, :24] (instant_ngp.py:37,49-51)
+__global__ void __launch_bounds__(256)
+ngp_mid_kernel(const float* __restrict__ d, const float* __restrict__ rays, int T, int64_t m, float* __restrict__ in2,
+               float* __restrict__ dens, float* __restrict__ amax) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) amax[6] = fmaxf(amax[8], 1.0f);  // max|in2|: |d_emb| <= 1
+  for (int64_t s = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; s < m; s += int64_t(gridDim.x) * blockDim.x) {
+    float dv[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) dv[k] = d ? __ldg(d + s * 3 + k) : __ldg(rays + (s / T) * 6 + 3 + k);
+    float de[kNgpDE];
+#pragma unroll
+    for (int dim = 0; dim < 3; ++dim)
+#pragma unroll
+      for (int f = 0; f < 4; ++f) sincosf(dv[dim] * float(1 << f), &de[dim * 8 + f], &de[dim * 8 + 4 + f]);
+    float4* dst = reinterpret_cast<float4*>(in2 + s * kNgpIn2);
+#pragma unroll
+    for (int k4 = 0; k4 < kNgpDE / 4; ++k4) dst[k4] = make_float4(de[k4 * 4], de[k4 * 4 + 1], de[k4 * 4 + 2], de[k4 * 4 + 3]);
+    dens[s] = expf(in2[s * kNgpIn2 + kNgpDE]);
+  }
+}
+
+// Dense_4 (64 -> 3) + tanh (:53): a warp takes 32 samples, lane = 2 hidden units, three shuffle reductions per sample
+// folded into one transposed pass (lane t ends up with the three sums of sample t).
+__global__ void __launch_bounds__(256)
+ngp_rgb_kernel(const float* __restrict__ h3, const float* __restrict__ w4, const float* __restrict__ b4, int64_t m,
+               float* __restrict__ rgb) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  float w[2][3];
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) w[k][j] = __ldg(w4 + (lane * 2 + k) * 3 + j);
+  const float bb[3] = {__ldg(b4), __ldg(b4 + 1), __ldg(b4 + 2)};
+  for (int64_t base = warp * 32; base < m; base += nwarps * 32) {
+    const int cnt = m - base < 32 ? int(m - base) : 32;
+    float o[3] = {0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int t = 0; t < cnt; ++t) {
+      const float2 a = __ldg(reinterpret_cast<const float2*>(h3 + (base + t) * kNgpHidden) + lane);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const float part = warp_sum(fmaf(a.x, w[0][j], a.y * w[1][j]));
+        if (lane == t) o[j] = part;
+      }
+    }
+    if (lane < cnt) {
+      const int64_t s = base + lane;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) rgb[s * 3 + j] = tanhf(o[j] + bb[j]);
+    }
+  }
+}
+
+// Backward of Dense_4: dp = d_rgb (1 - rgb^2); g3 = (dp @ W4^T) * [h3 > 0]; dW4 += h3^T dp; db4 += sum dp; max|g3|.
+__global__ void __launch_bounds__(256)
+ngp_head_bwd_kernel(const float* __restrict__ h3, const float* __restrict__ rgb, const float* __restrict__ d_rgb,
+                    const float* __restrict__ w4, int64_t m, float* __restrict__ g3, float* __restrict__ dw4,
+                    float* __restrict__ db4, float* __restrict__ g3_amax) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  float w[2][3], gw[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}}, gb[3] = {0.f, 0.f, 0.f}, mx = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) w[k][j] = __ldg(w4 + (lane * 2 + k) * 3 + j);
+  for (int64_t base = warp * 32; base < m; base += nwarps * 32) {
+    const int64_t s = base + lane;
+    float dp[3] = {0.f, 0.f, 0.f};
+    if (s < m) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const float y = __ldg(rgb + s * 3 + j);
+        dp[j] = __ldg(d_rgb + s * 3 + j) * (1.0f - y * y);
+        gb[j] += dp[j];
+      }
+    }
+    const int cnt = m - base < 32 ? int(m - base) : 32;
+#pragma unroll 4
+    for (int t = 0; t < cnt; ++t) {
+      const float d0 = __shfl_sync(0xffffffffu, dp[0], t), d1 = __shfl_sync(0xffffffffu, dp[1], t),
+                  d2 = __shfl_sync(0xffffffffu, dp[2], t);
+      const float2 a = __ldg(reinterpret_cast<const float2*>(h3 + (base + t) * kNgpHidden) + lane);
+      const float av[2] = {a.x, a.y};
+      float g[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float tt = d0 * w[k][0] + d1 * w[k][1] + d2 * w[k][2];
+        g[k] = av[k] > 0.0f ? tt : 0.0f;
+        mx = fmaxf(mx, fabsf(g[k]));
+        gw[k][0] = fmaf(av[k], d0, gw[k][0]);
+        gw[k][1] = fmaf(av[k], d1, gw[k][1]);
+        gw[k][2] = fmaf(av[k], d2, gw[k][2]);
+      }
+      reinterpret_cast<float2*>(g3 + (base + t) * kNgpHidden)[lane] = make_float2(g[0], g[1]);
+    }
+  }
+  __shared__ float s_gw[8][kNgpHidden * 3];
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) s_gw[wib][(lane * 2 + k) * 3 + j] = gw[k][j];
+  __syncthreads();
+  for (int i = threadIdx.x; i < kNgpHidden * 3; i += blockDim.x) {
+    float t = 0.0f;
+    for (int ww = 0; ww < 8; ++ww) t += s_gw[ww][i];
+    atomicAdd(dw4 + i, t);
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) gb[j] = warp_sum(gb[j]);
+  const uint32_t mw = __reduce_max_sync(0xffffffffu, __float_as_uint(mx < 3.0e38f ? mx : 0.0f));
+  if (lane == 0) {
+    atomicAdd(db4 + 0, gb[0]);
+    atomicAdd(db4 + 1, gb[1]);
+    atomicAdd(db4 + 2, gb[2]);
+    if (mw != 0u) atomicMax(reinterpret_cast<uint32_t*>(g3_amax), mw);
+  }
+}
+
+// density = exp(out[0]) (:49): g_out1[:, 0] += d_dens * density
+__global__ void __launch_bounds__(256)
+ngp_dens_bwd_kernel(const float* __restrict__ dens, const float* __restrict__ d_dens, int64_t m, float* __restrict__ go1,
+                    float* __restrict__ go1_amax) {
+  float mx = 0.0f;
+  for (int64_t s = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; s < m; s += int64_t(gridDim.x) * blockDim.x) {
+    const float v = go1[s * kNgpDensity] + __ldg(d_dens + s) * __ldg(dens + s);
+    go1[s * kNgpDensity] = v;
+    mx = fmaxf(mx, fabsf(v));
+  }
+  const uint32_t mw = __reduce_max_sync(0xffffffffu, __float_as_uint(mx < 3.0e38f ? mx : 0.0f));
+  if ((threadIdx.x & 31) == 0 && mw != 0u) atomicMax(reinterpret_cast<uint32_t*>(go1_amax), mw);
+}
+
+static int ngp_fwd_engine(cudaStream_t st, const float* P, const NgpLayout& nl, int E, const float* enc, const float* d,
+                          const float* rays, int T, int64_t m, const NgpWs& w, float* dens, float* rgb) {
+  int rc;
+  float* am = w.amax;
+  LNRF_CUDA(cudaMemsetAsync(am + 4, 0, 8 * sizeof(float), st));
+  if ((rc = tcg_amax(st, enc, m * E, am + 4))) return rc;  // fresh hash tables hold ~1e-4: the encoding needs its scale
+  // Dense_0 + relu                                                          instant_ngp.py:46-47
+  if ((rc = tcg_rows(st, TCG_BIAS_RELU, false, m, kNgpHidden, enc, E, E, nullptr, 0, 0, P + nl.w[0], kNgpHidden, w.h0,
+                     kNgpHidden, P + nl.b[0], nullptr, 0, nullptr, nullptr, am + 4, nullptr, am + 5, nullptr, w.mask0)))
+    return rc;
+  // Dense_1 -> in2[:, 24:40]                                                :48
+  if ((rc = tcg_rows(st, TCG_BIAS, false, m, kNgpDensity, w.h0, kNgpHidden, kNgpHidden, nullptr, 0, 0, P + nl.w[1],
+                     kNgpDensity, w.in2 + kNgpDE, kNgpIn2, P + nl.b[1], nullptr, 0, nullptr, nullptr, am + 5, nullptr,
+                     am + 8)))
+    return rc;
+  ngp_mid_kernel<<<ew_blocks(m, 256), 256, 0, st>>>(d, rays, T, m, w.in2, dens, am);
+  LNRF_LAUNCH_CHECK("ngp_mid_kernel");
+  // Dense_2 + relu, Dense_3 + relu                                          :51-52
+  if ((rc = tcg_rows(st, TCG_BIAS_RELU, false, m, kNgpHidden, w.in2, kNgpIn2, kNgpIn2, nullptr, 0, 0, P + nl.w[2],
+                     kNgpHidden, w.h2, kNgpHidden, P + nl.b[2], nullptr, 0, nullptr, nullptr, am + 6, nullptr, am + 7,
+                     nullptr, w.mask2)))
+    return rc;
+  if ((rc = tcg_rows(st, TCG_BIAS_RELU, false, m, kNgpHidden, w.h2, kNgpHidden, kNgpHidden, nullptr, 0, 0, P + nl.w[3],
+                     kNgpHidden, w.h3, kNgpHidden, P + nl.b[3], nullptr, 0, nullptr, nullptr, am + 7, nullptr, nullptr)))
+    return rc;
+  ngp_rgb_kernel<<<ew_blocks(m, 8 * 128), 256, 0, st>>>(w.h3, P + nl.w[4], P + nl.b[4], m, rgb);
+  LNRF_LAUNCH_CHECK("ngp_rgb_kernel");
+  return LNRF_OK;
+}
+
+static int ngp_bwd_engine(cudaStream_t st, const float* P, const NgpLayout& nl, int E, const float* enc, int64_t m,
+                          const NgpWs& w, const float* dens, const float* rgb, const float* d_dens, const float* d_rgb,
+                          float* G, float* d_enc) {
+  int rc;
+  float* am = w.amax;
+  LNRF_CUDA(cudaMemsetAsync(am, 0, 4 * sizeof(float), st));
+  ngp_head_bwd_kernel<<<ew_blocks(m, 8 * 128), 256, 0, st>>>(w.h3, rgb, d_rgb, P + nl.w[4], m, w.g3, G + nl.w[4],
+                                                             G + nl.b[4], am + 3);
+  LNRF_LAUNCH_CHECK("ngp_head_bwd_kernel");
+  // g2 = (g3 @ W3^T) * [h2 > 0]
+  if ((rc = tcg_rows(st, TCG_MASKBITS, true, m, kNgpHidden, w.g3, kNgpHidden, kNgpHidden, nullptr, 0, 0, P + nl.w[3],
+                     kNgpHidden, w.g2, kNgpHidden, nullptr, nullptr, 0, nullptr, nullptr, am + 3, nullptr, am + 2,
+                     w.mask2, nullptr)))
+    return rc;
+  // g_out1 = g2 @ W2[24:40]^T (d_emb carries no parameters), + d_dens * density on column 0
+  if ((rc = tcg_rows(st, TCG_STORE, true, m, kNgpDensity, w.g2, kNgpHidden, kNgpHidden, nullptr, 0, 0,
+                     P + nl.w[2] + kNgpDE * kNgpHidden, kNgpHidden, w.go1, kNgpDensity, nullptr, nullptr, 0, nullptr,
+                     nullptr, am + 2, nullptr, am + 1)))
+    return rc;
+  ngp_dens_bwd_kernel<<<ew_blocks(m, 256), 256, 0, st>>>(dens, d_dens, m, w.go1, am + 1);
+  LNRF_LAUNCH_CHECK("ngp_dens_bwd_kernel");
+  // g0 = (g_out1 @ W1^T) * [h0 > 0];  d_enc = g0 @ W0^T
+  if ((rc = tcg_rows(st, TCG_MASKBITS, true, m, kNgpHidden, w.go1, kNgpDensity, kNgpDensity, nullptr, 0, 0, P + nl.w[1],
+                     kNgpDensity, w.g0, kNgpHidden, nullptr, nullptr, 0, nullptr, nullptr, am + 1, nullptr, am + 0,
+                     w.mask0, nullptr)))
+    return rc;
+  if ((rc = tcg_rows(st, TCG_STORE, true, m, E, w.g0, kNgpHidden, kNgpHidden, nullptr, 0, 0, P + nl.w[0], kNgpHidden,
+                     d_enc, E, nullptr, nullptr, 0, nullptr, nullptr, am + 0, nullptr, nullptr)))
+    return rc;
+  // dW_l = input_l^T g_l, db_l = column sums of g_l
+  if ((rc = tcg_tn_acc(st, kNgpHidden, kNgpHidden, w.h2, kNgpHidden, w.g3, kNgpHidden, m, G + nl.w[3], kNgpHidden,
+                       G + nl.b[3], am + 7, am + 3))) return rc;
+  if ((rc = tcg_tn_acc(st, kNgpIn2, kNgpHidden, w.in2, kNgpIn2, w.g2, kNgpHidden, m, G + nl.w[2], kNgpHidden,
+                       G + nl.b[2], am + 6, am + 2))) return rc;
+  if ((rc = tcg_tn_acc(st, kNgpHidden, kNgpDensity, w.h0, kNgpHidden, w.go1, kNgpDensity, m, G + nl.w[1], kNgpDensity,
+                       G + nl.b[1], am + 5, am + 1))) return rc;
+  return tcg_tn_acc(st, E, kNgpHidden, enc, E, w.g0, kNgpHidden, m, G + nl.w[0], kNgpHidden, G + nl.b[0], am + 4, am + 0);
+}
+
 static int ngp_grid(int64_t m) {
   int64_t blocks = ceil_div(m, kTM);
   const int64_t cap = int64_t(sm_count()) * 2;  // two ~100 KB blocks per SM, persistent over tiles
@@ -605,6 +818,8 @@ int lnrf_ngp_mlp_fwd(const float* params, int32_t L, const float* enc, const flo
     w = carve_ngp(workspace, m);
   }
   const NgpLayout nl = ngp_layout(L);
+  if (save && !fp32_ffma() && tcg_supported(kNgpHidden, 2 * L, 0))
+    return ngp_fwd_engine(as_stream(stream), params, nl, 2 * L, enc, d, rays, T, m, w, dens, rgb);
   NgpFwdArgs a{params, nl, 2 * L, enc, d, rays, T, m, w, dens, rgb};
   const size_t smem = ngp_fwd_smem(nl);
   if (save) LNRF_CUDA(cudaMemsetAsync(w.amax + 4, 0, 4 * sizeof(float), as_stream(stream)));
@@ -629,6 +844,8 @@ int lnrf_ngp_mlp_bwd(const float* params, int32_t L, const float* enc, int64_t m
   const NgpWs w = carve_ngp(workspace, m);
   cudaStream_t st = as_stream(stream);
   float* G = d_params;
+  if (!fp32_ffma() && tcg_supported(kNgpHidden, 2 * L, 0))
+    return ngp_bwd_engine(st, params, nl, 2 * L, enc, m, w, dens, rgb, d_dens, d_rgb, G, d_enc);
   NgpBwdArgs a{params, nl, 2 * L, m, w, dens, rgb, d_dens, d_rgb, d_enc};
   LNRF_CUDA(cudaMemsetAsync(w.amax, 0, 4 * sizeof(float), st));
   ngp_mlp_bwd_kernel<<<ngp_grid(m), kNgpBwdThreads, size_t(ngp_bwd_smem(2 * L).total) * sizeof(float), st>>>(a);
