@@ -339,10 +339,23 @@ __global__ void __launch_bounds__(kRgThreads, 1) tcg_rows_kernel(const __grid_co
 #pragma unroll
         for (int i = 0; i < 8; ++i) r1[i] = row0 + i < a.M ? __ldg(a.r1s + row0 + i) : 0.0f;
       }
+      // columns of this warp: 64 per warp quad-pair member, 32 when the half has <= 64 columns (the 64-wide
+      // layers of the hash-grid heads: otherwise warps 4-7 would idle and one warp per scheduler drains the tile)
+      const int cw = a.nc <= 64 ? 32 : 64;
+      const int c_beg = (warp >> 2) * cw, c_end = a.nc < c_beg + cw ? a.nc : c_beg + cw;
+      // bit masks: one word per lane and 32 x 32 block = [rows row0 .. row0+7] x [columns n .. n+3], bit 4 i + e;
+      // words exist for the rows below ceil(M / 32) * 32.  Fetched BEFORE the wait on the accumulator (the load
+      // latency would otherwise sit in the drain chain of every tile).
+      const bool mrow_ok = row0 < ((a.M + 31) & ~int64_t(31));
+      const int64_t mword0 = ((row0 >> 5) * ((a.N + 31) >> 5) + ((n0 + c_beg) >> 5)) * 32 + lane;
+      uint32_t mpre0 = 0, mpre1 = 0;
+      if (EPI == TCG_MASKBITS && mrow_ok) {
+        if (c_beg < c_end) mpre0 = __ldg(a.mask_in + mword0);
+        if (c_beg + 32 < c_end) mpre1 = __ldg(a.mask_in + mword0 + 32);
+      }
       mbar_wait(bars + kRgAccFull + 8 * buf, uint32_t(it >> 1) & 1u);
       tc_fence_after();
       const uint32_t t_main = tmem + (uint32_t((warp & 3) * 32) << 16) + buf * 256u;
-      const int c_beg = (warp >> 2) * 64, c_end = a.nc < c_beg + 64 ? a.nc : c_beg + 64;
       for (int c0 = c_beg; c0 < c_end; c0 += 32) {
         uint32_t vm[32], vc[32];
         tmem_ld32(t_main + c0, vm);
@@ -351,10 +364,8 @@ __global__ void __launch_bounds__(kRgThreads, 1) tcg_rows_kernel(const __grid_co
         const bool col_ok = c0 + 4 * lb < a.nc && n < a.N;
         float4 mk[8];  // EPI_MASK: the mask values of this lane's eight outputs, all loads in flight at once
         float4 bw = make_float4(0.f, 0.f, 0.f, 0.f);  // bias (or the rank-1 row vector) of the four columns
-        // bit masks: one word per lane and 32 x 32 block = [rows row0 .. row0+7] x [columns n .. n+3], bit 4 i + e
-        const int64_t mword = ((row0 >> 5) * ((a.N + 31) >> 5) + ((n0 + c0) >> 5)) * 32 + lane;
-        uint32_t mbits = 0;
-        if (EPI == TCG_MASKBITS) mbits = __ldg(a.mask_in + mword);
+        const int64_t mword = mword0 + (c0 - c_beg);
+        uint32_t mbits = EPI == TCG_MASKBITS ? (c0 == c_beg ? mpre0 : mpre1) : 0u;
         if (EPI == TCG_MASK) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -415,7 +426,7 @@ __global__ void __launch_bounds__(kRgThreads, 1) tcg_rows_kernel(const __grid_co
             *reinterpret_cast<float4*>(a.C + (row0 + i) * a.ldc + n) = make_float4(v[0], v[1], v[2], v[3]);
           }
         }
-        if (EPI == TCG_BIAS_RELU && a.mask_out != nullptr) a.mask_out[mword] = mbits;
+        if (EPI == TCG_BIAS_RELU && a.mask_out != nullptr && mrow_ok) a.mask_out[mword] = mbits;
       }
       tc_fence_before();
       __syncwarp();

@@ -559,6 +559,35 @@ __global__ void __launch_bounds__(256)
 ngp_mid_kernel(const float* __restrict__ d, const float* __restrict__ rays, int T, int64_t m, float* __restrict__ in2,
                float* __restrict__ dens, float* __restrict__ amax) {
   if (blockIdx.x == 0 && threadIdx.x == 0) amax[6] = fmaxf(amax[8], 1.0f);  // max|in2|: |d_emb| <= 1
+  if (d == nullptr) {
+    // directions come per RAY: the few rays a block of 256 consecutive samples touches get their 12 sincos
+    // once (one per thread), every sample then copies its ray's 24 values
+    constexpr int kMaxRays = 20;  // 256 / T + 2 rays per block; larger blocks of rays fall through to the loop below
+    __shared__ __align__(16) float s_de[kMaxRays][kNgpDE];
+    if (256 / T + 2 <= kMaxRays) {
+      for (int64_t s0 = int64_t(blockIdx.x) * 256; s0 < m; s0 += int64_t(gridDim.x) * 256) {
+        const int64_t ray0 = s0 / T;
+        const int64_t s_last = s0 + 255 < m - 1 ? s0 + 255 : m - 1;
+        const int nr = int(s_last / T - ray0) + 1;
+        __syncthreads();
+        if (int(threadIdx.x) < nr * 12) {
+          const int r = threadIdx.x / 12, q = threadIdx.x % 12, dim = q >> 2, f = q & 3;
+          const float dv = __ldg(rays + (ray0 + r) * 6 + 3 + dim);
+          sincosf(dv * float(1 << f), &s_de[r][dim * 8 + f], &s_de[r][dim * 8 + 4 + f]);
+        }
+        __syncthreads();
+        const int64_t s = s0 + threadIdx.x;
+        if (s < m) {
+          const float4* src = reinterpret_cast<const float4*>(s_de[s / T - ray0]);
+          float4* dst = reinterpret_cast<float4*>(in2 + s * kNgpIn2);
+#pragma unroll
+          for (int k4 = 0; k4 < kNgpDE / 4; ++k4) dst[k4] = src[k4];
+          dens[s] = expf(in2[s * kNgpIn2 + kNgpDE]);
+        }
+      }
+      return;
+    }
+  }
   for (int64_t s = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; s < m; s += int64_t(gridDim.x) * blockDim.x) {
     float dv[3];
 #pragma unroll

@@ -123,9 +123,11 @@ def test_tn_vs_fp64(Ksamp, M, N):
     assert _rel(db.cpu().double().numpy(), refdb) < 1e-5
 
 
-@pytest.mark.parametrize("M,N", [(1000, 256), (4099, 128), (77, 64), (45000, 256)])
+@pytest.mark.parametrize("M,N", [(1000, 256), (4099, 128), (77, 64), (45000, 256), (4130, 64), (300, 16)])
 def test_relu_bit_masks_roundtrip(M, N):
-    """epi 0 writes the bits [relu output > 0]; epi 6 applies them: same result as masking by the fp32 activations."""
+    """epi 0 writes the bits [relu output > 0]; epi 6 applies them: same result as masking by the fp32 activations.
+    The mask buffer is exactly tcg_mask_words long; a sentinel region behind it must stay untouched (the last tile
+    of a ragged M spans row blocks that have no mask words)."""
     g = torch.Generator().manual_seed(M)
     K = 256
     A = torch.randn(M, K, generator=g).cuda()
@@ -133,8 +135,10 @@ def test_relu_bit_masks_roundtrip(M, N):
     bias = torch.randn(N, generator=g).cuda()
     Hh = torch.empty(M, N, device="cuda")
     words = ((M + 31) // 32) * ((N + 31) // 32) * 32
-    bits = torch.full((words,), -1, dtype=torch.int32, device="cuda")
+    guarded = torch.full((words + 8192,), -1, dtype=torch.int32, device="cuda")
+    bits = guarded[:words]
     _call(0, 0, M, N, A, K, K, None, 0, 0, W, N, Hh, N, bias, mask_out=bits)
+    assert bool((guarded[words:] == -1).all()), "mask_out written past tcg_mask_words"
     G = torch.randn(M, N, generator=g).cuda()
     Wt = (torch.randn(N, N, generator=g) / 16).cuda()   # [N rows (outputs), K = N cols]
     C_bits = torch.empty(M, N, device="cuda")
