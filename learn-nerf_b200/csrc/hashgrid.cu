@@ -271,6 +271,7 @@ static int launch_hash_bwd(const GridLevels& g, const float* x, const float* ray
 struct CornersD {
   uint32_t idx[8];
   float dw[8][3];  // d w_c / d x_a
+  float w[8];      // the trilinear weights themselves (same expression as level_corners)
 };
 __device__ __forceinline__ CornersD level_corners_dx(const GridLevels& g, int l, const float x[3]) {
   const int G = g.grid[l];
@@ -308,6 +309,8 @@ __device__ __forceinline__ CornersD level_corners_dx(const GridLevels& g, int l,
         out.dw[k][0] = (xo ? sa[0] : -sa[0]) * (wy * wz);
         out.dw[k][1] = (yo ? sa[1] : -sa[1]) * (wx * wz);
         out.dw[k][2] = (zo ? sa[2] : -sa[2]) * (wx * wy);
+        out.w[k] = (((1.0f + (2.0f * cf[0] - 1.0f) * float(xo)) - cf[0]) * ((1.0f + (2.0f * cf[1] - 1.0f) * float(yo)) - cf[1])) *
+                   ((1.0f + (2.0f * cf[2] - 1.0f) * float(zo)) - cf[2]);
         if (g.hashed[l]) out.idx[k] = (cx ^ (19349663u * cy) ^ (83492791u * cz)) % g.rows[l];
         else out.idx[k] = cx + uint32_t(G) * (cy + uint32_t(G) * cz);
       }
@@ -376,20 +379,24 @@ hashgrid_jtv_bwd_kernel(const float* __restrict__ tables, GridLevels g, const fl
 
 // The same, one thread per POINT (see hashgrid_bwd_pt_kernel: consecutive lanes are consecutive samples of a
 // ray, the gathers share L2 sectors, and on the dense levels a run of lanes in one cell issues ONE set of eight
-// atomics after a segmented shuffle reduction).
+// atomics after a segmented shuffle reduction).  With d_enc != nullptr the first-order scatter
+// d_table[idx_c] += w_c * d_enc rides on the same atomics (the Instant-NGP Ref-NeRF backward needs both: one
+// pass over the tables instead of two).
 template <int LT>
 __global__ void __launch_bounds__(256)
 hashgrid_jtv_bwd_pt_kernel(const float* __restrict__ tables, const __grid_constant__ GridLevels g,
                            const float* __restrict__ x, const float* __restrict__ rays, const float* __restrict__ ts,
                            int T, int64_t m, const float* __restrict__ vec, const float* __restrict__ u,
-                           float* __restrict__ tvec, float* __restrict__ d_tables) {
+                           const float* __restrict__ d_enc, float* __restrict__ tvec, float* __restrict__ d_tables) {
   const int lane = threadIdx.x & 31;
   const int64_t m_pad = (m + 31) / 32 * 32;  // whole warps stay in the loop (the reduction needs all 32 lanes)
   for (int64_t s = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; s < m_pad; s += int64_t(gridDim.x) * blockDim.x) {
     const bool in_range = s < m;
     float4 uu = make_float4(0.f, 0.f, 0.f, 0.f);
-    float2 v[LT], out[LT];
+    float2 v[LT], de[LT], out[LT];
     float p[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int l = 0; l < LT; ++l) v[l] = de[l] = make_float2(0.f, 0.f);
     if (in_range) {
       uu = __ldg(reinterpret_cast<const float4*>(u) + s);
       const float4* src = reinterpret_cast<const float4*>(vec + s * 2 * LT);
@@ -399,12 +406,18 @@ hashgrid_jtv_bwd_pt_kernel(const float* __restrict__ tables, const __grid_consta
         v[2 * q] = make_float2(t.x, t.y);
         v[2 * q + 1] = make_float2(t.z, t.w);
       }
-      load_point(x, rays, ts, T, s, p);
-    } else {
+      if (d_enc != nullptr) {
+        const float4* srcd = reinterpret_cast<const float4*>(d_enc + s * 2 * LT);
 #pragma unroll
-      for (int l = 0; l < LT; ++l) v[l] = make_float2(0.f, 0.f);
+        for (int q = 0; q < LT / 2; ++q) {
+          const float4 t = __ldg(srcd + q);
+          de[2 * q] = make_float2(t.x, t.y);
+          de[2 * q + 1] = make_float2(t.z, t.w);
+        }
+      }
+      load_point(x, rays, ts, T, s, p);
     }
-    const bool live = in_range && (uu.x != 0.0f || uu.y != 0.0f || uu.z != 0.0f);
+    const bool ulive = in_range && (uu.x != 0.0f || uu.y != 0.0f || uu.z != 0.0f);
 #pragma unroll
     for (int l = 0; l < LT; ++l) {
       const CornersD c = level_corners_dx(g, l, p);
@@ -420,11 +433,14 @@ hashgrid_jtv_bwd_pt_kernel(const float* __restrict__ tables, const __grid_consta
         acc.y = fmaf(du[k], t.y, acc.y);
       }
       out[l] = acc;
+      const bool live = ulive || de[l].x != 0.0f || de[l].y != 0.0f;
       if (g.hashed[l]) {
         if (live) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
-            if (du[k] != 0.0f) atomicAdd(dtab + c.idx[k], make_float2(du[k] * v[l].x, du[k] * v[l].y));
+          for (int k = 0; k < 8; ++k) {
+            const float ax = fmaf(c.w[k], de[l].x, du[k] * v[l].x), ay = fmaf(c.w[k], de[l].y, du[k] * v[l].y);
+            if (ax != 0.0f || ay != 0.0f) atomicAdd(dtab + c.idx[k], make_float2(ax, ay));
+          }
         }
         continue;
       }
@@ -437,8 +453,8 @@ hashgrid_jtv_bwd_pt_kernel(const float* __restrict__ tables, const __grid_consta
       float w[16];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        w[2 * k] = live ? du[k] * v[l].x : 0.0f;
-        w[2 * k + 1] = live ? du[k] * v[l].y : 0.0f;
+        w[2 * k] = live ? fmaf(c.w[k], de[l].x, du[k] * v[l].x) : 0.0f;
+        w[2 * k + 1] = live ? fmaf(c.w[k], de[l].y, du[k] * v[l].y) : 0.0f;
       }
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) {
@@ -493,7 +509,7 @@ static int make_levels(GridLevels& g, const int64_t* level_offsets, const int32_
 int hashgrid_launch(int which, const float* tables, const int64_t* level_offsets, const int32_t* grid_sizes,
                     const int32_t* table_sizes, int L, const float* bmin, const float* bmax, int smooth,
                     const float* x, const float* rays, const float* ts, int T, int64_t m, const float* in0,
-                    const float* in1, float* out0, float* out1, cudaStream_t st) {
+                    const float* in1, float* out0, float* out1, cudaStream_t st, const float* in2) {
   GridLevels g;
   int rc = make_levels(g, level_offsets, grid_sizes, table_sizes, L, bmin, bmax, smooth, "hashgrid_launch");
   if (rc) return rc;
@@ -507,16 +523,28 @@ int hashgrid_launch(int which, const float* tables, const int64_t* level_offsets
       hashgrid_jtv_kernel<<<ew_blocks(m, 256), 256, 0, st>>>(tables, g, x, rays, ts, T, m, in0, out0);
       LNRF_LAUNCH_CHECK("hashgrid_jtv_kernel");
       break;
-    case 3:  // out0 = J in1(u), d_tables(out1) += second-order scatter with vec = in0
-      if (L == 16 && (uintptr_t)in0 % 16 == 0 && (uintptr_t)out0 % 16 == 0)
-        hashgrid_jtv_bwd_pt_kernel<16><<<ew_blocks(m, 256), 256, 0, st>>>(tables, g, x, rays, ts, T, m, in0, in1, out0, out1);
-      else if (L == 6 && (uintptr_t)in0 % 16 == 0 && (uintptr_t)out0 % 16 == 0)
-        hashgrid_jtv_bwd_pt_kernel<6><<<ew_blocks(m, 256), 256, 0, st>>>(tables, g, x, rays, ts, T, m, in0, in1, out0, out1);
-      else
-        hashgrid_jtv_bwd_kernel<<<ew_blocks(m * L, 256), 256, 0, st>>>(tables, g, x, rays, ts, T, m, in0, in1, out0,
+    case 3: {  // out0 = J in1(u), d_tables(out1) += second-order scatter with vec = in0 (+ first-order scatter of
+               // d_enc = in2 when given)
+      const bool al = (uintptr_t)in0 % 16 == 0 && (uintptr_t)out0 % 16 == 0 && (uintptr_t)in2 % 16 == 0;
+      if (L == 16 && al) {
+        hashgrid_jtv_bwd_pt_kernel<16><<<ew_blocks(m, 256), 256, 0, st>>>(tables, g, x, rays, ts, T, m, in0, in1, in2, out0, out1);
+        LNRF_LAUNCH_CHECK("hashgrid_jtv_bwd_pt_kernel");
+        break;
+      }
+      if (L == 6 && al) {
+        hashgrid_jtv_bwd_pt_kernel<6><<<ew_blocks(m, 256), 256, 0, st>>>(tables, g, x, rays, ts, T, m, in0, in1, in2, out0, out1);
+        LNRF_LAUNCH_CHECK("hashgrid_jtv_bwd_pt_kernel");
+        break;
+      }
+      if (in2 != nullptr) {
+        const int rc2 = launch_hash_bwd(g, x, rays, ts, T, m, in2, out1, st);
+        if (rc2) return rc2;
+      }
+      hashgrid_jtv_bwd_kernel<<<ew_blocks(m * L, 256), 256, 0, st>>>(tables, g, x, rays, ts, T, m, in0, in1, out0,
                                                                        out1);
       LNRF_LAUNCH_CHECK("hashgrid_jtv_bwd_kernel");
       break;
+    }
     default:
       return LNRF_E_INVALID;
   }

@@ -652,7 +652,7 @@ static NgpRefWs carve_ngpref(void* base, int64_t m, int E, bool save) {
 int hashgrid_launch(int which, const float* tables, const int64_t* level_offsets, const int32_t* grid_sizes,
                     const int32_t* table_sizes, int L, const float* bmin, const float* bmax, int smooth,
                     const float* x, const float* rays, const float* ts, int T, int64_t m, const float* in0,
-                    const float* in1, float* out0, float* out1, cudaStream_t st);
+                    const float* in1, float* out0, float* out1, cudaStream_t st, const float* in2 = nullptr);
 
 }  // namespace lnrf
 
@@ -951,9 +951,10 @@ int lnrf_ngpref_bwd(const float* params, const int64_t* level_offsets_host, cons
 #define LNRF_GRID_B(which, in0, in1, out0, out1)                                                                \
   hashgrid_launch(which, P, level_offsets_host, grid_sizes_host, table_sizes_host, L, bbox_min_host, bbox_max_host, \
                   1, x, rays, ts, T, m, in0, in1, out0, out1, st)
-  if ((rc = LNRF_GRID_B(1, w.d_enc, nullptr, G, nullptr))) return rc;
-  // ---- second-order term through real_normal: tangent pass along u
-  if ((rc = LNRF_GRID_B(3, w.vec, w.u, w.tenc, G))) return rc;                                   // T_enc = J u; tables
+  // ---- table gradients: first-order scatter of d_enc and the second-order term through real_normal (tangent
+  //      pass along u) in ONE pass over the tables; T_enc = J u
+  if ((rc = hashgrid_launch(3, P, level_offsets_host, grid_sizes_host, table_sizes_host, L, bbox_min_host, bbox_max_host, 1,
+                            x, rays, ts, T, m, w.vec, w.u, w.tenc, G, st, w.d_enc))) return rc;
   if ((rc = tcg_amax(st, w.tenc, m * E, am + kNaTenc))) return rc;
   if ((rc = rg_tn(st, E, kNrHidden, w.tenc, w.gn0, m, G + nl.w[0], nullptr, am + kNaTenc, am + kNaGn0))) return rc;
   if ((rc = rg_nn<EPI_MASK>(st, m, kNrHidden, w.tenc, E, E, nullptr, 0, 0, P + nl.w[0], w.t0, nullptr, w.h0,
