@@ -399,7 +399,7 @@ def measure(args, rank, local_rank, world, dev, peaks):
         e2e_value = total_rays / (e2e_ms * 1e-3)
         train = args.workload == "train"
         what = {"nerf": "NeRF coarse+fine",
-                "ngp": "Instant-NGP coarse (L=6) + fine (L=16), " + ("bf16 tcgen05 heads" if prec == "bf16" else "fp32 FFMA heads"),
+                "ngp": "Instant-NGP coarse (L=6) + fine (L=16), " + ("bf16 tcgen05 heads" if prec == "bf16" else "fp32-accurate heads (split-fp16 tcgen05 GEMMs)"),
                 "ngpref": "Instant-NGP Ref-NeRF (smooth hash grid, sh_degree 4) coarse (L=6) + fine (L=16)",
                 "refnerf": "Ref-NeRF (sh_degree 4) coarse+fine"}[args.model]
         cfg_name = {("nerf", True): "configs[1]: ", ("ngp", True): "configs[2]: ", ("refnerf", True): "configs[3]: ",

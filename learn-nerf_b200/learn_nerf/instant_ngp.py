@@ -26,7 +26,7 @@ def hash_table_lookup(table: torch.Tensor, coords: torch.Tensor) -> torch.Tensor
 
 @dataclass
 class InstantNGPModel(ModelBase):
-    """instant_ngp.py:16-54.  ``precision``: "fp32" (FFMA heads, 1e-5) or "bf16" (heads on the tcgen05
+    """instant_ngp.py:16-54.  ``precision``: "fp32" (fp32-accurate heads: split-fp16 tcgen05 GEMMs when training, fused FFMA kernel for the workspace-free forward; 1e-5) or "bf16" (heads on the tcgen05
     tensor cores, 2e-2 abs on density / rgb); the hash grid itself is fp32 on both paths."""
 
     table_sizes: List[int]

@@ -105,7 +105,7 @@ def _rng_key(rngs):
 
 @dataclass
 class NeRFModel(ModelBase):
-    """model.py:30-62.  ``precision``: "fp32" (FFMA, 1e-5) or "bf16" (tcgen05, 2e-2)."""
+    """model.py:30-62.  ``precision``: "fp32" (split-fp16 tcgen05 GEMMs, 1e-5) or "bf16" (fused tcgen05 kernels, 2e-2)."""
 
     input_layers: int = 5
     mid_layers: int = 4
