@@ -1,2 +1,2 @@
-python -m pytest tests/test_gpu_ngpref.py tests/test_gpu_ngp.py -x -q 2>&1 | tail -3
-python bench.py --model ngpref --precision fp32 --no_extra --no_cpu_baseline --steps 10 --warmup 3 2>>gpurun_out/r07a.err | cut -c1-200
+python -m pytest tests/test_gpu_ngp.py -x -q -k "fp32_heads_train_path" -s 2>&1 | grep -v "^$" | tail -12
+LNRF_FP32_FFMA=1 python -m pytest tests/test_gpu_ngp.py tests/test_gpu_ngpref.py -x -q 2>&1 | tail -3
