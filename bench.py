@@ -438,8 +438,7 @@ def measure(args, rank, local_rank, world, dev, peaks):
               tf_peak, tf_name = ((peaks["tf"], "sustained") if train else (peaks["tf_burst"], "burst"))
               roofline = {"bound": "tensor",
                         "kernel": "nerf_fwd_cta2_kernel" + (" + nerf_bwd_dx_cta2_kernel + nerf_bwd_dw_kernel"
-                                                            if train else "") if prec == "bf16"
-                                  else "sgemm_kernel chain (fp32 FFMA)",
+                                                            if train else ""),
                         "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
                         "frac": achieved / tf_peak,
                         # DRAM bytes of the three MLP kernels per 4096-ray step, from the ncu --set full
