@@ -224,9 +224,10 @@ int lnrf_hashgrid_bwd(const int64_t* level_offsets_host, const int32_t* grid_siz
 
 /* InstantNGPModel heads (instant_ngp.py:37,46-53) on a precomputed encoding:
  * enc[m,2L] (+ d[m,3] or ray mode) -> dens[m], rgb[m,3].  params: Dense_0..4
- * flat (kernel then bias each).  One fused kernel per direction; with
- * save_for_backward the workspace keeps the layer inputs for lnrf_ngp_mlp_bwd
- * (workspace may be NULL otherwise).                                          */
+ * flat (kernel then bias each).  fp32-accurate (1e-5).  With save_for_backward
+ * the layers run as split-fp16 tcgen05 GEMMs and the workspace keeps the layer
+ * inputs, ReLU bit masks and operand ranges for lnrf_ngp_mlp_bwd; without it
+ * the forward is one fused kernel and workspace may be NULL.                  */
 int64_t lnrf_ngp_mlp_param_count(int32_t L); /* floats incl. 16-byte padding of each tensor */
 /* host out[10]: float offsets of kernel_i (out[2i]) and bias_i (out[2i+1]), i = 0..4. */
 int lnrf_ngp_mlp_param_offsets(int32_t L, int64_t* out_host);

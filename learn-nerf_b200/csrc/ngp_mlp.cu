@@ -2,13 +2,15 @@
 //   Dense_0: 2L -> 64 relu;  Dense_1: 64 -> 16 (col 0 -> exp -> density);
 //   [d_emb(24) | out(16)] -> Dense_2: 40 -> 64 relu;  Dense_3: 64 -> 64 relu;  Dense_4: 64 -> 3 tanh
 //
-// The five layers are tiny (9,920 MAC per sample), so the forward and the dX chain of the
-// backward are each ONE fused kernel: a block owns a tile of 128 samples, all weights (40 KB)
-// and the current activations sit in shared memory, and every layer is an 8x8 register-tiled
-// FFMA GEMM over that tile (64 FFMA per four 128-bit shared loads).  Only what the weight
-// gradients need (layer inputs and per-layer dL/dpre-activation) goes to HBM; dW = act^T g runs
-// on the split-fp16 tcgen05 GEMM of gemm_tc.cu (the dX kernel publishes max|g| per tensor for its operand
-// scales); LNRF_FP32_FFMA=1 keeps the 64x64 split-K FFMA kernel of sgemm.cuh for A/B measurements.
+// Two implementations:
+//  * train path (forward with save_for_backward + backward): the layers as split-fp16 tcgen05 GEMMs of gemm_tc.cu
+//    (ngp_fwd_engine / ngp_bwd_engine below: fp32-accurate, ReLU masks as bits, operand ranges through amax slots)
+//    with small kernels for the direction embedding, Dense_4 (64 -> 3) and the density exp;
+//  * workspace-free forward (render), and everything under LNRF_FP32_FFMA=1 (A/B measurements): the five layers are
+//    tiny (9,920 MAC per sample), so the forward and the dX chain of the backward are each ONE fused kernel: a block
+//    owns a tile of 128 samples, all weights (40 KB) and the current activations sit in shared memory, and every
+//    layer is an 8x8 register-tiled FFMA GEMM over that tile (64 FFMA per four 128-bit shared loads); dW = act^T g
+//    on the 64x64 split-K FFMA kernel of sgemm.cuh.
 #include "embed.cuh"
 #include "gemm_tc.cuh"
 #include "lnrf_common.cuh"
