@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import BBOX_MAX, BBOX_MIN, F, make_rays, make_uniforms
+from helpers import BBOX_MAX, BBOX_MIN, F, make_rays, make_uniforms, reproducible
 
 pytestmark = pytest.mark.gpu
 
@@ -359,7 +359,7 @@ def test_ngp_32768_rays_forward_vs_oracle_subsample():
     pts = (rays[sel, :1] + (rays[sel, 1:2] * ts[sel][:, :, None]).astype(F)).astype(F).reshape(-1, 3)
     dirs = np.ascontiguousarray(np.broadcast_to(rays[sel, 1:2], (2048, T, 3))).reshape(-1, 3)
     with torch.no_grad():
-        o_d, o_rgb, _ = o_ngp.apply(p, torch.from_numpy(pts), torch.from_numpy(dirs))
+        o_d, o_rgb, _ = reproducible(lambda: o_ngp.apply(p, torch.from_numpy(pts), torch.from_numpy(dirs)))
     got_d = dens.cpu().numpy()[sel].reshape(-1)
     got_rgb = rgb.cpu().numpy()[sel].reshape(-1, 3)
     np.testing.assert_allclose(got_d, o_d.numpy().reshape(-1), rtol=2e-5, atol=1e-6)

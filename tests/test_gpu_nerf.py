@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import BBOX_MAX, BBOX_MIN, F, make_rays, make_uniforms
+from helpers import BBOX_MAX, BBOX_MIN, F, make_rays, make_uniforms, reproducible
 
 pytestmark = pytest.mark.gpu
 
@@ -55,7 +55,7 @@ def test_mlp_fp32_forward_points(m_samples):
     d = rs.randn(m_samples, 3).astype(F)
     d /= np.linalg.norm(d, axis=1, keepdims=True)
     with torch.no_grad():
-        o_d, o_rgb, _ = nerf.apply(params["fine"], torch.from_numpy(x), torch.from_numpy(d))
+        o_d, o_rgb, _ = reproducible(lambda: nerf.apply(params["fine"], torch.from_numpy(x), torch.from_numpy(d)))
     model = NeRFModel(precision="fp32")
     dens, rgb, aux = model.apply(dict(params=to_native(model, params["fine"])), dev(x), dev(d))
     assert dens.shape == (m_samples, 1) and rgb.shape == (m_samples, 3) and aux == {}

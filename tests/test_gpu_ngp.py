@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import BBOX_MAX, BBOX_MIN, F, make_rays, make_uniforms
+from helpers import BBOX_MAX, BBOX_MIN, F, make_rays, make_uniforms, reproducible
 
 pytestmark = pytest.mark.gpu
 
@@ -101,7 +101,7 @@ def test_ngp_model_apply(levels):
     d = rs.randn(4097, 3).astype(F)
     d /= np.linalg.norm(d, axis=1, keepdims=True)
     with torch.no_grad():
-        o_d, o_rgb, _ = o.apply(p, torch.from_numpy(x), torch.from_numpy(d))
+        o_d, o_rgb, _ = reproducible(lambda: o.apply(p, torch.from_numpy(x), torch.from_numpy(d)))
     dens, rgb, aux = n.apply(dict(params=to_native(n, p)), dev(x), dev(d))
     assert dens.shape == (4097, 1) and aux == {}
     np.testing.assert_allclose(dens.cpu().numpy(), o_d.numpy(), rtol=2e-5, atol=1e-5)
@@ -300,7 +300,6 @@ def test_ngp_fp32_heads_train_path_vs_fp64(levels, n_rays, T):
     pts32 = (rays[:, :1] + (rays[:, 1:2] * ts[:, :, None]).astype(F)).astype(F)
     dirs = np.broadcast_to(rays[:, 1:2], (n_rays, T, 3)).reshape(-1, 3)
     grads = {}
-    outs = {}
     for name, dt in (("f64", torch.float64), ("f32", torch.float32)):
         pd = M.tree_map(lambda t: t.detach().clone().to(dt).requires_grad_(True), p)
         de, rgb, _ = o.apply(pd, torch.from_numpy(pts32).to(dt).reshape(-1, 3), torch.from_numpy(dirs.copy()).to(dt))
@@ -308,13 +307,14 @@ def test_ngp_fp32_heads_train_path_vs_fp64(levels, n_rays, T):
             (rgb.reshape(n_rays, T, 3) * torch.from_numpy(d_rgb).to(dt)).sum()
         loss.backward()
         grads[name] = {path: leaf.grad.double().numpy() for path, leaf in M.tree_leaves(pd)}
-        outs[name] = (de.detach().double().numpy(), rgb.detach().double().numpy())
     tree = to_native(n, p)
     dens, col, _, ctx = n.apply_rays(tree, dev(rays), dev(ts), save=True, slot="t32")
     # outputs against the fp32 oracle (the reference's dtype; as in test_ngp_model_apply): the fp32 cell fractions
     # of the 2048^3 level alone sit ~1e-4 from an fp64 evaluation
-    np.testing.assert_allclose(col.cpu().numpy().reshape(-1, 3), outs["f32"][1], atol=1e-5)
-    np.testing.assert_allclose(dens.cpu().numpy().reshape(-1), outs["f32"][0].reshape(-1), rtol=2e-5, atol=1e-5)
+    with torch.no_grad():
+        o32_d, o32_rgb, _ = reproducible(lambda: o.apply(p, torch.from_numpy(pts32).reshape(-1, 3), torch.from_numpy(dirs.copy())))
+    np.testing.assert_allclose(col.cpu().numpy().reshape(-1, 3), o32_rgb.numpy(), atol=1e-5)
+    np.testing.assert_allclose(dens.cpu().numpy().reshape(-1), o32_d.numpy().reshape(-1), rtol=2e-5, atol=1e-5)
     g = torch.zeros_like(tree.flat)
     n.backward_rays(ctx, dev(d_dens), dev(d_rgb), g)
     torch.cuda.synchronize()

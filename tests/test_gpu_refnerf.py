@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import BBOX_MAX, BBOX_MIN, F, make_rays, make_uniforms
+from helpers import BBOX_MAX, BBOX_MIN, F, make_rays, make_uniforms, reproducible
 
 pytestmark = pytest.mark.gpu
 
@@ -50,7 +50,7 @@ def test_refnerf_apply_vs_oracle(m):
     x = rs.uniform(-1, 1, (m, 3)).astype(F)
     d = rs.randn(m, 3).astype(F)
     d /= np.linalg.norm(d, axis=1, keepdims=True)
-    o_d, o_rgb, o_aux = o.apply(p, torch.from_numpy(x), torch.from_numpy(d), create_graph=False)
+    o_d, o_rgb, o_aux = reproducible(lambda: o.apply(p, torch.from_numpy(x), torch.from_numpy(d), create_graph=False))
     dens, rgb, aux = n.apply(dict(params=tree), dev(x), dev(d))
     assert dens.shape == (m, 1) and rgb.shape == (m, 3) and set(aux) == {"normal_mse", "neg_normal"}
     np.testing.assert_allclose(dens.cpu().numpy(), o_d.numpy(), rtol=2e-5, atol=1e-6)
