@@ -45,10 +45,15 @@ def reproducible(fn, tries=4):
             return [x for v in t for x in leaves(v)]
         return [t]
 
+    def same(a, b):
+        if isinstance(a, torch.Tensor):
+            return torch.equal(a.detach(), b.detach())
+        return bool(np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True))
+
     prev = fn()
     for _ in range(tries):
         cur = fn()
-        if all(torch.equal(a.detach(), b.detach()) for a, b in zip(leaves(prev), leaves(cur))):
+        if all(same(a, b) for a, b in zip(leaves(prev), leaves(cur))):
             return cur
         prev = cur
     return prev
