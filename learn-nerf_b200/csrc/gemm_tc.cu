@@ -443,7 +443,13 @@ __global__ void __launch_bounds__(kRgThreads, 1) tcg_rows_kernel(const __grid_co
 }
 
 // ================================================================ TN GEMM (K = samples)
-constexpr int kTnThreads = 288;             // warps 0-7 producers (0-3 also drain the accumulator), warp 8 MMA issuer
+// 16 producer warps: with 8 (two per scheduler, each thread holding a whole 24-load chunk) the producers' own
+// instruction stream (~1.2 k instructions per warp and chunk) and the exposed latency of their loads bounded the
+// kernel (0.39 ms per fine-level 256 x 256 dW, of which 0.15 ms remained with loads, conversion and MMAs all
+// removed; a CTA pair with cta_group::2 MMAs that loads B once instead of twice ran at the same 0.39 ms).
+// 16 warps: 0.345 ms (fp32 NeRF step -3 %, Ref-NeRF -1.3 % on the same box).
+// (The 64-wide SMALL variant below keeps 8: its chunks are 192 samples and 17 warps cap it at 96 registers, which it spills.)
+constexpr int kTnProdBig = 16, kTnProdSmall = 8;  // producer warps (0-3 also drain the accumulator); + the MMA issuer warp
 constexpr uint32_t kTnHalf = 64 * 128;      // one [64 samples x 64 features] fp16 block
 constexpr uint32_t kTnAPart = 2 * kTnHalf;  // A hi (or lo): features 0..127 of the CTA's M block
 constexpr uint32_t kTnBPart = 4 * kTnHalf;  // B hi (or lo): up to 256 columns
@@ -474,8 +480,8 @@ struct TnArgs {
   int64_t chunks_per_cta, chunks;
 };
 
-template <bool SMALL>
-__global__ void __launch_bounds__(kTnThreads, 1) tcg_tn_kernel(const __grid_constant__ TnArgs a) {
+template <bool SMALL, int kTnProd>
+__global__ void __launch_bounds__(32 * kTnProd + 32, 1) tcg_tn_kernel(const __grid_constant__ TnArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t sbase = smem_u32(smem_raw);
   if (sbase & 1023u) __trap();
@@ -491,13 +497,13 @@ __global__ void __launch_bounds__(kTnThreads, 1) tcg_tn_kernel(const __grid_cons
 
   if (tid == 0) {
     for (int s = 0; s < kTnStages; ++s) {
-      mbar_init(bars + kTnFull + 8 * s, 8);
+      mbar_init(bars + kTnFull + 8 * s, kTnProd);
       mbar_init(bars + kTnEmpty + 8 * s, 1);
     }
     mbar_init(bars + kTnDone, 1);
     fence_barrier_init();
   }
-  if (warp == 8) {
+  if (warp == kTnProd) {
     tmem_alloc(bars + kTnTmemSlot, 512);
     tmem_relinquish();
   }
@@ -508,10 +514,10 @@ __global__ void __launch_bounds__(kTnThreads, 1) tcg_tn_kernel(const __grid_cons
   const float sa = a.a_amax ? pow2_scale(__ldg(a.a_amax)) : 1.0f;
   const float sb = a.b_amax ? pow2_scale(__ldg(a.b_amax)) : 1.0f;
 
-  if (warp < 8) {
+  if (warp < kTnProd) {
     // ===== producers
-    const int ag8 = tid & 15, ar0 = tid >> 4;  // A pieces: rows ar0 + 16 j, features mb 128 + 8 ag8 ..
-    const int bg8 = tid & 31, br0 = tid >> 5;  // B pieces: rows br0 + 8 j, columns 8 bg8 ..  (fixed columns per thread)
+    const int ag8 = tid & 15, ar0 = tid >> 4;  // A pieces: features mb 128 + 8 ag8 ..
+    const int bg8 = tid & 31, br0 = tid >> 5;  // B pieces: columns 8 bg8 ..  (fixed columns per thread)
     const int af = mb * 128 + ag8 * 8, bc = bg8 * 8;
     const bool b_active = bg8 < a.nb * 8;
     float cs[8];
@@ -520,14 +526,15 @@ __global__ void __launch_bounds__(kTnThreads, 1) tcg_tn_kernel(const __grid_cons
     const bool do_db = a.db != nullptr && mb == 0;
     uint32_t stage = 0, phases = 0;
     if constexpr (SMALL) {
-      // pieces of 8 floats: p = tid + 256 j -> sample p / 8, features / columns 8 (tid & 7) .. (fixed per thread)
+      // pieces of 8 floats: p = tid + 32 kTnProd j -> sample p / 8, features / columns 8 (tid & 7) .. (fixed per thread)
       const int g8 = tid & 7, f0 = g8 * 8;
       for (int64_t q = 0; q < nq; ++q) {
         const int64_t k0 = (q0 + q) * kTnSmallRows;
-        float4 va[12], vb[12];
+        constexpr int kPieces = 48 / kTnProd;
+        float4 va[2 * kPieces], vb[2 * kPieces];
 #pragma unroll
-        for (int j = 0; j < 6; ++j) {
-          const int64_t row = k0 + (tid >> 3) + 32 * j;
+        for (int j = 0; j < kPieces; ++j) {
+          const int64_t row = k0 + (tid >> 3) + 4 * kTnProd * j;
           va[2 * j] = va[2 * j + 1] = vb[2 * j] = vb[2 * j + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (row < a.K) {
             const float* pa = a.At + row * a.lda + f0;
@@ -543,8 +550,8 @@ __global__ void __launch_bounds__(kTnThreads, 1) tcg_tn_kernel(const __grid_cons
         const uint32_t s_ah = sbase + stage * kTnStage, s_al = s_ah + kTnSmallPart;
         const uint32_t s_bh = s_al + kTnSmallPart, s_bl = s_bh + kTnSmallPart;
 #pragma unroll
-        for (int j = 0; j < 6; ++j) {
-          const int r = (tid >> 3) + 32 * j;
+        for (int j = 0; j < kPieces; ++j) {
+          const int r = (tid >> 3) + 4 * kTnProd * j;
           const uint32_t off = uint32_t(r) * 128u + (uint32_t((g8 ^ (r & 7)) & 7) << 4);
           split8_store(va[2 * j], va[2 * j + 1], sa, s_ah + off, s_al + off);
           split8_store(vb[2 * j], vb[2 * j + 1], sb, s_bh + off, s_bl + off);
@@ -559,15 +566,14 @@ __global__ void __launch_bounds__(kTnThreads, 1) tcg_tn_kernel(const __grid_cons
         if (++stage == kTnStages) stage = 0;
       }
     } else
-    // One chunk = 8 + 16 sixteen-byte loads per thread, all issued before the first use (96 KB in flight per
-    // SM); nine warps cap the kernel at 168 registers, which rules out a second chunk of register prefetch
-    // (measured: a three-deep ring of half chunks spills and runs 3x slower).
+    // One chunk = 4 + 8 sixteen-byte loads per thread, all issued before the first use (96 KB in flight per SM).
     for (int64_t q = 0; q < nq; ++q) {
       const int64_t k0 = (q0 + q) * 64;
-      float4 va[8], vb[16];
+      constexpr int kPa = 32 / kTnProd, kPb = 64 / kTnProd;  // pieces per thread: A rows ar0 + 2 kTnProd j, B rows br0 + kTnProd j
+      float4 va[2 * kPa], vb[2 * kPb];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int64_t row = k0 + ar0 + 16 * j;
+      for (int j = 0; j < kPa; ++j) {
+        const int64_t row = k0 + ar0 + 2 * kTnProd * j;
         va[2 * j] = make_float4(0.f, 0.f, 0.f, 0.f);
         va[2 * j + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (row < a.K) {
@@ -577,8 +583,8 @@ __global__ void __launch_bounds__(kTnThreads, 1) tcg_tn_kernel(const __grid_cons
         }
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int64_t row = k0 + br0 + 8 * j;
+      for (int j = 0; j < kPb; ++j) {
+        const int64_t row = k0 + br0 + kTnProd * j;
         vb[2 * j] = make_float4(0.f, 0.f, 0.f, 0.f);
         vb[2 * j + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (b_active && row < a.K) {
@@ -592,15 +598,15 @@ __global__ void __launch_bounds__(kTnThreads, 1) tcg_tn_kernel(const __grid_cons
       const uint32_t s_ah = sbase + stage * kTnStage, s_al = s_ah + kTnAPart;
       const uint32_t s_bh = s_al + kTnAPart, s_bl = s_bh + kTnBPart;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int r = ar0 + 16 * j;
+      for (int j = 0; j < kPa; ++j) {
+        const int r = ar0 + 2 * kTnProd * j;
         const uint32_t off = uint32_t(ag8 >> 3) * kTnHalf + uint32_t(r) * 128u + (uint32_t(((ag8 & 7) ^ (r & 7)) & 7) << 4);
         split8_store(va[2 * j], va[2 * j + 1], sa, s_ah + off, s_al + off);
       }
       if (b_active) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int r = br0 + 8 * j;
+        for (int j = 0; j < kPb; ++j) {
+          const int r = br0 + kTnProd * j;
           const uint32_t off = uint32_t(bg8 >> 3) * kTnHalf + uint32_t(r) * 128u + (uint32_t(((bg8 & 7) ^ (r & 7)) & 7) << 4);
           split8_store(vb[2 * j], vb[2 * j + 1], sb, s_bh + off, s_bl + off);
           if (do_db) {
@@ -617,25 +623,25 @@ __global__ void __launch_bounds__(kTnThreads, 1) tcg_tn_kernel(const __grid_cons
     // wait for the last MMAs: shared memory and the accumulator are then free / complete
     mbar_wait(bars + kTnDone, 0);
     tc_fence_after();
-    if (do_db) {  // fold the eight row groups of a column through shared memory, one atomic per column
+    if (do_db) {  // fold the row groups of a column (tid >> 5 resp. tid >> 3) through shared memory, one atomic per column
       float* s_cs = reinterpret_cast<float*>(smem_raw);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if constexpr (SMALL) {  // 32 row groups x 64 columns
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kTnProd) : "memory");
+      if constexpr (SMALL) {  // 4 kTnProd row groups x 64 columns
 #pragma unroll
         for (int j = 0; j < 8; ++j) s_cs[(tid >> 3) * 64 + (tid & 7) * 8 + j] = cs[j];
       } else if (b_active) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) s_cs[br0 * 256 + bc + j] = cs[j];
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kTnProd) : "memory");
       if (tid < a.N) {
         float t = 0.0f;
         if constexpr (SMALL) {
 #pragma unroll 8
-          for (int g = 0; g < 32; ++g) t += s_cs[g * 64 + tid];
+          for (int g = 0; g < 4 * kTnProd; ++g) t += s_cs[g * 64 + tid];
         } else {
 #pragma unroll
-          for (int g = 0; g < 8; ++g) t += s_cs[g * 256 + tid];
+          for (int g = 0; g < kTnProd; ++g) t += s_cs[g * 256 + tid];
         }
         atomicAdd(a.db + tid, t);
       }
@@ -694,7 +700,7 @@ __global__ void __launch_bounds__(kTnThreads, 1) tcg_tn_kernel(const __grid_cons
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, 512);
+  if (warp == kTnProd) tmem_dealloc(tmem, 512);
 }
 
 __global__ void __launch_bounds__(256) tcg_amax_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ amax) {
@@ -805,8 +811,8 @@ int tcg_tn_acc(cudaStream_t st, int M, int N, const float* At, int lda, const fl
   a.chunks_per_cta = ceil_div(a.chunks, splits);
   if (a.chunks_per_cta < 4) a.chunks_per_cta = 4;
   splits = ceil_div(a.chunks, a.chunks_per_cta);
-  if (small) tcg_tn_kernel<true><<<unsigned(splits * a.mblocks), kTnThreads, kTnSmem, st>>>(a);
-  else tcg_tn_kernel<false><<<unsigned(splits * a.mblocks), kTnThreads, kTnSmem, st>>>(a);
+  if (small) tcg_tn_kernel<true, kTnProdSmall><<<unsigned(splits * a.mblocks), 32 * kTnProdSmall + 32, kTnSmem, st>>>(a);
+  else tcg_tn_kernel<false, kTnProdBig><<<unsigned(splits * a.mblocks), 32 * kTnProdBig + 32, kTnSmem, st>>>(a);
   LNRF_LAUNCH_CHECK("tcg_tn_kernel");
   return LNRF_OK;
 }
@@ -835,8 +841,8 @@ int init_gemm_tc() {
   LNRF_CUDA(cudaFuncSetAttribute(tcg_rows_kernel<TCG_RANK1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRgSmem));
   LNRF_CUDA(cudaFuncSetAttribute(tcg_rows_kernel<TCG_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRgSmem));
   LNRF_CUDA(cudaFuncSetAttribute(tcg_rows_kernel<TCG_MASKBITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRgSmem));
-  LNRF_CUDA(cudaFuncSetAttribute(tcg_tn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTnSmem));
-  LNRF_CUDA(cudaFuncSetAttribute(tcg_tn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTnSmem));
+  LNRF_CUDA(cudaFuncSetAttribute(tcg_tn_kernel<false, kTnProdBig>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTnSmem));
+  LNRF_CUDA(cudaFuncSetAttribute(tcg_tn_kernel<true, kTnProdSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTnSmem));
   return LNRF_OK;
 }
 

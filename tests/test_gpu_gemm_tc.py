@@ -103,7 +103,9 @@ def test_rows_scaled_operand(scale):
                                        (200, 64, 64), (100000, 256, 256),
                                        # M, N <= 64: the 192-sample-chunk variant (the Instant-NGP head shapes)
                                        (100001, 64, 64), (50000, 40, 64), (7777, 64, 16), (191, 32, 64),
-                                       (193, 12, 64), (768, 64, 4)])
+                                       (193, 12, 64), (768, 64, 4),
+                                       # M > 128 and an even number of 64-column blocks: the CTA-pair (cta_group::2) variant
+                                       (7000, 192, 128), (300, 132, 256), (64, 256, 256), (31, 256, 128), (50001, 252, 244)])
 def test_tn_vs_fp64(Ksamp, M, N):
     g = torch.Generator().manual_seed(Ksamp)
     H = torch.relu(torch.randn(Ksamp, M, generator=g)).cuda()
