@@ -188,44 +188,77 @@ __global__ void __launch_bounds__(kRgThreads, 1) tcg_rows_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem = bar_words[kRgTmemSlot / 4];
 
-  // ---- resident W operand of this column half: max |w| first (its own power-of-two scale), then hi / lo
-  auto w_at = [&](int c, int n, int k) -> float {  // chunk c, row n of the half, column k of the chunk
-    const RgChunkDesc cd = a.ch[c];
-    if (k >= cd.kv || n0 + n >= a.N) return 0.0f;
-    const int64_t kk = cd.bk0 + k, nn = n0 + n;
-    return a.btrans ? __ldg(a.B + nn * a.ldb + kk) : __ldg(a.B + kk * a.ldb + nn);
-  };
-  // item -> (chunk c, row n, 8-column group g8); consecutive threads walk along the contiguous axis of W
-  // (n for W[k][n], k for Wt[n][k]) so that the loads of a warp coalesce
+  // ---- resident W operand of this column half.  ONE pass over global memory (every CTA reads the same W, so the
+  // pass is bound by the L2's broadcast bandwidth: the earlier max-then-convert version read W twice, ~3.7 us per
+  // 64-row chunk): each chunk lands as raw fp32 in its own 32 KB of shared memory ([64 k][128 n] for W[k][n],
+  // [128 n][64 k] for Wt[n][k]; zero outside the matrix) while max |w| is taken, then it is split in place into
+  // the hi / lo blocks (all of a chunk's items are read into registers before any is written).
   const int bt = a.btrans;
+  const int ncols = a.N - n0 < 128 ? a.N - n0 : 128;
+  float* rawf = reinterpret_cast<float*>(smem_raw);
   {
-    // max |w| over this CTA's part of W with coalesced 16-byte loads: [Ktot rows] x [ncols contiguous floats] for
-    // W[k][n], [ncols rows] x [Ktot contiguous floats] for Wt[n][k]
     float mx = 0.0f;
-    const int ktot = a.ch[a.nchunks - 1].bk0 + a.ch[a.nchunks - 1].kv;
-    const int ncols = a.N - n0 < 128 ? a.N - n0 : 128;
-    const int rows = bt ? ncols : ktot, q4 = (bt ? ktot : ncols) >> 2;
-    const float* base = bt ? a.B + int64_t(n0) * a.ldb : a.B + n0;
+    for (int c = 0; c < a.nchunks; ++c) {
+      const RgChunkDesc cd = a.ch[c];
+      float4* raw4 = reinterpret_cast<float4*>(rawf + c * (kRgChunk / 4));
+      if (!bt) {  // rows k = bk0 .. bk0 + kv - 1, 128 consecutive n from n0
+        const float* base = a.B + int64_t(cd.bk0) * a.ldb + n0;
 #pragma unroll 4
-    for (int i = tid; i < rows * q4; i += kRgThreads) {
-      const int r = i / q4, q = i - r * q4;
-      const float4 v = __ldg(reinterpret_cast<const float4*>(base + int64_t(r) * a.ldb) + q);
-      mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+        for (int i = tid; i < 64 * 32; i += kRgThreads) {
+          const int k = i >> 5, q = i & 31;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (k < cd.kv && 4 * q < ncols) v = __ldg(reinterpret_cast<const float4*>(base + int64_t(k) * a.ldb) + q);
+          mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+          raw4[i] = v;
+        }
+      } else {    // rows n = n0 .. n0 + ncols - 1, kv consecutive k from bk0
+        const float* base = a.B + int64_t(n0) * a.ldb + cd.bk0;
+#pragma unroll 4
+        for (int i = tid; i < 128 * 16; i += kRgThreads) {
+          const int n = i >> 4, q = i & 15;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (n < ncols && 4 * q < cd.kv) v = __ldg(reinterpret_cast<const float4*>(base + int64_t(n) * a.ldb) + q);
+          mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+          raw4[i] = v;
+        }
+      }
     }
     mx = warp_max(mx);
     if (lane == 0) atomicMax(const_cast<uint32_t*>(bar_words + kRgBMax / 4), __float_as_uint(mx));
   }
   __syncthreads();
   const float sb = pow2_scale(__uint_as_float(bar_words[kRgBMax / 4]));
-#pragma unroll 2
-  for (int item = tid; item < a.nchunks * 1024; item += kRgThreads) {
-    const int c = item >> 10, n = bt ? (item >> 3) & 127 : item & 127, g8 = bt ? item & 7 : (item >> 7) & 7;
-    float v[8];
+  for (int c = 0; c < a.nchunks; ++c) {
+    // item -> (row n, 8-column group g8); 1024 items per chunk, at most two per thread
+    const float* raw = rawf + c * (kRgChunk / 4);
+    float v[2][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = w_at(c, n, g8 * 8 + j);
-    const uint32_t off = uint32_t(n) * 128u + (uint32_t((g8 ^ (n & 7)) & 7) << 4);
-    split8_store(make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]), sb,
-                 sB + c * kRgChunk + off, sB + c * kRgChunk + kRgBlock + off);
+    for (int h = 0; h < 2; ++h) {
+      const int item = tid + h * kRgThreads;
+      if (item < 1024) {
+        const int n = bt ? item >> 3 : item & 127, g8 = bt ? item & 7 : item >> 7;
+        if (bt) {
+          const float4 x0 = *reinterpret_cast<const float4*>(raw + n * 64 + g8 * 8);
+          const float4 x1 = *reinterpret_cast<const float4*>(raw + n * 64 + g8 * 8 + 4);
+          v[h][0] = x0.x; v[h][1] = x0.y; v[h][2] = x0.z; v[h][3] = x0.w;
+          v[h][4] = x1.x; v[h][5] = x1.y; v[h][6] = x1.z; v[h][7] = x1.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[h][j] = raw[(g8 * 8 + j) * 128 + n];
+        }
+      }
+    }
+    __syncthreads();  // every raw value of this chunk is in registers
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int item = tid + h * kRgThreads;
+      if (item < 1024) {
+        const int n = bt ? item >> 3 : item & 127, g8 = bt ? item & 7 : item >> 7;
+        const uint32_t off = uint32_t(n) * 128u + (uint32_t((g8 ^ (n & 7)) & 7) << 4);
+        split8_store(make_float4(v[h][0], v[h][1], v[h][2], v[h][3]), make_float4(v[h][4], v[h][5], v[h][6], v[h][7]), sb,
+                     sB + c * kRgChunk + off, sB + c * kRgChunk + kRgBlock + off);
+      }
+    }
   }
   fence_proxy_async_smem();
   __syncthreads();
