@@ -606,36 +606,55 @@ ngp_mid_kernel(const float* __restrict__ d, const float* __restrict__ rays, int 
   }
 }
 
-// Dense_4 (64 -> 3) + tanh (:53): a warp takes 32 samples, lane = 2 hidden units, three shuffle reductions per sample
-// folded into one transposed pass (lane t ends up with the three sums of sample t).
+// Dense_4 (64 -> 3) + tanh (:53): a warp takes 32 samples, lane = sample.  The 32 x 64 tile of h3 comes in with
+// coalesced 16-byte loads (two halves of 32 features) and is transposed through a padded shared-memory tile, so
+// every lane then walks its own row against the broadcast weights: 5 instructions per feature and 32 samples
+// (the warp-per-sample version spent 15 shuffles + 15 adds per sample on the three reductions).
 __global__ void __launch_bounds__(256)
 ngp_rgb_kernel(const float* __restrict__ h3, const float* __restrict__ w4, const float* __restrict__ b4, int64_t m,
                float* __restrict__ rgb) {
-  const int lane = threadIdx.x & 31;
+  __shared__ float s_tile[8][32 * 33];
+  __shared__ __align__(16) float s_w[kNgpHidden * 4];
+  for (int i = threadIdx.x; i < kNgpHidden * 4; i += blockDim.x) s_w[i] = (i & 3) < 3 ? __ldg(w4 + (i >> 2) * 3 + (i & 3)) : 0.0f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float* tile = s_tile[wib];
   const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
-  float w[2][3];
-#pragma unroll
-  for (int k = 0; k < 2; ++k)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) w[k][j] = __ldg(w4 + (lane * 2 + k) * 3 + j);
   const float bb[3] = {__ldg(b4), __ldg(b4 + 1), __ldg(b4 + 2)};
+  const int lr = lane >> 3, lq = lane & 7;  // loads: row 4 it + lr of the tile, floats 4 lq .. 4 lq + 3 of the half row
   for (int64_t base = warp * 32; base < m; base += nwarps * 32) {
-    const int cnt = m - base < 32 ? int(m - base) : 32;
-    float o[3] = {0.f, 0.f, 0.f};
-#pragma unroll 4
-    for (int t = 0; t < cnt; ++t) {
-      const float2 a = __ldg(reinterpret_cast<const float2*>(h3 + (base + t) * kNgpHidden) + lane);
+    float o0 = bb[0], o1 = bb[1], o2 = bb[2];
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const float part = warp_sum(fmaf(a.x, w[0][j], a.y * w[1][j]));
-        if (lane == t) o[j] = part;
+    for (int half = 0; half < 2; ++half) {
+      float4 v[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int64_t row = base + 4 * it + lr;
+        v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < m) v[it] = __ldg(reinterpret_cast<const float4*>(h3 + row * kNgpHidden + half * 32) + lq);
+      }
+      __syncwarp();  // the previous half's readers are done
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        float* p = tile + (4 * it + lr) * 33 + 4 * lq;
+        p[0] = v[it].x; p[1] = v[it].y; p[2] = v[it].z; p[3] = v[it].w;
+      }
+      __syncwarp();
+#pragma unroll 8
+      for (int k = 0; k < 32; ++k) {
+        const float x = tile[lane * 33 + k];
+        const float4 w = *reinterpret_cast<const float4*>(s_w + (half * 32 + k) * 4);
+        o0 = fmaf(x, w.x, o0);
+        o1 = fmaf(x, w.y, o1);
+        o2 = fmaf(x, w.z, o2);
       }
     }
-    if (lane < cnt) {
-      const int64_t s = base + lane;
-#pragma unroll
-      for (int j = 0; j < 3; ++j) rgb[s * 3 + j] = tanhf(o[j] + bb[j]);
+    const int64_t s = base + lane;
+    if (s < m) {
+      rgb[s * 3 + 0] = tanhf(o0);
+      rgb[s * 3 + 1] = tanhf(o1);
+      rgb[s * 3 + 2] = tanhf(o2);
     }
   }
 }
